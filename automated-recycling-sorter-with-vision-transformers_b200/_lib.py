@@ -1,0 +1,123 @@
+"""ctypes binding of libvitk.so — the C ABI declared in include/vitk.h.
+
+There is deliberately no fallback: if the shared library is missing or a call fails, a
+`VitkError` is raised.  PyTorch only supplies device buffers (`Tensor.data_ptr()`) and the current
+CUDA stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+PKG_DIR = Path(__file__).resolve().parent
+LIB_PATH = PKG_DIR / "libvitk.so"
+
+ABI_VERSION = 1
+
+EPI_BF16 = 0
+EPI_GELU_BF16 = 1
+EPI_RESID_F32 = 2
+EPI_F32 = 3
+EPI_DGELU_BF16 = 4
+
+
+class VitkError(RuntimeError):
+    pass
+
+
+class VitkConfig(C.Structure):
+    _fields_ = [
+        ("image_size", C.c_int),
+        ("patch_size", C.c_int),
+        ("in_channels", C.c_int),
+        ("embed_dim", C.c_int),
+        ("num_layers", C.c_int),
+        ("num_heads", C.c_int),
+        ("mlp_dim", C.c_int),
+        ("n_prefix_tokens", C.c_int),
+        ("n_classes", C.c_int),
+        ("precision", C.c_int),
+        ("ln_eps", C.c_float),
+        ("dropout_p", C.c_float),
+        ("seed", C.c_uint64),
+    ]
+
+
+class VitkBlockWeights(C.Structure):
+    _fields_ = [
+        ("ln1_w", C.c_void_p), ("ln1_b", C.c_void_p),
+        ("qkv_w", C.c_void_p), ("qkv_b", C.c_void_p),
+        ("proj_w", C.c_void_p), ("proj_b", C.c_void_p),
+        ("ln2_w", C.c_void_p), ("ln2_b", C.c_void_p),
+        ("fc1_w", C.c_void_p), ("fc1_b", C.c_void_p),
+        ("fc2_w", C.c_void_p), ("fc2_b", C.c_void_p),
+    ]
+
+
+class VitkWeights(C.Structure):
+    _fields_ = [
+        ("patch_w", C.c_void_p), ("patch_b", C.c_void_p),
+        ("cls_token", C.c_void_p), ("dist_token", C.c_void_p), ("pos_embed", C.c_void_p),
+        ("blocks", C.POINTER(VitkBlockWeights)),
+        ("ln_f_w", C.c_void_p), ("ln_f_b", C.c_void_p),
+        ("head_w", C.c_void_p), ("head_b", C.c_void_p),
+    ]
+
+
+# name -> (restype, argtypes); must list every symbol include/vitk.h declares.
+_SIGNATURES = {
+    "vitk_abi_version": (C.c_int, []),
+    "vitk_last_error": (C.c_char_p, []),
+    "vitk_launch_count": (C.c_longlong, []),
+    "vitk_workspace_bytes": (C.c_int, [C.POINTER(VitkConfig), C.c_int, C.POINTER(C.c_size_t)]),
+    "vitk_forward": (C.c_int, [C.POINTER(VitkConfig), C.POINTER(VitkWeights), C.c_void_p, C.c_int,
+                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "vitk_gemm": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                            C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                            C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p]),
+    "vitk_layernorm": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_int, C.c_longlong, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                 C.c_float, C.c_void_p]),
+    "vitk_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                 C.c_int, C.c_void_p]),
+    "vitk_patchify": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                C.c_void_p]),
+    "vitk_cast_f32_to_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),
+}
+
+_lib = None
+
+
+def exported_symbols() -> list[str]:
+    return sorted(_SIGNATURES)
+
+
+def lib() -> C.CDLL:
+    """Loads libvitk.so (once). Raises VitkError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise VitkError(
+            f"{LIB_PATH} not found - build it with `python {PKG_DIR.name}/build.py` "
+            "(there is no CPU or PyTorch fallback)")
+    l = C.CDLL(str(LIB_PATH))
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(l, name)
+        fn.restype = res
+        fn.argtypes = args
+    got = l.vitk_abi_version()
+    if got != ABI_VERSION:
+        raise VitkError(f"libvitk ABI version {got}, binding expects {ABI_VERSION}")
+    _lib = l
+    return l
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = lib().vitk_last_error()
+        raise VitkError(f"vitk error {rc}: {msg.decode() if msg else '?'}")
+
+
+def launch_count() -> int:
+    return int(lib().vitk_launch_count())

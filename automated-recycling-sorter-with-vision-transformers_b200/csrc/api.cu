@@ -1,0 +1,250 @@
+// extern "C" surface of libvitk (include/vitk.h) and the forward orchestration: the kernel
+// sequence that replaces `self.backbone(images)` (reference evaluation.py:231 / train.py:831).
+#include "../../include/vitk.h"
+
+#include "common.h"
+#include "gemm_sm100.cuh"
+#include "rowops.cuh"
+
+namespace vitk {
+namespace {
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Dims {
+  int B, S, p, C, D, L, H, Mlp, prefix, P, N, Kp, hd;
+  long long M, Mp;
+};
+
+int check_config(const VitkConfig* cfg, int batch, Dims* d) {
+  VITK_REQUIRE(cfg != nullptr, "config is null");
+  VITK_REQUIRE(batch > 0, "batch must be positive (got %d)", batch);
+  VITK_REQUIRE(cfg->image_size > 0 && cfg->patch_size > 0 &&
+                   cfg->image_size % cfg->patch_size == 0,
+               "image_size %d must be a positive multiple of patch_size %d", cfg->image_size,
+               cfg->patch_size);
+  VITK_REQUIRE(cfg->embed_dim > 0 && cfg->num_heads > 0 && cfg->embed_dim % cfg->num_heads == 0,
+               "embed_dim %d must be divisible by num_heads %d", cfg->embed_dim, cfg->num_heads);
+  VITK_REQUIRE(cfg->n_prefix_tokens == 1 || cfg->n_prefix_tokens == 2,
+               "n_prefix_tokens must be 1 (ViT) or 2 (DeiT)");
+  VITK_REQUIRE(cfg->num_layers > 0 && cfg->mlp_dim > 0 && cfg->in_channels > 0, "bad layer sizes");
+  VITK_REQUIRE(cfg->embed_dim % 8 == 0 && cfg->mlp_dim % 8 == 0,
+               "embed_dim and mlp_dim must be multiples of 8");
+  d->B = batch;
+  d->S = cfg->image_size;
+  d->p = cfg->patch_size;
+  d->C = cfg->in_channels;
+  d->D = cfg->embed_dim;
+  d->L = cfg->num_layers;
+  d->H = cfg->num_heads;
+  d->Mlp = cfg->mlp_dim;
+  d->prefix = cfg->n_prefix_tokens;
+  const int gw = d->S / d->p;
+  d->P = gw * gw;
+  d->N = d->P + d->prefix;
+  d->Kp = d->C * d->p * d->p;
+  d->hd = d->D / d->H;
+  d->M = static_cast<long long>(batch) * d->N;
+  d->Mp = static_cast<long long>(batch) * d->P;
+  VITK_REQUIRE(d->M < (1ll << 31) / 4, "batch too large");
+  return VITK_OK;
+}
+
+struct Workspace {
+  float* x;     // residual stream f32 [M, D]
+  void* xn;     // LN output bf16 [M, D]
+  void* qkv;    // bf16 [M, 3D]
+  void* ctx;    // bf16 [M, D]
+  void* h;      // bf16 [M, Mlp]
+  void* patch;  // bf16 [Mp, Kp]
+  size_t bytes;
+};
+
+Workspace carve(const Dims& d, void* base) {
+  Workspace w;
+  size_t off = 0;
+  auto take = [&](size_t n) {
+    void* p = base ? static_cast<char*>(base) + off : nullptr;
+    off += align_up(n, 1024);
+    return p;
+  };
+  w.x = static_cast<float*>(take(d.M * d.D * 4));
+  w.xn = take(d.M * d.D * 2);
+  w.qkv = take(d.M * 3 * d.D * 2);
+  w.ctx = take(d.M * d.D * 2);
+  w.h = take(d.M * d.Mlp * 2);
+  w.patch = take(d.Mp * d.Kp * 2);
+  w.bytes = off;
+  return w;
+}
+
+int linear(const void* A, int lda, const void* W, int M, int N, int K, GemmEpi epi,
+           const float* bias, const float* resid, int ldr, void* out, void* out2, int ldo,
+           cudaStream_t stream) {
+  GemmProblem p;
+  p.A = A;
+  p.lda = lda;
+  p.B = W;
+  p.ldb = K;
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.epi = epi;
+  p.e.bias = bias;
+  p.e.resid = resid;
+  p.e.ldr = ldr;
+  p.e.out = out;
+  p.e.out2 = out2;
+  p.e.ldo = ldo;
+  return gemm_bf16_tn(p, stream);
+}
+
+int forward_bf16(const VitkConfig* cfg, const VitkWeights* w, const float* images, const Dims& d,
+                 float* tokens_out, float* logits_out, const Workspace& ws, cudaStream_t stream) {
+  const int M = static_cast<int>(d.M), D = d.D;
+  // -- patch embedding as a GEMM; epilogue adds bias + position embedding and writes each patch
+  //    row at its token slot (evaluation.py:142-149)
+  VITK_TRY(patchify(images, ws.patch, d.B, d.C, d.S, d.p, stream));
+  VITK_TRY(prefix_tokens(ws.x, w->cls_token, w->dist_token, w->pos_embed, d.B, d.N, D, d.prefix,
+                         stream));
+  {
+    GemmProblem p;
+    p.A = ws.patch;
+    p.lda = d.Kp;
+    p.B = w->patch_w;
+    p.ldb = d.Kp;
+    p.M = static_cast<int>(d.Mp);
+    p.N = D;
+    p.K = d.Kp;
+    p.epi = EPI_RESID_F32;
+    p.e.bias = w->patch_b;
+    p.e.resid = w->pos_embed;
+    p.e.ldr = D;
+    p.e.out = ws.x;
+    p.e.ldo = D;
+    p.e.rows_per_group = d.P;
+    p.e.group_stride = d.N;
+    p.e.group_offset = d.prefix;
+    VITK_TRY(gemm_bf16_tn(p, stream));
+  }
+  // -- encoder blocks (train.py:584-593)
+  for (int l = 0; l < d.L; ++l) {
+    const VitkBlockWeights& bw = w->blocks[l];
+    VITK_TRY(layernorm_fwd(ws.x, D, bw.ln1_w, bw.ln1_b, ws.xn, 0, D, nullptr, nullptr, M, D,
+                           cfg->ln_eps, stream));
+    VITK_TRY(linear(ws.xn, D, bw.qkv_w, M, 3 * D, D, EPI_BF16, bw.qkv_b, nullptr, 0, ws.qkv,
+                    nullptr, 3 * D, stream));
+    VITK_TRY(attention_fwd(ws.qkv, ws.ctx, nullptr, d.B, d.N, d.H, d.hd, stream));
+    VITK_TRY(linear(ws.ctx, D, bw.proj_w, M, D, D, EPI_RESID_F32, bw.proj_b, ws.x, D, ws.x,
+                    nullptr, D, stream));
+    VITK_TRY(layernorm_fwd(ws.x, D, bw.ln2_w, bw.ln2_b, ws.xn, 0, D, nullptr, nullptr, M, D,
+                           cfg->ln_eps, stream));
+    VITK_TRY(linear(ws.xn, D, bw.fc1_w, M, d.Mlp, D, EPI_GELU_BF16, bw.fc1_b, nullptr, 0, ws.h,
+                    nullptr, d.Mlp, stream));
+    VITK_TRY(linear(ws.h, d.Mlp, bw.fc2_w, M, D, d.Mlp, EPI_RESID_F32, bw.fc2_b, ws.x, D, ws.x,
+                    nullptr, D, stream));
+  }
+  // -- final LayerNorm: all tokens for the backbone contract, CLS row only for the classifier
+  if (tokens_out)
+    VITK_TRY(layernorm_fwd(ws.x, D, w->ln_f_w, w->ln_f_b, tokens_out, 1, D, nullptr, nullptr, M, D,
+                           cfg->ln_eps, stream));
+  if (logits_out)
+    VITK_TRY(cls_head(ws.x, static_cast<long long>(d.N) * D, w->ln_f_w, w->ln_f_b, w->head_w,
+                      w->head_b, nullptr, logits_out, d.B, D, cfg->n_classes, cfg->ln_eps, stream));
+  return VITK_OK;
+}
+
+}  // namespace
+}  // namespace vitk
+
+using namespace vitk;
+
+extern "C" {
+
+int vitk_abi_version(void) { return VITK_ABI_VERSION; }
+const char* vitk_last_error(void) { return last_error(); }
+long long vitk_launch_count(void) { return launch_count(); }
+
+int vitk_workspace_bytes(const VitkConfig* cfg, int batch, size_t* out_bytes) {
+  Dims d;
+  VITK_TRY(check_config(cfg, batch, &d));
+  VITK_REQUIRE(out_bytes != nullptr, "out_bytes is null");
+  *out_bytes = carve(d, nullptr).bytes;
+  return VITK_OK;
+}
+
+int vitk_forward(const VitkConfig* cfg, const VitkWeights* w, const float* images, int batch,
+                 float* tokens_out, float* logits_out, void* workspace, size_t workspace_bytes,
+                 vitk_stream_t stream) {
+  Dims d;
+  VITK_TRY(check_config(cfg, batch, &d));
+  VITK_REQUIRE(w != nullptr && images != nullptr && workspace != nullptr, "null argument");
+  VITK_REQUIRE(tokens_out != nullptr || logits_out != nullptr,
+               "at least one of tokens_out / logits_out must be non-null");
+  VITK_REQUIRE(w->blocks != nullptr && w->patch_w && w->patch_b && w->cls_token && w->pos_embed &&
+                   w->ln_f_w && w->ln_f_b,
+               "weights struct has null members");
+  VITK_REQUIRE(d.prefix == 1 || w->dist_token != nullptr, "DeiT needs dist_token");
+  if (logits_out)
+    VITK_REQUIRE(cfg->n_classes > 0 && w->head_w && w->head_b,
+                 "logits requested but no classifier head configured");
+  VITK_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0,
+               "workspace must be 1024-byte aligned");
+  const Workspace ws = carve(d, workspace);
+  if (ws.bytes > workspace_bytes)
+    return set_error(VITK_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", ws.bytes,
+                     workspace_bytes);
+  VITK_REQUIRE(cfg->precision == 0, "precision mode %d not available in this build", cfg->precision);
+  VITK_REQUIRE(d.hd == 64, "bf16 path needs head_dim 64 (got %d)", d.hd);
+  return forward_bf16(cfg, w, images, d, tokens_out, logits_out, ws,
+                      static_cast<cudaStream_t>(stream));
+}
+
+int vitk_gemm(const void* A, int lda, const void* B, int ldb, int M, int N, int K, int epilogue,
+              const float* bias, const float* resid, int ldr, const void* aux, void* out, void* out2,
+              int ldo, float alpha, float beta, vitk_stream_t stream) {
+  GemmProblem p;
+  p.A = A;
+  p.lda = lda;
+  p.B = B;
+  p.ldb = ldb;
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.epi = static_cast<GemmEpi>(epilogue);
+  p.e.bias = bias;
+  p.e.resid = resid;
+  p.e.ldr = ldr;
+  p.e.aux = aux;
+  p.e.out = out;
+  p.e.out2 = out2;
+  p.e.ldo = ldo;
+  p.e.alpha = alpha;
+  p.e.beta = beta;
+  return gemm_bf16_tn(p, static_cast<cudaStream_t>(stream));
+}
+
+int vitk_layernorm(const float* x, long long in_stride, const float* gamma, const float* beta,
+                   void* y, int y_is_f32, long long out_stride, float* mean_out, float* rstd_out,
+                   int rows, int D, float eps, vitk_stream_t stream) {
+  return layernorm_fwd(x, in_stride, gamma, beta, y, y_is_f32, out_stride, mean_out, rstd_out, rows,
+                       D, eps, static_cast<cudaStream_t>(stream));
+}
+
+int vitk_attention(const void* qkv_bf16, void* ctx_bf16, float* lse_or_null, int batch, int n_tokens,
+                   int num_heads, int head_dim, vitk_stream_t stream) {
+  return attention_fwd(qkv_bf16, ctx_bf16, lse_or_null, batch, n_tokens, num_heads, head_dim,
+                       static_cast<cudaStream_t>(stream));
+}
+
+int vitk_patchify(const float* images, void* patches_bf16, int batch, int channels, int image_size,
+                  int patch_size, vitk_stream_t stream) {
+  return patchify(images, patches_bf16, batch, channels, image_size, patch_size,
+                  static_cast<cudaStream_t>(stream));
+}
+
+int vitk_cast_f32_to_bf16(const float* in, void* out_bf16, long long n, vitk_stream_t stream) {
+  return cast_f32_to_bf16(in, out_bf16, n, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,110 @@
+#include "common.h"
+
+#include <cstdarg>
+#include <cstring>
+#include <atomic>
+#include <mutex>
+
+namespace vitk {
+
+static thread_local char g_err[1024] = "";
+static std::atomic<long long> g_launches{0};
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+const char* last_error() { return g_err; }
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
+
+static std::mutex g_dev_mu;
+static int g_sm_count[64];
+static int g_cc[64];
+static bool g_dev_init[64];
+
+static void init_dev(int dev) {
+  std::lock_guard<std::mutex> lk(g_dev_mu);
+  if (g_dev_init[dev]) return;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) {
+    g_sm_count[dev] = prop.multiProcessorCount;
+    g_cc[dev] = prop.major * 10 + prop.minor;
+  }
+  g_dev_init[dev] = true;
+}
+int sm_count() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!g_dev_init[dev]) init_dev(dev);
+  return g_sm_count[dev];
+}
+int device_cc() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!g_dev_init[dev]) init_dev(dev);
+  return g_cc[dev];
+}
+
+// cuTensorMapEncodeTiled is a driver entry point; resolve it through the runtime so libvitk does
+// not link against libcuda (only stubs exist on the build box).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+static std::once_flag g_encode_once;
+
+static EncodeTiledFn get_encode() {
+  std::call_once(g_encode_once, [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) ==
+            cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  });
+  return g_encode;
+}
+
+int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t inner,
+                 uint64_t outer, uint64_t pitch_bytes, uint32_t box_inner, uint32_t box_outer,
+                 bool swizzle128) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return set_error(VITK_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (pitch_bytes & 15) != 0)
+    return set_error(VITK_ERR_INVALID,
+                     "TMA operand must be 16-byte aligned (base %p, pitch %llu bytes)", base,
+                     (unsigned long long)pitch_bytes);
+  if (box_inner * (uint32_t)elem_bytes > 128 && swizzle128)
+    return set_error(VITK_ERR_INVALID, "128B-swizzled TMA box inner extent exceeds 128 bytes");
+  if (box_outer > 256 || box_inner > 256)
+    return set_error(VITK_ERR_INVALID, "TMA box extent exceeds 256");
+  CUtensorMapDataType dt;
+  switch (elem_bytes) {
+    case 2: dt = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16; break;
+    case 4: dt = CU_TENSOR_MAP_DATA_TYPE_FLOAT32; break;
+    default: return set_error(VITK_ERR_INVALID, "unsupported TMA element size %d", elem_bytes);
+  }
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {pitch_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, dt, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(VITK_ERR_CUDA,
+                     "cuTensorMapEncodeTiled failed (%d): base %p dims {%llu,%llu} pitch %llu box "
+                     "{%u,%u}",
+                     (int)r, base, (unsigned long long)inner, (unsigned long long)outer,
+                     (unsigned long long)pitch_bytes, box_inner, box_outer);
+  return VITK_OK;
+}
+
+}  // namespace vitk

@@ -1,0 +1,60 @@
+// Host-side plumbing shared by every translation unit of libvitk: error reporting that never
+// throws across the C ABI, launch accounting, device properties, TMA descriptor encoding.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "../../include/vitk.h"
+
+namespace vitk {
+
+// Error codes are the VITK_* macros of include/vitk.h.
+
+// printf-style; stores into a thread-local buffer, returns `code`.
+int set_error(int code, const char* fmt, ...);
+const char* last_error();
+
+#define VITK_CHECK_CUDA(expr)                                                              \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess)                                                                 \
+      return ::vitk::set_error(VITK_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,      \
+                               cudaGetErrorString(_e), __FILE__, __LINE__);                \
+  } while (0)
+
+#define VITK_CHECK_LAUNCH(name)                                                            \
+  do {                                                                                     \
+    cudaError_t _e = cudaGetLastError();                                                   \
+    if (_e != cudaSuccess)                                                                 \
+      return ::vitk::set_error(VITK_ERR_CUDA, "launch of %s failed: %s", name,     \
+                               cudaGetErrorString(_e));                                    \
+    ::vitk::count_launch();                                                                \
+  } while (0)
+
+#define VITK_REQUIRE(cond, ...)                                                            \
+  do {                                                                                     \
+    if (!(cond)) return ::vitk::set_error(VITK_ERR_INVALID, __VA_ARGS__);          \
+  } while (0)
+
+#define VITK_TRY(expr)                 \
+  do {                                 \
+    int _rc = (expr);                  \
+    if (_rc != 0) return _rc;          \
+  } while (0)
+
+void count_launch();
+long long launch_count();
+
+// Cached per current device.
+int sm_count();
+int device_cc();  // e.g. 100
+
+// 2-D bf16 (or any 2-byte / 4-byte element) row-major tensor map: dims {inner, outer},
+// row pitch in bytes, box {box_inner, box_outer}, 128-byte swizzle. Cached by value.
+int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t inner,
+                 uint64_t outer, uint64_t pitch_bytes, uint32_t box_inner, uint32_t box_outer,
+                 bool swizzle128 = true);
+
+}  // namespace vitk

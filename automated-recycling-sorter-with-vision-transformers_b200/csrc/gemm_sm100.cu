@@ -1,0 +1,405 @@
+// C[M,N] = A[M,K] * B[N,K]^T with a fused epilogue — the dense-contraction kernel behind every
+// nn.Linear / the patch-embedding Conv2d of the reference encoder
+// (reference train.py:505-515 patch conv, :527-553 qkv/projection, :561-572 linear1/GELU/linear2).
+//
+// sm_100a design:
+//   * persistent kernel, one CTA per SM, static round-robin over 128 x BLOCK_N output tiles
+//   * warp 0 lane 0 : TMA producer  (cp.async.bulk.tensor, 128B swizzle, kStages-deep mbarrier ring)
+//   * warp 1 lane 0 : tcgen05.mma issuer (bf16 x bf16 -> fp32 in TMEM, 128 x BLOCK_N x 16 per MMA)
+//   * warp 2        : TMEM allocator (2 accumulator stages so tile i's epilogue overlaps tile
+//                     i+1's main loop)
+//   * warps 4..11   : epilogue — tcgen05.ld (thread == accumulator row), bias / GELU / residual /
+//                     token-row remap in registers, 16-byte vector stores to global
+#include "gemm_sm100.cuh"
+
+#include <mutex>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace vitk {
+using namespace ptx;
+
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;  // 64 bf16 = 128 bytes = one swizzle row
+constexpr int kUmmaK = 16;
+constexpr int kNumEpiWarps = 8;
+constexpr int kFirstEpiWarp = 4;
+constexpr int kNumThreads = (kFirstEpiWarp + kNumEpiWarps) * 32;  // 384
+constexpr int kAccStages = 2;
+
+template <int BLOCK_N>
+struct Cfg {
+  static constexpr int kABytes = kBlockM * kBlockK * 2;
+  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BLOCK_N == 256) ? 4 : 6;
+  static constexpr int kTmemCols = kAccStages * BLOCK_N;  // 512 or 256 (power of two)
+  static constexpr int kBarBytes = 256;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;
+  static_assert(kSmemBytes <= 232448, "exceeds 227 KB of shared memory");
+};
+
+__device__ __forceinline__ float gelu_erf(float x) {
+  return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
+}
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+  const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752440f));
+  const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+
+// Processes one 32-column chunk of one accumulator row held in v[] (raw fp32 bits).
+template <int EPI>
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int m, int n0, int N,
+                                               const GemmEpilogue& e) {
+  const bool full = (n0 + 32 <= N);
+  float x[32];
+  // ---- alpha * accumulator (+ bias); alpha is only honoured by EPI_F32
+  float acc_scale = 1.f;
+  if constexpr (EPI == EPI_F32) acc_scale = e.alpha;
+  if (full) {
+    if (e.bias != nullptr) {
+      const float4* b4 = reinterpret_cast<const float4*>(e.bias + n0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 b = __ldg(b4 + j);
+        x[4 * j + 0] = fmaf(acc_scale, __uint_as_float(v[4 * j + 0]), b.x);
+        x[4 * j + 1] = fmaf(acc_scale, __uint_as_float(v[4 * j + 1]), b.y);
+        x[4 * j + 2] = fmaf(acc_scale, __uint_as_float(v[4 * j + 2]), b.z);
+        x[4 * j + 3] = fmaf(acc_scale, __uint_as_float(v[4 * j + 3]), b.w);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) x[j] = acc_scale * __uint_as_float(v[j]);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float b = (e.bias != nullptr && n0 + j < N) ? __ldg(e.bias + n0 + j) : 0.f;
+      x[j] = fmaf(acc_scale, __uint_as_float(v[j]), b);
+    }
+  }
+
+  if constexpr (EPI == EPI_BF16 || EPI == EPI_GELU_BF16 || EPI == EPI_DGELU_BF16) {
+    const size_t off = static_cast<size_t>(m) * e.ldo + n0;
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(e.out) + off;
+    if constexpr (EPI == EPI_GELU_BF16) {
+      if (e.out2 != nullptr) {
+        __nv_bfloat16* out2 = reinterpret_cast<__nv_bfloat16*>(e.out2) + off;
+        if (full) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 pk;
+            pk.x = pack_bf16x2(x[8 * j + 0], x[8 * j + 1]);
+            pk.y = pack_bf16x2(x[8 * j + 2], x[8 * j + 3]);
+            pk.z = pack_bf16x2(x[8 * j + 4], x[8 * j + 5]);
+            pk.w = pack_bf16x2(x[8 * j + 6], x[8 * j + 7]);
+            reinterpret_cast<uint4*>(out2)[j] = pk;
+          }
+        } else {
+          _Pragma("unroll") for (int j = 0; j < 32; ++j)
+            if (n0 + j < N) out2[j] = __float2bfloat16_rn(x[j]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) x[j] = gelu_erf(x[j]);
+    }
+    if constexpr (EPI == EPI_DGELU_BF16) {
+      const __nv_bfloat16* aux = reinterpret_cast<const __nv_bfloat16*>(e.aux) + off;
+      if (full) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint4 a = __ldg(reinterpret_cast<const uint4*>(aux) + j);
+          x[8 * j + 0] *= gelu_erf_grad(bf16lo_to_f32(a.x));
+          x[8 * j + 1] *= gelu_erf_grad(bf16hi_to_f32(a.x));
+          x[8 * j + 2] *= gelu_erf_grad(bf16lo_to_f32(a.y));
+          x[8 * j + 3] *= gelu_erf_grad(bf16hi_to_f32(a.y));
+          x[8 * j + 4] *= gelu_erf_grad(bf16lo_to_f32(a.z));
+          x[8 * j + 5] *= gelu_erf_grad(bf16hi_to_f32(a.z));
+          x[8 * j + 6] *= gelu_erf_grad(bf16lo_to_f32(a.w));
+          x[8 * j + 7] *= gelu_erf_grad(bf16hi_to_f32(a.w));
+        }
+      } else {
+        _Pragma("unroll") for (int j = 0; j < 32; ++j)
+          if (n0 + j < N) x[j] *= gelu_erf_grad(__bfloat162float(aux[j]));
+      }
+    }
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 pk;
+        pk.x = pack_bf16x2(x[8 * j + 0], x[8 * j + 1]);
+        pk.y = pack_bf16x2(x[8 * j + 2], x[8 * j + 3]);
+        pk.z = pack_bf16x2(x[8 * j + 4], x[8 * j + 5]);
+        pk.w = pack_bf16x2(x[8 * j + 6], x[8 * j + 7]);
+        reinterpret_cast<uint4*>(out)[j] = pk;
+      }
+    } else {
+      _Pragma("unroll") for (int j = 0; j < 32; ++j)
+        if (n0 + j < N) out[j] = __float2bfloat16_rn(x[j]);
+    }
+  } else if constexpr (EPI == EPI_RESID_F32) {
+    int out_row = m, res_row = m;
+    if (e.rows_per_group > 0) {
+      const int g = m / e.rows_per_group;
+      const int r = m - g * e.rows_per_group;
+      out_row = g * e.group_stride + e.group_offset + r;
+      res_row = e.group_offset + r;
+    }
+    float* out = reinterpret_cast<float*>(e.out) + static_cast<size_t>(out_row) * e.ldo + n0;
+    const float* res = e.resid + static_cast<size_t>(res_row) * e.ldr + n0;
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 r = *(reinterpret_cast<const float4*>(res) + j);
+        float4 o;
+        o.x = x[4 * j + 0] + r.x;
+        o.y = x[4 * j + 1] + r.y;
+        o.z = x[4 * j + 2] + r.z;
+        o.w = x[4 * j + 3] + r.w;
+        reinterpret_cast<float4*>(out)[j] = o;
+      }
+    } else {
+      _Pragma("unroll") for (int j = 0; j < 32; ++j)
+        if (n0 + j < N) out[j] = x[j] + res[j];
+    }
+  } else if constexpr (EPI == EPI_F32) {
+    float* out = reinterpret_cast<float*>(e.out) + static_cast<size_t>(m) * e.ldo + n0;
+    const float beta = e.beta;
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 o = make_float4(x[4 * j + 0], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+        if (beta != 0.f) {
+          const float4 p = reinterpret_cast<const float4*>(out)[j];
+          o.x = fmaf(beta, p.x, o.x);
+          o.y = fmaf(beta, p.y, o.y);
+          o.z = fmaf(beta, p.z, o.z);
+          o.w = fmaf(beta, p.w, o.w);
+        }
+        reinterpret_cast<float4*>(out)[j] = o;
+      }
+    } else {
+      _Pragma("unroll") for (int j = 0; j < 32; ++j)
+        if (n0 + j < N) out[j] = (beta != 0.f) ? fmaf(beta, out[j], x[j]) : x[j];
+    }
+  }
+}
+
+template <int BLOCK_N, int EPI>
+__global__ void __launch_bounds__(kNumThreads, 1)
+gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
+               const __grid_constant__ CUtensorMap tmap_b, int M, int N, int K,
+               const GemmEpilogue e) {
+  using C = Cfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024B alignment
+  uint8_t* smem = smem_raw + (base - raw_addr);
+
+  const uint32_t bar_base = base + C::kStages * C::kStageBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (C::kStages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * C::kStages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * C::kStages + kAccStages + a); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(
+      smem + C::kStages * C::kStageBytes + 8 * (2 * C::kStages + 2 * kAccStages));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int num_m_tiles = (M + kBlockM - 1) / kBlockM;
+  const int num_n_tiles = (N + BLOCK_N - 1) / BLOCK_N;
+  const int num_tiles = num_m_tiles * num_n_tiles;
+  const int num_kb = (K + kBlockK - 1) / kBlockK;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < C::kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < kAccStages; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), kNumEpiWarps);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), C::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ======================= TMA producer =======================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / num_n_tiles;
+        const int n_blk = tile - m_blk * num_n_tiles;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sa = base + stage * C::kStageBytes;
+          const uint32_t sb = sa + C::kABytes;
+          mbar_arrive_expect_tx(full_bar(stage), C::kStageBytes);
+          tma_load_2d(sa, &tmap_a, full_bar(stage), kb * kBlockK, m_blk * kBlockM);
+          tma_load_2d(sb, &tmap_b, full_bar(stage), kb * kBlockK, n_blk * BLOCK_N);
+          if (++stage == C::kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ======================= MMA issuer =======================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = base + stage * C::kStageBytes;
+          const uint32_t sb = sa + C::kABytes;
+          const uint64_t a_desc = make_desc_sw128(sa, 16, 1024);
+          const uint64_t b_desc = make_desc_sw128(sb, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            // advance 16 elements (32 bytes) along K inside the 128-byte swizzle row
+            mma_bf16_ss(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc,
+                        (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          mma_commit(empty_bar(stage));  // frees the smem slot when these MMAs retire
+          if (++stage == C::kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        mma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+        if (++acc == kAccStages) {
+          acc = 0;
+          acc_phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp >= kFirstEpiWarp) {
+    // ======================= epilogue =======================
+    const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    const int half = (warp - kFirstEpiWarp) >> 2; // which half of the tile's columns
+    constexpr int kColsPerWarp = BLOCK_N / 2;
+    const int row_in_tile = q * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / num_n_tiles;
+      const int n_blk = tile - m_blk * num_n_tiles;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const int m = m_blk * kBlockM + row_in_tile;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                             static_cast<uint32_t>(acc * BLOCK_N + half * kColsPerWarp);
+#pragma unroll 1
+      for (int c = 0; c < kColsPerWarp / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(t_row + c * 32, v);
+        tmem_ld_wait();
+        const int n0 = n_blk * BLOCK_N + half * kColsPerWarp + c * 32;
+        if (m < M && n0 < N) epilogue_chunk<EPI>(v, m, n0, N, e);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == kAccStages) {
+        acc = 0;
+        acc_phase ^= 1u;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::kTmemCols);
+  }
+}
+
+template <int BLOCK_N, int EPI>
+int launch(const GemmProblem& p, cudaStream_t stream) {
+  using C = Cfg<BLOCK_N>;
+  auto kernel = gemm_tn_kernel<BLOCK_N, EPI>;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [&] {
+    attr_err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    C::kSmemBytes);
+  });
+  if (attr_err != cudaSuccess)
+    return set_error(VITK_ERR_CUDA, "cudaFuncSetAttribute(gemm smem %d) failed: %s", C::kSmemBytes,
+                     cudaGetErrorString(attr_err));
+  CUtensorMap ta, tb;
+  VITK_TRY(make_tmap_2d(&ta, p.A, 2, (uint64_t)p.K, (uint64_t)p.M, (uint64_t)p.lda * 2, kBlockK,
+                        kBlockM));
+  VITK_TRY(make_tmap_2d(&tb, p.B, 2, (uint64_t)p.K, (uint64_t)p.N, (uint64_t)p.ldb * 2, kBlockK,
+                        BLOCK_N));
+  const int num_tiles = ((p.M + kBlockM - 1) / kBlockM) * ((p.N + BLOCK_N - 1) / BLOCK_N);
+  int grid = sm_count();
+  if (grid <= 0) return set_error(VITK_ERR_NO_DEVICE, "no CUDA device");
+  if (num_tiles < grid) grid = num_tiles;
+  kernel<<<grid, kNumThreads, C::kSmemBytes, stream>>>(ta, tb, p.M, p.N, p.K, p.e);
+  VITK_CHECK_LAUNCH("gemm_tn_kernel");
+  return VITK_OK;
+}
+
+template <int EPI>
+int dispatch_n(const GemmProblem& p, cudaStream_t stream) {
+  // 256-wide tiles unless they would waste more than a 128-wide tiling does.
+  const int waste256 = ((p.N + 255) / 256) * 256 - p.N;
+  const int waste128 = ((p.N + 127) / 128) * 128 - p.N;
+  if (waste128 < waste256) return launch<128, EPI>(p, stream);
+  return launch<256, EPI>(p, stream);
+}
+
+}  // namespace
+
+int gemm_bf16_tn(const GemmProblem& p, cudaStream_t stream) {
+  VITK_REQUIRE(p.A && p.B && p.e.out, "gemm: null operand");
+  VITK_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, "gemm: empty problem %dx%dx%d", p.M, p.N, p.K);
+  VITK_REQUIRE(p.K % 8 == 0 && p.lda % 8 == 0 && p.ldb % 8 == 0,
+               "gemm: K/lda/ldb must be multiples of 8 (got K=%d lda=%d ldb=%d)", p.K, p.lda,
+               p.ldb);
+  VITK_REQUIRE(p.N % 8 == 0 && p.e.ldo % 8 == 0, "gemm: N and ldo must be multiples of 8");
+  VITK_REQUIRE(device_cc() >= 100, "gemm: requires an sm_100 device (found sm_%d)", device_cc());
+  switch (p.epi) {
+    case EPI_BF16: return dispatch_n<EPI_BF16>(p, stream);
+    case EPI_GELU_BF16: return dispatch_n<EPI_GELU_BF16>(p, stream);
+    case EPI_RESID_F32:
+      VITK_REQUIRE(p.e.resid != nullptr && p.e.ldr % 4 == 0, "gemm: residual epilogue needs resid");
+      return dispatch_n<EPI_RESID_F32>(p, stream);
+    case EPI_F32: return dispatch_n<EPI_F32>(p, stream);
+    case EPI_DGELU_BF16:
+      VITK_REQUIRE(p.e.aux != nullptr, "gemm: dgelu epilogue needs aux");
+      return dispatch_n<EPI_DGELU_BF16>(p, stream);
+    default: return set_error(VITK_ERR_INVALID, "gemm: unknown epilogue %d", (int)p.epi);
+  }
+}
+
+}  // namespace vitk

@@ -1,0 +1,50 @@
+// Host-visible declarations for the tcgen05 GEMM (gemm_sm100.cu).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace vitk {
+
+// Epilogue selector (compile-time variants of one kernel).
+enum GemmEpi : int {
+  EPI_BF16 = 0,        // out_bf16 = acc + bias
+  EPI_GELU_BF16 = 1,   // out_bf16 = gelu_erf(acc + bias); optional out2_bf16 = acc + bias
+  EPI_RESID_F32 = 2,   // out_f32 = acc + bias + resid_f32   (optional row remap: patch embed)
+  EPI_F32 = 3,         // out_f32 = alpha * acc + bias (+ beta * out_f32)
+  EPI_DGELU_BF16 = 4,  // out_bf16 = (acc + bias) * gelu'(aux_bf16)            (fc2 dgrad)
+  EPI_RESID_BF16 = 5,  // out_bf16 = acc + bias + resid_bf16 ... reserved for bf16 residual stream
+};
+
+struct GemmEpilogue {
+  const float* bias = nullptr;   // [N] or null
+  const float* resid = nullptr;  // EPI_RESID_F32: fp32 [*, ldr]
+  const void* aux = nullptr;     // EPI_DGELU_BF16: bf16 [M, ldo] pre-activation
+  void* out = nullptr;           // [M(out rows), ldo]
+  void* out2 = nullptr;          // EPI_GELU_BF16 optional pre-activation copy (bf16, ldo)
+  int ldo = 0;                   // elements
+  int ldr = 0;                   // elements
+  // Row remap (token assembly, reference evaluation.py:145-148 / train.py:673-678):
+  //   out_row   = (m / rows_per_group) * group_stride + group_offset + m % rows_per_group
+  //   resid_row = group_offset + m % rows_per_group        (position-embedding row)
+  // rows_per_group == 0 disables the remap (out_row = resid_row = m).
+  int rows_per_group = 0;
+  int group_stride = 0;
+  int group_offset = 0;
+  float alpha = 1.f;
+  float beta = 0.f;
+};
+
+struct GemmProblem {
+  const void* A = nullptr;  // bf16 [M, lda], K contiguous
+  const void* B = nullptr;  // bf16 [N, ldb], K contiguous  (C = A * B^T)
+  int M = 0, N = 0, K = 0;
+  int lda = 0, ldb = 0;     // elements
+  GemmEpi epi = EPI_BF16;
+  GemmEpilogue e;
+};
+
+// Returns 0 on success, else a vitk error code (message via vitk_last_error()).
+int gemm_bf16_tn(const GemmProblem& p, cudaStream_t stream);
+
+// Number of GEMM kernel launches since process start (for bench's gpu_launches accounting).
+}  // namespace vitk

@@ -1,0 +1,286 @@
+// HBM-bound row kernels of the encoder: LayerNorm, patch extraction (im2col of non-overlapping
+// patches), prefix-token rows, CLS-row LayerNorm + classifier head, dtype casts.
+// All are vectorised (16-byte accesses), coalesced along the feature dimension, warp-per-row where
+// a row reduction is needed.
+#include "rowops.cuh"
+
+#include <cuda_bf16.h>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace vitk {
+using namespace ptx;
+
+namespace {
+
+constexpr int kLnMaxVec = 8;  // 8 float4 per lane -> D <= 1024
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ void store4(float* p, float a, float b, float c, float d) {
+  *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
+}
+__device__ __forceinline__ void store4(__nv_bfloat16* p, float a, float b, float c, float d) {
+  uint2 pk;
+  pk.x = pack_bf16x2(a, b);
+  pk.y = pack_bf16x2(c, d);
+  *reinterpret_cast<uint2*>(p) = pk;
+}
+
+// nn.LayerNorm(D), eps inside the sqrt, biased variance (reference train.py:581-582,586,590;
+// evaluation.py:136,156). One warp per row, two-pass statistics in registers.
+template <typename OutT>
+__global__ void __launch_bounds__(256)
+layernorm_fwd_kernel(const float* __restrict__ x, long long in_stride,
+                     const float* __restrict__ gamma, const float* __restrict__ beta,
+                     OutT* __restrict__ y, long long out_stride, float* __restrict__ mean_out,
+                     float* __restrict__ rstd_out, int rows, int D, float eps) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const float* xr = x + static_cast<long long>(warp) * in_stride;
+  const int nvec = D >> 2;
+  float4 v[kLnMaxVec];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < kLnMaxVec; ++j) {
+    const int i = lane + 32 * j;
+    if (i < nvec) {
+      v[j] = *reinterpret_cast<const float4*>(xr + 4 * i);
+      s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+    }
+  }
+  const float mean = warp_sum(s) / static_cast<float>(D);
+  float sq = 0.f;
+#pragma unroll
+  for (int j = 0; j < kLnMaxVec; ++j) {
+    const int i = lane + 32 * j;
+    if (i < nvec) {
+      const float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
+      sq += (a * a + b * b) + (c * c + d * d);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / static_cast<float>(D) + eps);
+  if (lane == 0) {
+    if (mean_out) mean_out[warp] = mean;
+    if (rstd_out) rstd_out[warp] = rstd;
+  }
+  OutT* yr = y + static_cast<long long>(warp) * out_stride;
+#pragma unroll
+  for (int j = 0; j < kLnMaxVec; ++j) {
+    const int i = lane + 32 * j;
+    if (i < nvec) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + i);
+      const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + i);
+      store4(yr + 4 * i, (v[j].x - mean) * rstd * g.x + b.x, (v[j].y - mean) * rstd * g.y + b.y,
+             (v[j].z - mean) * rstd * g.z + b.z, (v[j].w - mean) * rstd * g.w + b.w);
+    }
+  }
+}
+
+// images f32 NCHW [B,C,S,S] -> patch rows bf16 [B*P, C*p*p], column order (c, kh, kw) ==
+// conv.weight.reshape(D, -1) (reference train.py:505-515). Each thread moves 8 pixels of one
+// image row: 32-byte read, 16-byte write.
+__global__ void __launch_bounds__(256)
+patchify_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int B, int C, int S,
+                int p) {
+  const int groups_per_row = S >> 3;
+  const long long total = static_cast<long long>(B) * C * S * groups_per_row;
+  const int grid_w = S / p;
+  const int P = grid_w * grid_w;
+  const int Kp = C * p * p;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int xg = static_cast<int>(idx % groups_per_row);
+    long long t = idx / groups_per_row;
+    const int y = static_cast<int>(t % S);
+    t /= S;
+    const int c = static_cast<int>(t % C);
+    const int b = static_cast<int>(t / C);
+    const float4* src = reinterpret_cast<const float4*>(img + idx * 8);
+    const float4 a0 = __ldg(src), a1 = __ldg(src + 1);
+    const int x0 = xg * 8;
+    const int px = x0 / p, kw0 = x0 - px * p;
+    const int py = y / p, kh = y - py * p;
+    const long long row = static_cast<long long>(b) * P + py * grid_w + px;
+    const int col = c * p * p + kh * p + kw0;
+    uint4 pk;
+    pk.x = pack_bf16x2(a0.x, a0.y);
+    pk.y = pack_bf16x2(a0.z, a0.w);
+    pk.z = pack_bf16x2(a1.x, a1.y);
+    pk.w = pack_bf16x2(a1.z, a1.w);
+    *reinterpret_cast<uint4*>(out + row * Kp + col) = pk;
+  }
+}
+
+// x[b, t, :] = token[t] + pos[t]  for the n_prefix learned tokens (CLS, and DIST for DeiT)
+// (reference evaluation.py:145-149, train.py:669-680).
+__global__ void prefix_tokens_kernel(float* __restrict__ x, const float* __restrict__ cls,
+                                     const float* __restrict__ dist, const float* __restrict__ pos,
+                                     int B, int Ntok, int D, int n_prefix) {
+  const int nvec = D >> 2;
+  const long long total = static_cast<long long>(B) * n_prefix * nvec;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int i = static_cast<int>(idx % nvec);
+    const int t = static_cast<int>((idx / nvec) % n_prefix);
+    const int b = static_cast<int>(idx / (static_cast<long long>(nvec) * n_prefix));
+    const float4 tok = __ldg(reinterpret_cast<const float4*>(t == 0 ? cls : dist) + i);
+    const float4 pe = __ldg(reinterpret_cast<const float4*>(pos + static_cast<long long>(t) * D) + i);
+    float* dst = x + (static_cast<long long>(b) * Ntok + t) * D + 4 * i;
+    store4(dst, tok.x + pe.x, tok.y + pe.y, tok.z + pe.z, tok.w + pe.w);
+  }
+}
+
+// Final LayerNorm on the CLS row only + Linear(D, n_classes): logits[b, c].
+// (north_star's classifier: Linear(D,6) on features[:,0]; LN per evaluation.py:156.)
+// One block of 128 threads per image; the normalised row lives in shared memory.
+__global__ void __launch_bounds__(128)
+cls_head_kernel(const float* __restrict__ x, long long row_stride, const float* __restrict__ gamma,
+                const float* __restrict__ beta, const float* __restrict__ head_w,
+                const float* __restrict__ head_b, float* __restrict__ feat_out,
+                float* __restrict__ logits, int D, int n_classes, float eps) {
+  extern __shared__ float srow[];  // D floats + 8 scratch
+  float* red = srow + D;
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* xr = x + static_cast<long long>(b) * row_stride;
+  float s = 0.f;
+  for (int i = tid; i < D; i += 128) {
+    const float v = xr[i];
+    srow[i] = v;
+    s += v;
+  }
+  s = warp_sum(s);
+  if (lane == 0) red[warp] = s;
+  __syncthreads();
+  const float mean = (red[0] + red[1] + red[2] + red[3]) / static_cast<float>(D);
+  __syncthreads();
+  float sq = 0.f;
+  for (int i = tid; i < D; i += 128) {
+    const float d = srow[i] - mean;
+    sq += d * d;
+  }
+  sq = warp_sum(sq);
+  if (lane == 0) red[warp] = sq;
+  __syncthreads();
+  const float rstd = rsqrtf((red[0] + red[1] + red[2] + red[3]) / static_cast<float>(D) + eps);
+  for (int i = tid; i < D; i += 128) {
+    const float v = (srow[i] - mean) * rstd * gamma[i] + beta[i];
+    srow[i] = v;
+    if (feat_out) feat_out[static_cast<long long>(b) * D + i] = v;
+  }
+  __syncthreads();
+  for (int c = warp; c < n_classes; c += 4) {
+    const float* w = head_w + static_cast<long long>(c) * D;
+    float acc = 0.f;
+    for (int i = lane; i < D; i += 32) acc = fmaf(srow[i], __ldg(w + i), acc);
+    acc = warp_sum(acc);
+    if (lane == 0) logits[static_cast<long long>(b) * n_classes + c] = acc + head_b[c];
+  }
+}
+
+__global__ void __launch_bounds__(256)
+cast_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n) {
+  const long long nvec = n >> 3;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(in) + 2 * i);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(in) + 2 * i + 1);
+    uint4 pk;
+    pk.x = pack_bf16x2(a.x, a.y);
+    pk.y = pack_bf16x2(a.z, a.w);
+    pk.z = pack_bf16x2(b.x, b.y);
+    pk.w = pack_bf16x2(b.z, b.w);
+    reinterpret_cast<uint4*>(out)[i] = pk;
+  }
+  // tail
+  const long long tail0 = nvec << 3;
+  for (long long i = tail0 + blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    out[i] = __float2bfloat16_rn(in[i]);
+}
+
+int grid_for(long long work_items, int block, int max_blocks_per_sm = 8) {
+  long long g = (work_items + block - 1) / block;
+  const long long cap = static_cast<long long>(sm_count()) * max_blocks_per_sm;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return static_cast<int>(g);
+}
+
+}  // namespace
+
+int layernorm_fwd(const float* x, long long in_stride, const float* gamma, const float* beta,
+                  void* y, int y_is_f32, long long out_stride, float* mean_out, float* rstd_out,
+                  int rows, int D, float eps, cudaStream_t stream) {
+  VITK_REQUIRE(x && gamma && beta && y, "layernorm: null operand");
+  VITK_REQUIRE(rows > 0, "layernorm: rows must be positive");
+  VITK_REQUIRE(D % 4 == 0 && D <= 128 * kLnMaxVec, "layernorm: D=%d unsupported (need D%%4==0, D<=%d)",
+               D, 128 * kLnMaxVec);
+  VITK_REQUIRE(in_stride % 4 == 0 && out_stride % 4 == 0, "layernorm: strides must be multiples of 4");
+  const int block = 256;
+  const int grid = (rows + 7) / 8;
+  if (y_is_f32)
+    layernorm_fwd_kernel<float><<<grid, block, 0, stream>>>(
+        x, in_stride, gamma, beta, static_cast<float*>(y), out_stride, mean_out, rstd_out, rows, D,
+        eps);
+  else
+    layernorm_fwd_kernel<__nv_bfloat16><<<grid, block, 0, stream>>>(
+        x, in_stride, gamma, beta, static_cast<__nv_bfloat16*>(y), out_stride, mean_out, rstd_out,
+        rows, D, eps);
+  VITK_CHECK_LAUNCH("layernorm_fwd_kernel");
+  return VITK_OK;
+}
+
+int patchify(const float* img, void* out_bf16, int B, int C, int S, int p, cudaStream_t stream) {
+  VITK_REQUIRE(img && out_bf16, "patchify: null operand");
+  VITK_REQUIRE(B > 0 && C > 0 && S > 0 && p > 0, "patchify: bad shape");
+  VITK_REQUIRE(S % p == 0 && p % 8 == 0, "patchify: need image %% patch == 0 and patch %% 8 == 0");
+  const long long work = static_cast<long long>(B) * C * S * (S / 8);
+  patchify_kernel<<<grid_for(work, 256, 16), 256, 0, stream>>>(
+      img, static_cast<__nv_bfloat16*>(out_bf16), B, C, S, p);
+  VITK_CHECK_LAUNCH("patchify_kernel");
+  return VITK_OK;
+}
+
+int prefix_tokens(float* x, const float* cls, const float* dist, const float* pos, int B, int Ntok,
+                  int D, int n_prefix, cudaStream_t stream) {
+  VITK_REQUIRE(x && cls && pos, "prefix_tokens: null operand");
+  VITK_REQUIRE(n_prefix == 1 || (n_prefix == 2 && dist), "prefix_tokens: n_prefix must be 1 or 2");
+  VITK_REQUIRE(D % 4 == 0, "prefix_tokens: D %% 4 != 0");
+  const long long work = static_cast<long long>(B) * n_prefix * (D / 4);
+  prefix_tokens_kernel<<<grid_for(work, 256), 256, 0, stream>>>(x, cls, dist, pos, B, Ntok, D,
+                                                                n_prefix);
+  VITK_CHECK_LAUNCH("prefix_tokens_kernel");
+  return VITK_OK;
+}
+
+int cls_head(const float* x, long long row_stride, const float* gamma, const float* beta,
+             const float* head_w, const float* head_b, float* feat_out, float* logits, int B, int D,
+             int n_classes, float eps, cudaStream_t stream) {
+  VITK_REQUIRE(x && gamma && beta && head_w && head_b && logits, "cls_head: null operand");
+  VITK_REQUIRE(B > 0 && D > 0 && n_classes > 0, "cls_head: bad shape");
+  cls_head_kernel<<<B, 128, (D + 8) * sizeof(float), stream>>>(x, row_stride, gamma, beta, head_w,
+                                                               head_b, feat_out, logits, D,
+                                                               n_classes, eps);
+  VITK_CHECK_LAUNCH("cls_head_kernel");
+  return VITK_OK;
+}
+
+int cast_f32_to_bf16(const float* in, void* out, long long n, cudaStream_t stream) {
+  VITK_REQUIRE(in && out && n > 0, "cast: bad argument");
+  VITK_REQUIRE((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+               "cast: pointers must be 16-byte aligned");
+  cast_f32_bf16_kernel<<<grid_for(n / 8 + 1, 256), 256, 0, stream>>>(
+      in, static_cast<__nv_bfloat16*>(out), n);
+  VITK_CHECK_LAUNCH("cast_f32_bf16_kernel");
+  return VITK_OK;
+}
+
+}  // namespace vitk

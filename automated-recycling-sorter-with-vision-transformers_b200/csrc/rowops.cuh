@@ -1,0 +1,32 @@
+// HBM-bound row kernels (rowops.cu) and the attention core (attention.cu): host launchers.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace vitk {
+
+// y[r,:] = LN(x[r,:]) * gamma + beta ; x fp32 rows at `in_stride` elements, y bf16 or fp32 rows at
+// `out_stride`; optional per-row mean / rstd outputs (saved for backward).
+int layernorm_fwd(const float* x, long long in_stride, const float* gamma, const float* beta,
+                  void* y, int y_is_f32, long long out_stride, float* mean_out, float* rstd_out,
+                  int rows, int D, float eps, cudaStream_t stream);
+
+// f32 NCHW images -> bf16 patch rows [B*P, C*p*p] in conv-weight column order.
+int patchify(const float* img, void* out_bf16, int B, int C, int S, int p, cudaStream_t stream);
+
+// Rows of the learned prefix tokens (+ their position embeddings) of the residual stream.
+int prefix_tokens(float* x, const float* cls, const float* dist, const float* pos, int B, int Ntok,
+                  int D, int n_prefix, cudaStream_t stream);
+
+// Final LayerNorm on row 0 of every image + Linear(D, n_classes).
+int cls_head(const float* x, long long row_stride, const float* gamma, const float* beta,
+             const float* head_w, const float* head_b, float* feat_out, float* logits, int B, int D,
+             int n_classes, float eps, cudaStream_t stream);
+
+int cast_f32_to_bf16(const float* in, void* out, long long n, cudaStream_t stream);
+
+// softmax(q k^T / sqrt(hd)) v for every (image, head); qkv bf16 [B*N, 3*D] packed as the reference
+// packs it (column = which*D + h*hd + d); ctx bf16 [B*N, D]; optional lse fp32 [B, H, N].
+int attention_fwd(const void* qkv, void* ctx, float* lse, int B, int N, int H, int hd,
+                  cudaStream_t stream);
+
+}  // namespace vitk

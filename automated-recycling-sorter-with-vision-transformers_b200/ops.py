@@ -1,0 +1,103 @@
+"""Tensor-level wrappers over the per-operator C-ABI entry points (include/vitk.h).
+
+Each function takes CUDA tensors, passes raw pointers + the current stream to libvitk and returns
+the output tensor.  Used by the sub-module forwards and by the parity tests; `vitk_forward` (see
+engine.py) runs the same kernels back to back without returning to Python.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import check, lib
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(*ts: torch.Tensor) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.VitkError("vitk operators need CUDA tensors (there is no CPU fallback)")
+
+
+def _ptr(t) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+def cast_bf16(x: torch.Tensor) -> torch.Tensor:
+    """fp32 -> bf16 (round to nearest even) with the library's own kernel."""
+    _need_cuda(x)
+    x = x.contiguous()
+    assert x.dtype == torch.float32
+    out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    if x.numel():
+        check(lib().vitk_cast_f32_to_bf16(x.data_ptr(), out.data_ptr(), x.numel(), _stream()))
+    return out
+
+
+def gemm(a: torch.Tensor, b: torch.Tensor, epilogue: int = _lib.EPI_BF16, *, bias=None, resid=None,
+         aux=None, out=None, out2=None, alpha: float = 1.0, beta: float = 0.0) -> torch.Tensor:
+    """out = epilogue(a @ b.T); a bf16 [M,K], b bf16 [N,K] (nn.Linear weight layout)."""
+    _need_cuda(a, b)
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
+    assert a.dim() == 2 and b.dim() == 2 and a.shape[1] == b.shape[1]
+    assert a.stride(1) == 1 and b.stride(1) == 1
+    M, K = a.shape
+    N = b.shape[0]
+    f32_out = epilogue in (_lib.EPI_RESID_F32, _lib.EPI_F32)
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32 if f32_out else torch.bfloat16, device=a.device)
+    assert out.stride(1) == 1
+    ldr = resid.stride(0) if resid is not None else 0
+    check(lib().vitk_gemm(a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), M, N, K, epilogue,
+                          _ptr(bias), _ptr(resid), ldr, _ptr(aux), out.data_ptr(), _ptr(out2),
+                          out.stride(0), alpha, beta, _stream()))
+    return out
+
+
+def layernorm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float = 1e-5,
+              out_dtype: torch.dtype = torch.bfloat16, return_stats: bool = False):
+    """nn.LayerNorm over the last dim of an fp32 [rows, D] tensor."""
+    _need_cuda(x)
+    assert x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
+    rows, D = x.shape
+    y = torch.empty((rows, D), dtype=out_dtype, device=x.device)
+    mean = rstd = None
+    if return_stats:
+        mean = torch.empty(rows, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+    check(lib().vitk_layernorm(x.data_ptr(), x.stride(0), weight.data_ptr(), bias.data_ptr(),
+                               y.data_ptr(), 1 if out_dtype == torch.float32 else 0, D, _ptr(mean),
+                               _ptr(rstd), rows, D, eps, _stream()))
+    return (y, mean, rstd) if return_stats else y
+
+
+def attention(qkv: torch.Tensor, batch: int, n_tokens: int, num_heads: int,
+              return_lse: bool = False):
+    """softmax(q k^T / sqrt(hd)) v on the packed [B*N, 3*D] bf16 qkv activation -> [B*N, D]."""
+    _need_cuda(qkv)
+    assert qkv.dtype == torch.bfloat16 and qkv.is_contiguous()
+    D = qkv.shape[-1] // 3
+    ctx = torch.empty((batch * n_tokens, D), dtype=torch.bfloat16, device=qkv.device)
+    lse = None
+    if return_lse:
+        lse = torch.empty((batch, num_heads, n_tokens), dtype=torch.float32, device=qkv.device)
+    check(lib().vitk_attention(qkv.data_ptr(), ctx.data_ptr(), _ptr(lse), batch, n_tokens,
+                               num_heads, D // num_heads, _stream()))
+    return (ctx, lse) if return_lse else ctx
+
+
+def patchify(images: torch.Tensor, patch_size: int) -> torch.Tensor:
+    """f32 NCHW -> bf16 [B*P, C*p*p] rows in conv-weight column order."""
+    _need_cuda(images)
+    assert images.dtype == torch.float32 and images.dim() == 4
+    images = images.contiguous()
+    B, Cc, S, S2 = images.shape
+    assert S == S2
+    P = (S // patch_size) ** 2
+    out = torch.empty((B * P, Cc * patch_size * patch_size), dtype=torch.bfloat16,
+                      device=images.device)
+    check(lib().vitk_patchify(images.data_ptr(), out.data_ptr(), B, Cc, S, patch_size, _stream()))
+    return out

@@ -1,0 +1,138 @@
+/* vitk — C ABI of the B200-native ViT/DeiT encoder hot path.
+ *
+ * The reference (akavkl/Automated-Recycling-Sorter-with-Vision-Transformers) has no FFI of its
+ * own: the only seam on this path is the nn.Module protocol,
+ *     features = self.backbone(images)            evaluation.py:231, train.py:831
+ *     losses.backward(); optimizer.step()         train.py:1455-1460
+ * with `backbone = VisionTransformer(...)` (evaluation.py:120-157) or
+ * `DataEfficientImageTransformer(...)` (train.py:637-688).  This header is what a Python (ctypes)
+ * or C++ host binds to replace that call; INTEGRATION.md shows the reference-side stub.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the comment says "host"
+ *   - the caller owns all memory (inputs, outputs, workspace, saved activations); the library
+ *     never allocates on the hot path and keeps no references after a call returns
+ *   - all work is enqueued on the caller's stream; nothing synchronises
+ *   - every function returns 0 on success, otherwise a VITK_ERR_* code whose text is available
+ *     from vitk_last_error() (thread-local); no C++ exception crosses this boundary
+ *   - there is no CPU fallback: without an sm_100 device every compute entry point fails
+ */
+#ifndef VITK_H_
+#define VITK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VITK_ABI_VERSION 1
+
+#define VITK_OK 0
+#define VITK_ERR_INVALID 1
+#define VITK_ERR_CUDA 2
+#define VITK_ERR_WORKSPACE 3
+#define VITK_ERR_NO_DEVICE 4
+
+typedef void* vitk_stream_t; /* cudaStream_t */
+
+/* Constructor arguments of VisionTransformer / DataEfficientImageTransformer
+ * (evaluation.py:121-122, train.py:638-639) plus what the wrapper adds. */
+typedef struct VitkConfig {
+  int image_size;      /* S */
+  int patch_size;      /* p (16) */
+  int in_channels;     /* 3 */
+  int embed_dim;       /* D */
+  int num_layers;      /* L */
+  int num_heads;       /* H */
+  int mlp_dim;         /* M */
+  int n_prefix_tokens; /* 1 = ViT (CLS), 2 = DeiT (CLS + DIST) */
+  int n_classes;       /* classifier head on the CLS row; 0 = no head */
+  int precision;       /* 0 = bf16 operands / fp32 accumulate; 1 = fp32-parity (split-bf16) */
+  float ln_eps;        /* nn.LayerNorm default 1e-5 */
+  float dropout_p;     /* applied only when training != 0 */
+  uint64_t seed;
+} VitkConfig;
+
+/* One pre-LN encoder block (train.py:576-593); names follow the state_dict keys
+ * transformer_blocks.{i}.{layer_norm1,attention.qkv,attention.projection,layer_norm2,
+ * mlp.linear1,mlp.linear2}.{weight,bias}.  Matrix weights are bf16 row-major [out, in]
+ * (nn.Linear layout); everything else fp32. */
+typedef struct VitkBlockWeights {
+  const float* ln1_w;
+  const float* ln1_b;
+  const void* qkv_w; /* bf16 [3D, D] */
+  const float* qkv_b;
+  const void* proj_w; /* bf16 [D, D] */
+  const float* proj_b;
+  const float* ln2_w;
+  const float* ln2_b;
+  const void* fc1_w; /* bf16 [M, D] */
+  const float* fc1_b;
+  const void* fc2_w; /* bf16 [D, M] */
+  const float* fc2_b;
+} VitkBlockWeights;
+
+typedef struct VitkWeights {
+  const void* patch_w;  /* bf16 [D, C*p*p] == patch_embedding.projection.weight.reshape(D,-1) */
+  const float* patch_b; /* [D] */
+  const float* cls_token;  /* [D] */
+  const float* dist_token; /* [D] or NULL (ViT) */
+  const float* pos_embed;  /* [N, D] */
+  const VitkBlockWeights* blocks; /* HOST array of num_layers entries */
+  const float* ln_f_w; /* layer_norm.weight */
+  const float* ln_f_b;
+  const float* head_w; /* fp32 [n_classes, D] or NULL */
+  const float* head_b;
+} VitkWeights;
+
+int vitk_abi_version(void);
+const char* vitk_last_error(void);
+/* Kernels launched by this library since process start (bench.py's gpu_launches). */
+long long vitk_launch_count(void);
+
+/* Scratch bytes vitk_forward needs for `batch` images. */
+int vitk_workspace_bytes(const VitkConfig* cfg, int batch, size_t* out_bytes);
+
+/* The model call.  images: f32 NCHW [batch, C, S, S] (the tensor evaluation.py:499-502 feeds).
+ * tokens_out: f32 [batch, N, D] = backbone(images) (all tokens after the final LayerNorm), or NULL.
+ * logits_out: f32 [batch, n_classes] = head(LN(x)[:,0]), or NULL.  At least one must be given. */
+int vitk_forward(const VitkConfig* cfg, const VitkWeights* w, const float* images, int batch,
+                 float* tokens_out, float* logits_out, void* workspace, size_t workspace_bytes,
+                 vitk_stream_t stream);
+
+/* ---- per-operator entry points (unit-tested individually; same kernels vitk_forward uses) ---- */
+
+/* epilogue ids for vitk_gemm */
+#define VITK_EPI_BF16 0      /* out bf16 = A B^T + bias */
+#define VITK_EPI_GELU_BF16 1 /* out bf16 = gelu_erf(A B^T + bias) [, out2 bf16 = pre-activation] */
+#define VITK_EPI_RESID_F32 2 /* out f32  = A B^T + bias + resid f32 */
+#define VITK_EPI_F32 3       /* out f32  = alpha * A B^T + bias + beta * out */
+#define VITK_EPI_DGELU_BF16 4 /* out bf16 = (A B^T + bias) * gelu'(aux bf16) */
+
+/* C[M,N] = A[M,K] * B[N,K]^T (bf16 operands, fp32 accumulate on tcgen05) + fused epilogue.
+ * Replaces nn.Linear / F.linear at train.py:527,529,561,564 and the Conv2d at train.py:505. */
+int vitk_gemm(const void* A, int lda, const void* B, int ldb, int M, int N, int K, int epilogue,
+              const float* bias, const float* resid, int ldr, const void* aux, void* out, void* out2,
+              int ldo, float alpha, float beta, vitk_stream_t stream);
+
+/* nn.LayerNorm(D) over `rows` rows (train.py:581-582). y is bf16 (y_is_f32 = 0) or f32. */
+int vitk_layernorm(const float* x, long long in_stride, const float* gamma, const float* beta,
+                   void* y, int y_is_f32, long long out_stride, float* mean_out, float* rstd_out,
+                   int rows, int D, float eps, vitk_stream_t stream);
+
+/* MultiHeadSelfAttention core (train.py:537-549) on the packed qkv activation. */
+int vitk_attention(const void* qkv_bf16, void* ctx_bf16, float* lse_or_null, int batch, int n_tokens,
+                   int num_heads, int head_dim, vitk_stream_t stream);
+
+/* Conv2d(k=p, s=p) input gather: f32 NCHW -> bf16 [B*P, C*p*p] (train.py:505-515). */
+int vitk_patchify(const float* images, void* patches_bf16, int batch, int channels, int image_size,
+                  int patch_size, vitk_stream_t stream);
+
+int vitk_cast_f32_to_bf16(const float* in, void* out_bf16, long long n, vitk_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VITK_H_ */

@@ -1,0 +1,72 @@
+"""Loads the reference's two scripts as modules (build container only; /root/reference does not
+exist on the GPU box).  Third-party imports the scripts make at module top but only use for data
+loading / visualisation (albumentations, pycocotools, matplotlib - absent here) are stubbed in
+sys.modules.  Test/fixture infrastructure only."""
+from __future__ import annotations
+
+import importlib.util
+import sys
+import types
+from pathlib import Path
+
+REFERENCE_DIR = Path("/root/reference")
+
+
+def reference_available() -> bool:
+    return (REFERENCE_DIR / "evaluation.py").exists()
+
+
+def _stub(name: str, **attrs):
+    if name in sys.modules:
+        return sys.modules[name]
+    m = types.ModuleType(name)
+    for k, v in attrs.items():
+        setattr(m, k, v)
+    sys.modules[name] = m
+    return m
+
+
+def _install_stubs():
+    try:
+        import albumentations  # noqa: F401
+    except Exception:
+        _stub("albumentations")
+        _stub("albumentations.pytorch", ToTensorV2=object)
+    try:
+        import pycocotools  # noqa: F401
+    except Exception:
+        _stub("pycocotools")
+        _stub("pycocotools.coco", COCO=object)
+        _stub("pycocotools.cocoeval", COCOeval=object)
+    try:
+        import matplotlib  # noqa: F401
+    except Exception:
+        _stub("matplotlib")
+        _stub("matplotlib.pyplot")
+        _stub("matplotlib.patches")
+    try:
+        import wandb  # noqa: F401
+    except Exception:
+        _stub("wandb")
+
+
+def load(script: str = "evaluation"):
+    """Returns the reference script as a module. `evaluation` has no import side effects;
+    `train` sets the fork start method and TF32 matmul precision (train.py:17-19) - the latter is
+    reset to 'highest' here."""
+    name = f"_reference_{script}"
+    if name in sys.modules:
+        return sys.modules[name]
+    _install_stubs()
+    spec = importlib.util.spec_from_file_location(name, REFERENCE_DIR / f"{script}.py")
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    try:
+        spec.loader.exec_module(mod)
+    except RuntimeError as e:  # mp.set_start_method raised because a context already exists
+        if "context has already been set" not in str(e):
+            raise
+    if script == "train":
+        import torch
+        torch.set_float32_matmul_precision("highest")
+    return mod

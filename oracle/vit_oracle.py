@@ -1,0 +1,182 @@
+"""ORACLE - test infrastructure only.  NOT part of the product path.
+
+A CPU restatement (PyTorch tensor arithmetic, fp32 or fp64) of the reference's ViT/DeiT encoder
+forward, the north-star 6-class CLS head, and one fine-tune train step, written from the
+reference's algorithm and citing the lines it follows.  Only `tests/`, `__graft_entry__.smoke()`
+and `bench.py`'s cpu-baseline / `--impl reference` legs may import this file; the product
+(`automated-recycling-sorter-with-vision-transformers_b200/`) never does and has no CPU fallback.
+
+Pinning: the reference ships no tests, golden vectors or fixtures for this path, so
+the oracle is pinned against the reference's OWN classes executed in the build container:
+`oracle/gen_golden.py` imports /root/reference/{evaluation,train}.py, runs them on seeded inputs and
+commits the outputs under tests/golden/; `tests/test_oracle.py` checks this restatement against
+those fixtures (and, when /root/reference is present, against the live classes).
+
+The third-party arithmetic underneath the reference is PyTorch (unpinned by the reference;
+2.11.0 in this image): nn.Conv2d, nn.Linear, torch.matmul, torch.softmax, nn.GELU (erf form),
+nn.LayerNorm (eps 1e-5, biased variance), torch.optim.AdamW.  Each is restated below from its
+published definition rather than by calling the nn.Module.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+IMAGENET_MEAN = (0.485, 0.456, 0.406)
+IMAGENET_STD = (0.229, 0.224, 0.225)
+
+
+# --------------------------------------------------------------------------------------------
+# synthetic inputs: what Resize->Normalize->ToTensorV2 (evaluation.py:360-366)
+# yields for an 8-bit RGB image
+# --------------------------------------------------------------------------------------------
+def synthetic_images(batch: int, size: int = 224, seed: int = 1234) -> torch.Tensor:
+    g = torch.Generator().manual_seed(seed)
+    u8 = torch.randint(0, 256, (batch, size, size, 3), generator=g, dtype=torch.uint8)
+    x = u8.to(torch.float32) / 255.0
+    mean = torch.tensor(IMAGENET_MEAN, dtype=torch.float32)
+    std = torch.tensor(IMAGENET_STD, dtype=torch.float32)
+    x = (x - mean) / std
+    return x.permute(0, 3, 1, 2).contiguous()
+
+
+def synthetic_labels(batch: int, n_classes: int = 6, seed: int = 1) -> torch.Tensor:
+    g = torch.Generator().manual_seed(seed)
+    return torch.randint(0, n_classes, (batch,), generator=g)
+
+
+# --------------------------------------------------------------------------------------------
+# operators
+# --------------------------------------------------------------------------------------------
+def layer_norm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float = 1e-5):
+    """nn.LayerNorm(D) - train.py:581-582,586,590,656,687: per-row mean, biased variance,
+    eps inside the square root, affine."""
+    mu = x.mean(dim=-1, keepdim=True)
+    var = ((x - mu) ** 2).mean(dim=-1, keepdim=True)
+    return (x - mu) / torch.sqrt(var + eps) * w + b
+
+
+def gelu_erf(x: torch.Tensor) -> torch.Tensor:
+    """nn.GELU() default (approximate='none') - train.py:562: 0.5 x (1 + erf(x / sqrt 2))."""
+    return 0.5 * x * (1.0 + torch.erf(x / math.sqrt(2.0)))
+
+
+def patch_embed(images: torch.Tensor, w: torch.Tensor, b: torch.Tensor, p: int) -> torch.Tensor:
+    """PatchEmbedding.forward - train.py:511-515.  Conv2d(k=p, stride=p) over non-overlapping
+    patches == one matrix product of the gathered patches [B*P, C*p*p] (column order c, kh, kw,
+    the order of conv.weight.reshape(D, -1)) with the weight; `flatten(2).transpose(1, 2)` makes
+    the token order ph * (S/p) + pw."""
+    B, C, S, _ = images.shape
+    g = S // p
+    cols = images.reshape(B, C, g, p, g, p).permute(0, 2, 4, 1, 3, 5).reshape(B, g * g, C * p * p)
+    return cols @ w.reshape(w.shape[0], -1).t() + b
+
+
+def attention(x: torch.Tensor, qkv_w, qkv_b, proj_w, proj_b, num_heads: int) -> torch.Tensor:
+    """MultiHeadSelfAttention.forward - train.py:532-555 (dropout = identity)."""
+    B, N, D = x.shape
+    hd = D // num_heads
+    qkv = x @ qkv_w.t() + qkv_b                                    # :536
+    qkv = qkv.reshape(B, N, 3, num_heads, hd).permute(2, 0, 3, 1, 4)  # :537-538
+    q, k, v = qkv[0], qkv[1], qkv[2]                               # :540
+    scores = (q @ k.transpose(-2, -1)) / (hd ** 0.5)               # :543 (divide AFTER the product)
+    probs = torch.softmax(scores, dim=-1)                          # :544
+    ctx = probs @ v                                                # :548
+    ctx = ctx.transpose(1, 2).reshape(B, N, D)                     # :549
+    return ctx @ proj_w.t() + proj_b                               # :552
+
+
+def mlp(x: torch.Tensor, w1, b1, w2, b2) -> torch.Tensor:
+    """MLPBlock.forward - train.py:567-573."""
+    return gelu_erf(x @ w1.t() + b1) @ w2.t() + b2
+
+
+def encoder_block(x: torch.Tensor, sd: dict, prefix: str, num_heads: int) -> torch.Tensor:
+    """TransformerBlock.forward - train.py:584-593 (pre-LN residual block)."""
+    g = lambda k: sd[prefix + k]
+    x = x + attention(layer_norm(x, g("layer_norm1.weight"), g("layer_norm1.bias")),
+                      g("attention.qkv.weight"), g("attention.qkv.bias"),
+                      g("attention.projection.weight"), g("attention.projection.bias"), num_heads)
+    x = x + mlp(layer_norm(x, g("layer_norm2.weight"), g("layer_norm2.bias")),
+                g("mlp.linear1.weight"), g("mlp.linear1.bias"),
+                g("mlp.linear2.weight"), g("mlp.linear2.bias"))
+    return x
+
+
+def infer_dims(sd: dict, prefix: str = "") -> dict:
+    w = sd[prefix + "patch_embedding.projection.weight"]
+    n_layers = 1 + max(int(k[len(prefix):].split(".")[1]) for k in sd
+                       if k.startswith(prefix + "transformer_blocks."))
+    return dict(embed_dim=w.shape[0], in_channels=w.shape[1], patch_size=w.shape[2],
+                num_layers=n_layers, n_tokens=sd[prefix + "position_embedding"].shape[1],
+                n_prefix=2 if (prefix + "dist_token") in sd else 1)
+
+
+def backbone_forward(sd: dict, images: torch.Tensor, num_heads: int, prefix: str = "",
+                     dtype: torch.dtype = torch.float32) -> torch.Tensor:
+    """VisionTransformer.forward (evaluation.py:138-157) / DataEfficientImageTransformer.forward
+    (train.py:666-688) in eval mode: returns all tokens after the final LayerNorm."""
+    sd = {k: v.to(dtype) for k, v in sd.items() if k.startswith(prefix)}
+    dims = infer_dims(sd, prefix)
+    g = lambda k: sd[prefix + k]
+    x = patch_embed(images.to(dtype), g("patch_embedding.projection.weight"),
+                    g("patch_embedding.projection.bias"), dims["patch_size"])
+    B = x.shape[0]
+    toks = [g("cls_token").expand(B, -1, -1)]
+    if dims["n_prefix"] == 2:
+        toks.append(g("dist_token").expand(B, -1, -1))         # train.py:670-673
+    x = torch.cat(toks + [x], dim=1) + g("position_embedding")  # evaluation.py:145-149
+    for i in range(dims["num_layers"]):                          # evaluation.py:153-154
+        x = encoder_block(x, sd, f"{prefix}transformer_blocks.{i}.", num_heads)
+    return layer_norm(x, g("layer_norm.weight"), g("layer_norm.bias"))  # evaluation.py:156
+
+
+def classifier_forward(sd: dict, images: torch.Tensor, num_heads: int,
+                       dtype: torch.dtype = torch.float32):
+    """RefClassifier of SURVEY.md 8c: Linear(D, C)(backbone(images)[:, 0]).
+    sd uses the keys of ViTClassifier: 'backbone.*', 'head.weight', 'head.bias'."""
+    tokens = backbone_forward(sd, images, num_heads, prefix="backbone.", dtype=dtype)
+    logits = tokens[:, 0] @ sd["head.weight"].to(dtype).t() + sd["head.bias"].to(dtype)
+    return tokens, logits
+
+
+# --------------------------------------------------------------------------------------------
+# train step (train.py:1441-1460 with the north-star's 6-class cross-entropy in place of the
+# detection loss; optimizer per train.py:1598-1602)
+# --------------------------------------------------------------------------------------------
+def cross_entropy(logits: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+    """mean over the batch of -log softmax(logits)[label] (F.cross_entropy default reduction)."""
+    lse = torch.logsumexp(logits, dim=-1)
+    return (lse - logits.gather(1, labels[:, None]).squeeze(1)).mean()
+
+
+def adamw_step(params: dict, grads: dict, m: dict, v: dict, step: int, lr=1e-4, betas=(0.9, 0.999),
+               eps=1e-8, weight_decay=1e-4) -> None:
+    """torch.optim.AdamW as train.py:1598-1602 configures it: one group, decoupled decay on every
+    parameter.  In place on params / m / v; `step` is 1-based."""
+    b1, b2 = betas
+    bc1 = 1.0 - b1 ** step
+    bc2 = 1.0 - b2 ** step
+    for k, p in params.items():
+        g = grads[k]
+        p.mul_(1.0 - lr * weight_decay)
+        m[k].mul_(b1).add_(g, alpha=1.0 - b1)
+        v[k].mul_(b2).addcmul_(g, g, value=1.0 - b2)
+        denom = (v[k].sqrt() / math.sqrt(bc2)).add_(eps)
+        p.addcdiv_(m[k], denom, value=-lr / bc1)
+
+
+def train_step(sd: dict, images: torch.Tensor, labels: torch.Tensor, num_heads: int,
+               dtype: torch.dtype = torch.float32, lr=1e-4, weight_decay=1e-4):
+    """One fine-tune step with dropout = 0: returns (loss, grads, new_params)."""
+    params = {k: v.detach().to(dtype).clone().requires_grad_(True) for k, v in sd.items()}
+    _, logits = classifier_forward(params, images, num_heads, dtype=dtype)
+    loss = cross_entropy(logits, labels)
+    grads_list = torch.autograd.grad(loss, list(params.values()))
+    grads = dict(zip(params.keys(), grads_list))
+    new = {k: v.detach().clone() for k, v in params.items()}
+    m = {k: torch.zeros_like(v) for k, v in new.items()}
+    vv = {k: torch.zeros_like(v) for k, v in new.items()}
+    adamw_step(new, grads, m, vv, step=1, lr=lr, weight_decay=weight_decay)
+    return loss.detach(), grads, new

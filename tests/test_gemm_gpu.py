@@ -1,0 +1,99 @@
+"""tcgen05 GEMM (vitk_gemm through the C ABI) vs an fp32 matmul of the same bf16 operands."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [
+    (128, 256, 64),      # one tile, one k-block
+    (128, 256, 256),     # k pipeline wraps the 4-stage ring
+    (256, 512, 768),     # 2x2 tiles
+    (300, 768, 768),     # ragged M
+    (1000, 400, 400),    # ragged N and K (train.py Config dims D=400)
+    (197 * 32, 2304, 768),   # C1 qkv
+    (197 * 8, 768, 3072),    # fc2 shape, long K
+    (64, 128, 64),       # BLOCK_N=128 path, M < tile
+]
+
+
+def _ref(a, b):
+    return a.float() @ b.float().t()
+
+
+def _mk(M, N, K, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    a = torch.randn(M, K, generator=g, device="cuda").bfloat16()
+    b = (torch.randn(N, K, generator=g, device="cuda") / K ** 0.5).bfloat16()
+    bias = torch.randn(N, generator=g, device="cuda")
+    return a, b, bias
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES)
+def test_gemm_f32_epilogue(vitk, M, N, K):
+    a, b, bias = _mk(M, N, K)
+    out = vitk.ops.gemm(a, b, vitk._lib.EPI_F32, bias=bias)
+    ref = _ref(a, b) + bias
+    torch.testing.assert_close(out, ref, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES)
+def test_gemm_bf16_epilogue(vitk, M, N, K):
+    a, b, bias = _mk(M, N, K, seed=1)
+    out = vitk.ops.gemm(a, b, vitk._lib.EPI_BF16, bias=bias)
+    ref = (_ref(a, b) + bias).bfloat16()
+    torch.testing.assert_close(out.float(), ref.float(), rtol=1e-2, atol=1e-2)
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES[:5])
+def test_gemm_gelu_epilogue(vitk, M, N, K):
+    a, b, bias = _mk(M, N, K, seed=2)
+    pre = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    out = vitk.ops.gemm(a, b, vitk._lib.EPI_GELU_BF16, bias=bias, out2=pre)
+    x = _ref(a, b) + bias
+    torch.testing.assert_close(pre.float(), x.bfloat16().float(), rtol=1e-2, atol=1e-2)
+    ref = torch.nn.functional.gelu(x)  # erf form
+    torch.testing.assert_close(out.float(), ref.bfloat16().float(), rtol=1e-2, atol=1e-2)
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES[:5])
+def test_gemm_residual_epilogue_inplace(vitk, M, N, K):
+    a, b, bias = _mk(M, N, K, seed=3)
+    resid = torch.randn(M, N, device="cuda")
+    ref = _ref(a, b) + bias + resid
+    x = resid.clone()
+    out = vitk.ops.gemm(a, b, vitk._lib.EPI_RESID_F32, bias=bias, resid=x, out=x)
+    assert out.data_ptr() == x.data_ptr()
+    torch.testing.assert_close(x, ref, rtol=1e-4, atol=1e-4)
+
+
+def test_gemm_alpha_beta(vitk):
+    a, b, bias = _mk(256, 256, 128, seed=4)
+    c0 = torch.randn(256, 256, device="cuda")
+    out = vitk.ops.gemm(a, b, vitk._lib.EPI_F32, out=c0.clone(), alpha=0.5, beta=2.0)
+    torch.testing.assert_close(out, 0.5 * _ref(a, b) + 2.0 * c0, rtol=1e-4, atol=1e-4)
+
+
+def test_gemm_dgelu_epilogue(vitk):
+    a, b, _ = _mk(256, 256, 128, seed=5)
+    pre = torch.randn(256, 256, device="cuda").bfloat16()
+    out = vitk.ops.gemm(a, b, vitk._lib.EPI_DGELU_BF16, aux=pre)
+    x = pre.float().requires_grad_(True)
+    torch.nn.functional.gelu(x).sum().backward()
+    ref = _ref(a, b) * x.grad
+    torch.testing.assert_close(out.float(), ref.bfloat16().float(), rtol=2e-2, atol=2e-2)
+
+
+def test_gemm_rejects_bad_arguments(vitk):
+    a, b, _ = _mk(128, 256, 64)
+    with pytest.raises(vitk.VitkError):
+        vitk.ops.gemm(a[:, :60], b[:, :60])          # K not a multiple of 8
+    with pytest.raises(vitk.VitkError):
+        vitk.ops.gemm(a.cpu(), b.cpu())              # no CPU fallback
+
+
+def test_gemm_many_tiles_deterministic(vitk):
+    a, b, bias = _mk(197 * 64, 768, 768, seed=6)
+    o1 = vitk.ops.gemm(a, b, vitk._lib.EPI_F32, bias=bias)
+    o2 = vitk.ops.gemm(a, b, vitk._lib.EPI_F32, bias=bias)
+    assert torch.equal(o1, o2)
+    torch.testing.assert_close(o1, _ref(a, b) + bias, rtol=1e-4, atol=1e-4)

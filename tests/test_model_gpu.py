@@ -1,0 +1,72 @@
+"""End-to-end parity of the CUDA path (through vitk_forward) with the oracle on seeded inputs.
+
+Tolerances are north_star's: logits within 2e-2 abs in bf16, top-1 identical."""
+import pytest
+import torch
+
+from oracle import vit_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TINY = dict(image_size=32, patch_size=16, embed_dim=64, num_layers=2, num_heads=1, mlp_dim=128)
+SMALL = dict(image_size=64, patch_size=16, embed_dim=128, num_layers=3, num_heads=2, mlp_dim=512)
+
+
+def _run(vitk, kw, B, deit, seed=0):
+    torch.manual_seed(seed)
+    model = vitk.ViTClassifier(num_classes=6, deit=deit, dropout=0.0, **kw)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    x = O.synthetic_images(B, kw["image_size"])
+    with torch.no_grad():
+        t_ref, l_ref = O.classifier_forward(sd, x, kw["num_heads"], dtype=torch.float64)
+    model = model.cuda().eval()
+    with torch.no_grad():
+        tokens = model.backbone(x.cuda())
+        logits = model(x.cuda())
+    torch.cuda.synchronize()
+    return tokens.cpu().double(), logits.cpu().double(), t_ref, l_ref
+
+
+@pytest.mark.parametrize("kw,B,deit", [(TINY, 3, False), (TINY, 2, True), (SMALL, 5, False),
+                                       (SMALL, 9, True)])
+def test_small_configs_match_oracle(vitk, kw, B, deit):
+    tokens, logits, t_ref, l_ref = _run(vitk, kw, B, deit)
+    assert tokens.shape == t_ref.shape and logits.shape == l_ref.shape
+    assert (logits - l_ref).abs().max() < 2e-2
+    assert (tokens - t_ref).abs().max() < 6e-2
+    assert torch.equal(logits.argmax(-1), l_ref.argmax(-1))
+
+
+def test_vit_b16_matches_oracle(vitk):
+    kw = dict(image_size=224, patch_size=16, embed_dim=768, num_layers=12, num_heads=12, mlp_dim=3072)
+    tokens, logits, t_ref, l_ref = _run(vitk, kw, 4, False)
+    err = (logits - l_ref).abs().max().item()
+    print("ViT-B/16 logits max abs err vs fp64 oracle:", err, "tokens:", (tokens - t_ref).abs().max().item())
+    assert err < 2e-2
+    assert torch.equal(logits.argmax(-1), l_ref.argmax(-1))
+
+
+def test_deit_b16_image_dependent_logits(vitk):
+    # DeiT init (trunc-normal 0.02 tokens, train.py:661-664) makes the CLS output depend on the
+    # image, so top-1 agreement is not vacuous (SURVEY.md section 4 warning).
+    kw = dict(image_size=224, patch_size=16, embed_dim=768, num_layers=12, num_heads=12, mlp_dim=3072)
+    tokens, logits, t_ref, l_ref = _run(vitk, kw, 4, True, seed=3)
+    assert (logits - l_ref).abs().max() < 2e-2
+    assert torch.equal(logits.argmax(-1), l_ref.argmax(-1))
+
+
+def test_batch_independence(vitk):
+    # image i's logits do not depend on what else is in the batch (sharding invariant)
+    torch.manual_seed(0)
+    model = vitk.ViTClassifier(num_classes=6, dropout=0.0, **SMALL).cuda().eval()
+    x = O.synthetic_images(6, 64).cuda()
+    with torch.no_grad():
+        full = model(x)
+        part = torch.cat([model(x[:2]), model(x[2:])])
+    assert torch.equal(full, part)
+
+
+def test_no_cpu_fallback(vitk):
+    model = vitk.ViTClassifier(num_classes=6, **TINY).eval()
+    with pytest.raises(vitk.VitkError), torch.no_grad():
+        model(O.synthetic_images(1, 32))

@@ -1,0 +1,72 @@
+"""LayerNorm / patchify / attention kernels through the C ABI vs fp32 PyTorch on the same inputs."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("rows,D", [(1, 768), (197, 768), (6304, 768), (50, 1024), (33, 400), (7, 64)])
+@pytest.mark.parametrize("out_dtype", [torch.bfloat16, torch.float32])
+def test_layernorm(vitk, rows, D, out_dtype):
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randn(rows, D, generator=g, device="cuda") * 3 + 1.5
+    w = torch.randn(D, generator=g, device="cuda")
+    b = torch.randn(D, generator=g, device="cuda")
+    y, mean, rstd = vitk.ops.layernorm(x, w, b, 1e-5, out_dtype, return_stats=True)
+    ref = torch.nn.functional.layer_norm(x, (D,), w, b, 1e-5)
+    if out_dtype == torch.float32:
+        torch.testing.assert_close(y, ref, rtol=1e-5, atol=1e-5)
+    else:
+        torch.testing.assert_close(y.float(), ref.bfloat16().float(), rtol=1e-2, atol=1e-2)
+    torch.testing.assert_close(mean, x.mean(-1), rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(rstd, 1 / torch.sqrt(x.var(-1, unbiased=False) + 1e-5), rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("B,C,S,p", [(2, 3, 224, 16), (3, 3, 32, 16), (1, 3, 384, 16), (2, 1, 64, 8)])
+def test_patchify(vitk, B, C, S, p):
+    x = torch.randn(B, C, S, S, device="cuda")
+    out = vitk.ops.patchify(x, p)
+    g = S // p
+    ref = x.reshape(B, C, g, p, g, p).permute(0, 2, 4, 1, 3, 5).reshape(B * g * g, C * p * p)
+    assert torch.equal(out, ref.bfloat16())  # pure gather + round-to-nearest: bit exact
+
+
+def _attn_ref(qkv, B, N, H):
+    D = qkv.shape[-1] // 3
+    hd = D // H
+    q, k, v = qkv.float().reshape(B, N, 3, H, hd).permute(2, 0, 3, 1, 4)
+    s = (q @ k.transpose(-2, -1)) / math.sqrt(hd)
+    p = torch.softmax(s, dim=-1)
+    ctx = (p @ v).transpose(1, 2).reshape(B * N, D)
+    lse = torch.logsumexp(s, dim=-1)
+    return ctx, lse
+
+
+@pytest.mark.parametrize("B,N,H", [(2, 197, 12), (1, 5, 1), (3, 17, 2), (2, 64, 3), (1, 198, 12),
+                                   (1, 577, 4), (2, 16, 1), (1, 65, 2)])
+def test_attention(vitk, B, N, H):
+    g = torch.Generator(device="cuda").manual_seed(N)
+    qkv = (torch.randn(B * N, 3 * H * 64, generator=g, device="cuda") * 1.5).bfloat16()
+    ctx, lse = vitk.ops.attention(qkv, B, N, H, return_lse=True)
+    ref, lse_ref = _attn_ref(qkv, B, N, H)
+    torch.testing.assert_close(ctx.float(), ref, rtol=2e-2, atol=2e-2)
+    torch.testing.assert_close(lse, lse_ref, rtol=1e-3, atol=1e-3)
+
+
+def test_attention_peaked_softmax(vitk):
+    # large logits: exercises the running-max rescale across key blocks
+    B, N, H = 1, 197, 2
+    g = torch.Generator(device="cuda").manual_seed(7)
+    qkv = (torch.randn(B * N, 3 * H * 64, generator=g, device="cuda") * 6).bfloat16()
+    ctx = vitk.ops.attention(qkv, B, N, H)
+    ref, _ = _attn_ref(qkv, B, N, H)
+    assert torch.isfinite(ctx.float()).all()
+    torch.testing.assert_close(ctx.float(), ref, rtol=3e-2, atol=3e-2)
+
+
+def test_attention_rejects_other_head_dims(vitk):
+    qkv = torch.zeros(10, 3 * 32, device="cuda").bfloat16()
+    with pytest.raises(vitk.VitkError):
+        vitk.ops.attention(qkv, 1, 10, 2)   # head_dim 16
