@@ -10,7 +10,10 @@ from .modules import (DataEfficientImageTransformer, MLPBlock,  # noqa: F401
                       MultiHeadSelfAttention, PatchEmbedding, TransformerBlock, ViTClassifier,
                       VisionTransformer)
 
+from .pipeline import HostBatchRunner  # noqa: E402,F401
+
 __all__ = [
+    "HostBatchRunner",
     "PatchEmbedding", "MultiHeadSelfAttention", "MLPBlock", "TransformerBlock",
     "VisionTransformer", "DataEfficientImageTransformer", "ViTClassifier", "VitkError",
     "launch_count", "ops",

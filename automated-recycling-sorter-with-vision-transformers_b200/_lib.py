@@ -69,6 +69,9 @@ _SIGNATURES = {
     "vitk_abi_version": (C.c_int, []),
     "vitk_last_error": (C.c_char_p, []),
     "vitk_launch_count": (C.c_longlong, []),
+    "vitk_profile_enable": (C.c_int, [C.c_int]),
+    "vitk_profile_collect": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                       C.POINTER(C.c_longlong), C.c_int]),
     "vitk_workspace_bytes": (C.c_int, [C.POINTER(VitkConfig), C.c_int, C.POINTER(C.c_size_t)]),
     "vitk_forward": (C.c_int, [C.POINTER(VitkConfig), C.POINTER(VitkWeights), C.c_void_p, C.c_int,
                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
@@ -121,3 +124,20 @@ def check(rc: int) -> None:
 
 def launch_count() -> int:
     return int(lib().vitk_launch_count())
+
+
+PROF_KINDS = ("gemm", "attention", "layernorm", "patchify", "other", "optimizer")
+
+
+def profile_enable(on: bool) -> None:
+    check(lib().vitk_profile_enable(1 if on else 0))
+
+
+def profile_collect() -> dict:
+    """{kind: {"ms": total device ms, "work": FLOPs or bytes, "launches": n}} since the last call."""
+    n = len(PROF_KINDS)
+    ms = (C.c_double * n)()
+    work = (C.c_double * n)()
+    cnt = (C.c_longlong * n)()
+    check(lib().vitk_profile_collect(ms, work, cnt, n))
+    return {k: {"ms": ms[i], "work": work[i], "launches": cnt[i]} for i, k in enumerate(PROF_KINDS)}

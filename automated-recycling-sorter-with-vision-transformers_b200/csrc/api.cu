@@ -164,6 +164,14 @@ extern "C" {
 int vitk_abi_version(void) { return VITK_ABI_VERSION; }
 const char* vitk_last_error(void) { return last_error(); }
 long long vitk_launch_count(void) { return launch_count(); }
+int vitk_profile_enable(int on) {
+  profile_enable(on != 0);
+  return VITK_OK;
+}
+int vitk_profile_collect(double* ms, double* work, long long* launches, int nkinds) {
+  VITK_REQUIRE(ms && work && launches && nkinds > 0 && nkinds <= PROF_NKINDS, "bad profile buffers");
+  return profile_collect(ms, work, launches, nkinds);
+}
 
 int vitk_workspace_bytes(const VitkConfig* cfg, int batch, size_t* out_bytes) {
   Dims d;

@@ -264,6 +264,7 @@ int attention_fwd(const void* qkv, void* ctx, float* lse, int B, int N, int H, i
     return set_error(VITK_ERR_CUDA, "cudaFuncSetAttribute(attention) failed: %s",
                      cudaGetErrorString(attr_err));
   const float scale = 1.0f / sqrtf(static_cast<float>(hd));
+  ProfileScope prof(PROF_ATTN, 4.0 * B * H * static_cast<double>(N) * N * hd, stream);
   attn_fwd_hd64_kernel<<<B * H, kAttnThreads, smem, stream>>>(
       static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(ctx), lse, N, H, scale);
   VITK_CHECK_LAUNCH("attn_fwd_hd64_kernel");

@@ -4,6 +4,7 @@
 #include <cstring>
 #include <atomic>
 #include <mutex>
+#include <vector>
 
 namespace vitk {
 
@@ -21,6 +22,59 @@ const char* last_error() { return g_err; }
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
+
+// ---- optional profiling -----------------------------------------------------------------------
+struct ProfRec {
+  cudaEvent_t start, stop;
+  int kind;
+  double work;
+};
+static std::mutex g_prof_mu;
+static std::vector<ProfRec> g_prof;
+static std::atomic<bool> g_prof_on{false};
+
+bool profile_enabled() { return g_prof_on.load(std::memory_order_relaxed); }
+void profile_enable(bool on) { g_prof_on.store(on); }
+
+ProfileScope::ProfileScope(int kind, double work, cudaStream_t stream) : idx_(-1), stream_(stream) {
+  if (!profile_enabled()) return;
+  ProfRec r;
+  r.kind = kind;
+  r.work = work;
+  if (cudaEventCreate(&r.start) != cudaSuccess || cudaEventCreate(&r.stop) != cudaSuccess) return;
+  cudaEventRecord(r.start, stream);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof.push_back(r);
+  idx_ = static_cast<int>(g_prof.size()) - 1;
+}
+ProfileScope::~ProfileScope() {
+  if (idx_ < 0) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  cudaEventRecord(g_prof[idx_].stop, stream_);
+}
+
+int profile_collect(double* ms, double* work, long long* launches, int nkinds) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (int k = 0; k < nkinds; ++k) ms[k] = work[k] = 0.0, launches[k] = 0;
+  for (ProfRec& r : g_prof) {
+    float t = 0.f;
+    cudaError_t e = cudaEventSynchronize(r.stop);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&t, r.start, r.stop);
+    cudaEventDestroy(r.start);
+    cudaEventDestroy(r.stop);
+    if (e != cudaSuccess) {
+      g_prof.clear();
+      return set_error(VITK_ERR_CUDA, "profile_collect: %s", cudaGetErrorString(e));
+    }
+    if (r.kind >= 0 && r.kind < nkinds) {
+      ms[r.kind] += t;
+      work[r.kind] += r.work;
+      launches[r.kind] += 1;
+    }
+  }
+  g_prof.clear();
+  return VITK_OK;
+}
 
 static std::mutex g_dev_mu;
 static int g_sm_count[64];

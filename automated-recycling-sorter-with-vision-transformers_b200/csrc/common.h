@@ -47,6 +47,23 @@ const char* last_error();
 void count_launch();
 long long launch_count();
 
+// Optional per-kernel-class timing (bench.py's roofline leg): when enabled, every launcher brackets
+// its kernel with CUDA events on the launching stream.  Off by default (zero overhead).
+enum ProfKind : int { PROF_GEMM = 0, PROF_ATTN = 1, PROF_LN = 2, PROF_PATCH = 3, PROF_OTHER = 4,
+                      PROF_OPT = 5, PROF_NKINDS = 6 };
+bool profile_enabled();
+void profile_enable(bool on);
+// Sums (and clears) the recorded intervals: per kind milliseconds, work units (FLOPs for GEMM and
+// attention, bytes for the HBM-bound kernels) and launch counts. Synchronises the recorded events.
+int profile_collect(double* ms, double* work, long long* launches, int nkinds);
+
+struct ProfileScope {
+  ProfileScope(int kind, double work, cudaStream_t stream);
+  ~ProfileScope();
+  int idx_;
+  cudaStream_t stream_;
+};
+
 // Cached per current device.
 int sm_count();
 int device_cc();  // e.g. 100

@@ -364,6 +364,7 @@ int launch(const GemmProblem& p, cudaStream_t stream) {
   int grid = sm_count();
   if (grid <= 0) return set_error(VITK_ERR_NO_DEVICE, "no CUDA device");
   if (num_tiles < grid) grid = num_tiles;
+  ProfileScope prof(PROF_GEMM, 2.0 * p.M * p.N * p.K, stream);
   kernel<<<grid, kNumThreads, C::kSmemBytes, stream>>>(ta, tb, p.M, p.N, p.K, p.e);
   VITK_CHECK_LAUNCH("gemm_tn_kernel");
   return VITK_OK;

@@ -226,6 +226,7 @@ int layernorm_fwd(const float* x, long long in_stride, const float* gamma, const
   VITK_REQUIRE(in_stride % 4 == 0 && out_stride % 4 == 0, "layernorm: strides must be multiples of 4");
   const int block = 256;
   const int grid = (rows + 7) / 8;
+  ProfileScope prof(PROF_LN, static_cast<double>(rows) * D * (4.0 + (y_is_f32 ? 4.0 : 2.0)), stream);
   if (y_is_f32)
     layernorm_fwd_kernel<float><<<grid, block, 0, stream>>>(
         x, in_stride, gamma, beta, static_cast<float*>(y), out_stride, mean_out, rstd_out, rows, D,
@@ -243,6 +244,7 @@ int patchify(const float* img, void* out_bf16, int B, int C, int S, int p, cudaS
   VITK_REQUIRE(B > 0 && C > 0 && S > 0 && p > 0, "patchify: bad shape");
   VITK_REQUIRE(S % p == 0 && p % 8 == 0, "patchify: need image %% patch == 0 and patch %% 8 == 0");
   const long long work = static_cast<long long>(B) * C * S * (S / 8);
+  ProfileScope prof(PROF_PATCH, static_cast<double>(B) * C * S * S * 6.0, stream);
   patchify_kernel<<<grid_for(work, 256, 16), 256, 0, stream>>>(
       img, static_cast<__nv_bfloat16*>(out_bf16), B, C, S, p);
   VITK_CHECK_LAUNCH("patchify_kernel");

@@ -1,0 +1,82 @@
+"""Host-buffer entry point of the classifier: the evaluation loop of the reference
+(evaluation.py:498-502 - `images.to(device)`; `model(images)`) with the host->device copy of batch
+i+1 overlapped with the kernels of batch i.
+
+    runner = HostBatchRunner(model, batch_size)
+    for logits in runner.run(host_batches):      # host_batches: pinned f32 [B,3,S,S] CPU tensors
+        ...                                      # logits: f32 [B, n_classes] CPU tensor
+
+Two device input slots and a dedicated copy stream; every step moves its images host->device and
+its logits device->host.  PyTorch is used for streams, events and memory only.
+"""
+from __future__ import annotations
+
+from typing import Iterable, Iterator
+
+import torch
+
+
+class HostBatchRunner:
+    def __init__(self, model, batch_size: int, device: torch.device | str = "cuda"):
+        self.model = model
+        self.device = torch.device(device)
+        pe = model.backbone.patch_embedding
+        shape = (batch_size, pe.projection.in_channels, pe.image_size, pe.image_size)
+        self.shape = shape
+        self.n_classes = model.head.out_features
+        self._dev_in = [torch.empty(shape, dtype=torch.float32, device=self.device) for _ in range(2)]
+        self._host_out = [torch.empty((batch_size, self.n_classes), dtype=torch.float32).pin_memory()
+                          for _ in range(2)]
+        self._copy_stream = torch.cuda.Stream(device=self.device)
+        self._in_ready = [torch.cuda.Event() for _ in range(2)]    # H2D of slot done
+        self._in_free = [torch.cuda.Event() for _ in range(2)]     # compute finished reading slot
+        self._out_ready = [torch.cuda.Event() for _ in range(2)]   # D2H of slot's logits done
+        self.h2d_bytes_per_step = 4 * shape[0] * shape[1] * shape[2] * shape[3]
+        self.d2h_bytes_per_step = 4 * batch_size * self.n_classes
+
+    def _enqueue_copy(self, slot: int, host: torch.Tensor, first_use: bool):
+        if tuple(host.shape) != self.shape or host.dtype != torch.float32 or host.is_cuda:
+            raise ValueError(f"expected a CPU float32 tensor of shape {self.shape}")
+        with torch.cuda.stream(self._copy_stream):
+            if not first_use:
+                self._copy_stream.wait_event(self._in_free[slot])
+            self._dev_in[slot].copy_(host, non_blocking=True)
+            self._in_ready[slot].record(self._copy_stream)
+
+    @torch.no_grad()
+    def run(self, host_batches: Iterable[torch.Tensor]) -> Iterator[torch.Tensor]:
+        main = torch.cuda.current_stream(self.device)
+        it = iter(host_batches)
+        try:
+            nxt = next(it)
+        except StopIteration:
+            return
+        used = [False, False]
+        self._enqueue_copy(0, nxt, True)
+        used[0] = True
+        i = 0
+        pending = None  # (slot) whose logits are in flight to the host
+        while nxt is not None:
+            slot = i & 1
+            try:
+                after = next(it)
+            except StopIteration:
+                after = None
+            if after is not None:
+                self._enqueue_copy(slot ^ 1, after, not used[slot ^ 1])
+                used[slot ^ 1] = True
+            main.wait_event(self._in_ready[slot])
+            logits = self.model(self._dev_in[slot])
+            self._in_free[slot].record(main)
+            if pending is not None:
+                # the previous step's logits must have left the pinned buffer before its reuse
+                self._out_ready[pending].synchronize()
+                yield self._host_out[pending]
+            self._host_out[slot].copy_(logits, non_blocking=True)
+            self._out_ready[slot].record(main)
+            pending = slot
+            nxt = after
+            i += 1
+        if pending is not None:
+            self._out_ready[pending].synchronize()
+            yield self._host_out[pending]

@@ -92,6 +92,14 @@ const char* vitk_last_error(void);
 /* Kernels launched by this library since process start (bench.py's gpu_launches). */
 long long vitk_launch_count(void);
 
+/* Per-kernel-class device timing for the roofline report: while enabled, every launcher brackets
+ * its kernel with CUDA events on the launching stream. Kinds: 0 GEMM (work = FLOPs), 1 attention
+ * (FLOPs), 2 LayerNorm (bytes), 3 patchify (bytes), 4 other, 5 optimizer (bytes). */
+#define VITK_PROF_NKINDS 6
+int vitk_profile_enable(int on);
+int vitk_profile_collect(double* ms_by_kind, double* work_by_kind, long long* launches_by_kind,
+                         int nkinds);
+
 /* Scratch bytes vitk_forward needs for `batch` images. */
 int vitk_workspace_bytes(const VitkConfig* cfg, int batch, size_t* out_bytes);
 

@@ -8,6 +8,20 @@ from oracle import vit_oracle as O
 
 pytestmark = pytest.mark.gpu
 
+TOL = 2e-2  # north_star: logits within 2e-2 abs in bf16
+
+
+def assert_top1(logits, l_ref, tol=TOL):
+    """top-1 identical wherever the oracle's decision is not a tie at the stated logit tolerance;
+    inside a tie the prediction must still be one of the tied classes."""
+    pred, ref = logits.argmax(-1), l_ref.argmax(-1)
+    top2 = l_ref.topk(2, dim=-1).values
+    decided = (top2[:, 0] - top2[:, 1]) > 2 * tol
+    assert torch.equal(pred[decided], ref[decided])
+    gap = l_ref.max(-1).values - l_ref.gather(1, pred[:, None]).squeeze(1)
+    assert (gap <= 2 * tol).all()
+
+
 TINY = dict(image_size=32, patch_size=16, embed_dim=64, num_layers=2, num_heads=1, mlp_dim=128)
 SMALL = dict(image_size=64, patch_size=16, embed_dim=128, num_layers=3, num_heads=2, mlp_dim=512)
 
@@ -34,7 +48,7 @@ def test_small_configs_match_oracle(vitk, kw, B, deit):
     assert tokens.shape == t_ref.shape and logits.shape == l_ref.shape
     assert (logits - l_ref).abs().max() < 2e-2
     assert (tokens - t_ref).abs().max() < 6e-2
-    assert torch.equal(logits.argmax(-1), l_ref.argmax(-1))
+    assert_top1(logits, l_ref)
 
 
 def test_vit_b16_matches_oracle(vitk):
@@ -43,7 +57,7 @@ def test_vit_b16_matches_oracle(vitk):
     err = (logits - l_ref).abs().max().item()
     print("ViT-B/16 logits max abs err vs fp64 oracle:", err, "tokens:", (tokens - t_ref).abs().max().item())
     assert err < 2e-2
-    assert torch.equal(logits.argmax(-1), l_ref.argmax(-1))
+    assert_top1(logits, l_ref)
 
 
 def test_deit_b16_image_dependent_logits(vitk):
@@ -52,7 +66,7 @@ def test_deit_b16_image_dependent_logits(vitk):
     kw = dict(image_size=224, patch_size=16, embed_dim=768, num_layers=12, num_heads=12, mlp_dim=3072)
     tokens, logits, t_ref, l_ref = _run(vitk, kw, 4, True, seed=3)
     assert (logits - l_ref).abs().max() < 2e-2
-    assert torch.equal(logits.argmax(-1), l_ref.argmax(-1))
+    assert_top1(logits, l_ref)
 
 
 def test_batch_independence(vitk):
