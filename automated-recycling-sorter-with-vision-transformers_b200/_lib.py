@@ -69,6 +69,7 @@ _SIGNATURES = {
     "vitk_abi_version": (C.c_int, []),
     "vitk_last_error": (C.c_char_p, []),
     "vitk_launch_count": (C.c_longlong, []),
+    "vitk_gemm_set_cta_group": (C.c_int, [C.c_int]),
     "vitk_profile_enable": (C.c_int, [C.c_int]),
     "vitk_profile_collect": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double),
                                        C.POINTER(C.c_longlong), C.c_int]),
@@ -120,6 +121,11 @@ def check(rc: int) -> None:
     if rc != 0:
         msg = lib().vitk_last_error()
         raise VitkError(f"vitk error {rc}: {msg.decode() if msg else '?'}")
+
+
+def set_gemm_cta_group(ctas: int) -> None:
+    """0 = auto, 1 = single-CTA tiles, 2 = CTA-pair (cta_group::2) tiles."""
+    check(lib().vitk_gemm_set_cta_group(ctas))
 
 
 def launch_count() -> int:

@@ -164,6 +164,11 @@ extern "C" {
 int vitk_abi_version(void) { return VITK_ABI_VERSION; }
 const char* vitk_last_error(void) { return last_error(); }
 long long vitk_launch_count(void) { return launch_count(); }
+int vitk_gemm_set_cta_group(int ctas) {
+  VITK_REQUIRE(ctas >= 0 && ctas <= 2, "cta_group must be 0 (auto), 1 or 2");
+  gemm_force_cta_group(ctas);
+  return VITK_OK;
+}
 int vitk_profile_enable(int on) {
   profile_enable(on != 0);
   return VITK_OK;

@@ -30,16 +30,22 @@ constexpr int kFirstEpiWarp = 4;
 constexpr int kNumThreads = (kFirstEpiWarp + kNumEpiWarps) * 32;  // 384
 constexpr int kAccStages = 2;
 
-template <int BLOCK_N>
+// CTAS == 1: one CTA computes a 128 x BLOCK_N tile (tcgen05.mma.cta_group::1, M = 128).
+// CTAS == 2: a CTA pair (cluster of 2, same TPC) computes a 256 x BLOCK_N tile with
+//            tcgen05.mma.cta_group::2 (M = 256): each CTA stages its own 128 A rows and HALF of
+//            the B rows, so per-SM L2->SMEM traffic and SMEM read bandwidth per flop drop by 1/3.
+template <int BLOCK_N, int CTAS>
 struct Cfg {
   static constexpr int kABytes = kBlockM * kBlockK * 2;
-  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kBRows = BLOCK_N / CTAS;  // B rows staged by this CTA
+  static constexpr int kBBytes = kBRows * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BLOCK_N == 256) ? 4 : 6;
+  static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
   static constexpr int kTmemCols = kAccStages * BLOCK_N;  // 512 or 256 (power of two)
   static constexpr int kBarBytes = 256;
   static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;
   static_assert(kSmemBytes <= 232448, "exceeds 227 KB of shared memory");
+  static_assert(8 * (2 * kStages + 2 * kAccStages) + 4 <= kBarBytes, "barrier block too small");
 };
 
 __device__ __forceinline__ float gelu_erf(float x) {
@@ -189,12 +195,13 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int m, i
   }
 }
 
-template <int BLOCK_N, int EPI>
+template <int BLOCK_N, int EPI, int CTAS>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
                const __grid_constant__ CUtensorMap tmap_b, int M, int N, int K,
                const GemmEpilogue e) {
-  using C = Cfg<BLOCK_N>;
+  using C = Cfg<BLOCK_N, CTAS>;
+  constexpr int kTileM = kBlockM * CTAS;  // rows of C per cluster tile
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024B alignment
@@ -210,8 +217,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (CTAS == 2) ? cluster_ctarank() : 0u;  // 0 = MMA leader of the pair
+  const bool is_leader = (cta_rank == 0);
+  const int cluster_id = blockIdx.x / CTAS;
+  const int num_clusters = gridDim.x / CTAS;
 
-  const int num_m_tiles = (M + kBlockM - 1) / kBlockM;
+  const int num_m_tiles = (M + kTileM - 1) / kTileM;
   const int num_n_tiles = (N + BLOCK_N - 1) / BLOCK_N;
   const int num_tiles = num_m_tiles * num_n_tiles;
   const int num_kb = (K + kBlockK - 1) / kBlockK;
@@ -222,39 +233,64 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::kStages; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(full_bar(s), 1);   // leader: one arrive.expect_tx covering both CTAs' bytes
+      mbar_init(empty_bar(s), 1);  // one (multicast) tcgen05.commit
     }
     for (int a = 0; a < kAccStages; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), kNumEpiWarps);
+      mbar_init(tempty_bar(a), kNumEpiWarps * CTAS);  // leader collects both CTAs' epilogues
     }
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), C::kTmemCols);
-    tmem_relinquish();
+    if constexpr (CTAS == 2) {
+      tmem_alloc_2sm(smem_u32(const_cast<uint32_t*>(tmem_slot)), C::kTmemCols);
+      tmem_relinquish_2sm();
+    } else {
+      tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), C::kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CTAS == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ======================= TMA producer =======================
+    // ======================= TMA producer (every CTA stages its own operand slices) ==========
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
         const int m_blk = tile / num_n_tiles;
         const int n_blk = tile - m_blk * num_n_tiles;
+        const int m0 = m_blk * kTileM + static_cast<int>(cta_rank) * kBlockM;
+        const int n0 = n_blk * BLOCK_N + static_cast<int>(cta_rank) * C::kBRows;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = base + stage * C::kStageBytes;
           const uint32_t sb = sa + C::kABytes;
-          mbar_arrive_expect_tx(full_bar(stage), C::kStageBytes);
-          tma_load_2d(sa, &tmap_a, full_bar(stage), kb * kBlockK, m_blk * kBlockM);
-          tma_load_2d(sb, &tmap_b, full_bar(stage), kb * kBlockK, n_blk * BLOCK_N);
+          if constexpr (CTAS == 2) {
+            if (is_leader) mbar_arrive_expect_tx(full_bar(stage), 2 * C::kStageBytes);
+            const uint32_t lbar = full_bar(stage) & kPeerBitMask;
+            tma_load_2d_2sm(sa, &tmap_a, lbar, kb * kBlockK, m0);
+            tma_load_2d_2sm(sb, &tmap_b, lbar, kb * kBlockK, n0);
+          } else {
+            mbar_arrive_expect_tx(full_bar(stage), C::kStageBytes);
+            tma_load_2d(sa, &tmap_a, full_bar(stage), kb * kBlockK, m0);
+            tma_load_2d(sb, &tmap_b, full_bar(stage), kb * kBlockK, n0);
+          }
+          if (++stage == C::kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+      if constexpr (CTAS == 2) {
+        // tail: every slot this CTA filled has been consumed, i.e. all multicast commits aimed at
+        // this CTA's barriers have landed before it may reach the final cluster barrier and exit
+        for (int s = 0; s < C::kStages; ++s) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
           if (++stage == C::kStages) {
             stage = 0;
             phase ^= 1u;
@@ -263,14 +299,14 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
       }
     }
   } else if (warp == 1) {
-    // ======================= MMA issuer =======================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N);
+    // ======================= MMA issuer (pair leader only) =======================
+    if (lane == 0 && is_leader) {
+      constexpr uint32_t idesc = make_idesc_bf16(kTileM, BLOCK_N);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
@@ -284,16 +320,21 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
             // advance 16 elements (32 bytes) along K inside the 128-byte swizzle row
-            mma_bf16_ss(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc,
-                        (kb > 0 || k > 0) ? 1u : 0u);
+            const uint32_t accum = (kb > 0 || k > 0) ? 1u : 0u;
+            if constexpr (CTAS == 2)
+              mma_bf16_ss_2sm(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, accum);
+            else
+              mma_bf16_ss(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, accum);
           }
-          mma_commit(empty_bar(stage));  // frees the smem slot when these MMAs retire
+          // frees the smem slot (in both CTAs) when these MMAs retire
+          if constexpr (CTAS == 2) mma_commit_2sm_mc(empty_bar(stage), 3); else mma_commit(empty_bar(stage));
           if (++stage == C::kStages) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        mma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue warps of both CTAs
+        if constexpr (CTAS == 2) mma_commit_2sm_mc(tfull_bar(acc), 3); else mma_commit(tfull_bar(acc));
         if (++acc == kAccStages) {
           acc = 0;
           acc_phase ^= 1u;
@@ -305,28 +346,36 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
     const int half = (warp - kFirstEpiWarp) >> 2; // which half of the tile's columns
     constexpr int kColsPerWarp = BLOCK_N / 2;
-    const int row_in_tile = q * 32 + lane;
+    const int row_in_tile = static_cast<int>(cta_rank) * kBlockM + q * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
       const int m_blk = tile / num_n_tiles;
       const int n_blk = tile - m_blk * num_n_tiles;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const int m = m_blk * kBlockM + row_in_tile;
+      const int m = m_blk * kTileM + row_in_tile;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                              static_cast<uint32_t>(acc * BLOCK_N + half * kColsPerWarp);
-#pragma unroll 1
+      const int n_base = n_blk * BLOCK_N + half * kColsPerWarp;
+      // two 32-column chunks in flight: the TMEM read of chunk c+1 overlaps the math of chunk c
+      uint32_t v[2][32];
+      tmem_ld_32x32b_x32(t_row, v[0]);
+#pragma unroll
       for (int c = 0; c < kColsPerWarp / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(t_row + c * 32, v);
         tmem_ld_wait();
-        const int n0 = n_blk * BLOCK_N + half * kColsPerWarp + c * 32;
-        if (m < M && n0 < N) epilogue_chunk<EPI>(v, m, n0, N, e);
+        if (c + 1 < kColsPerWarp / 32) tmem_ld_32x32b_x32(t_row + (c + 1) * 32, v[(c + 1) & 1]);
+        const int n0 = n_base + c * 32;
+        if (m < M && n0 < N) epilogue_chunk<EPI>(v[c & 1], m, n0, N, e);
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) {
+        if (CTAS == 2 && !is_leader)
+          mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));
+        else
+          mbar_arrive(tempty_bar(acc));
+      }
       if (++acc == kAccStages) {
         acc = 0;
         acc_phase ^= 1u;
@@ -335,17 +384,20 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CTAS == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, C::kTmemCols);
+    if constexpr (CTAS == 2) tmem_dealloc_2sm(tmem_base, C::kTmemCols);
+    else tmem_dealloc(tmem_base, C::kTmemCols);
   }
 }
 
-template <int BLOCK_N, int EPI>
+int g_force_ctas = 0;  // 0 = auto, 1 / 2 = forced (tests, A/B timing)
+
+template <int BLOCK_N, int EPI, int CTAS>
 int launch(const GemmProblem& p, cudaStream_t stream) {
-  using C = Cfg<BLOCK_N>;
-  auto kernel = gemm_tn_kernel<BLOCK_N, EPI>;
+  using C = Cfg<BLOCK_N, CTAS>;
+  auto kernel = gemm_tn_kernel<BLOCK_N, EPI, CTAS>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [&] {
@@ -359,13 +411,30 @@ int launch(const GemmProblem& p, cudaStream_t stream) {
   VITK_TRY(make_tmap_2d(&ta, p.A, 2, (uint64_t)p.K, (uint64_t)p.M, (uint64_t)p.lda * 2, kBlockK,
                         kBlockM));
   VITK_TRY(make_tmap_2d(&tb, p.B, 2, (uint64_t)p.K, (uint64_t)p.N, (uint64_t)p.ldb * 2, kBlockK,
-                        BLOCK_N));
-  const int num_tiles = ((p.M + kBlockM - 1) / kBlockM) * ((p.N + BLOCK_N - 1) / BLOCK_N);
+                        C::kBRows));
+  const int tile_m = kBlockM * CTAS;
+  const int num_tiles = ((p.M + tile_m - 1) / tile_m) * ((p.N + BLOCK_N - 1) / BLOCK_N);
   int grid = sm_count();
   if (grid <= 0) return set_error(VITK_ERR_NO_DEVICE, "no CUDA device");
-  if (num_tiles < grid) grid = num_tiles;
+  grid = grid / CTAS * CTAS;
+  if (num_tiles * CTAS < grid) grid = num_tiles * CTAS;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.dynamicSmemBytes = C::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CTAS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
   ProfileScope prof(PROF_GEMM, 2.0 * p.M * p.N * p.K, stream);
-  kernel<<<grid, kNumThreads, C::kSmemBytes, stream>>>(ta, tb, p.M, p.N, p.K, p.e);
+  cudaError_t le = cudaLaunchKernelEx(&cfg, kernel, ta, tb, p.M, p.N, p.K, p.e);
+  if (le != cudaSuccess)
+    return set_error(VITK_ERR_CUDA, "launch of gemm_tn_kernel<%d,%d,%d> failed: %s", BLOCK_N, EPI,
+                     CTAS, cudaGetErrorString(le));
   VITK_CHECK_LAUNCH("gemm_tn_kernel");
   return VITK_OK;
 }
@@ -375,11 +444,17 @@ int dispatch_n(const GemmProblem& p, cudaStream_t stream) {
   // 256-wide tiles unless they would waste more than a 128-wide tiling does.
   const int waste256 = ((p.N + 255) / 256) * 256 - p.N;
   const int waste128 = ((p.N + 127) / 128) * 128 - p.N;
-  if (waste128 < waste256) return launch<128, EPI>(p, stream);
-  return launch<256, EPI>(p, stream);
+  const bool n128 = waste128 < waste256;
+  // CTA pairs (256-row tiles) whenever there is more than one 128-row tile of work
+  int ctas = (p.M > kBlockM) ? 2 : 1;
+  if (g_force_ctas == 1 || g_force_ctas == 2) ctas = g_force_ctas;
+  if (ctas == 2) return n128 ? launch<128, EPI, 2>(p, stream) : launch<256, EPI, 2>(p, stream);
+  return n128 ? launch<128, EPI, 1>(p, stream) : launch<256, EPI, 1>(p, stream);
 }
 
 }  // namespace
+
+void gemm_force_cta_group(int ctas) { g_force_ctas = ctas; }
 
 int gemm_bf16_tn(const GemmProblem& p, cudaStream_t stream) {
   VITK_REQUIRE(p.A && p.B && p.e.out, "gemm: null operand");

@@ -46,5 +46,6 @@ struct GemmProblem {
 // Returns 0 on success, else a vitk error code (message via vitk_last_error()).
 int gemm_bf16_tn(const GemmProblem& p, cudaStream_t stream);
 
-// Number of GEMM kernel launches since process start (for bench's gpu_launches accounting).
+// 0 = choose automatically (CTA pairs whenever M > 128), 1 / 2 = force the cta_group (tests, A/B).
+void gemm_force_cta_group(int ctas);
 }  // namespace vitk

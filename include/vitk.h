@@ -100,6 +100,10 @@ int vitk_profile_enable(int on);
 int vitk_profile_collect(double* ms_by_kind, double* work_by_kind, long long* launches_by_kind,
                          int nkinds);
 
+/* GEMM tile mode: 0 = automatic (CTA pairs / tcgen05 cta_group::2 whenever M > 128), 1 = single
+ * CTA 128-row tiles, 2 = CTA-pair 256-row tiles.  Process-wide; meant for tests and A/B timing. */
+int vitk_gemm_set_cta_group(int ctas);
+
 /* Scratch bytes vitk_forward needs for `batch` images. */
 int vitk_workspace_bytes(const VitkConfig* cfg, int batch, size_t* out_bytes);
 

@@ -32,6 +32,9 @@ def report(name, out, ref):
 def main():
     dev = "cuda"
     ok = True
+    mode = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+    vitk._lib.set_gemm_cta_group(mode)
+    print("cta_group mode", mode)
     # 1. identity-like: A = one-hot rows selecting k; B random -> out[m, n] = B[n, k(m)]
     for K in (64, 128, 256):
         M, N = 128, 256
@@ -51,7 +54,7 @@ def main():
         torch.cuda.synchronize()
         ok &= report(f"kslice {ks}", out, a.bfloat16().float() @ b.bfloat16().float().t())
     # 3. random, growing sizes
-    for (M, N, K) in [(128, 256, 64), (128, 128, 64), (256, 512, 512), (1024, 768, 768),
+    for (M, N, K) in [(256, 256, 64), (128, 256, 64), (128, 128, 64), (256, 512, 512), (1024, 768, 768),
                       (6304, 2304, 768), (300, 400, 400)]:
         a = torch.randn(M, K, device=dev).bfloat16()
         b = (torch.randn(N, K, device=dev) / K ** 0.5).bfloat16()

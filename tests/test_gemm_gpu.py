@@ -16,6 +16,14 @@ SHAPES = [
 ]
 
 
+@pytest.fixture(params=[1, 2], ids=["cta1", "cta2"], autouse=True)
+def cta_group(request, vitk):
+    """Every GEMM test runs with single-CTA tiles and with CTA-pair (cta_group::2) tiles."""
+    vitk._lib.set_gemm_cta_group(request.param)
+    yield request.param
+    vitk._lib.set_gemm_cta_group(0)
+
+
 def _ref(a, b):
     return a.float() @ b.float().t()
 
