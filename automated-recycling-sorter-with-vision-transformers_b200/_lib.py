@@ -70,6 +70,7 @@ _SIGNATURES = {
     "vitk_last_error": (C.c_char_p, []),
     "vitk_launch_count": (C.c_longlong, []),
     "vitk_gemm_set_cta_group": (C.c_int, [C.c_int]),
+    "vitk_gemm_set_direct_epilogue": (C.c_int, [C.c_int]),
     "vitk_profile_enable": (C.c_int, [C.c_int]),
     "vitk_profile_collect": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double),
                                        C.POINTER(C.c_longlong), C.c_int]),
@@ -126,6 +127,10 @@ def check(rc: int) -> None:
 def set_gemm_cta_group(ctas: int) -> None:
     """0 = auto, 1 = single-CTA tiles, 2 = CTA-pair (cta_group::2) tiles."""
     check(lib().vitk_gemm_set_cta_group(ctas))
+
+
+def set_gemm_direct_epilogue(on: bool) -> None:
+    check(lib().vitk_gemm_set_direct_epilogue(1 if on else 0))
 
 
 def launch_count() -> int:

@@ -169,6 +169,10 @@ int vitk_gemm_set_cta_group(int ctas) {
   gemm_force_cta_group(ctas);
   return VITK_OK;
 }
+int vitk_gemm_set_direct_epilogue(int on) {
+  gemm_force_direct_epilogue(on != 0);
+  return VITK_OK;
+}
 int vitk_profile_enable(int on) {
   profile_enable(on != 0);
   return VITK_OK;

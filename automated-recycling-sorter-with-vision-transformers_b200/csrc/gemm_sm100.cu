@@ -8,8 +8,11 @@
 //   * warp 1 lane 0 : tcgen05.mma issuer (bf16 x bf16 -> fp32 in TMEM, 128 x BLOCK_N x 16 per MMA)
 //   * warp 2        : TMEM allocator (2 accumulator stages so tile i's epilogue overlaps tile
 //                     i+1's main loop)
-//   * warps 4..11   : epilogue — tcgen05.ld (thread == accumulator row), bias / GELU / residual /
-//                     token-row remap in registers, 16-byte vector stores to global
+//   * warps 4..11   : epilogue — tcgen05.ld (thread == accumulator row), bias / GELU in registers,
+//                     then 32-row x 128-byte slabs staged in swizzled shared memory and written
+//                     by TMA (bulk tensor store; the fp32 residual update x += acc + bias is a
+//                     TMA reduce-add, so the residual stream is never read by the SM).  A direct
+//                     register->global path remains for the token-row remap of the patch embed.
 #include "gemm_sm100.cuh"
 
 #include <mutex>
@@ -34,16 +37,21 @@ constexpr int kAccStages = 2;
 // CTAS == 2: a CTA pair (cluster of 2, same TPC) computes a 256 x BLOCK_N tile with
 //            tcgen05.mma.cta_group::2 (M = 256): each CTA stages its own 128 A rows and HALF of
 //            the B rows, so per-SM L2->SMEM traffic and SMEM read bandwidth per flop drop by 1/3.
+constexpr int kStagingPerWarp = 2 * 4096;  // two 32-row x 128-byte output staging buffers
+constexpr int kStagingBytes = kNumEpiWarps * kStagingPerWarp;
+
 template <int BLOCK_N, int CTAS>
 struct Cfg {
   static constexpr int kABytes = kBlockM * kBlockK * 2;
   static constexpr int kBRows = BLOCK_N / CTAS;  // B rows staged by this CTA
   static constexpr int kBBytes = kBRows * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
-  static constexpr int kTmemCols = kAccStages * BLOCK_N;  // 512 or 256 (power of two)
   static constexpr int kBarBytes = 256;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;
+  static constexpr int kBudget = 232448 - 1024 - kBarBytes - kStagingBytes;
+  static constexpr int kStages = kBudget / kStageBytes > 8 ? 8 : kBudget / kStageBytes;
+  static constexpr int kTmemCols = kAccStages * BLOCK_N;  // 512 or 256 (power of two)
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + kBarBytes + 1024;
+  static_assert(kStages >= 3, "pipeline too shallow");
   static_assert(kSmemBytes <= 232448, "exceeds 227 KB of shared memory");
   static_assert(8 * (2 * kStages + 2 * kAccStages) + 4 <= kBarBytes, "barrier block too small");
 };
@@ -51,6 +59,36 @@ struct Cfg {
 __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
 }
+// erf-GELU for the bf16 epilogue: x * Phi(x) with the normal CDF written as a logistic of an odd
+// polynomial, Phi(x) = 1 / (1 + 2^(-x (c0 + c1 x^2 + c2 x^4))), coefficients fitted to
+// 0.5 (1 + erf(x / sqrt 2)) (max |Phi error| 4.5e-5, max |gelu error| 8.6e-5 over all x - far
+// below bf16 resolution).  6 FMA-pipe ops + 2 MUFU per element instead of ~25 for erff, which
+// made the fc1 epilogue the bottleneck of the GEMM.  x^2 is clamped so the polynomial stays
+// monotone; the logistic then saturates to exactly 0 / 1.
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float x2 = fminf(x * x, 100.f);
+  // -log2(e) * {1.595603281, 0.07344414456, -0.000640974726}
+  const float p = fmaf(x2, fmaf(x2, 9.2473074e-4f, -0.10595751f), -2.3019681f);
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * p));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+  return x * r;
+}
+// Same CDF through the hardware tanh: Phi(x) = 0.5 + 0.5 tanh(x (a0 + a1 x^2 + a2 x^4)).
+__device__ __forceinline__ float gelu_fast_tanh(float x) {
+  const float x2 = fminf(x * x, 64.f);
+  const float p = fmaf(x2, fmaf(x2, -3.5651449e-4f, 0.037011533f), 0.79753114f);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x * p));
+  return x * fmaf(0.5f, t, 0.5f);
+}
+template <int EPI>
+__device__ __forceinline__ float gelu_for(float x) {
+  if constexpr (EPI == EPI_GELU_TANH_BF16) return gelu_fast_tanh(x);
+  else return gelu_fast(x);
+}
+template <int EPI>
+constexpr bool is_gelu_epi() { return EPI == EPI_GELU_BF16 || EPI == EPI_GELU_TANH_BF16; }
 __device__ __forceinline__ float gelu_erf_grad(float x) {
   const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752440f));
   const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
@@ -89,10 +127,10 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int m, i
     }
   }
 
-  if constexpr (EPI == EPI_BF16 || EPI == EPI_GELU_BF16 || EPI == EPI_DGELU_BF16) {
+  if constexpr (EPI == EPI_BF16 || is_gelu_epi<EPI>() || EPI == EPI_DGELU_BF16) {
     const size_t off = static_cast<size_t>(m) * e.ldo + n0;
     __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(e.out) + off;
-    if constexpr (EPI == EPI_GELU_BF16) {
+    if constexpr (is_gelu_epi<EPI>()) {
       if (e.out2 != nullptr) {
         __nv_bfloat16* out2 = reinterpret_cast<__nv_bfloat16*>(e.out2) + off;
         if (full) {
@@ -111,7 +149,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int m, i
         }
       }
 #pragma unroll
-      for (int j = 0; j < 32; ++j) x[j] = gelu_erf(x[j]);
+      for (int j = 0; j < 32; ++j) x[j] = gelu_for<EPI>(x[j]);
     }
     if constexpr (EPI == EPI_DGELU_BF16) {
       const __nv_bfloat16* aux = reinterpret_cast<const __nv_bfloat16*>(e.aux) + off;
@@ -195,10 +233,67 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int m, i
   }
 }
 
-template <int BLOCK_N, int EPI, int CTAS>
+// alpha * acc + bias for one 32-column chunk (alpha only for EPI_F32).
+template <int EPI>
+__device__ __forceinline__ void acc_plus_bias(const uint32_t (&v)[32], int n0, int N,
+                                              const GemmEpilogue& e, float (&x)[32]) {
+  float acc_scale = 1.f;
+  if constexpr (EPI == EPI_F32) acc_scale = e.alpha;
+  if (n0 + 32 <= N) {
+    if (e.bias != nullptr) {
+      const float4* b4 = reinterpret_cast<const float4*>(e.bias + n0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 b = __ldg(b4 + j);
+        x[4 * j + 0] = fmaf(acc_scale, __uint_as_float(v[4 * j + 0]), b.x);
+        x[4 * j + 1] = fmaf(acc_scale, __uint_as_float(v[4 * j + 1]), b.y);
+        x[4 * j + 2] = fmaf(acc_scale, __uint_as_float(v[4 * j + 2]), b.z);
+        x[4 * j + 3] = fmaf(acc_scale, __uint_as_float(v[4 * j + 3]), b.w);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) x[j] = acc_scale * __uint_as_float(v[j]);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float b = (e.bias != nullptr && n0 + j < N) ? __ldg(e.bias + n0 + j) : 0.f;
+      x[j] = fmaf(acc_scale, __uint_as_float(v[j]), b);
+    }
+  }
+}
+
+// One epilogue warp: stage a 32-row x 128-byte slab (row = lane) in swizzled smem and hand it to
+// the TMA engine.  `pk` holds the lane's 128 output bytes. Two buffers alternate per warp.
+__device__ __forceinline__ void stage_and_store(const uint32_t (&pk)[32], uint32_t stg, int& buf,
+                                                int lane, const CUtensorMap* tmap, int c0, int c1,
+                                                bool reduce) {
+  if (lane == 0) tma_store_wait_read<1>();  // the slab stored two steps ago has been read out
+  __syncwarp();
+  const uint32_t slab = stg + static_cast<uint32_t>(buf) * 4096u;
+  const uint32_t row = slab + static_cast<uint32_t>(lane) * 128u;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    st_shared_v4(row + (static_cast<uint32_t>(j ^ (lane & 7)) << 4), pk[4 * j], pk[4 * j + 1],
+                 pk[4 * j + 2], pk[4 * j + 3]);
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    if (reduce)
+      tma_reduce_add_2d(tmap, slab, c0, c1);
+    else
+      tma_store_2d(tmap, slab, c0, c1);
+    tma_store_commit();
+  }
+  buf ^= 1;
+}
+
+template <int BLOCK_N, int EPI, int CTAS, bool TMA_EPI>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
-               const __grid_constant__ CUtensorMap tmap_b, int M, int N, int K,
+               const __grid_constant__ CUtensorMap tmap_b,
+               const __grid_constant__ CUtensorMap tmap_c,
+               const __grid_constant__ CUtensorMap tmap_c2, int M, int N, int K,
                const GemmEpilogue e) {
   using C = Cfg<BLOCK_N, CTAS>;
   constexpr int kTileM = kBlockM * CTAS;  // rows of C per cluster tile
@@ -207,13 +302,14 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
   const uint32_t base = (raw_addr + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024B alignment
   uint8_t* smem = smem_raw + (base - raw_addr);
 
-  const uint32_t bar_base = base + C::kStages * C::kStageBytes;
+  const uint32_t staging_base = base + C::kStages * C::kStageBytes;  // 1024-aligned
+  const uint32_t bar_base = staging_base + kStagingBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (C::kStages + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * C::kStages + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * C::kStages + kAccStages + a); };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(
-      smem + C::kStages * C::kStageBytes + 8 * (2 * C::kStages + 2 * kAccStages));
+      smem + C::kStages * C::kStageBytes + kStagingBytes + 8 * (2 * C::kStages + 2 * kAccStages));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -230,6 +326,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
+    if constexpr (TMA_EPI) prefetch_tmap(&tmap_c);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::kStages; ++s) {
@@ -327,14 +424,16 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
               mma_bf16_ss(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, accum);
           }
           // frees the smem slot (in both CTAs) when these MMAs retire
-          if constexpr (CTAS == 2) mma_commit_2sm_mc(empty_bar(stage), 3); else mma_commit(empty_bar(stage));
+          if constexpr (CTAS == 2) mma_commit_2sm_mc(empty_bar(stage), 3);
+          else mma_commit(empty_bar(stage));
           if (++stage == C::kStages) {
             stage = 0;
             phase ^= 1u;
           }
         }
         // accumulator complete -> epilogue warps of both CTAs
-        if constexpr (CTAS == 2) mma_commit_2sm_mc(tfull_bar(acc), 3); else mma_commit(tfull_bar(acc));
+        if constexpr (CTAS == 2) mma_commit_2sm_mc(tfull_bar(acc), 3);
+        else mma_commit(tfull_bar(acc));
         if (++acc == kAccStages) {
           acc = 0;
           acc_phase ^= 1u;
@@ -343,10 +442,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
   } else if (warp >= kFirstEpiWarp) {
     // ======================= epilogue =======================
-    const int q = warp & 3;                       // TMEM lane quarter this warp may access
-    const int half = (warp - kFirstEpiWarp) >> 2; // which half of the tile's columns
+    const int q = warp & 3;                        // TMEM lane quarter this warp may access
+    const int half = (warp - kFirstEpiWarp) >> 2;  // which half of the tile's columns
     constexpr int kColsPerWarp = BLOCK_N / 2;
-    const int row_in_tile = static_cast<int>(cta_rank) * kBlockM + q * 32 + lane;
+    const int slab_row = static_cast<int>(cta_rank) * kBlockM + q * 32;  // first row of this warp
+    const uint32_t stg = staging_base + static_cast<uint32_t>(warp - kFirstEpiWarp) * kStagingPerWarp;
+    int buf = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
@@ -354,19 +455,79 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const int n_blk = tile - m_blk * num_n_tiles;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const int m = m_blk * kTileM + row_in_tile;
+      const int row0 = m_blk * kTileM + slab_row;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                              static_cast<uint32_t>(acc * BLOCK_N + half * kColsPerWarp);
       const int n_base = n_blk * BLOCK_N + half * kColsPerWarp;
-      // two 32-column chunks in flight: the TMEM read of chunk c+1 overlaps the math of chunk c
-      uint32_t v[2][32];
-      tmem_ld_32x32b_x32(t_row, v[0]);
+      if constexpr (TMA_EPI) {
+        constexpr bool kOutF32 = (EPI == EPI_RESID_F32 || EPI == EPI_F32);
+        if constexpr (kOutF32) {
+          const bool reduce = (EPI == EPI_RESID_F32) || (e.beta != 0.f);
+          uint32_t v[2][32];
+          tmem_ld_32x32b_x32(t_row, v[0]);
 #pragma unroll
-      for (int c = 0; c < kColsPerWarp / 32; ++c) {
-        tmem_ld_wait();
-        if (c + 1 < kColsPerWarp / 32) tmem_ld_32x32b_x32(t_row + (c + 1) * 32, v[(c + 1) & 1]);
-        const int n0 = n_base + c * 32;
-        if (m < M && n0 < N) epilogue_chunk<EPI>(v[c & 1], m, n0, N, e);
+          for (int c = 0; c < kColsPerWarp / 32; ++c) {
+            tmem_ld_wait();
+            if (c + 1 < kColsPerWarp / 32) tmem_ld_32x32b_x32(t_row + (c + 1) * 32, v[(c + 1) & 1]);
+            const int n0 = n_base + c * 32;
+            if (row0 < M && n0 < N) {
+              float x[32];
+              acc_plus_bias<EPI>(v[c & 1], n0, N, e, x);
+              uint32_t pk[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) pk[j] = __float_as_uint(x[j]);
+              stage_and_store(pk, stg, buf, lane, &tmap_c, n0, row0, reduce);
+            }
+          }
+        } else {
+#pragma unroll 1
+          for (int g = 0; g < kColsPerWarp / 64; ++g) {
+            uint32_t v0[32], v1[32];
+            tmem_ld_32x32b_x32(t_row + g * 64, v0);
+            tmem_ld_32x32b_x32(t_row + g * 64 + 32, v1);
+            tmem_ld_wait();
+            const int n0 = n_base + g * 64;
+            if (row0 < M && n0 < N) {
+              float x0[32], x1[32];
+              acc_plus_bias<EPI>(v0, n0, N, e, x0);
+              acc_plus_bias<EPI>(v1, n0 + 32, N, e, x1);
+              uint32_t pk[32];
+              if constexpr (is_gelu_epi<EPI>()) {
+                if (e.out2 != nullptr) {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) {
+                    pk[j] = pack_bf16x2(x0[2 * j], x0[2 * j + 1]);
+                    pk[16 + j] = pack_bf16x2(x1[2 * j], x1[2 * j + 1]);
+                  }
+                  stage_and_store(pk, stg, buf, lane, &tmap_c2, n0, row0, false);
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  x0[j] = gelu_for<EPI>(x0[j]);
+                  x1[j] = gelu_for<EPI>(x1[j]);
+                }
+              }
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                pk[j] = pack_bf16x2(x0[2 * j], x0[2 * j + 1]);
+                pk[16 + j] = pack_bf16x2(x1[2 * j], x1[2 * j + 1]);
+              }
+              stage_and_store(pk, stg, buf, lane, &tmap_c, n0, row0, false);
+            }
+          }
+        }
+      } else {
+        const int m = row0 + lane;
+        // two 32-column chunks in flight: the TMEM read of chunk c+1 overlaps the math of chunk c
+        uint32_t v[2][32];
+        tmem_ld_32x32b_x32(t_row, v[0]);
+#pragma unroll
+        for (int c = 0; c < kColsPerWarp / 32; ++c) {
+          tmem_ld_wait();
+          if (c + 1 < kColsPerWarp / 32) tmem_ld_32x32b_x32(t_row + (c + 1) * 32, v[(c + 1) & 1]);
+          const int n0 = n_base + c * 32;
+          if (m < M && n0 < N) epilogue_chunk<EPI>(v[c & 1], m, n0, N, e);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -381,6 +542,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
         acc_phase ^= 1u;
       }
     }
+    if constexpr (TMA_EPI) {
+      if (lane == 0) tma_store_wait<0>();  // all bulk stores of this warp have completed
+    }
   }
 
   tc_fence_before();
@@ -392,12 +556,13 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
   }
 }
 
-int g_force_ctas = 0;  // 0 = auto, 1 / 2 = forced (tests, A/B timing)
+int g_force_ctas = 0;        // 0 = auto, 1 / 2 = forced (tests, A/B timing)
+int g_force_direct_epi = 0;  // 1 = never use the TMA-store epilogue (tests, A/B timing)
 
-template <int BLOCK_N, int EPI, int CTAS>
+template <int BLOCK_N, int EPI, int CTAS, bool TMA_EPI>
 int launch(const GemmProblem& p, cudaStream_t stream) {
   using C = Cfg<BLOCK_N, CTAS>;
-  auto kernel = gemm_tn_kernel<BLOCK_N, EPI, CTAS>;
+  auto kernel = gemm_tn_kernel<BLOCK_N, EPI, CTAS, TMA_EPI>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [&] {
@@ -407,11 +572,24 @@ int launch(const GemmProblem& p, cudaStream_t stream) {
   if (attr_err != cudaSuccess)
     return set_error(VITK_ERR_CUDA, "cudaFuncSetAttribute(gemm smem %d) failed: %s", C::kSmemBytes,
                      cudaGetErrorString(attr_err));
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, tc, tc2;
   VITK_TRY(make_tmap_2d(&ta, p.A, 2, (uint64_t)p.K, (uint64_t)p.M, (uint64_t)p.lda * 2, kBlockK,
                         kBlockM));
   VITK_TRY(make_tmap_2d(&tb, p.B, 2, (uint64_t)p.K, (uint64_t)p.N, (uint64_t)p.ldb * 2, kBlockK,
                         C::kBRows));
+  if constexpr (TMA_EPI) {
+    constexpr bool kOutF32 = (EPI == EPI_RESID_F32 || EPI == EPI_F32);
+    constexpr int eb = kOutF32 ? 4 : 2;
+    VITK_TRY(make_tmap_2d(&tc, p.e.out, eb, (uint64_t)p.N, (uint64_t)p.M, (uint64_t)p.e.ldo * eb,
+                          128 / eb, 32));
+    tc2 = tc;
+    if (is_gelu_epi<EPI>() && p.e.out2 != nullptr)
+      VITK_TRY(make_tmap_2d(&tc2, p.e.out2, eb, (uint64_t)p.N, (uint64_t)p.M,
+                            (uint64_t)p.e.ldo * eb, 128 / eb, 32));
+  } else {
+    tc = ta;
+    tc2 = ta;
+  }
   const int tile_m = kBlockM * CTAS;
   const int num_tiles = ((p.M + tile_m - 1) / tile_m) * ((p.N + BLOCK_N - 1) / BLOCK_N);
   int grid = sm_count();
@@ -431,16 +609,16 @@ int launch(const GemmProblem& p, cudaStream_t stream) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   ProfileScope prof(PROF_GEMM, 2.0 * p.M * p.N * p.K, stream);
-  cudaError_t le = cudaLaunchKernelEx(&cfg, kernel, ta, tb, p.M, p.N, p.K, p.e);
+  cudaError_t le = cudaLaunchKernelEx(&cfg, kernel, ta, tb, tc, tc2, p.M, p.N, p.K, p.e);
   if (le != cudaSuccess)
-    return set_error(VITK_ERR_CUDA, "launch of gemm_tn_kernel<%d,%d,%d> failed: %s", BLOCK_N, EPI,
-                     CTAS, cudaGetErrorString(le));
+    return set_error(VITK_ERR_CUDA, "launch of gemm_tn_kernel<%d,%d,%d,%d> failed: %s", BLOCK_N,
+                     EPI, CTAS, (int)TMA_EPI, cudaGetErrorString(le));
   VITK_CHECK_LAUNCH("gemm_tn_kernel");
   return VITK_OK;
 }
 
-template <int EPI>
-int dispatch_n(const GemmProblem& p, cudaStream_t stream) {
+template <int EPI, bool TMA_EPI>
+int dispatch_tile(const GemmProblem& p, cudaStream_t stream) {
   // 256-wide tiles unless they would waste more than a 128-wide tiling does.
   const int waste256 = ((p.N + 255) / 256) * 256 - p.N;
   const int waste128 = ((p.N + 127) / 128) * 128 - p.N;
@@ -448,13 +626,44 @@ int dispatch_n(const GemmProblem& p, cudaStream_t stream) {
   // CTA pairs (256-row tiles) whenever there is more than one 128-row tile of work
   int ctas = (p.M > kBlockM) ? 2 : 1;
   if (g_force_ctas == 1 || g_force_ctas == 2) ctas = g_force_ctas;
-  if (ctas == 2) return n128 ? launch<128, EPI, 2>(p, stream) : launch<256, EPI, 2>(p, stream);
-  return n128 ? launch<128, EPI, 1>(p, stream) : launch<256, EPI, 1>(p, stream);
+  if (ctas == 2)
+    return n128 ? launch<128, EPI, 2, TMA_EPI>(p, stream) : launch<256, EPI, 2, TMA_EPI>(p, stream);
+  return n128 ? launch<128, EPI, 1, TMA_EPI>(p, stream) : launch<256, EPI, 1, TMA_EPI>(p, stream);
+}
+
+// The TMA epilogue needs 16-byte aligned output rows and, for the residual form, an in-place
+// update without row remapping.
+bool tma_epilogue_ok(const GemmProblem& p) {
+  if (g_force_direct_epi) return false;
+  const bool f32 = (p.epi == EPI_RESID_F32 || p.epi == EPI_F32);
+  const int eb = f32 ? 4 : 2;
+  if ((reinterpret_cast<uintptr_t>(p.e.out) & 15) != 0 || (p.e.ldo * eb) % 16 != 0) return false;
+  switch (p.epi) {
+    case EPI_BF16: return true;
+    case EPI_GELU_BF16:
+    case EPI_GELU_TANH_BF16:
+      return p.e.out2 == nullptr || (reinterpret_cast<uintptr_t>(p.e.out2) & 15) == 0;
+    case EPI_RESID_F32:
+      return p.e.rows_per_group == 0 && p.e.resid == p.e.out && p.e.ldr == p.e.ldo;
+    case EPI_F32: return p.e.beta == 0.f || p.e.beta == 1.f;
+    default: return false;
+  }
+}
+
+template <int EPI>
+int dispatch(const GemmProblem& p, cudaStream_t stream) {
+  if constexpr (EPI == EPI_DGELU_BF16) {
+    return dispatch_tile<EPI, false>(p, stream);
+  } else {
+    if (tma_epilogue_ok(p)) return dispatch_tile<EPI, true>(p, stream);
+    return dispatch_tile<EPI, false>(p, stream);
+  }
 }
 
 }  // namespace
 
 void gemm_force_cta_group(int ctas) { g_force_ctas = ctas; }
+void gemm_force_direct_epilogue(int on) { g_force_direct_epi = on; }
 
 int gemm_bf16_tn(const GemmProblem& p, cudaStream_t stream) {
   VITK_REQUIRE(p.A && p.B && p.e.out, "gemm: null operand");
@@ -465,15 +674,16 @@ int gemm_bf16_tn(const GemmProblem& p, cudaStream_t stream) {
   VITK_REQUIRE(p.N % 8 == 0 && p.e.ldo % 8 == 0, "gemm: N and ldo must be multiples of 8");
   VITK_REQUIRE(device_cc() >= 100, "gemm: requires an sm_100 device (found sm_%d)", device_cc());
   switch (p.epi) {
-    case EPI_BF16: return dispatch_n<EPI_BF16>(p, stream);
-    case EPI_GELU_BF16: return dispatch_n<EPI_GELU_BF16>(p, stream);
+    case EPI_BF16: return dispatch<EPI_BF16>(p, stream);
+    case EPI_GELU_BF16: return dispatch<EPI_GELU_BF16>(p, stream);
+    case EPI_GELU_TANH_BF16: return dispatch<EPI_GELU_TANH_BF16>(p, stream);
     case EPI_RESID_F32:
       VITK_REQUIRE(p.e.resid != nullptr && p.e.ldr % 4 == 0, "gemm: residual epilogue needs resid");
-      return dispatch_n<EPI_RESID_F32>(p, stream);
-    case EPI_F32: return dispatch_n<EPI_F32>(p, stream);
+      return dispatch<EPI_RESID_F32>(p, stream);
+    case EPI_F32: return dispatch<EPI_F32>(p, stream);
     case EPI_DGELU_BF16:
       VITK_REQUIRE(p.e.aux != nullptr, "gemm: dgelu epilogue needs aux");
-      return dispatch_n<EPI_DGELU_BF16>(p, stream);
+      return dispatch<EPI_DGELU_BF16>(p, stream);
     default: return set_error(VITK_ERR_INVALID, "gemm: unknown epilogue %d", (int)p.epi);
   }
 }

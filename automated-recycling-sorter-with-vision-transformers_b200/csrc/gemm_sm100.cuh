@@ -12,7 +12,7 @@ enum GemmEpi : int {
   EPI_RESID_F32 = 2,   // out_f32 = acc + bias + resid_f32   (optional row remap: patch embed)
   EPI_F32 = 3,         // out_f32 = alpha * acc + bias (+ beta * out_f32)
   EPI_DGELU_BF16 = 4,  // out_bf16 = (acc + bias) * gelu'(aux_bf16)            (fc2 dgrad)
-  EPI_RESID_BF16 = 5,  // out_bf16 = acc + bias + resid_bf16 ... reserved for bf16 residual stream
+  EPI_GELU_TANH_BF16 = 6,  // as EPI_GELU_BF16 with the tanh.approx form of the normal CDF (A/B)
 };
 
 struct GemmEpilogue {
@@ -48,4 +48,6 @@ int gemm_bf16_tn(const GemmProblem& p, cudaStream_t stream);
 
 // 0 = choose automatically (CTA pairs whenever M > 128), 1 / 2 = force the cta_group (tests, A/B).
 void gemm_force_cta_group(int ctas);
+// 1 = always use the register->global epilogue instead of the smem-staged TMA store/reduce.
+void gemm_force_direct_epilogue(int on);
 }  // namespace vitk

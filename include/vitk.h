@@ -103,6 +103,9 @@ int vitk_profile_collect(double* ms_by_kind, double* work_by_kind, long long* la
 /* GEMM tile mode: 0 = automatic (CTA pairs / tcgen05 cta_group::2 whenever M > 128), 1 = single
  * CTA 128-row tiles, 2 = CTA-pair 256-row tiles.  Process-wide; meant for tests and A/B timing. */
 int vitk_gemm_set_cta_group(int ctas);
+/* 1 = write GEMM outputs with per-thread global stores instead of the smem-staged TMA
+ * store / reduce-add epilogue (tests, A/B timing). */
+int vitk_gemm_set_direct_epilogue(int on);
 
 /* Scratch bytes vitk_forward needs for `batch` images. */
 int vitk_workspace_bytes(const VitkConfig* cfg, int batch, size_t* out_bytes);

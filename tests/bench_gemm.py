@@ -13,7 +13,7 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 M = B * 197
 SHAPES = [("qkv", M, 2304, 768, vitk._lib.EPI_BF16), ("proj", M, 768, 768, vitk._lib.EPI_RESID_F32),
           ("fc1", M, 3072, 768, vitk._lib.EPI_GELU_BF16), ("fc2", M, 768, 3072, vitk._lib.EPI_RESID_F32),
-          ("fc1_nogelu", M, 3072, 768, vitk._lib.EPI_BF16)]
+          ("fc1_nogelu", M, 3072, 768, vitk._lib.EPI_BF16), ("fc1_tanh", M, 3072, 768, 6)]
 
 
 def timeit(fn, iters=20):

@@ -16,12 +16,17 @@ SHAPES = [
 ]
 
 
-@pytest.fixture(params=[1, 2], ids=["cta1", "cta2"], autouse=True)
-def cta_group(request, vitk):
-    """Every GEMM test runs with single-CTA tiles and with CTA-pair (cta_group::2) tiles."""
-    vitk._lib.set_gemm_cta_group(request.param)
+@pytest.fixture(params=[(1, False), (2, False), (1, True), (2, True)],
+                ids=["cta1-tma", "cta2-tma", "cta1-direct", "cta2-direct"], autouse=True)
+def gemm_mode(request, vitk):
+    """Every GEMM test runs with single-CTA and CTA-pair (cta_group::2) tiles, and with the
+    TMA-store and the direct epilogue."""
+    ctas, direct = request.param
+    vitk._lib.set_gemm_cta_group(ctas)
+    vitk._lib.set_gemm_direct_epilogue(direct)
     yield request.param
     vitk._lib.set_gemm_cta_group(0)
+    vitk._lib.set_gemm_direct_epilogue(False)
 
 
 def _ref(a, b):
