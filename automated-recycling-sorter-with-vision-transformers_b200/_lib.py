@@ -71,6 +71,7 @@ _SIGNATURES = {
     "vitk_launch_count": (C.c_longlong, []),
     "vitk_gemm_set_cta_group": (C.c_int, [C.c_int]),
     "vitk_gemm_set_direct_epilogue": (C.c_int, [C.c_int]),
+    "vitk_attention_set_impl": (C.c_int, [C.c_int]),
     "vitk_profile_enable": (C.c_int, [C.c_int]),
     "vitk_profile_collect": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double),
                                        C.POINTER(C.c_longlong), C.c_int]),
@@ -131,6 +132,11 @@ def set_gemm_cta_group(ctas: int) -> None:
 
 def set_gemm_direct_epilogue(on: bool) -> None:
     check(lib().vitk_gemm_set_direct_epilogue(1 if on else 0))
+
+
+def set_attention_impl(impl: int) -> None:
+    """0 = auto, 1 = flash (mma.sync), 2 = tcgen05 single-key-block kernel."""
+    check(lib().vitk_attention_set_impl(impl))
 
 
 def launch_count() -> int:

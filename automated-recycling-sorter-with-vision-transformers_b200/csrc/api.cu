@@ -173,6 +173,11 @@ int vitk_gemm_set_direct_epilogue(int on) {
   gemm_force_direct_epilogue(on != 0);
   return VITK_OK;
 }
+int vitk_attention_set_impl(int impl) {
+  VITK_REQUIRE(impl >= 0 && impl <= 2, "attention impl must be 0 (auto), 1 (flash) or 2 (tcgen05)");
+  attention_force_impl(impl);
+  return VITK_OK;
+}
 int vitk_profile_enable(int on) {
   profile_enable(on != 0);
   return VITK_OK;

@@ -161,4 +161,32 @@ int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t in
   return VITK_OK;
 }
 
+int make_tmap_3d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t inner, uint64_t rows,
+                 uint64_t batch, uint64_t row_pitch_bytes, uint64_t batch_pitch_bytes,
+                 uint32_t box_inner, uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return set_error(VITK_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (row_pitch_bytes & 15) != 0 ||
+      (batch_pitch_bytes & 15) != 0)
+    return set_error(VITK_ERR_INVALID, "TMA operand must be 16-byte aligned");
+  if (box_inner * (uint32_t)elem_bytes != 128 || box_rows > 256 || box_rows == 0)
+    return set_error(VITK_ERR_INVALID, "bad 3-D TMA box {%u,%u}", box_inner, box_rows);
+  CUtensorMapDataType dt;
+  switch (elem_bytes) {
+    case 2: dt = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16; break;
+    case 4: dt = CU_TENSOR_MAP_DATA_TYPE_FLOAT32; break;
+    default: return set_error(VITK_ERR_INVALID, "unsupported TMA element size %d", elem_bytes);
+  }
+  cuuint64_t dims[3] = {inner, rows, batch};
+  cuuint64_t strides[2] = {row_pitch_bytes, batch_pitch_bytes};
+  cuuint32_t box[3] = {box_inner, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(out, dt, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(VITK_ERR_CUDA, "cuTensorMapEncodeTiled(3d) failed (%d)", (int)r);
+  return VITK_OK;
+}
+
 }  // namespace vitk

@@ -74,4 +74,11 @@ int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t in
                  uint64_t outer, uint64_t pitch_bytes, uint32_t box_inner, uint32_t box_outer,
                  bool swizzle128 = true);
 
+// 3-D variant: dims {inner, rows, batch}, pitches (bytes) of the rows and batch dimensions, box
+// {box_inner, box_rows, 1}. Rows beyond `rows` are zero-filled on load and clipped on store, which
+// keeps per-image token tiles from touching the neighbouring image.
+int make_tmap_3d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t inner, uint64_t rows,
+                 uint64_t batch, uint64_t row_pitch_bytes, uint64_t batch_pitch_bytes,
+                 uint32_t box_inner, uint32_t box_rows);
+
 }  // namespace vitk

@@ -29,4 +29,9 @@ int cast_f32_to_bf16(const float* in, void* out, long long n, cudaStream_t strea
 int attention_fwd(const void* qkv, void* ctx, float* lse, int B, int N, int H, int hd,
                   cudaStream_t stream);
 
+// tcgen05 variant for N <= 256 (attention_tc.cu); attention_fwd dispatches to it automatically.
+int attention_fwd_tc(const void* qkv, void* ctx, float* lse, int B, int N, int H, int hd,
+                     cudaStream_t stream);
+void attention_force_impl(int impl);
+
 }  // namespace vitk

@@ -107,6 +107,10 @@ int vitk_gemm_set_cta_group(int ctas);
  * store / reduce-add epilogue (tests, A/B timing). */
 int vitk_gemm_set_direct_epilogue(int on);
 
+/* Attention kernel choice: 0 = automatic (tcgen05 single-key-block kernel when N <= 256, else the
+ * flash kernel), 1 = flash (mma.sync, any N), 2 = tcgen05.  Tests and A/B timing. */
+int vitk_attention_set_impl(int impl);
+
 /* Scratch bytes vitk_forward needs for `batch` images. */
 int vitk_workspace_bytes(const VitkConfig* cfg, int batch, size_t* out_bytes);
 

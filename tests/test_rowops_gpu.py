@@ -33,6 +33,13 @@ def test_patchify(vitk, B, C, S, p):
     assert torch.equal(out, ref.bfloat16())  # pure gather + round-to-nearest: bit exact
 
 
+@pytest.fixture(params=[1, 2], ids=["flash", "tcgen05"])
+def attn_impl(request, vitk):
+    vitk._lib.set_attention_impl(request.param)
+    yield request.param
+    vitk._lib.set_attention_impl(0)
+
+
 def _attn_ref(qkv, B, N, H):
     D = qkv.shape[-1] // 3
     hd = D // H
@@ -45,8 +52,11 @@ def _attn_ref(qkv, B, N, H):
 
 
 @pytest.mark.parametrize("B,N,H", [(2, 197, 12), (1, 5, 1), (3, 17, 2), (2, 64, 3), (1, 198, 12),
-                                   (1, 577, 4), (2, 16, 1), (1, 65, 2)])
-def test_attention(vitk, B, N, H):
+                                   (1, 577, 4), (2, 16, 1), (1, 65, 2), (2, 128, 2), (1, 129, 1),
+                                   (1, 256, 2), (40, 197, 12)])
+def test_attention(vitk, attn_impl, B, N, H):
+    if attn_impl == 2 and N > 256:
+        pytest.skip("tcgen05 kernel covers N <= 256")
     g = torch.Generator(device="cuda").manual_seed(N)
     qkv = (torch.randn(B * N, 3 * H * 64, generator=g, device="cuda") * 1.5).bfloat16()
     ctx, lse = vitk.ops.attention(qkv, B, N, H, return_lse=True)
@@ -55,7 +65,7 @@ def test_attention(vitk, B, N, H):
     torch.testing.assert_close(lse, lse_ref, rtol=1e-3, atol=1e-3)
 
 
-def test_attention_peaked_softmax(vitk):
+def test_attention_peaked_softmax(vitk, attn_impl):
     # large logits: exercises the running-max rescale across key blocks
     B, N, H = 1, 197, 2
     g = torch.Generator(device="cuda").manual_seed(7)
