@@ -81,6 +81,8 @@ _SIGNATURES = {
     "vitk_gemm": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                             C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                             C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p]),
+    "vitk_gemm_wgrad": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                  C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_int, C.c_void_p]),
     "vitk_layernorm": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_int, C.c_longlong, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                  C.c_float, C.c_void_p]),

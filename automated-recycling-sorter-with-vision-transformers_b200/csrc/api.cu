@@ -246,6 +246,26 @@ int vitk_gemm(const void* A, int lda, const void* B, int ldb, int M, int N, int 
   return gemm_bf16_tn(p, static_cast<cudaStream_t>(stream));
 }
 
+int vitk_gemm_wgrad(const void* A, int lda, const void* B, int ldb, int M, int N, int K, float* out,
+                    int ldo, float alpha, float beta, int split_k, vitk_stream_t stream) {
+  GemmProblem p;
+  p.A = A;
+  p.lda = lda;
+  p.B = B;
+  p.ldb = ldb;
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.epi = EPI_F32;
+  p.mn_major = true;
+  p.split_k = split_k;
+  p.e.out = out;
+  p.e.ldo = ldo;
+  p.e.alpha = alpha;
+  p.e.beta = beta;
+  return gemm_bf16_tn(p, static_cast<cudaStream_t>(stream));
+}
+
 int vitk_layernorm(const float* x, long long in_stride, const float* gamma, const float* beta,
                    void* y, int y_is_f32, long long out_stride, float* mean_out, float* rstd_out,
                    int rows, int D, float eps, vitk_stream_t stream) {

@@ -288,13 +288,18 @@ __device__ __forceinline__ void stage_and_store(const uint32_t (&pk)[32], uint32
   buf ^= 1;
 }
 
-template <int BLOCK_N, int EPI, int CTAS, bool TMA_EPI>
+// MN == false: A[M,K], B[N,K] with K contiguous (activations x nn.Linear weights).
+// MN == true : A[K,M], B[K,N] with M / N contiguous - the weight-gradient contraction
+//              dW[out,in] = sum_tokens dY[token,out] * X[token,in] reads both activations in place
+//              as MN-major tcgen05 operands (64x64 TMA boxes, LBO = 8 KB between 64-wide chunks).
+// The K range can be split across `num_splits` work items per tile (reduce-add epilogue).
+template <int BLOCK_N, int EPI, int CTAS, bool TMA_EPI, bool MN>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
                const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_c,
                const __grid_constant__ CUtensorMap tmap_c2, int M, int N, int K,
-               const GemmEpilogue e) {
+               int kb_per_split, int num_splits, const GemmEpilogue e) {
   using C = Cfg<BLOCK_N, CTAS>;
   constexpr int kTileM = kBlockM * CTAS;  // rows of C per cluster tile
   extern __shared__ uint8_t smem_raw[];
@@ -320,8 +325,14 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
 
   const int num_m_tiles = (M + kTileM - 1) / kTileM;
   const int num_n_tiles = (N + BLOCK_N - 1) / BLOCK_N;
-  const int num_tiles = num_m_tiles * num_n_tiles;
-  const int num_kb = (K + kBlockK - 1) / kBlockK;
+  const int num_out_tiles = num_m_tiles * num_n_tiles;
+  const int num_tiles = num_out_tiles * num_splits;  // work items: (output tile, K split)
+  const int num_kb_total = (K + kBlockK - 1) / kBlockK;
+  auto kb_begin = [&](int work) { return (work / num_out_tiles) * kb_per_split; };
+  auto kb_end = [&](int work) {
+    const int e2 = (work / num_out_tiles + 1) * kb_per_split;
+    return e2 < num_kb_total ? e2 : num_kb_total;
+  };
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
@@ -358,24 +369,46 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      for (int work = cluster_id; work < num_tiles; work += num_clusters) {
+        const int tile = work % num_out_tiles;
         const int m_blk = tile / num_n_tiles;
         const int n_blk = tile - m_blk * num_n_tiles;
         const int m0 = m_blk * kTileM + static_cast<int>(cta_rank) * kBlockM;
         const int n0 = n_blk * BLOCK_N + static_cast<int>(cta_rank) * C::kBRows;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb_begin(work); kb < kb_end(work); ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = base + stage * C::kStageBytes;
           const uint32_t sb = sa + C::kABytes;
+          const uint32_t fbar = (CTAS == 2) ? (full_bar(stage) & kPeerBitMask) : full_bar(stage);
           if constexpr (CTAS == 2) {
             if (is_leader) mbar_arrive_expect_tx(full_bar(stage), 2 * C::kStageBytes);
-            const uint32_t lbar = full_bar(stage) & kPeerBitMask;
-            tma_load_2d_2sm(sa, &tmap_a, lbar, kb * kBlockK, m0);
-            tma_load_2d_2sm(sb, &tmap_b, lbar, kb * kBlockK, n0);
           } else {
             mbar_arrive_expect_tx(full_bar(stage), C::kStageBytes);
-            tma_load_2d(sa, &tmap_a, full_bar(stage), kb * kBlockK, m0);
-            tma_load_2d(sb, &tmap_b, full_bar(stage), kb * kBlockK, n0);
+          }
+          if constexpr (!MN) {
+            if constexpr (CTAS == 2) {
+              tma_load_2d_2sm(sa, &tmap_a, fbar, kb * kBlockK, m0);
+              tma_load_2d_2sm(sb, &tmap_b, fbar, kb * kBlockK, n0);
+            } else {
+              tma_load_2d(sa, &tmap_a, fbar, kb * kBlockK, m0);
+              tma_load_2d(sb, &tmap_b, fbar, kb * kBlockK, n0);
+            }
+          } else {
+            // 64 (M or N, contiguous) x 64 (K) boxes; chunk j of the tile sits 8 KB after chunk j-1
+#pragma unroll
+            for (int j = 0; j < kBlockM / 64; ++j) {
+              if constexpr (CTAS == 2)
+                tma_load_2d_2sm(sa + j * 8192, &tmap_a, fbar, m0 + 64 * j, kb * kBlockK);
+              else
+                tma_load_2d(sa + j * 8192, &tmap_a, fbar, m0 + 64 * j, kb * kBlockK);
+            }
+#pragma unroll
+            for (int j = 0; j < C::kBRows / 64; ++j) {
+              if constexpr (CTAS == 2)
+                tma_load_2d_2sm(sb + j * 8192, &tmap_b, fbar, n0 + 64 * j, kb * kBlockK);
+              else
+                tma_load_2d(sb + j * 8192, &tmap_b, fbar, n0 + 64 * j, kb * kBlockK);
+            }
           }
           if (++stage == C::kStages) {
             stage = 0;
@@ -398,30 +431,34 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
   } else if (warp == 1) {
     // ======================= MMA issuer (pair leader only) =======================
     if (lane == 0 && is_leader) {
-      constexpr uint32_t idesc = make_idesc_bf16(kTileM, BLOCK_N);
+      constexpr uint32_t idesc = make_idesc_bf16(kTileM, BLOCK_N, MN ? 1 : 0, MN ? 1 : 0);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      for (int work = cluster_id; work < num_tiles; work += num_clusters) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int kb0 = kb_begin(work);
+        for (int kb = kb0; kb < kb_end(work); ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t sa = base + stage * C::kStageBytes;
           const uint32_t sb = sa + C::kABytes;
-          const uint64_t a_desc = make_desc_sw128(sa, 16, 1024);
-          const uint64_t b_desc = make_desc_sw128(sb, 16, 1024);
+          // K-major: LBO unused, 8-row groups 1024 B apart, +32 B per 16-element K step.
+          // MN-major: 64-wide M/N chunks 8192 B apart (LBO), 8-row K groups 1024 B apart (SBO),
+          //           +2048 B (16 K rows of 128 B) per K step.
+          const uint64_t a_desc = make_desc_sw128(sa, MN ? 8192 : 16, 1024);
+          const uint64_t b_desc = make_desc_sw128(sb, MN ? 8192 : 16, 1024);
+          constexpr uint32_t kstep = MN ? 128u : 2u;  // descriptor start-address units of 16 B
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-            // advance 16 elements (32 bytes) along K inside the 128-byte swizzle row
-            const uint32_t accum = (kb > 0 || k > 0) ? 1u : 0u;
+            const uint32_t accum = (kb > kb0 || k > 0) ? 1u : 0u;
             if constexpr (CTAS == 2)
-              mma_bf16_ss_2sm(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, accum);
+              mma_bf16_ss_2sm(d_tmem, a_desc + kstep * k, b_desc + kstep * k, idesc, accum);
             else
-              mma_bf16_ss(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, accum);
+              mma_bf16_ss(d_tmem, a_desc + kstep * k, b_desc + kstep * k, idesc, accum);
           }
           // frees the smem slot (in both CTAs) when these MMAs retire
           if constexpr (CTAS == 2) mma_commit_2sm_mc(empty_bar(stage), 3);
@@ -450,7 +487,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
     int buf = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+    for (int work = cluster_id; work < num_tiles; work += num_clusters) {
+      const int tile = work % num_out_tiles;
       const int m_blk = tile / num_n_tiles;
       const int n_blk = tile - m_blk * num_n_tiles;
       mbar_wait(tfull_bar(acc), acc_phase);
@@ -559,10 +597,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
 int g_force_ctas = 0;        // 0 = auto, 1 / 2 = forced (tests, A/B timing)
 int g_force_direct_epi = 0;  // 1 = never use the TMA-store epilogue (tests, A/B timing)
 
-template <int BLOCK_N, int EPI, int CTAS, bool TMA_EPI>
+template <int BLOCK_N, int EPI, int CTAS, bool TMA_EPI, bool MN>
 int launch(const GemmProblem& p, cudaStream_t stream) {
   using C = Cfg<BLOCK_N, CTAS>;
-  auto kernel = gemm_tn_kernel<BLOCK_N, EPI, CTAS, TMA_EPI>;
+  auto kernel = gemm_tn_kernel<BLOCK_N, EPI, CTAS, TMA_EPI, MN>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [&] {
@@ -573,10 +611,15 @@ int launch(const GemmProblem& p, cudaStream_t stream) {
     return set_error(VITK_ERR_CUDA, "cudaFuncSetAttribute(gemm smem %d) failed: %s", C::kSmemBytes,
                      cudaGetErrorString(attr_err));
   CUtensorMap ta, tb, tc, tc2;
-  VITK_TRY(make_tmap_2d(&ta, p.A, 2, (uint64_t)p.K, (uint64_t)p.M, (uint64_t)p.lda * 2, kBlockK,
-                        kBlockM));
-  VITK_TRY(make_tmap_2d(&tb, p.B, 2, (uint64_t)p.K, (uint64_t)p.N, (uint64_t)p.ldb * 2, kBlockK,
-                        C::kBRows));
+  if constexpr (MN) {
+    VITK_TRY(make_tmap_2d(&ta, p.A, 2, (uint64_t)p.M, (uint64_t)p.K, (uint64_t)p.lda * 2, 64, 64));
+    VITK_TRY(make_tmap_2d(&tb, p.B, 2, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)p.ldb * 2, 64, 64));
+  } else {
+    VITK_TRY(make_tmap_2d(&ta, p.A, 2, (uint64_t)p.K, (uint64_t)p.M, (uint64_t)p.lda * 2, kBlockK,
+                          kBlockM));
+    VITK_TRY(make_tmap_2d(&tb, p.B, 2, (uint64_t)p.K, (uint64_t)p.N, (uint64_t)p.ldb * 2, kBlockK,
+                          C::kBRows));
+  }
   if constexpr (TMA_EPI) {
     constexpr bool kOutF32 = (EPI == EPI_RESID_F32 || EPI == EPI_F32);
     constexpr int eb = kOutF32 ? 4 : 2;
@@ -591,7 +634,12 @@ int launch(const GemmProblem& p, cudaStream_t stream) {
     tc2 = ta;
   }
   const int tile_m = kBlockM * CTAS;
-  const int num_tiles = ((p.M + tile_m - 1) / tile_m) * ((p.N + BLOCK_N - 1) / BLOCK_N);
+  const int num_kb = (p.K + kBlockK - 1) / kBlockK;
+  int splits = p.split_k < 1 ? 1 : p.split_k;
+  if (splits > num_kb) splits = num_kb;
+  const int kb_per_split = (num_kb + splits - 1) / splits;
+  splits = (num_kb + kb_per_split - 1) / kb_per_split;  // no empty K ranges
+  const int num_tiles = ((p.M + tile_m - 1) / tile_m) * ((p.N + BLOCK_N - 1) / BLOCK_N) * splits;
   int grid = sm_count();
   if (grid <= 0) return set_error(VITK_ERR_NO_DEVICE, "no CUDA device");
   grid = grid / CTAS * CTAS;
@@ -609,7 +657,8 @@ int launch(const GemmProblem& p, cudaStream_t stream) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   ProfileScope prof(PROF_GEMM, 2.0 * p.M * p.N * p.K, stream);
-  cudaError_t le = cudaLaunchKernelEx(&cfg, kernel, ta, tb, tc, tc2, p.M, p.N, p.K, p.e);
+  cudaError_t le = cudaLaunchKernelEx(&cfg, kernel, ta, tb, tc, tc2, p.M, p.N, p.K, kb_per_split,
+                                      splits, p.e);
   if (le != cudaSuccess)
     return set_error(VITK_ERR_CUDA, "launch of gemm_tn_kernel<%d,%d,%d,%d> failed: %s", BLOCK_N,
                      EPI, CTAS, (int)TMA_EPI, cudaGetErrorString(le));
@@ -617,7 +666,7 @@ int launch(const GemmProblem& p, cudaStream_t stream) {
   return VITK_OK;
 }
 
-template <int EPI, bool TMA_EPI>
+template <int EPI, bool TMA_EPI, bool MN>
 int dispatch_tile(const GemmProblem& p, cudaStream_t stream) {
   // 256-wide tiles unless they would waste more than a 128-wide tiling does.
   const int waste256 = ((p.N + 255) / 256) * 256 - p.N;
@@ -627,14 +676,16 @@ int dispatch_tile(const GemmProblem& p, cudaStream_t stream) {
   int ctas = (p.M > kBlockM) ? 2 : 1;
   if (g_force_ctas == 1 || g_force_ctas == 2) ctas = g_force_ctas;
   if (ctas == 2)
-    return n128 ? launch<128, EPI, 2, TMA_EPI>(p, stream) : launch<256, EPI, 2, TMA_EPI>(p, stream);
-  return n128 ? launch<128, EPI, 1, TMA_EPI>(p, stream) : launch<256, EPI, 1, TMA_EPI>(p, stream);
+    return n128 ? launch<128, EPI, 2, TMA_EPI, MN>(p, stream)
+                : launch<256, EPI, 2, TMA_EPI, MN>(p, stream);
+  return n128 ? launch<128, EPI, 1, TMA_EPI, MN>(p, stream)
+              : launch<256, EPI, 1, TMA_EPI, MN>(p, stream);
 }
 
 // The TMA epilogue needs 16-byte aligned output rows and, for the residual form, an in-place
 // update without row remapping.
-bool tma_epilogue_ok(const GemmProblem& p) {
-  if (g_force_direct_epi) return false;
+bool tma_epilogue_ok(const GemmProblem& p, bool honour_force = true) {
+  if (honour_force && g_force_direct_epi) return false;
   const bool f32 = (p.epi == EPI_RESID_F32 || p.epi == EPI_F32);
   const int eb = f32 ? 4 : 2;
   if ((reinterpret_cast<uintptr_t>(p.e.out) & 15) != 0 || (p.e.ldo * eb) % 16 != 0) return false;
@@ -653,10 +704,20 @@ bool tma_epilogue_ok(const GemmProblem& p) {
 template <int EPI>
 int dispatch(const GemmProblem& p, cudaStream_t stream) {
   if constexpr (EPI == EPI_DGELU_BF16) {
-    return dispatch_tile<EPI, false>(p, stream);
+    return dispatch_tile<EPI, false, false>(p, stream);
+  } else if constexpr (EPI == EPI_F32) {
+    if (p.mn_major) {
+      // weight-gradient form: fp32 output through the TMA store / reduce-add epilogue only
+      if (!tma_epilogue_ok(p, false) || (p.split_k > 1 && p.e.beta != 1.f))
+        return set_error(VITK_ERR_INVALID,
+                         "gemm: MN-major operands need beta in {0,1} (beta = 1 when split_k > 1)");
+      return dispatch_tile<EPI, true, true>(p, stream);
+    }
+    if (tma_epilogue_ok(p)) return dispatch_tile<EPI, true, false>(p, stream);
+    return dispatch_tile<EPI, false, false>(p, stream);
   } else {
-    if (tma_epilogue_ok(p)) return dispatch_tile<EPI, true>(p, stream);
-    return dispatch_tile<EPI, false>(p, stream);
+    if (tma_epilogue_ok(p)) return dispatch_tile<EPI, true, false>(p, stream);
+    return dispatch_tile<EPI, false, false>(p, stream);
   }
 }
 
@@ -668,9 +729,13 @@ void gemm_force_direct_epilogue(int on) { g_force_direct_epi = on; }
 int gemm_bf16_tn(const GemmProblem& p, cudaStream_t stream) {
   VITK_REQUIRE(p.A && p.B && p.e.out, "gemm: null operand");
   VITK_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, "gemm: empty problem %dx%dx%d", p.M, p.N, p.K);
-  VITK_REQUIRE(p.K % 8 == 0 && p.lda % 8 == 0 && p.ldb % 8 == 0,
+  VITK_REQUIRE(p.lda % 8 == 0 && p.ldb % 8 == 0 && (p.mn_major || p.K % 8 == 0),
                "gemm: K/lda/ldb must be multiples of 8 (got K=%d lda=%d ldb=%d)", p.K, p.lda,
                p.ldb);
+  VITK_REQUIRE(!p.mn_major || p.epi == EPI_F32, "gemm: MN-major operands only with EPI_F32");
+  VITK_REQUIRE(p.split_k <= 1 || p.epi == EPI_F32, "gemm: split_k only with EPI_F32");
+  VITK_REQUIRE(p.split_k <= 1 || (p.e.beta == 1.f && p.e.bias == nullptr),
+               "gemm: split_k > 1 accumulates (beta must be 1, no bias)");
   VITK_REQUIRE(p.N % 8 == 0 && p.e.ldo % 8 == 0, "gemm: N and ldo must be multiples of 8");
   VITK_REQUIRE(device_cc() >= 100, "gemm: requires an sm_100 device (found sm_%d)", device_cc());
   switch (p.epi) {

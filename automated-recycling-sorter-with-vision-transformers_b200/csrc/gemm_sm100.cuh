@@ -39,6 +39,10 @@ struct GemmProblem {
   const void* B = nullptr;  // bf16 [N, ldb], K contiguous  (C = A * B^T)
   int M = 0, N = 0, K = 0;
   int lda = 0, ldb = 0;     // elements
+  // mn_major: A is stored [K, lda] with M contiguous and B [K, ldb] with N contiguous
+  // (C = A^T B, the weight-gradient contraction over tokens).  EPI_F32 only.
+  bool mn_major = false;
+  int split_k = 1;          // K range split across work items; needs EPI_F32 with beta == 1
   GemmEpi epi = EPI_BF16;
   GemmEpilogue e;
 };

@@ -57,6 +57,22 @@ def gemm(a: torch.Tensor, b: torch.Tensor, epilogue: int = _lib.EPI_BF16, *, bia
     return out
 
 
+def gemm_wgrad(dy: torch.Tensor, x: torch.Tensor, out: torch.Tensor | None = None, *,
+               alpha: float = 1.0, accumulate: bool = False, split_k: int = 1) -> torch.Tensor:
+    """out[o, i] (+)= alpha * sum_t dy[t, o] * x[t, i]; dy bf16 [T, O], x bf16 [T, I], out f32."""
+    _need_cuda(dy, x)
+    assert dy.dtype == torch.bfloat16 and x.dtype == torch.bfloat16
+    assert dy.shape[0] == x.shape[0] and dy.stride(1) == 1 and x.stride(1) == 1
+    T, O = dy.shape
+    I = x.shape[1]
+    if out is None:
+        out = torch.zeros((O, I), dtype=torch.float32, device=dy.device)
+    check(lib().vitk_gemm_wgrad(dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0), O, I, T,
+                                out.data_ptr(), out.stride(0), alpha, 1.0 if accumulate else 0.0,
+                                split_k, _stream()))
+    return out
+
+
 def layernorm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float = 1e-5,
               out_dtype: torch.dtype = torch.bfloat16, return_stats: bool = False):
     """nn.LayerNorm over the last dim of an fp32 [rows, D] tensor."""

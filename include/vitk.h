@@ -136,6 +136,14 @@ int vitk_gemm(const void* A, int lda, const void* B, int ldb, int M, int N, int 
               const float* bias, const float* resid, int ldr, const void* aux, void* out, void* out2,
               int ldo, float alpha, float beta, vitk_stream_t stream);
 
+/* Weight-gradient contraction C[M,N] (+)= A^T B with A stored [K, lda] (M contiguous) and B stored
+ * [K, ldb] (N contiguous): dW[out,in] = sum over tokens of dY[token,out] * X[token,in] - the
+ * backward of nn.Linear w.r.t. its weight (autograd of train.py:1455).  fp32 output,
+ * out = alpha * A^T B + beta * out with beta in {0, 1}; split_k > 1 spreads the token range over
+ * several CTAs that accumulate with TMA reduce-add (then beta must be 1 and out pre-initialised). */
+int vitk_gemm_wgrad(const void* A, int lda, const void* B, int ldb, int M, int N, int K, float* out,
+                    int ldo, float alpha, float beta, int split_k, vitk_stream_t stream);
+
 /* nn.LayerNorm(D) over `rows` rows (train.py:581-582). y is bf16 (y_is_f32 = 0) or f32. */
 int vitk_layernorm(const float* x, long long in_stride, const float* gamma, const float* beta,
                    void* y, int y_is_f32, long long out_stride, float* mean_out, float* rstd_out,

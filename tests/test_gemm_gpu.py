@@ -110,3 +110,21 @@ def test_gemm_many_tiles_deterministic(vitk):
     o2 = vitk.ops.gemm(a, b, vitk._lib.EPI_F32, bias=bias)
     assert torch.equal(o1, o2)
     torch.testing.assert_close(o1, _ref(a, b) + bias, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("T,O,I,split", [(64, 128, 256, 1), (256, 128, 256, 1), (1000, 768, 768, 1),
+                                         (197 * 16, 768, 3072, 4), (197 * 16, 2304, 768, 3),
+                                         (5000, 400, 400, 2), (197 * 32, 3072, 768, 8)])
+def test_gemm_wgrad_mn_major(vitk, T, O, I, split):
+    """dW = dY^T X with both operands read in place (MN-major tcgen05 descriptors), split-K."""
+    g = torch.Generator(device="cuda").manual_seed(T)
+    dy = torch.randn(T, O, generator=g, device="cuda").bfloat16()
+    x = torch.randn(T, I, generator=g, device="cuda").bfloat16()
+    ref = dy.float().t() @ x.float()
+    out = torch.zeros(O, I, device="cuda")
+    vitk.ops.gemm_wgrad(dy, x, out, accumulate=(split > 1), split_k=split)
+    torch.testing.assert_close(out, ref, rtol=2e-4, atol=2e-3 * (T / 256) ** 0.5)
+    # accumulate on top of an existing gradient
+    out2 = ref.clone()
+    vitk.ops.gemm_wgrad(dy, x, out2, alpha=0.5, accumulate=True, split_k=split)
+    torch.testing.assert_close(out2, 1.5 * ref, rtol=2e-4, atol=3e-3 * (T / 256) ** 0.5)
