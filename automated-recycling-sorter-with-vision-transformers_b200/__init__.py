@@ -11,9 +11,10 @@ from .modules import (DataEfficientImageTransformer, MLPBlock,  # noqa: F401
                       VisionTransformer)
 
 from .pipeline import HostBatchRunner  # noqa: E402,F401
+from .trainer import FineTuner, TrainState  # noqa: E402,F401
 
 __all__ = [
-    "HostBatchRunner",
+    "HostBatchRunner", "FineTuner", "TrainState",
     "PatchEmbedding", "MultiHeadSelfAttention", "MLPBlock", "TransformerBlock",
     "VisionTransformer", "DataEfficientImageTransformer", "ViTClassifier", "VitkError",
     "launch_count", "ops",

@@ -91,7 +91,53 @@ _SIGNATURES = {
     "vitk_patchify": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                 C.c_void_p]),
     "vitk_cast_f32_to_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),
+    # ---- training step
+    "vitk_train_workspace_bytes": (C.c_int, [C.POINTER(VitkConfig), C.c_int, C.POINTER(C.c_size_t),
+                                             C.POINTER(C.c_size_t)]),
+    "vitk_forward_train": (C.c_int, [C.POINTER(VitkConfig), C.POINTER(VitkWeights), C.c_void_p,
+                                     C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p,
+                                     C.c_size_t, C.c_void_p]),
+    "vitk_classifier_loss_backward": (C.c_int, [C.POINTER(VitkConfig), C.POINTER(VitkWeights),
+                                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                                C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                C.c_void_p, C.c_void_p]),
+    "vitk_backward_tokens": (C.c_int, [C.POINTER(VitkConfig), C.POINTER(VitkWeights), C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                       C.c_void_p]),
+    "vitk_adamw_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_longlong, C.c_float, C.c_float, C.c_float, C.c_float,
+                                  C.c_float, C.c_int, C.c_float, C.c_void_p]),
+    "vitk_transpose_bf16_batched": (C.c_int, [C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                              C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p]),
+    "vitk_layernorm_bwd": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "vitk_attention_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "vitk_colsum_bf16": (C.c_int, [C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p,
+                                   C.c_void_p]),
 }
+
+
+class VitkBlockWeightsT(C.Structure):
+    _fields_ = [("qkv_wt", C.c_void_p), ("proj_wt", C.c_void_p), ("fc1_wt", C.c_void_p),
+                ("fc2_wt", C.c_void_p)]
+
+
+class VitkWeightsT(C.Structure):
+    _fields_ = [("blocks", C.POINTER(VitkBlockWeightsT))]
+
+
+class VitkBlockGrads(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("ln1_w", "ln1_b", "qkv_w", "qkv_b", "proj_w", "proj_b",
+                                          "ln2_w", "ln2_b", "fc1_w", "fc1_b", "fc2_w", "fc2_b")]
+
+
+class VitkGrads(C.Structure):
+    _fields_ = [("patch_w", C.c_void_p), ("patch_b", C.c_void_p), ("cls_token", C.c_void_p),
+                ("dist_token", C.c_void_p), ("pos_embed", C.c_void_p),
+                ("blocks", C.POINTER(VitkBlockGrads)), ("ln_f_w", C.c_void_p),
+                ("ln_f_b", C.c_void_p), ("head_w", C.c_void_p), ("head_b", C.c_void_p)]
 
 _lib = None
 

@@ -39,7 +39,8 @@ __global__ void __launch_bounds__(256)
 layernorm_fwd_kernel(const float* __restrict__ x, long long in_stride,
                      const float* __restrict__ gamma, const float* __restrict__ beta,
                      OutT* __restrict__ y, long long out_stride, float* __restrict__ mean_out,
-                     float* __restrict__ rstd_out, int rows, int D, float eps) {
+                     float* __restrict__ rstd_out, float* __restrict__ x_copy, int rows, int D,
+                     float eps) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
@@ -52,6 +53,8 @@ layernorm_fwd_kernel(const float* __restrict__ x, long long in_stride,
     const int i = lane + 32 * j;
     if (i < nvec) {
       v[j] = *reinterpret_cast<const float4*>(xr + 4 * i);
+      if (x_copy != nullptr)
+        *reinterpret_cast<float4*>(x_copy + static_cast<long long>(warp) * D + 4 * i) = v[j];
       s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
     }
   }
@@ -218,7 +221,7 @@ int grid_for(long long work_items, int block, int max_blocks_per_sm = 8) {
 
 int layernorm_fwd(const float* x, long long in_stride, const float* gamma, const float* beta,
                   void* y, int y_is_f32, long long out_stride, float* mean_out, float* rstd_out,
-                  int rows, int D, float eps, cudaStream_t stream) {
+                  int rows, int D, float eps, cudaStream_t stream, float* x_copy) {
   VITK_REQUIRE(x && gamma && beta && y, "layernorm: null operand");
   VITK_REQUIRE(rows > 0, "layernorm: rows must be positive");
   VITK_REQUIRE(D % 4 == 0 && D <= 128 * kLnMaxVec, "layernorm: D=%d unsupported (need D%%4==0, D<=%d)",
@@ -229,12 +232,12 @@ int layernorm_fwd(const float* x, long long in_stride, const float* gamma, const
   ProfileScope prof(PROF_LN, static_cast<double>(rows) * D * (4.0 + (y_is_f32 ? 4.0 : 2.0)), stream);
   if (y_is_f32)
     layernorm_fwd_kernel<float><<<grid, block, 0, stream>>>(
-        x, in_stride, gamma, beta, static_cast<float*>(y), out_stride, mean_out, rstd_out, rows, D,
-        eps);
+        x, in_stride, gamma, beta, static_cast<float*>(y), out_stride, mean_out, rstd_out, x_copy,
+        rows, D, eps);
   else
     layernorm_fwd_kernel<__nv_bfloat16><<<grid, block, 0, stream>>>(
         x, in_stride, gamma, beta, static_cast<__nv_bfloat16*>(y), out_stride, mean_out, rstd_out,
-        rows, D, eps);
+        x_copy, rows, D, eps);
   VITK_CHECK_LAUNCH("layernorm_fwd_kernel");
   return VITK_OK;
 }

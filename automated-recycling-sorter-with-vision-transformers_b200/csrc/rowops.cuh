@@ -8,7 +8,7 @@ namespace vitk {
 // `out_stride`; optional per-row mean / rstd outputs (saved for backward).
 int layernorm_fwd(const float* x, long long in_stride, const float* gamma, const float* beta,
                   void* y, int y_is_f32, long long out_stride, float* mean_out, float* rstd_out,
-                  int rows, int D, float eps, cudaStream_t stream);
+                  int rows, int D, float eps, cudaStream_t stream, float* x_copy = nullptr);
 
 // f32 NCHW images -> bf16 patch rows [B*P, C*p*p] in conv-weight column order.
 int patchify(const float* img, void* out_bf16, int B, int C, int S, int p, cudaStream_t stream);

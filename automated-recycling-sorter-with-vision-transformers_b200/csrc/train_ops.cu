@@ -1,0 +1,537 @@
+// Row / elementwise kernels of the training step (reference train.py:1441-1460): LayerNorm
+// backward, bias-gradient column sums, cross-entropy + classifier-head backward on the CLS rows,
+// token/position-embedding gradients, weight transposes and the fused multi-tensor AdamW of
+// train.py:1598-1602.  All HBM-bound: vectorised 8/16-byte accesses, warp-per-row reductions,
+// shared-memory partials before global atomics.
+#include "train_ops.cuh"
+
+#include <cuda_bf16.h>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace vitk {
+using namespace ptx;
+
+namespace {
+
+constexpr int kLnMaxVec = 8;  // D <= 1024
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float4 load4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 load4(const __nv_bfloat16* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  return make_float4(bf16lo_to_f32(u.x), bf16hi_to_f32(u.x), bf16lo_to_f32(u.y), bf16hi_to_f32(u.y));
+}
+
+int grid_for(long long work_items, int block, int max_blocks_per_sm = 8) {
+  long long g = (work_items + block - 1) / block;
+  const long long cap = static_cast<long long>(sm_count()) * max_blocks_per_sm;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return static_cast<int>(g);
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm backward.  y = (x - mean) * rstd * gamma + beta  (reference nn.LayerNorm, train.py:581).
+//   dx = rstd * (g - mean_D(g) - xhat * mean_D(g * xhat)),  g = dy * gamma
+//   dgamma += sum_rows dy * xhat ;  dbeta += sum_rows dy
+// dx_io: if add_resid, the residual-stream gradient already stored there is added (pre-LN block:
+// x feeds both the LN and the skip connection).  Optionally emits a bf16 copy of the result (the
+// A operand of the next dgrad GEMM).
+// ------------------------------------------------------------------------------------------------
+template <typename DyT>
+__global__ void __launch_bounds__(256)
+layernorm_bwd_kernel(const DyT* __restrict__ dy, long long dy_stride, const float* __restrict__ x,
+                     long long x_stride, const float* __restrict__ mean,
+                     const float* __restrict__ rstd, const float* __restrict__ gamma,
+                     float* __restrict__ dx_io, long long dx_stride, int add_resid,
+                     __nv_bfloat16* __restrict__ dx_bf16, long long dxb_stride,
+                     float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, int D) {
+  extern __shared__ float s_part[];  // [2][D]
+  const int nvec = D >> 2;
+  for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) s_part[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int num_warps = (gridDim.x * blockDim.x) >> 5;
+  float4 gam[kLnMaxVec], dg[kLnMaxVec], db[kLnMaxVec];
+#pragma unroll
+  for (int j = 0; j < kLnMaxVec; ++j) {
+    const int i = lane + 32 * j;
+    gam[j] = (i < nvec) ? __ldg(reinterpret_cast<const float4*>(gamma) + i) : make_float4(0, 0, 0, 0);
+    dg[j] = make_float4(0, 0, 0, 0);
+    db[j] = make_float4(0, 0, 0, 0);
+  }
+  const float inv_d = 1.f / static_cast<float>(D);
+  for (int r = warp_global; r < rows; r += num_warps) {
+    const float mu = mean[r], rs = rstd[r];
+    float4 xh[kLnMaxVec], g[kLnMaxVec];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < kLnMaxVec; ++j) {
+      const int i = lane + 32 * j;
+      if (i < nvec) {
+        const float4 xv = load4(x + r * x_stride + 4 * i);
+        const float4 d = load4(dy + r * dy_stride + 4 * i);
+        xh[j] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+        g[j] = make_float4(d.x * gam[j].x, d.y * gam[j].y, d.z * gam[j].z, d.w * gam[j].w);
+        s1 += (g[j].x + g[j].y) + (g[j].z + g[j].w);
+        s2 += (g[j].x * xh[j].x + g[j].y * xh[j].y) + (g[j].z * xh[j].z + g[j].w * xh[j].w);
+        dg[j].x += d.x * xh[j].x;
+        dg[j].y += d.y * xh[j].y;
+        dg[j].z += d.z * xh[j].z;
+        dg[j].w += d.w * xh[j].w;
+        db[j].x += d.x;
+        db[j].y += d.y;
+        db[j].z += d.z;
+        db[j].w += d.w;
+      }
+    }
+    s1 = warp_sum(s1) * inv_d;
+    s2 = warp_sum(s2) * inv_d;
+#pragma unroll
+    for (int j = 0; j < kLnMaxVec; ++j) {
+      const int i = lane + 32 * j;
+      if (i < nvec) {
+        float4 o;
+        o.x = rs * (g[j].x - s1 - xh[j].x * s2);
+        o.y = rs * (g[j].y - s1 - xh[j].y * s2);
+        o.z = rs * (g[j].z - s1 - xh[j].z * s2);
+        o.w = rs * (g[j].w - s1 - xh[j].w * s2);
+        float* dst = dx_io + r * dx_stride + 4 * i;
+        if (add_resid) {
+          const float4 p = *reinterpret_cast<const float4*>(dst);
+          o.x += p.x;
+          o.y += p.y;
+          o.z += p.z;
+          o.w += p.w;
+        }
+        *reinterpret_cast<float4*>(dst) = o;
+        if (dx_bf16 != nullptr) {
+          uint2 pk;
+          pk.x = pack_bf16x2(o.x, o.y);
+          pk.y = pack_bf16x2(o.z, o.w);
+          *reinterpret_cast<uint2*>(dx_bf16 + r * dxb_stride + 4 * i) = pk;
+        }
+      }
+    }
+  }
+  if (dgamma != nullptr) {
+#pragma unroll
+    for (int j = 0; j < kLnMaxVec; ++j) {
+      const int i = lane + 32 * j;
+      if (i < nvec) {
+        atomicAdd(&s_part[4 * i + 0], dg[j].x);
+        atomicAdd(&s_part[4 * i + 1], dg[j].y);
+        atomicAdd(&s_part[4 * i + 2], dg[j].z);
+        atomicAdd(&s_part[4 * i + 3], dg[j].w);
+        atomicAdd(&s_part[D + 4 * i + 0], db[j].x);
+        atomicAdd(&s_part[D + 4 * i + 1], db[j].y);
+        atomicAdd(&s_part[D + 4 * i + 2], db[j].z);
+        atomicAdd(&s_part[D + 4 * i + 3], db[j].w);
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < D; i += blockDim.x) {
+      atomicAdd(dgamma + i, s_part[i]);
+      atomicAdd(dbeta + i, s_part[D + i]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// out[n] += scale * sum_m Y[m, n]  (bias gradients; Y bf16 [M, ld]).  Each thread owns 8 columns.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+colsum_bf16_kernel(const __nv_bfloat16* __restrict__ y, long long ld, int M, int N,
+                   float* __restrict__ out, int rows_per_block) {
+  __shared__ float s_acc[4][512];
+  const int tcol = threadIdx.x & 63;  // 64 threads x 8 columns = 512-column strip
+  const int trow = threadIdx.x >> 6;  // 4 row lanes
+  const int col0 = blockIdx.x * 512 + tcol * 8;
+  const int r_begin = blockIdx.y * rows_per_block;
+  const int r_end = min(M, r_begin + rows_per_block);
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (col0 < N) {
+    for (int r = r_begin + trow; r < r_end; r += 4) {
+      const uint4 u = *reinterpret_cast<const uint4*>(y + r * ld + col0);
+      acc[0] += bf16lo_to_f32(u.x);
+      acc[1] += bf16hi_to_f32(u.x);
+      acc[2] += bf16lo_to_f32(u.y);
+      acc[3] += bf16hi_to_f32(u.y);
+      acc[4] += bf16lo_to_f32(u.z);
+      acc[5] += bf16hi_to_f32(u.z);
+      acc[6] += bf16lo_to_f32(u.w);
+      acc[7] += bf16hi_to_f32(u.w);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s_acc[trow][tcol * 8 + j] = acc[j];
+  __syncthreads();
+  for (int c = threadIdx.x; c < 512; c += 256) {
+    const int col = blockIdx.x * 512 + c;
+    if (col < N) atomicAdd(out + col, s_acc[0][c] + s_acc[1][c] + s_acc[2][c] + s_acc[3][c]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Classifier tail, forward + backward in one pass over the CLS rows (north_star's 6-class head on
+// features[:,0]; loss = mean cross-entropy, cf. F.cross_entropy):
+//   feat = LN_f(x[b, 0]) ; logits = feat W^T + b ; loss += scale * (lse - logit[label])
+//   dlogits = scale * (softmax - onehot) ; dfeat = dlogits W ; dx[b, 0] = LN_f backward(dfeat)
+// One block per image.  dx must be zero elsewhere (the caller memsets it).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+cls_loss_bwd_kernel(const float* __restrict__ x, long long row_stride, const float* __restrict__ gamma,
+                    const float* __restrict__ beta, const float* __restrict__ head_w,
+                    const float* __restrict__ head_b, const long long* __restrict__ labels,
+                    float scale, float eps, int D, int C, float* __restrict__ logits_out,
+                    float* __restrict__ loss_out, float* __restrict__ feat_out,
+                    float* __restrict__ dlogits_out, float* __restrict__ dx,
+                    __nv_bfloat16* __restrict__ dx_bf16, float* __restrict__ dgamma,
+                    float* __restrict__ dbeta) {
+  extern __shared__ float sm[];  // xhat[D], feat/dfeat[D], red[8], logit[C], dl[C]
+  float* xhat = sm;
+  float* feat = sm + D;
+  float* red = sm + 2 * D;
+  float* logit = red + 8;
+  float* dl = logit + C;
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* xr = x + b * row_stride;
+  auto block_sum = [&](float v) {
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    return red[0] + red[1] + red[2] + red[3];
+  };
+  float s = 0.f;
+  for (int i = tid; i < D; i += 128) {
+    xhat[i] = xr[i];
+    s += xhat[i];
+  }
+  const float mean = block_sum(s) / D;
+  float sq = 0.f;
+  for (int i = tid; i < D; i += 128) {
+    const float d = xhat[i] - mean;
+    sq += d * d;
+  }
+  const float rstd = rsqrtf(block_sum(sq) / D + eps);
+  for (int i = tid; i < D; i += 128) {
+    const float h = (xhat[i] - mean) * rstd;
+    xhat[i] = h;
+    const float f = h * gamma[i] + beta[i];
+    feat[i] = f;
+    if (feat_out) feat_out[static_cast<long long>(b) * D + i] = f;
+  }
+  __syncthreads();
+  for (int c = warp; c < C; c += 4) {
+    const float* w = head_w + static_cast<long long>(c) * D;
+    float acc = 0.f;
+    for (int i = lane; i < D; i += 32) acc = fmaf(feat[i], __ldg(w + i), acc);
+    acc = warp_sum(acc);
+    if (lane == 0) logit[c] = acc + head_b[c];
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float m = -INFINITY;
+    for (int c = 0; c < C; ++c) m = fmaxf(m, logit[c]);
+    float z = 0.f;
+    for (int c = 0; c < C; ++c) z += expf(logit[c] - m);
+    const float lse = m + logf(z);
+    const int lab = static_cast<int>(labels[b]);
+    for (int c = 0; c < C; ++c) {
+      const float p = expf(logit[c] - lse);
+      dl[c] = scale * (p - (c == lab ? 1.f : 0.f));
+      if (logits_out) logits_out[static_cast<long long>(b) * C + c] = logit[c];
+      if (dlogits_out) dlogits_out[static_cast<long long>(b) * C + c] = dl[c];
+    }
+    if (loss_out) atomicAdd(loss_out, scale * (lse - logit[lab]));
+  }
+  __syncthreads();
+  // dfeat (reuse feat[]), then LayerNorm backward of the row
+  float s1 = 0.f, s2 = 0.f;
+  for (int i = tid; i < D; i += 128) {
+    float df = 0.f;
+    for (int c = 0; c < C; ++c) df = fmaf(dl[c], __ldg(head_w + static_cast<long long>(c) * D + i), df);
+    if (dgamma) {
+      atomicAdd(dgamma + i, df * xhat[i]);
+      atomicAdd(dbeta + i, df);
+    }
+    const float g = df * gamma[i];
+    feat[i] = g;
+    s1 += g;
+    s2 += g * xhat[i];
+  }
+  s1 = block_sum(s1) / D;
+  s2 = block_sum(s2) / D;
+  for (int i = tid; i < D; i += 128) {
+    const float o = rstd * (feat[i] - s1 - xhat[i] * s2);
+    dx[b * row_stride + i] = o;
+    if (dx_bf16) dx_bf16[b * row_stride + i] = __float2bfloat16_rn(o);
+  }
+}
+
+// dW[c, :] = sum_b dlogits[b, c] * feat[b, :] ; db[c] = sum_b dlogits[b, c].  One block per class.
+__global__ void __launch_bounds__(256)
+head_wgrad_kernel(const float* __restrict__ dlogits, const float* __restrict__ feat, int B, int D,
+                  int C, float* __restrict__ dW, float* __restrict__ db) {
+  const int c = blockIdx.x;
+  for (int i = threadIdx.x; i < D; i += blockDim.x) {
+    float acc = 0.f;
+    for (int b = 0; b < B; ++b) acc = fmaf(dlogits[b * C + c], feat[static_cast<long long>(b) * D + i], acc);
+    dW[static_cast<long long>(c) * D + i] += acc;
+  }
+  if (threadIdx.x == 0) {
+    float acc = 0.f;
+    for (int b = 0; b < B; ++b) acc += dlogits[b * C + c];
+    db[c] += acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Token-assembly backward (x = cat(cls[, dist], patches) + pos, evaluation.py:145-149):
+//   dpos[t, :] += sum_b dx[b, t, :]   (dcls = dpos[0], ddist = dpos[1] are copied by the caller)
+//   dxp[b*P + p, :] = bf16(dx[b, prefix + p, :])   (A operand of the patch-embedding wgrad)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+token_grads_kernel(const float* __restrict__ dx, int B, int Ntok, int D, int prefix,
+                   float* __restrict__ dpos, float* __restrict__ dcls, float* __restrict__ ddist,
+                   __nv_bfloat16* __restrict__ dxp) {
+  const int nvec = D >> 2;
+  const long long total = static_cast<long long>(Ntok) * nvec;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int i = static_cast<int>(idx % nvec);
+    const int t = static_cast<int>(idx / nvec);
+    float4 acc = make_float4(0, 0, 0, 0);
+    for (int b = 0; b < B; ++b) {
+      const float4 v = *reinterpret_cast<const float4*>(dx + (static_cast<long long>(b) * Ntok + t) * D + 4 * i);
+      acc.x += v.x;
+      acc.y += v.y;
+      acc.z += v.z;
+      acc.w += v.w;
+      if (t >= prefix && dxp != nullptr) {
+        uint2 pk;
+        pk.x = pack_bf16x2(v.x, v.y);
+        pk.y = pack_bf16x2(v.z, v.w);
+        *reinterpret_cast<uint2*>(dxp + (static_cast<long long>(b) * (Ntok - prefix) + (t - prefix)) * D + 4 * i) = pk;
+      }
+    }
+    float* dst = dpos + static_cast<long long>(t) * D + 4 * i;
+    float4 p = *reinterpret_cast<float4*>(dst);
+    p.x += acc.x;
+    p.y += acc.y;
+    p.z += acc.z;
+    p.w += acc.w;
+    *reinterpret_cast<float4*>(dst) = p;
+    float* tok = (t == 0) ? dcls : ((t == 1 && prefix == 2) ? ddist : nullptr);
+    if (tok != nullptr) {  // x[b, t] = token + pos[t]  ->  same gradient as pos[t]
+      float4 q = *reinterpret_cast<float4*>(tok + 4 * i);
+      q.x += acc.x;
+      q.y += acc.y;
+      q.z += acc.z;
+      q.w += acc.w;
+      *reinterpret_cast<float4*>(tok + 4 * i) = q;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Batched bf16 transposes (W [R, C] -> W^T [C, R]): the dgrad GEMMs consume nn.Linear weights as
+// K-major operands with the roles of the two dimensions swapped.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+transpose_batched_kernel(const TransposeBatch tb) {
+  __shared__ __nv_bfloat16 tile[64][66];
+  int job = 0;
+  int t = blockIdx.x;
+  while (job < tb.n && t >= tb.tiles[job]) {
+    t -= tb.tiles[job];
+    ++job;
+  }
+  if (job >= tb.n) return;
+  const int R = tb.rows[job], Cc = tb.cols[job];
+  const __nv_bfloat16* src = static_cast<const __nv_bfloat16*>(tb.src[job]);
+  __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(tb.dst[job]);
+  const int tiles_c = (Cc + 63) / 64;
+  const int r0 = (t / tiles_c) * 64, c0 = (t % tiles_c) * 64;
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  for (int r = ty; r < 64; r += 4)
+    if (r0 + r < R && c0 + tx < Cc) tile[r][tx] = src[static_cast<long long>(r0 + r) * Cc + c0 + tx];
+  __syncthreads();
+  for (int c = ty; c < 64; c += 4)
+    if (c0 + c < Cc && r0 + tx < R) dst[static_cast<long long>(c0 + c) * R + r0 + tx] = tile[tx][c];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused AdamW over one flat parameter arena (train.py:1598-1602: one group, decoupled weight decay
+// on EVERY parameter, betas (0.9, 0.999), eps 1e-8; update rule of torch.optim.AdamW):
+//   p *= 1 - lr*wd ; m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2
+//   p -= (lr / bc1) * m / (sqrt(v) / sqrt(bc2) + eps)
+// One launch for all 85.8 M parameters; also refreshes the bf16 shadow the GEMMs read.
+// Traffic: 16 B read + 12 B write (+2 B shadow) per parameter.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+             float* __restrict__ v, __nv_bfloat16* __restrict__ shadow, long long n, float decay,
+             float b1, float b2, float step_size, float inv_sqrt_bc2, float eps, float grad_scale) {
+  const long long nvec = n >> 2;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float4 pv = reinterpret_cast<float4*>(p)[i];
+    const float4 gv = reinterpret_cast<const float4*>(g)[i];
+    float4 mv = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    float* pp = reinterpret_cast<float*>(&pv);
+    const float* gp = reinterpret_cast<const float*>(&gv);
+    float* mp = reinterpret_cast<float*>(&mv);
+    float* vp = reinterpret_cast<float*>(&vv);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float gr = gp[k] * grad_scale;
+      pp[k] *= decay;
+      mp[k] = b1 * mp[k] + (1.f - b1) * gr;
+      vp[k] = b2 * vp[k] + (1.f - b2) * gr * gr;
+      const float denom = sqrtf(vp[k]) * inv_sqrt_bc2 + eps;
+      pp[k] -= step_size * (mp[k] / denom);
+    }
+    reinterpret_cast<float4*>(p)[i] = pv;
+    reinterpret_cast<float4*>(m)[i] = mv;
+    reinterpret_cast<float4*>(v)[i] = vv;
+    if (shadow != nullptr) {
+      uint2 pk;
+      pk.x = pack_bf16x2(pv.x, pv.y);
+      pk.y = pack_bf16x2(pv.z, pv.w);
+      reinterpret_cast<uint2*>(shadow)[i] = pk;
+    }
+  }
+  // tail (n not a multiple of 4)
+  for (long long i = (nvec << 2) + blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+       i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float gr = g[i] * grad_scale;
+    float pv = p[i] * decay;
+    const float mv = b1 * m[i] + (1.f - b1) * gr;
+    const float vv = b2 * v[i] + (1.f - b2) * gr * gr;
+    pv -= step_size * (mv / (sqrtf(vv) * inv_sqrt_bc2 + eps));
+    p[i] = pv;
+    m[i] = mv;
+    v[i] = vv;
+    if (shadow != nullptr) shadow[i] = __float2bfloat16_rn(pv);
+  }
+}
+
+}  // namespace
+
+int layernorm_bwd(const void* dy, int dy_is_f32, long long dy_stride, const float* x,
+                  long long x_stride, const float* mean, const float* rstd, const float* gamma,
+                  float* dx_io, long long dx_stride, int add_resid, void* dx_bf16,
+                  long long dxb_stride, float* dgamma, float* dbeta, int rows, int D,
+                  cudaStream_t stream) {
+  VITK_REQUIRE(dy && x && mean && rstd && gamma && dx_io, "layernorm_bwd: null operand");
+  VITK_REQUIRE(rows > 0 && D % 4 == 0 && D <= 128 * kLnMaxVec, "layernorm_bwd: bad shape");
+  VITK_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), "layernorm_bwd: dgamma/dbeta together");
+  const int block = 256;
+  int grid = (rows + 7) / 8;
+  const int cap = sm_count() * 4;
+  if (grid > cap) grid = cap;
+  const size_t smem = 2 * static_cast<size_t>(D) * sizeof(float);
+  ProfileScope prof(PROF_LN, static_cast<double>(rows) * D * (dy_is_f32 ? 14.0 : 12.0), stream);
+  if (dy_is_f32)
+    layernorm_bwd_kernel<float><<<grid, block, smem, stream>>>(
+        static_cast<const float*>(dy), dy_stride, x, x_stride, mean, rstd, gamma, dx_io, dx_stride,
+        add_resid, static_cast<__nv_bfloat16*>(dx_bf16), dxb_stride, dgamma, dbeta, rows, D);
+  else
+    layernorm_bwd_kernel<__nv_bfloat16><<<grid, block, smem, stream>>>(
+        static_cast<const __nv_bfloat16*>(dy), dy_stride, x, x_stride, mean, rstd, gamma, dx_io,
+        dx_stride, add_resid, static_cast<__nv_bfloat16*>(dx_bf16), dxb_stride, dgamma, dbeta, rows,
+        D);
+  VITK_CHECK_LAUNCH("layernorm_bwd_kernel");
+  return VITK_OK;
+}
+
+int colsum_bf16(const void* y, long long ld, int M, int N, float* out, cudaStream_t stream) {
+  VITK_REQUIRE(y && out && M > 0 && N > 0 && N % 8 == 0 && ld % 8 == 0, "colsum: bad argument");
+  const int strips = (N + 511) / 512;
+  int chunks = (sm_count() * 4 + strips - 1) / strips;
+  if (chunks > (M + 31) / 32) chunks = (M + 31) / 32;
+  if (chunks < 1) chunks = 1;
+  const int rows_per_block = (M + chunks - 1) / chunks;
+  chunks = (M + rows_per_block - 1) / rows_per_block;
+  ProfileScope prof(PROF_OTHER, static_cast<double>(M) * N * 2.0, stream);
+  colsum_bf16_kernel<<<dim3(strips, chunks), 256, 0, stream>>>(
+      static_cast<const __nv_bfloat16*>(y), ld, M, N, out, rows_per_block);
+  VITK_CHECK_LAUNCH("colsum_bf16_kernel");
+  return VITK_OK;
+}
+
+int cls_loss_bwd(const float* x, long long row_stride, const float* gamma, const float* beta,
+                 const float* head_w, const float* head_b, const long long* labels, float scale,
+                 float eps, int B, int D, int C, float* logits_out, float* loss_out, float* feat_ws,
+                 float* dlogits_ws, float* dx, void* dx_bf16, float* dgamma, float* dbeta,
+                 float* dhead_w, float* dhead_b, cudaStream_t stream) {
+  VITK_REQUIRE(x && gamma && beta && head_w && head_b && labels && dx && feat_ws && dlogits_ws,
+               "cls_loss_bwd: null operand");
+  VITK_REQUIRE(B > 0 && D > 0 && C > 0 && C <= 1024, "cls_loss_bwd: bad shape");
+  const size_t smem = (2 * static_cast<size_t>(D) + 8 + 2 * C) * sizeof(float);
+  cls_loss_bwd_kernel<<<B, 128, smem, stream>>>(x, row_stride, gamma, beta, head_w, head_b, labels,
+                                                scale, eps, D, C, logits_out, loss_out, feat_ws,
+                                                dlogits_ws, dx,
+                                                static_cast<__nv_bfloat16*>(dx_bf16), dgamma, dbeta);
+  VITK_CHECK_LAUNCH("cls_loss_bwd_kernel");
+  if (dhead_w != nullptr) {
+    VITK_REQUIRE(dhead_b != nullptr, "cls_loss_bwd: dhead_b missing");
+    head_wgrad_kernel<<<C, 256, 0, stream>>>(dlogits_ws, feat_ws, B, D, C, dhead_w, dhead_b);
+    VITK_CHECK_LAUNCH("head_wgrad_kernel");
+  }
+  return VITK_OK;
+}
+
+int token_grads(const float* dx, int B, int Ntok, int D, int prefix, float* dpos, float* dcls,
+                float* ddist, void* dxp_bf16, cudaStream_t stream) {
+  VITK_REQUIRE(dx && dpos && dcls && D % 4 == 0, "token_grads: bad argument");
+  VITK_REQUIRE(prefix == 1 || ddist != nullptr, "token_grads: ddist missing");
+  const long long work = static_cast<long long>(Ntok) * (D / 4);
+  token_grads_kernel<<<grid_for(work, 256), 256, 0, stream>>>(
+      dx, B, Ntok, D, prefix, dpos, dcls, ddist, static_cast<__nv_bfloat16*>(dxp_bf16));
+  VITK_CHECK_LAUNCH("token_grads_kernel");
+  return VITK_OK;
+}
+
+int transpose_batched(const TransposeBatch& tb, cudaStream_t stream) {
+  VITK_REQUIRE(tb.n > 0 && tb.n <= kMaxTransposeJobs, "transpose: bad job count");
+  int total = 0;
+  for (int i = 0; i < tb.n; ++i) total += tb.tiles[i];
+  transpose_batched_kernel<<<total, 256, 0, stream>>>(tb);
+  VITK_CHECK_LAUNCH("transpose_batched_kernel");
+  return VITK_OK;
+}
+
+int adamw_flat(float* p, const float* g, float* m, float* v, void* shadow_bf16, long long n,
+               float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+               float grad_scale, cudaStream_t stream) {
+  VITK_REQUIRE(p && g && m && v && n > 0 && step >= 1, "adamw: bad argument");
+  VITK_REQUIRE((reinterpret_cast<uintptr_t>(p) & 15) == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(m) & 15) == 0 && (reinterpret_cast<uintptr_t>(v) & 15) == 0,
+               "adamw: arenas must be 16-byte aligned");
+  const double bc1 = 1.0 - pow(static_cast<double>(beta1), step);
+  const double bc2 = 1.0 - pow(static_cast<double>(beta2), step);
+  const float step_size = static_cast<float>(lr / bc1);
+  const float inv_sqrt_bc2 = static_cast<float>(1.0 / sqrt(bc2));
+  const float decay = static_cast<float>(1.0 - static_cast<double>(lr) * weight_decay);
+  ProfileScope prof(PROF_OPT, static_cast<double>(n) * 30.0, stream);
+  adamw_kernel<<<grid_for(n / 4 + 1, 256, 8), 256, 0, stream>>>(
+      p, g, m, v, static_cast<__nv_bfloat16*>(shadow_bf16), n, decay, beta1, beta2, step_size,
+      inv_sqrt_bc2, eps, grad_scale);
+  VITK_CHECK_LAUNCH("adamw_kernel");
+  return VITK_OK;
+}
+
+}  // namespace vitk

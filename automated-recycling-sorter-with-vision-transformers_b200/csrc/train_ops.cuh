@@ -1,0 +1,48 @@
+// Host launchers of the training-step kernels (train_ops.cu, attention_bwd.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace vitk {
+
+// dx_io (+)= LN backward; optional bf16 copy; dgamma/dbeta accumulate (atomics).
+int layernorm_bwd(const void* dy, int dy_is_f32, long long dy_stride, const float* x,
+                  long long x_stride, const float* mean, const float* rstd, const float* gamma,
+                  float* dx_io, long long dx_stride, int add_resid, void* dx_bf16,
+                  long long dxb_stride, float* dgamma, float* dbeta, int rows, int D,
+                  cudaStream_t stream);
+
+// out[n] += sum_m y[m, n]   (y bf16)
+int colsum_bf16(const void* y, long long ld, int M, int N, float* out, cudaStream_t stream);
+
+// CLS-row LayerNorm + head + mean cross-entropy, forward and backward. `scale` = 1 / global batch.
+// dx (fp32 [B*N, D]) must be zero-filled by the caller; only the CLS rows are written.
+int cls_loss_bwd(const float* x, long long row_stride, const float* gamma, const float* beta,
+                 const float* head_w, const float* head_b, const long long* labels, float scale,
+                 float eps, int B, int D, int C, float* logits_out, float* loss_out, float* feat_ws,
+                 float* dlogits_ws, float* dx, void* dx_bf16, float* dgamma, float* dbeta,
+                 float* dhead_w, float* dhead_b, cudaStream_t stream);
+
+// dpos[t,:] += sum_b dx[b,t,:]; dxp = bf16 copy of the patch rows of dx.
+int token_grads(const float* dx, int B, int Ntok, int D, int prefix, float* dpos, float* dcls,
+                float* ddist, void* dxp_bf16, cudaStream_t stream);
+
+constexpr int kMaxTransposeJobs = 64;
+struct TransposeBatch {
+  const void* src[kMaxTransposeJobs];
+  void* dst[kMaxTransposeJobs];
+  int rows[kMaxTransposeJobs];
+  int cols[kMaxTransposeJobs];
+  int tiles[kMaxTransposeJobs];
+  int n;
+};
+int transpose_batched(const TransposeBatch& tb, cudaStream_t stream);
+
+int adamw_flat(float* p, const float* g, float* m, float* v, void* shadow_bf16, long long n,
+               float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+               float grad_scale, cudaStream_t stream);
+
+// dqkv = backward of softmax(q k^T / sqrt(hd)) v given d_ctx, using the saved log-sum-exp.
+int attention_bwd(const void* qkv, const void* ctx, const void* dctx, const float* lse, void* dqkv,
+                  int B, int N, int H, int hd, cudaStream_t stream);
+
+}  // namespace vitk

@@ -105,6 +105,56 @@ def attention(qkv: torch.Tensor, batch: int, n_tokens: int, num_heads: int,
     return (ctx, lse) if return_lse else ctx
 
 
+def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, mean: torch.Tensor, rstd: torch.Tensor,
+                  weight: torch.Tensor, dx_resid: torch.Tensor | None = None):
+    """Backward of nn.LayerNorm: returns (dx f32 [= dx_resid + dLN], dx bf16 copy, dgamma, dbeta)."""
+    _need_cuda(dy, x)
+    rows, D = x.shape
+    assert dy.shape == x.shape and dy.is_contiguous() and x.is_contiguous()
+    dx = dx_resid.clone() if dx_resid is not None else torch.empty_like(x)
+    dxb = torch.empty((rows, D), dtype=torch.bfloat16, device=x.device)
+    dg = torch.zeros(D, dtype=torch.float32, device=x.device)
+    db = torch.zeros(D, dtype=torch.float32, device=x.device)
+    check(lib().vitk_layernorm_bwd(dy.data_ptr(), 1 if dy.dtype == torch.float32 else 0,
+                                   x.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                   weight.data_ptr(), dx.data_ptr(), 1 if dx_resid is not None else 0,
+                                   dxb.data_ptr(), dg.data_ptr(), db.data_ptr(), rows, D, _stream()))
+    return dx, dxb, dg, db
+
+
+def attention_bwd(qkv: torch.Tensor, ctx: torch.Tensor, dctx: torch.Tensor, lse: torch.Tensor,
+                  batch: int, n_tokens: int, num_heads: int) -> torch.Tensor:
+    """d_qkv (bf16 [B*N, 3D]) of the attention core given d_ctx and the saved log-sum-exp."""
+    _need_cuda(qkv, ctx, dctx, lse)
+    assert qkv.is_contiguous() and ctx.is_contiguous() and dctx.is_contiguous()
+    D = ctx.shape[-1]
+    dqkv = torch.empty_like(qkv)
+    check(lib().vitk_attention_bwd(qkv.data_ptr(), ctx.data_ptr(), dctx.data_ptr(), lse.data_ptr(),
+                                   dqkv.data_ptr(), batch, n_tokens, num_heads, D // num_heads,
+                                   _stream()))
+    return dqkv
+
+
+def colsum(y: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """out[n] += sum_m y[m, n] for a bf16 matrix (bias gradients)."""
+    _need_cuda(y)
+    assert y.dtype == torch.bfloat16 and y.stride(1) == 1
+    if out is None:
+        out = torch.zeros(y.shape[1], dtype=torch.float32, device=y.device)
+    check(lib().vitk_colsum_bf16(y.data_ptr(), y.stride(0), y.shape[0], y.shape[1], out.data_ptr(),
+                                 _stream()))
+    return out
+
+
+def adamw_step(p, g, m, v, step: int, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4,
+               shadow=None, grad_scale: float = 1.0) -> None:
+    """In-place fused AdamW over flat fp32 tensors (torch.optim.AdamW update rule)."""
+    _need_cuda(p, g, m, v)
+    check(lib().vitk_adamw_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), _ptr(shadow),
+                                p.numel(), lr, betas[0], betas[1], eps, weight_decay, step,
+                                grad_scale, _stream()))
+
+
 def patchify(images: torch.Tensor, patch_size: int) -> torch.Tensor:
     """f32 NCHW -> bf16 [B*P, C*p*p] rows in conv-weight column order."""
     _need_cuda(images)

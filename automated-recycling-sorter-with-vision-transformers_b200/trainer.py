@@ -1,0 +1,251 @@
+"""Host side of the training step (reference train.py:1425-1479, lines 1441-1460).
+
+`TrainState` re-homes a module's parameters into one flat fp32 arena (plus flat gradient, Adam
+moment, bf16-shadow and transposed-shadow arenas) so that
+
+  * the optimizer is ONE kernel launch over 85.8 M parameters (vitk_adamw_step),
+  * data-parallel gradient reduction is a handful of NCCL all-reduces over contiguous slices,
+    issued on a side stream as soon as the backward has produced each slice,
+  * every kernel reads weights through stable pointers (VitkWeights / VitkWeightsT / VitkGrads).
+
+`FineTuner` is the fused 6-class fine-tune step of north_star: forward (saving activations) ->
+cross-entropy on the CLS head -> backward -> gradient all-reduce -> AdamW.  PyTorch supplies
+memory, streams and torch.distributed; all arithmetic runs in libvitk.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from ._lib import (VitkBlockGrads, VitkBlockWeights, VitkBlockWeightsT, VitkConfig, VitkGrads,
+                   VitkWeights, VitkWeightsT, check, lib)
+
+_ALIGN = 64  # elements: keeps every parameter 256-byte (fp32) / 128-byte (bf16) aligned
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+class TrainState:
+    def __init__(self, backbone: torch.nn.Module, head: torch.nn.Linear | None, n_prefix: int):
+        self.backbone, self.head, self.n_prefix = backbone, head, n_prefix
+        named = [("backbone." + n, p) for n, p in backbone.named_parameters()]
+        if head is not None:
+            named += [("head." + n, p) for n, p in head.named_parameters()]
+        dev = named[0][1].device
+        if dev.type != "cuda":
+            raise _lib.VitkError("training runs on CUDA only - call .to('cuda') first")
+        self.device = dev
+        self.names = [n for n, _ in named]
+        self.params = [p for _, p in named]
+        self.offsets, off = {}, 0
+        for n, p in named:
+            self.offsets[n] = off
+            off += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+        self.numel = off
+        z = lambda dt: torch.zeros(self.numel, dtype=dt, device=dev)
+        self.flat, self.grad, self.exp_avg, self.exp_avg_sq = (z(torch.float32) for _ in range(4))
+        self.shadow = z(torch.bfloat16)
+        for n, p in named:                      # re-home parameters into the arena
+            o = self.offsets[n]
+            view = self.flat[o:o + p.numel()].view(p.shape)
+            view.copy_(p.detach().contiguous())
+            p.data = view
+            p.grad = self.grad[o:o + p.numel()].view(p.shape)
+        # transposed bf16 copies of the four Linear weights of every block
+        self._t_jobs = []
+        toff = 0
+        for i, blk in enumerate(backbone.transformer_blocks):
+            for key in ("attention.qkv", "attention.projection", "mlp.linear1", "mlp.linear2"):
+                name = f"backbone.transformer_blocks.{i}.{key}.weight"
+                w = dict(named)[name]
+                self._t_jobs.append((name, w.shape[0], w.shape[1], toff))
+                toff += w.numel()
+        self.shadow_t = torch.zeros(toff, dtype=torch.bfloat16, device=dev)
+        self._build_structs()
+        self._bufs_batch = None
+        self.step_count = 0
+        self.refresh_shadows()
+
+    # ------------------------------------------------------------------ pointer structs
+    def _p(self, name):   # fp32 parameter
+        return self.flat.data_ptr() + 4 * self.offsets[name]
+
+    def _s(self, name):   # bf16 shadow
+        return self.shadow.data_ptr() + 2 * self.offsets[name]
+
+    def _g(self, name):   # fp32 gradient
+        return self.grad.data_ptr() + 4 * self.offsets[name]
+
+    def _build_structs(self):
+        bb = self.backbone
+        L = len(bb.transformer_blocks)
+        self._bw = (VitkBlockWeights * L)()
+        self._bt = (VitkBlockWeightsT * L)()
+        self._bg = (VitkBlockGrads * L)()
+        tptr = {n: self.shadow_t.data_ptr() + 2 * o for n, _, _, o in self._t_jobs}
+        for i in range(L):
+            pre = f"backbone.transformer_blocks.{i}."
+            w, t, g = self._bw[i], self._bt[i], self._bg[i]
+            for field, key in (("ln1", "layer_norm1"), ("ln2", "layer_norm2")):
+                setattr(w, field + "_w", self._p(pre + key + ".weight"))
+                setattr(w, field + "_b", self._p(pre + key + ".bias"))
+                setattr(g, field + "_w", self._g(pre + key + ".weight"))
+                setattr(g, field + "_b", self._g(pre + key + ".bias"))
+            for field, key in (("qkv", "attention.qkv"), ("proj", "attention.projection"),
+                               ("fc1", "mlp.linear1"), ("fc2", "mlp.linear2")):
+                setattr(w, field + "_w", self._s(pre + key + ".weight"))
+                setattr(w, field + "_b", self._p(pre + key + ".bias"))
+                setattr(g, field + "_w", self._g(pre + key + ".weight"))
+                setattr(g, field + "_b", self._g(pre + key + ".bias"))
+                setattr(t, field + "_wt", tptr[pre + key + ".weight"])
+        W, G = VitkWeights(), VitkGrads()
+        W.patch_w = self._s("backbone.patch_embedding.projection.weight")
+        W.patch_b = self._p("backbone.patch_embedding.projection.bias")
+        G.patch_w = self._g("backbone.patch_embedding.projection.weight")
+        G.patch_b = self._g("backbone.patch_embedding.projection.bias")
+        W.cls_token, G.cls_token = self._p("backbone.cls_token"), self._g("backbone.cls_token")
+        if self.n_prefix == 2:
+            W.dist_token, G.dist_token = self._p("backbone.dist_token"), self._g("backbone.dist_token")
+        W.pos_embed = self._p("backbone.position_embedding")
+        G.pos_embed = self._g("backbone.position_embedding")
+        W.blocks = C.cast(self._bw, C.POINTER(VitkBlockWeights))
+        G.blocks = C.cast(self._bg, C.POINTER(VitkBlockGrads))
+        W.ln_f_w, W.ln_f_b = self._p("backbone.layer_norm.weight"), self._p("backbone.layer_norm.bias")
+        G.ln_f_w, G.ln_f_b = self._g("backbone.layer_norm.weight"), self._g("backbone.layer_norm.bias")
+        if self.head is not None:
+            W.head_w, W.head_b = self._p("head.weight"), self._p("head.bias")
+            G.head_w, G.head_b = self._g("head.weight"), self._g("head.bias")
+        T = VitkWeightsT()
+        T.blocks = C.cast(self._bt, C.POINTER(VitkBlockWeightsT))
+        self.W, self.G, self.T = W, G, T
+        n = len(self._t_jobs)
+        self._t_src = (C.c_void_p * n)(*[self._s(name) for name, _, _, _ in self._t_jobs])
+        self._t_dst = (C.c_void_p * n)(*[tptr[name] for name, _, _, _ in self._t_jobs])
+        self._t_rows = (C.c_int * n)(*[r for _, r, _, _ in self._t_jobs])
+        self._t_cols = (C.c_int * n)(*[c for _, _, c, _ in self._t_jobs])
+
+    def config(self) -> VitkConfig:
+        m = self.backbone
+        pe, blk = m.patch_embedding, m.transformer_blocks[0]
+        return VitkConfig(
+            image_size=pe.image_size, patch_size=pe.patch_size,
+            in_channels=pe.projection.in_channels, embed_dim=pe.projection.out_channels,
+            num_layers=len(m.transformer_blocks), num_heads=blk.attention.num_heads,
+            mlp_dim=blk.mlp.linear1.out_features, n_prefix_tokens=self.n_prefix,
+            n_classes=self.head.out_features if self.head is not None else 0, precision=0,
+            ln_eps=m.layer_norm.eps, dropout_p=float(m.dropout.p), seed=0)
+
+    # ------------------------------------------------------------------ shadows
+    def refresh_transposes(self):
+        check(lib().vitk_transpose_bf16_batched(len(self._t_jobs), self._t_src, self._t_dst,
+                                                self._t_rows, self._t_cols, _stream()))
+
+    def refresh_shadows(self):
+        """bf16 shadow (and W^T copies) from the fp32 arena - after an external parameter update."""
+        check(lib().vitk_cast_f32_to_bf16(self.flat.data_ptr(), self.shadow.data_ptr(), self.numel,
+                                          _stream()))
+        self.refresh_transposes()
+        self._versions = [p._version for p in self.params]
+
+    def shadows_stale(self) -> bool:
+        return any(p._version != v for p, v in zip(self.params, self._versions))
+
+    # ------------------------------------------------------------------ buffers
+    def buffers(self, batch: int):
+        if self._bufs_batch != batch:
+            cfg = self.config()
+            sv, ws = C.c_size_t(0), C.c_size_t(0)
+            check(lib().vitk_train_workspace_bytes(C.byref(cfg), batch, C.byref(sv), C.byref(ws)))
+            self._saved = torch.empty(sv.value + 1024, dtype=torch.uint8, device=self.device)
+            self._ws = torch.empty(ws.value + 1024, dtype=torch.uint8, device=self.device)
+            self._sizes = (sv.value, ws.value)
+            self._bufs_batch = batch
+        al = lambda t: (t.data_ptr() + 1023) // 1024 * 1024
+        return al(self._saved), self._sizes[0], al(self._ws), self._sizes[1]
+
+    # ------------------------------------------------------------------ gradient slices
+    def bucket_slices(self):
+        """Contiguous gradient slices in the order the backward completes them:
+        [final LN + head], block L-1, ..., block 0, [tokens + position + patch embedding]."""
+        L = len(self.backbone.transformer_blocks)
+        first_block = self.offsets["backbone.transformer_blocks.0.attention.qkv.weight"]
+        # named_parameters order inside a block starts with attention.qkv.weight
+        starts = [min(o for n, o in self.offsets.items()
+                      if n.startswith(f"backbone.transformer_blocks.{i}.")) for i in range(L)]
+        tail = self.offsets["backbone.layer_norm.weight"]
+        out = [(tail, self.numel)]
+        for i in reversed(range(L)):
+            end = starts[i + 1] if i + 1 < L else tail
+            out.append((starts[i], end))
+        out.append((0, first_block if first_block == starts[0] else starts[0]))
+        return out
+
+
+class FineTuner:
+    """Fused fine-tune step: AdamW(lr=1e-4, weight_decay=1e-4) as train.py:1598-1602."""
+
+    def __init__(self, model, lr=1e-4, weight_decay=1e-4, betas=(0.9, 0.999), eps=1e-8,
+                 process_group=None):
+        self.model = model
+        self.lr, self.wd, self.betas, self.eps = lr, weight_decay, betas, eps
+        self.state = TrainState(model.backbone, model.head, model.backbone._n_prefix)
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        self._comm_stream = torch.cuda.Stream(device=self.state.device) if self.world > 1 else None
+        self._loss = torch.zeros(1, dtype=torch.float32, device=self.state.device)
+
+    @torch.no_grad()
+    def step(self, images: torch.Tensor, labels: torch.Tensor):
+        """One optimisation step on this rank's shard; returns (loss tensor [1], logits [B, C]).
+        The loss is this rank's contribution to the global-batch mean."""
+        st = self.state
+        if not images.is_cuda or not labels.is_cuda:
+            raise _lib.VitkError("images / labels must be CUDA tensors (no CPU fallback)")
+        images = images.float().contiguous()
+        labels = labels.long().contiguous()
+        B = images.shape[0]
+        if st.shadows_stale():
+            st.refresh_shadows()
+        cfg = st.config()
+        saved, saved_bytes, ws, ws_bytes = st.buffers(B)
+        logits = torch.empty((B, cfg.n_classes), dtype=torch.float32, device=st.device)
+        st.grad.zero_()
+        self._loss.zero_()
+        s = _stream()
+        check(lib().vitk_forward_train(C.byref(cfg), C.byref(st.W), images.data_ptr(), B, None,
+                                       saved, saved_bytes, ws, ws_bytes, s))
+        check(lib().vitk_classifier_loss_backward(
+            C.byref(cfg), C.byref(st.W), C.byref(st.T), C.byref(st.G), labels.data_ptr(), B,
+            1.0 / (B * self.world), logits.data_ptr(), self._loss.data_ptr(), saved, ws, s))
+        if self.world > 1:
+            self._allreduce_grads()
+        st.step_count += 1
+        check(lib().vitk_adamw_step(st.flat.data_ptr(), st.grad.data_ptr(), st.exp_avg.data_ptr(),
+                                    st.exp_avg_sq.data_ptr(), st.shadow.data_ptr(), st.numel,
+                                    self.lr, self.betas[0], self.betas[1], self.eps, self.wd,
+                                    st.step_count, 1.0, s))
+        st.refresh_transposes()
+        for p in st.params:       # the arena was updated behind autograd's back
+            p._version  # noqa: B018  (kept for clarity: versions are not bumped by raw kernels)
+        st._versions = [p._version for p in st.params]
+        return self._loss, logits
+
+    def _allreduce_grads(self):
+        """Sum gradients over the data-parallel group: a few large all-reduces over contiguous
+        slices of the flat gradient arena on a side stream (NCCL over NVLink/NVSwitch)."""
+        st = self.state
+        main = torch.cuda.current_stream()
+        self._comm_stream.wait_stream(main)
+        works = []
+        with torch.cuda.stream(self._comm_stream):
+            for a, b in st.bucket_slices():
+                if b > a:
+                    works.append(dist.all_reduce(st.grad[a:b], group=self.pg, async_op=True))
+        for w in works:
+            w.wait()
+        main.wait_stream(self._comm_stream)

@@ -159,6 +159,105 @@ int vitk_patchify(const float* images, void* patches_bf16, int batch, int channe
 
 int vitk_cast_f32_to_bf16(const float* in, void* out_bf16, long long n, vitk_stream_t stream);
 
+/* =========================== training step (train.py:1441-1460) ===========================
+ * forward (saving activations) -> loss -> backward -> AdamW, replacing
+ *     outputs = model(images) ; losses.backward() ; optimizer.step()
+ * The loss of north_star's fine-tune is the mean cross-entropy of the 6-class CLS head; the
+ * generic vitk_backward_tokens serves any loss computed by the caller on backbone(images).
+ * Dropout: only p = 0 semantics are implemented (config.dropout_p must be 0). */
+
+/* W^T copies ([in, out], bf16) of the four nn.Linear weights of a block: the input-gradient GEMMs
+ * read the weight with its two dimensions swapped. Kept current by the caller after every
+ * optimizer step (vitk_transpose_bf16_batched). */
+typedef struct VitkBlockWeightsT {
+  const void* qkv_wt;  /* [D, 3D] */
+  const void* proj_wt; /* [D, D]  */
+  const void* fc1_wt;  /* [D, M]  */
+  const void* fc2_wt;  /* [M, D]  */
+} VitkBlockWeightsT;
+
+typedef struct VitkWeightsT {
+  const VitkBlockWeightsT* blocks; /* HOST array of num_layers entries */
+} VitkWeightsT;
+
+/* fp32 gradient buffers, one per parameter, same shapes as the parameters (state_dict order).
+ * Every backward entry point ACCUMULATES into them; the caller zeroes them once per step. */
+typedef struct VitkBlockGrads {
+  float* ln1_w;
+  float* ln1_b;
+  float* qkv_w;
+  float* qkv_b;
+  float* proj_w;
+  float* proj_b;
+  float* ln2_w;
+  float* ln2_b;
+  float* fc1_w;
+  float* fc1_b;
+  float* fc2_w;
+  float* fc2_b;
+} VitkBlockGrads;
+
+typedef struct VitkGrads {
+  float* patch_w;
+  float* patch_b;
+  float* cls_token;
+  float* dist_token; /* NULL for ViT */
+  float* pos_embed;
+  const VitkBlockGrads* blocks; /* HOST array */
+  float* ln_f_w;
+  float* ln_f_b;
+  float* head_w; /* NULL when there is no classifier head */
+  float* head_b;
+} VitkGrads;
+
+/* Bytes of the saved-activation arena and of the scratch workspace for `batch` images. */
+int vitk_train_workspace_bytes(const VitkConfig* cfg, int batch, size_t* saved_bytes,
+                               size_t* workspace_bytes);
+
+/* Forward in training mode: same arithmetic as vitk_forward, every activation the backward needs
+ * is written into `saved`; the residual stream stays in `workspace`. tokens_out (f32 [B,N,D],
+ * optional) = backbone(images). */
+int vitk_forward_train(const VitkConfig* cfg, const VitkWeights* w, const float* images, int batch,
+                       float* tokens_out, void* saved, size_t saved_bytes, void* workspace,
+                       size_t workspace_bytes, vitk_stream_t stream);
+
+/* After vitk_forward_train: logits = head(LN(x)[:,0]); loss_out += loss_scale * sum_b CE(logits_b,
+ * labels_b) (loss_scale = 1 / global batch gives F.cross_entropy's mean); then the full backward.
+ * labels: int64 [batch]. logits_out f32 [batch, n_classes] and loss_out (f32 scalar, pre-zeroed)
+ * are optional. */
+int vitk_classifier_loss_backward(const VitkConfig* cfg, const VitkWeights* w,
+                                  const VitkWeightsT* wt, const VitkGrads* g,
+                                  const long long* labels, int batch, float loss_scale,
+                                  float* logits_out, float* loss_out, void* saved, void* workspace,
+                                  vitk_stream_t stream);
+
+/* After vitk_forward_train with tokens_out: backward from d_tokens = dLoss/d backbone(images)
+ * (f32 [B,N,D]) - what autograd hands to the backbone at train.py:1455. */
+int vitk_backward_tokens(const VitkConfig* cfg, const VitkWeights* w, const VitkWeightsT* wt,
+                         const VitkGrads* g, const float* d_tokens, int batch, void* saved,
+                         void* workspace, vitk_stream_t stream);
+
+/* torch.optim.AdamW (train.py:1598-1602: one group, decay on every parameter) over a flat fp32
+ * arena of n parameters in ONE launch; grads are multiplied by grad_scale first; refreshes the
+ * bf16 shadow arena (same element order) when shadow_bf16 != NULL. step is 1-based. */
+int vitk_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                    void* shadow_bf16, long long n, float lr, float beta1, float beta2, float eps,
+                    float weight_decay, int step, float grad_scale, vitk_stream_t stream);
+
+/* dst_i [cols_i, rows_i] = src_i [rows_i, cols_i]^T for n bf16 matrices (host pointer arrays). */
+int vitk_transpose_bf16_batched(int n, const void* const* src, void* const* dst, const int* rows,
+                                const int* cols, vitk_stream_t stream);
+
+/* Per-operator backward entry points (unit tests; the same kernels the step uses). */
+int vitk_layernorm_bwd(const void* dy, int dy_is_f32, const float* x, const float* mean,
+                       const float* rstd, const float* gamma, float* dx_io, int add_resid,
+                       void* dx_bf16, float* dgamma, float* dbeta, int rows, int D,
+                       vitk_stream_t stream);
+int vitk_attention_bwd(const void* qkv_bf16, const void* ctx_bf16, const void* dctx_bf16,
+                       const float* lse, void* dqkv_bf16, int batch, int n_tokens, int num_heads,
+                       int head_dim, vitk_stream_t stream);
+int vitk_colsum_bf16(const void* y, long long ld, int M, int N, float* out, vitk_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
