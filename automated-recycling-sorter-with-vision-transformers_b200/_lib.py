@@ -105,8 +105,8 @@ _SIGNATURES = {
                                        C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                        C.c_void_p]),
     "vitk_adamw_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                  C.c_longlong, C.c_float, C.c_float, C.c_float, C.c_float,
-                                  C.c_float, C.c_int, C.c_float, C.c_void_p]),
+                                  C.c_longlong, C.c_double, C.c_double, C.c_double, C.c_double,
+                                  C.c_double, C.c_int, C.c_float, C.c_void_p]),
     "vitk_transpose_bf16_batched": (C.c_int, [C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                               C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p]),
     "vitk_layernorm_bwd": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -392,8 +392,9 @@ int vitk_backward_tokens(const VitkConfig* cfg, const VitkWeights* w, const Vitk
 }
 
 int vitk_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
-                    void* shadow_bf16, long long n, float lr, float beta1, float beta2, float eps,
-                    float weight_decay, int step, float grad_scale, vitk_stream_t stream) {
+                    void* shadow_bf16, long long n, double lr, double beta1, double beta2,
+                    double eps, double weight_decay, int step, float grad_scale,
+                    vitk_stream_t stream) {
   return adamw_flat(params, grads, exp_avg, exp_avg_sq, shadow_bf16, n, lr, beta1, beta2, eps,
                     weight_decay, step, grad_scale, static_cast<cudaStream_t>(stream));
 }

@@ -382,7 +382,8 @@ transpose_batched_kernel(const TransposeBatch tb) {
 __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
              float* __restrict__ v, __nv_bfloat16* __restrict__ shadow, long long n, float decay,
-             float b1, float b2, float step_size, float inv_sqrt_bc2, float eps, float grad_scale) {
+             float b1, float b2, float omb1, float omb2, float step_size, float inv_sqrt_bc2,
+             float eps, float grad_scale) {
   const long long nvec = n >> 2;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -398,8 +399,8 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
     for (int k = 0; k < 4; ++k) {
       const float gr = gp[k] * grad_scale;
       pp[k] *= decay;
-      mp[k] = b1 * mp[k] + (1.f - b1) * gr;
-      vp[k] = b2 * vp[k] + (1.f - b2) * gr * gr;
+      mp[k] = b1 * mp[k] + omb1 * gr;
+      vp[k] = b2 * vp[k] + omb2 * gr * gr;
       const float denom = sqrtf(vp[k]) * inv_sqrt_bc2 + eps;
       pp[k] -= step_size * (mp[k] / denom);
     }
@@ -418,8 +419,8 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
        i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const float gr = g[i] * grad_scale;
     float pv = p[i] * decay;
-    const float mv = b1 * m[i] + (1.f - b1) * gr;
-    const float vv = b2 * v[i] + (1.f - b2) * gr * gr;
+    const float mv = b1 * m[i] + omb1 * gr;
+    const float vv = b2 * v[i] + omb2 * gr * gr;
     pv -= step_size * (mv / (sqrtf(vv) * inv_sqrt_bc2 + eps));
     p[i] = pv;
     m[i] = mv;
@@ -515,21 +516,23 @@ int transpose_batched(const TransposeBatch& tb, cudaStream_t stream) {
 }
 
 int adamw_flat(float* p, const float* g, float* m, float* v, void* shadow_bf16, long long n,
-               float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+               double lr, double beta1, double beta2, double eps, double weight_decay, int step,
                float grad_scale, cudaStream_t stream) {
   VITK_REQUIRE(p && g && m && v && n > 0 && step >= 1, "adamw: bad argument");
   VITK_REQUIRE((reinterpret_cast<uintptr_t>(p) & 15) == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0 &&
                    (reinterpret_cast<uintptr_t>(m) & 15) == 0 && (reinterpret_cast<uintptr_t>(v) & 15) == 0,
                "adamw: arenas must be 16-byte aligned");
-  const double bc1 = 1.0 - pow(static_cast<double>(beta1), step);
-  const double bc2 = 1.0 - pow(static_cast<double>(beta2), step);
+  // hyper-parameters are combined in double and rounded once, as torch.optim.AdamW does
+  const double bc1 = 1.0 - pow(beta1, step);
+  const double bc2 = 1.0 - pow(beta2, step);
   const float step_size = static_cast<float>(lr / bc1);
   const float inv_sqrt_bc2 = static_cast<float>(1.0 / sqrt(bc2));
-  const float decay = static_cast<float>(1.0 - static_cast<double>(lr) * weight_decay);
+  const float decay = static_cast<float>(1.0 - lr * weight_decay);
   ProfileScope prof(PROF_OPT, static_cast<double>(n) * 30.0, stream);
   adamw_kernel<<<grid_for(n / 4 + 1, 256, 8), 256, 0, stream>>>(
-      p, g, m, v, static_cast<__nv_bfloat16*>(shadow_bf16), n, decay, beta1, beta2, step_size,
-      inv_sqrt_bc2, eps, grad_scale);
+      p, g, m, v, static_cast<__nv_bfloat16*>(shadow_bf16), n, decay, static_cast<float>(beta1),
+      static_cast<float>(beta2), static_cast<float>(1.0 - beta1), static_cast<float>(1.0 - beta2),
+      step_size, inv_sqrt_bc2, static_cast<float>(eps), grad_scale);
   VITK_CHECK_LAUNCH("adamw_kernel");
   return VITK_OK;
 }

@@ -38,7 +38,7 @@ struct TransposeBatch {
 int transpose_batched(const TransposeBatch& tb, cudaStream_t stream);
 
 int adamw_flat(float* p, const float* g, float* m, float* v, void* shadow_bf16, long long n,
-               float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+               double lr, double beta1, double beta2, double eps, double weight_decay, int step,
                float grad_scale, cudaStream_t stream);
 
 // dqkv = backward of softmax(q k^T / sqrt(hd)) v given d_ctx, using the saved log-sum-exp.

@@ -241,8 +241,9 @@ int vitk_backward_tokens(const VitkConfig* cfg, const VitkWeights* w, const Vitk
  * arena of n parameters in ONE launch; grads are multiplied by grad_scale first; refreshes the
  * bf16 shadow arena (same element order) when shadow_bf16 != NULL. step is 1-based. */
 int vitk_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
-                    void* shadow_bf16, long long n, float lr, float beta1, float beta2, float eps,
-                    float weight_decay, int step, float grad_scale, vitk_stream_t stream);
+                    void* shadow_bf16, long long n, double lr, double beta1, double beta2,
+                    double eps, double weight_decay, int step, float grad_scale,
+                    vitk_stream_t stream);
 
 /* dst_i [cols_i, rows_i] = src_i [rows_i, cols_i]^T for n bf16 matrices (host pointer arrays). */
 int vitk_transpose_bf16_batched(int n, const void* const* src, void* const* dst, const int* rows,

@@ -32,7 +32,10 @@ def _check_step(vitk, model, x, y, loss_ref, g_ref, n_ref, lr=1e-4):
         # first AdamW step moves every weight by ~lr * sign(g): a sign flip of a near-zero gradient
         # costs 2 * lr, everything else must agree closely
         assert err.max() < 2.2 * lr, (k, err.max().item())
-        assert err.mean() < 0.15 * lr, (k, err.mean().item())
+        g = g_ref[k].double().abs()
+        solid = g > 1e-2 * g.max()          # e.g. the key bias has an exactly-zero gradient
+        if solid.any():
+            assert err[solid].mean() < 0.1 * lr, (k, err[solid].mean().item())
     return tuner
 
 
