@@ -1,0 +1,86 @@
+"""Multi-GPU host logic (one process per GPU, torch.distributed for the plumbing).
+
+The reference is single-device (train.py:1392, no DDP).  The hot path shards over images:
+
+  * inference (evaluation.py:498-502): rank r owns a contiguous slice of the batch, runs the whole
+    network on it, and the [B, n_classes] logits are optionally all-gathered - no collective on
+    the critical path;
+  * training (train.py:1441-1460): data parallel - identical replicas, the loss is averaged over
+    the global batch, ONE exchange per step: a sum all-reduce of the flat gradient arena, issued
+    as a few large contiguous slices in the order the backward produces them.
+
+Everything here is device-agnostic so that the logic is covered by world_size-2 gloo tests on CPU.
+"""
+from __future__ import annotations
+
+from typing import Callable, Sequence
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_items: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous, balanced partition of n_items units: the first n % world ranks get one more."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError(f"bad rank/world {rank}/{world}")
+    base, extra = divmod(n_items, world)
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+def allreduce_slices(flat: torch.Tensor, slices: Sequence[tuple[int, int]], group=None,
+                     comm_stream=None) -> None:
+    """In-place sum all-reduce of flat[a:b] for every slice, in the given order.  On CUDA the
+    collectives are enqueued on `comm_stream` (after everything already queued on the current
+    stream) and the current stream waits for them at the end."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return
+    if flat.is_cuda and comm_stream is not None:
+        main = torch.cuda.current_stream(flat.device)
+        comm_stream.wait_stream(main)
+        works = []
+        with torch.cuda.stream(comm_stream):
+            for a, b in slices:
+                if b > a:
+                    works.append(dist.all_reduce(flat[a:b], group=group, async_op=True))
+        for w in works:
+            w.wait()
+        main.wait_stream(comm_stream)
+    else:
+        for a, b in slices:
+            if b > a:
+                dist.all_reduce(flat[a:b], group=group)
+
+
+def gather_rows(local: torch.Tensor, n_total: int, group=None) -> torch.Tensor:
+    """All-gather row shards produced with shard_range(n_total, rank, world) back into [n_total, ...]
+    on every rank (shards may differ by one row; they are padded for the collective)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return local
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    longest = (n_total + world - 1) // world
+    pad = torch.zeros((longest,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[:local.shape[0]] = local
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad, group=group)
+    out = []
+    for r, part in enumerate(parts):
+        a, b = shard_range(n_total, r, world)
+        out.append(part[:b - a])
+    return torch.cat(out, dim=0)
+
+
+def sharded_apply(fn: Callable[[torch.Tensor], torch.Tensor], batch: torch.Tensor, group=None,
+                  gather: bool = True) -> torch.Tensor:
+    """Batch-sharded inference: apply `fn` (e.g. a ViTClassifier) to this rank's slice of `batch`
+    and, if `gather`, assemble the full result on every rank."""
+    world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    rank = dist.get_rank(group) if world > 1 else 0
+    a, b = shard_range(batch.shape[0], rank, world)
+    local = fn(batch[a:b]) if b > a else None
+    if not gather or world == 1:
+        return local
+    if local is None:   # more ranks than images: contribute an empty shard of the right width
+        probe = fn(batch[:1])
+        local = probe[:0]
+    return gather_rows(local, batch.shape[0], group)

@@ -230,22 +230,10 @@ class FineTuner:
                                     self.lr, self.betas[0], self.betas[1], self.eps, self.wd,
                                     st.step_count, 1.0, s))
         st.refresh_transposes()
-        for p in st.params:       # the arena was updated behind autograd's back
-            p._version  # noqa: B018  (kept for clarity: versions are not bumped by raw kernels)
-        st._versions = [p._version for p in st.params]
         return self._loss, logits
 
     def _allreduce_grads(self):
         """Sum gradients over the data-parallel group: a few large all-reduces over contiguous
         slices of the flat gradient arena on a side stream (NCCL over NVLink/NVSwitch)."""
-        st = self.state
-        main = torch.cuda.current_stream()
-        self._comm_stream.wait_stream(main)
-        works = []
-        with torch.cuda.stream(self._comm_stream):
-            for a, b in st.bucket_slices():
-                if b > a:
-                    works.append(dist.all_reduce(st.grad[a:b], group=self.pg, async_op=True))
-        for w in works:
-            w.wait()
-        main.wait_stream(self._comm_stream)
+        from .dist import allreduce_slices
+        allreduce_slices(self.state.grad, self.state.bucket_slices(), self.pg, self._comm_stream)

@@ -178,6 +178,58 @@ def run_reference(args) -> None:
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+TRAIN_BATCH = 128
+
+
+def measure_train_step(vitk, O, dev, world, rank, barrier, steps: int = 8, warmup: int = 3) -> dict:
+    """BASELINE.json configs[2]: ViT-B/16 6-class fine-tune step (forward saving activations ->
+    cross-entropy -> hand-written backward -> NCCL gradient all-reduce -> fused AdamW), bf16,
+    128 images per GPU, data parallel. Reported next to the headline inference metric."""
+    import torch
+    import torch.distributed as dist
+    B = TRAIN_BATCH
+    torch.manual_seed(0)
+    model = vitk.ViTClassifier(num_classes=N_CLASSES, dropout=0.0, **VIT_B16).to(dev)
+    tuner = vitk.FineTuner(model, lr=1e-4, weight_decay=1e-4)
+    x = O.synthetic_images(B, VIT_B16["image_size"], seed=99 + rank).to(dev)
+    y = O.synthetic_labels(B, N_CLASSES, seed=5 + rank).to(dev)
+    for _ in range(warmup):
+        loss, _ = tuner.step(x, y)
+    barrier()
+    n0 = vitk.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(steps):
+        loss, _ = tuner.step(x, y)
+    ev1.record()
+    barrier()
+    launches = vitk.launch_count() - n0
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    vitk._lib.profile_enable(True)
+    for _ in range(2):
+        tuner.step(x, y)
+    torch.cuda.synchronize()
+    prof = vitk._lib.profile_collect()
+    vitk._lib.profile_enable(False)
+    ips = world * B * steps / (ms * 1e-3)
+    flops = 3.0 * fwd_flops_per_image()
+    peaks, _ = measured_peaks()
+    del tuner, model
+    torch.cuda.empty_cache()
+    return {"metric": "vit_b16_224_finetune_images_per_sec", "value": ips, "unit": UNIT,
+            "ms_per_step": ms / steps, "batch_per_gpu": B, "global_batch": B * world,
+            "steps": steps, "warmup": warmup, "gpu_launches": int(launches),
+            "loss_after": float(loss.item()) * world,
+            "tflops": ips / world * flops / 1e12,
+            "frac_of_burst_peak": ips / world * flops / 1e12 / float(peaks["bf16_tflops"]),
+            "by_kind_ms_per_step": {k: v["ms"] / 2 for k, v in prof.items() if v["launches"]},
+            "optimizer": "fused AdamW lr 1e-4 wd 1e-4 (train.py:1598-1602), dropout 0"}
+
+
 def run_vitk(args) -> None:
     import torch
     import torch.distributed as dist
@@ -197,6 +249,8 @@ def run_vitk(args) -> None:
     n_gpus = world
 
     B = args.batch
+    global TRAIN_BATCH
+    TRAIN_BATCH = args.train_batch
     torch.manual_seed(0)
     model = vitk.ViTClassifier(num_classes=N_CLASSES, dropout=0.0, **VIT_B16).to(dev).eval()
     # every rank owns a different shard of the global batch (weak scaling: B images per GPU)
@@ -254,6 +308,8 @@ def run_vitk(args) -> None:
         assert n_out == B * args.steps
         e2e_value = n_gpus * B * args.steps / e2e_s
 
+    train = None if args.no_train else measure_train_step(vitk, O, dev, world, rank, barrier)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -297,6 +353,8 @@ def run_vitk(args) -> None:
         "gpu_launches": int(launches),
         "roofline": roofline,
     }
+    if train is not None:
+        line["train_step"] = train
     if cpu is not None:
         line["cpu_baseline"] = cpu
     print(json.dumps(line))
@@ -312,6 +370,8 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
     ap.add_argument("--impl", choices=["vitk", "reference"], default="vitk")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the fine-tune step measurement")
+    ap.add_argument("--train-batch", type=int, default=128, help="images per GPU per train step")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
