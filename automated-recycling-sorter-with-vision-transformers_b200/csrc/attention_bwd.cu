@@ -104,31 +104,20 @@ __device__ __forceinline__ void mma_pv(float (&out)[8][4], const float (&p)[8][4
   }
 }
 
-// 16 x 64 fp32 tile -> bf16 rows of `dst` (row pitch ld elements) through a per-warp smem slab.
-__device__ __forceinline__ void store_tile(const float (&o)[8][4], uint32_t slab, int lane,
-                                           __nv_bfloat16* dst, long long ld, int row0, int row_limit) {
+// 16 x 64 fp32 tile -> bf16 rows of `dst` (row pitch ld elements), straight from the MMA
+// accumulator layout: every lane writes bf16 pairs, 16 contiguous bytes per row and instruction.
+// (d_qkv is ~1 % of this kernel's traffic; not staging it frees 16 KB of shared memory so that two
+// CTAs are resident per SM.)
+__device__ __forceinline__ void store_tile(const float (&o)[8][4], int lane, __nv_bfloat16* dst,
+                                           long long ld, int row0, int row_limit) {
   const int g = lane >> 2, t = lane & 3;
-  __syncwarp();
+  const int r0 = row0 + g, r1 = row0 + g + 8;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const uint32_t w0 = pack_bf16x2(o[j][0], o[j][1]);
-    const uint32_t w1 = pack_bf16x2(o[j][2], o[j][3]);
-    asm volatile("st.shared.b32 [%0], %1;" ::"r"(swz(slab, g, j) + t * 4), "r"(w0) : "memory");
-    asm volatile("st.shared.b32 [%0], %1;" ::"r"(swz(slab, g + 8, j) + t * 4), "r"(w1) : "memory");
-  }
-  __syncwarp();
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int idx = lane + 32 * i;
-    const int row = idx >> 3, ch = idx & 7;
-    if (row0 + row < row_limit) {
-      uint4 val;
-      asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
-                   : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w)
-                   : "r"(swz(slab, row, ch))
-                   : "memory");
-      *reinterpret_cast<uint4*>(dst + (row0 + row) * ld + ch * 8) = val;
-    }
+    if (r0 < row_limit)
+      *reinterpret_cast<uint32_t*>(dst + r0 * ld + j * 8 + t * 2) = pack_bf16x2(o[j][0], o[j][1]);
+    if (r1 < row_limit)
+      *reinterpret_cast<uint32_t*>(dst + r1 * ld + j * 8 + t * 2) = pack_bf16x2(o[j][2], o[j][3]);
   }
 }
 
@@ -142,8 +131,7 @@ attn_bwd_hd64_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16*
   const uint32_t sK = sQ + Nkv * 128;
   const uint32_t sV = sK + Nkv * 128;
   const uint32_t sdO = sV + Nkv * 128;
-  const uint32_t sSlab = sdO + Nkv * 128;  // kWarps * 2048
-  float* sLse = reinterpret_cast<float*>(smem + 4 * Nkv * 128 + kWarps * 2048);
+  float* sLse = reinterpret_cast<float*>(smem + 4 * Nkv * 128);
   float* sD = sLse + 256;
 
   const int b = blockIdx.x / H;
@@ -192,7 +180,6 @@ attn_bwd_hd64_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16*
   __syncthreads();
 
   const float c = scale * kLog2e;
-  const uint32_t slab = sSlab + warp * 2048;
 
   // ================= pass 1: query tiles -> dq =================
   for (int qt = warp; qt * 16 < N; qt += kWarps) {
@@ -224,7 +211,7 @@ attn_bwd_hd64_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16*
       }
       mma_pv(dq, s, sK, kb * 64, rem, lane);
     }
-    store_tile(dq, slab, lane, dqbase, D3, q0, N);
+    store_tile(dq, lane, dqbase, D3, q0, N);
   }
 
   // ================= pass 2: key tiles -> dk, dv =================
@@ -266,8 +253,8 @@ attn_bwd_hd64_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16*
       mma_pv(dv, st, sdO, qb * 64, rem, lane);  // dv += P^T d_ctx
       mma_pv(dk, dpt, sQ, qb * 64, rem, lane);  // dk += dS^T q
     }
-    store_tile(dk, slab, lane, dqbase + D, D3, k0, N);
-    store_tile(dv, slab, lane, dqbase + 2 * D, D3, k0, N);
+    store_tile(dk, lane, dqbase + D, D3, k0, N);
+    store_tile(dv, lane, dqbase + 2 * D, D3, k0, N);
   }
 }
 
@@ -280,7 +267,7 @@ int attention_bwd(const void* qkv, const void* ctx, const void* dctx, const floa
   VITK_REQUIRE(hd == 64 && N <= 256, "attention_bwd: needs head_dim 64 and N <= 256 (got %d, %d)",
                hd, N);
   const int Nkv = (N + 15) & ~15;
-  const size_t smem = 4 * static_cast<size_t>(Nkv) * 128 + kWarps * 2048 + 2 * 256 * sizeof(float);
+  const size_t smem = 4 * static_cast<size_t>(Nkv) * 128 + 2 * 256 * sizeof(float);
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [&] {

@@ -45,103 +45,115 @@ int grid_for(long long work_items, int block, int max_blocks_per_sm = 8) {
 // x feeds both the LN and the skip connection).  Optionally emits a bf16 copy of the result (the
 // A operand of the next dgrad GEMM).
 // ------------------------------------------------------------------------------------------------
+// Kernel A: dx (warp per row, row kept in registers; ~60 registers so that many warps are
+// resident and the kernel runs at HBM speed).
 template <typename DyT>
 __global__ void __launch_bounds__(256)
-layernorm_bwd_kernel(const DyT* __restrict__ dy, long long dy_stride, const float* __restrict__ x,
-                     long long x_stride, const float* __restrict__ mean,
-                     const float* __restrict__ rstd, const float* __restrict__ gamma,
-                     float* __restrict__ dx_io, long long dx_stride, int add_resid,
-                     __nv_bfloat16* __restrict__ dx_bf16, long long dxb_stride,
-                     float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, int D) {
-  extern __shared__ float s_part[];  // [2][D]
+layernorm_bwd_dx_kernel(const DyT* __restrict__ dy, long long dy_stride, const float* __restrict__ x,
+                        long long x_stride, const float* __restrict__ mean,
+                        const float* __restrict__ rstd, const float* __restrict__ gamma,
+                        float* __restrict__ dx_io, long long dx_stride, int add_resid,
+                        __nv_bfloat16* __restrict__ dx_bf16, long long dxb_stride, int rows, int D) {
   const int nvec = D >> 2;
-  for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) s_part[i] = 0.f;
-  __syncthreads();
   const int lane = threadIdx.x & 31;
-  const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int num_warps = (gridDim.x * blockDim.x) >> 5;
-  float4 gam[kLnMaxVec], dg[kLnMaxVec], db[kLnMaxVec];
+  const long long r = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (r >= rows) return;
+  const float mu = mean[r], rs = rstd[r];
+  const float inv_d = 1.f / static_cast<float>(D);
+  float4 xh[kLnMaxVec], g[kLnMaxVec];
+  float s1 = 0.f, s2 = 0.f;
 #pragma unroll
   for (int j = 0; j < kLnMaxVec; ++j) {
     const int i = lane + 32 * j;
-    gam[j] = (i < nvec) ? __ldg(reinterpret_cast<const float4*>(gamma) + i) : make_float4(0, 0, 0, 0);
-    dg[j] = make_float4(0, 0, 0, 0);
-    db[j] = make_float4(0, 0, 0, 0);
-  }
-  const float inv_d = 1.f / static_cast<float>(D);
-  for (int r = warp_global; r < rows; r += num_warps) {
-    const float mu = mean[r], rs = rstd[r];
-    float4 xh[kLnMaxVec], g[kLnMaxVec];
-    float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-    for (int j = 0; j < kLnMaxVec; ++j) {
-      const int i = lane + 32 * j;
-      if (i < nvec) {
-        const float4 xv = load4(x + r * x_stride + 4 * i);
-        const float4 d = load4(dy + r * dy_stride + 4 * i);
-        xh[j] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
-        g[j] = make_float4(d.x * gam[j].x, d.y * gam[j].y, d.z * gam[j].z, d.w * gam[j].w);
-        s1 += (g[j].x + g[j].y) + (g[j].z + g[j].w);
-        s2 += (g[j].x * xh[j].x + g[j].y * xh[j].y) + (g[j].z * xh[j].z + g[j].w * xh[j].w);
-        dg[j].x += d.x * xh[j].x;
-        dg[j].y += d.y * xh[j].y;
-        dg[j].z += d.z * xh[j].z;
-        dg[j].w += d.w * xh[j].w;
-        db[j].x += d.x;
-        db[j].y += d.y;
-        db[j].z += d.z;
-        db[j].w += d.w;
-      }
+    if (i < nvec) {
+      const float4 xv = load4(x + r * x_stride + 4 * i);
+      const float4 d = load4(dy + r * dy_stride + 4 * i);
+      const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + i);
+      xh[j] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+      g[j] = make_float4(d.x * gm.x, d.y * gm.y, d.z * gm.z, d.w * gm.w);
+      s1 += (g[j].x + g[j].y) + (g[j].z + g[j].w);
+      s2 += (g[j].x * xh[j].x + g[j].y * xh[j].y) + (g[j].z * xh[j].z + g[j].w * xh[j].w);
     }
-    s1 = warp_sum(s1) * inv_d;
-    s2 = warp_sum(s2) * inv_d;
+  }
+  s1 = warp_sum(s1) * inv_d;
+  s2 = warp_sum(s2) * inv_d;
 #pragma unroll
-    for (int j = 0; j < kLnMaxVec; ++j) {
-      const int i = lane + 32 * j;
-      if (i < nvec) {
-        float4 o;
-        o.x = rs * (g[j].x - s1 - xh[j].x * s2);
-        o.y = rs * (g[j].y - s1 - xh[j].y * s2);
-        o.z = rs * (g[j].z - s1 - xh[j].z * s2);
-        o.w = rs * (g[j].w - s1 - xh[j].w * s2);
-        float* dst = dx_io + r * dx_stride + 4 * i;
-        if (add_resid) {
-          const float4 p = *reinterpret_cast<const float4*>(dst);
-          o.x += p.x;
-          o.y += p.y;
-          o.z += p.z;
-          o.w += p.w;
-        }
-        *reinterpret_cast<float4*>(dst) = o;
-        if (dx_bf16 != nullptr) {
-          uint2 pk;
-          pk.x = pack_bf16x2(o.x, o.y);
-          pk.y = pack_bf16x2(o.z, o.w);
-          *reinterpret_cast<uint2*>(dx_bf16 + r * dxb_stride + 4 * i) = pk;
-        }
+  for (int j = 0; j < kLnMaxVec; ++j) {
+    const int i = lane + 32 * j;
+    if (i < nvec) {
+      float4 o;
+      o.x = rs * (g[j].x - s1 - xh[j].x * s2);
+      o.y = rs * (g[j].y - s1 - xh[j].y * s2);
+      o.z = rs * (g[j].z - s1 - xh[j].z * s2);
+      o.w = rs * (g[j].w - s1 - xh[j].w * s2);
+      float* dst = dx_io + r * dx_stride + 4 * i;
+      if (add_resid) {
+        const float4 p = *reinterpret_cast<const float4*>(dst);
+        o.x += p.x;
+        o.y += p.y;
+        o.z += p.z;
+        o.w += p.w;
+      }
+      *reinterpret_cast<float4*>(dst) = o;
+      if (dx_bf16 != nullptr) {
+        uint2 pk;
+        pk.x = pack_bf16x2(o.x, o.y);
+        pk.y = pack_bf16x2(o.z, o.w);
+        *reinterpret_cast<uint2*>(dx_bf16 + r * dxb_stride + 4 * i) = pk;
       }
     }
   }
-  if (dgamma != nullptr) {
+}
+
+// Kernel B: dgamma / dbeta - a column reduction over rows. Thread = 4 columns, block = 64 threads
+// (256 columns) x 4 row lanes, each block sweeps `rows_per_block` rows.
+template <typename DyT>
+__global__ void __launch_bounds__(256)
+layernorm_bwd_params_kernel(const DyT* __restrict__ dy, long long dy_stride,
+                            const float* __restrict__ x, long long x_stride,
+                            const float* __restrict__ mean, const float* __restrict__ rstd,
+                            float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, int D,
+                            int rows_per_block) {
+  __shared__ float4 s_g[4][64], s_b[4][64];
+  const int tcol = threadIdx.x & 63, trow = threadIdx.x >> 6;
+  const int col = blockIdx.x * 256 + tcol * 4;
+  const int r_begin = blockIdx.y * rows_per_block;
+  const int r_end = min(rows, r_begin + rows_per_block);
+  float4 ag = make_float4(0, 0, 0, 0), ab = make_float4(0, 0, 0, 0);
+  if (col < D) {
+#pragma unroll 4
+    for (int r = r_begin + trow; r < r_end; r += 4) {
+      const float mu = __ldg(mean + r), rs = __ldg(rstd + r);
+      const float4 xv = load4(x + r * x_stride + col);
+      const float4 d = load4(dy + r * dy_stride + col);
+      ag.x = fmaf(d.x, (xv.x - mu) * rs, ag.x);
+      ag.y = fmaf(d.y, (xv.y - mu) * rs, ag.y);
+      ag.z = fmaf(d.z, (xv.z - mu) * rs, ag.z);
+      ag.w = fmaf(d.w, (xv.w - mu) * rs, ag.w);
+      ab.x += d.x;
+      ab.y += d.y;
+      ab.z += d.z;
+      ab.w += d.w;
+    }
+  }
+  s_g[trow][tcol] = ag;
+  s_b[trow][tcol] = ab;
+  __syncthreads();
+  if (trow == 0 && col < D) {
 #pragma unroll
-    for (int j = 0; j < kLnMaxVec; ++j) {
-      const int i = lane + 32 * j;
-      if (i < nvec) {
-        atomicAdd(&s_part[4 * i + 0], dg[j].x);
-        atomicAdd(&s_part[4 * i + 1], dg[j].y);
-        atomicAdd(&s_part[4 * i + 2], dg[j].z);
-        atomicAdd(&s_part[4 * i + 3], dg[j].w);
-        atomicAdd(&s_part[D + 4 * i + 0], db[j].x);
-        atomicAdd(&s_part[D + 4 * i + 1], db[j].y);
-        atomicAdd(&s_part[D + 4 * i + 2], db[j].z);
-        atomicAdd(&s_part[D + 4 * i + 3], db[j].w);
-      }
+    for (int k = 1; k < 4; ++k) {
+      const float4 a = s_g[k][tcol], b = s_b[k][tcol];
+      ag.x += a.x; ag.y += a.y; ag.z += a.z; ag.w += a.w;
+      ab.x += b.x; ab.y += b.y; ab.z += b.z; ab.w += b.w;
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < D; i += blockDim.x) {
-      atomicAdd(dgamma + i, s_part[i]);
-      atomicAdd(dbeta + i, s_part[D + i]);
-    }
+    atomicAdd(dgamma + col + 0, ag.x);
+    atomicAdd(dgamma + col + 1, ag.y);
+    atomicAdd(dgamma + col + 2, ag.z);
+    atomicAdd(dgamma + col + 3, ag.w);
+    atomicAdd(dbeta + col + 0, ab.x);
+    atomicAdd(dbeta + col + 1, ab.y);
+    atomicAdd(dbeta + col + 2, ab.z);
+    atomicAdd(dbeta + col + 3, ab.w);
   }
 }
 
@@ -440,21 +452,36 @@ int layernorm_bwd(const void* dy, int dy_is_f32, long long dy_stride, const floa
   VITK_REQUIRE(rows > 0 && D % 4 == 0 && D <= 128 * kLnMaxVec, "layernorm_bwd: bad shape");
   VITK_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), "layernorm_bwd: dgamma/dbeta together");
   const int block = 256;
-  int grid = (rows + 7) / 8;
-  const int cap = sm_count() * 4;
-  if (grid > cap) grid = cap;
-  const size_t smem = 2 * static_cast<size_t>(D) * sizeof(float);
+  const int grid = (rows + 7) / 8;
+  const __nv_bfloat16* dyb = static_cast<const __nv_bfloat16*>(dy);
+  const float* dyf = static_cast<const float*>(dy);
+  if (dgamma != nullptr) {
+    // parameter gradients first: they read dy / x only, before dx_io is updated in place
+    const int strips = (D + 255) / 256;
+    int chunks = (sm_count() * 6 + strips - 1) / strips;
+    if (chunks > (rows + 15) / 16) chunks = (rows + 15) / 16;
+    if (chunks < 1) chunks = 1;
+    const int rows_per_block = (rows + chunks - 1) / chunks;
+    chunks = (rows + rows_per_block - 1) / rows_per_block;
+    ProfileScope prof(PROF_LN, static_cast<double>(rows) * D * (dy_is_f32 ? 8.0 : 6.0), stream);
+    if (dy_is_f32)
+      layernorm_bwd_params_kernel<float><<<dim3(strips, chunks), block, 0, stream>>>(
+          dyf, dy_stride, x, x_stride, mean, rstd, dgamma, dbeta, rows, D, rows_per_block);
+    else
+      layernorm_bwd_params_kernel<__nv_bfloat16><<<dim3(strips, chunks), block, 0, stream>>>(
+          dyb, dy_stride, x, x_stride, mean, rstd, dgamma, dbeta, rows, D, rows_per_block);
+    VITK_CHECK_LAUNCH("layernorm_bwd_params_kernel");
+  }
   ProfileScope prof(PROF_LN, static_cast<double>(rows) * D * (dy_is_f32 ? 14.0 : 12.0), stream);
   if (dy_is_f32)
-    layernorm_bwd_kernel<float><<<grid, block, smem, stream>>>(
-        static_cast<const float*>(dy), dy_stride, x, x_stride, mean, rstd, gamma, dx_io, dx_stride,
-        add_resid, static_cast<__nv_bfloat16*>(dx_bf16), dxb_stride, dgamma, dbeta, rows, D);
+    layernorm_bwd_dx_kernel<float><<<grid, block, 0, stream>>>(
+        dyf, dy_stride, x, x_stride, mean, rstd, gamma, dx_io, dx_stride, add_resid,
+        static_cast<__nv_bfloat16*>(dx_bf16), dxb_stride, rows, D);
   else
-    layernorm_bwd_kernel<__nv_bfloat16><<<grid, block, smem, stream>>>(
-        static_cast<const __nv_bfloat16*>(dy), dy_stride, x, x_stride, mean, rstd, gamma, dx_io,
-        dx_stride, add_resid, static_cast<__nv_bfloat16*>(dx_bf16), dxb_stride, dgamma, dbeta, rows,
-        D);
-  VITK_CHECK_LAUNCH("layernorm_bwd_kernel");
+    layernorm_bwd_dx_kernel<__nv_bfloat16><<<grid, block, 0, stream>>>(
+        dyb, dy_stride, x, x_stride, mean, rstd, gamma, dx_io, dx_stride, add_resid,
+        static_cast<__nv_bfloat16*>(dx_bf16), dxb_stride, rows, D);
+  VITK_CHECK_LAUNCH("layernorm_bwd_dx_kernel");
   return VITK_OK;
 }
 

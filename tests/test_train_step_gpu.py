@@ -84,3 +84,30 @@ def test_dropout_is_rejected_loudly(vitk):
     tuner = vitk.FineTuner(model)
     with pytest.raises(vitk.VitkError):
         tuner.step(O.synthetic_images(2, 32).cuda(), O.synthetic_labels(2).cuda())
+
+
+def test_vit_b16_three_steps_track_the_oracle(vitk):
+    """ViT-B/16 at full width: 3 consecutive fused steps (batch 8) follow the oracle's fp32 loss
+    trajectory (the oracle's tensor arithmetic is evaluated on the GPU here only to keep the test
+    fast; it is the same restatement that is pinned against the reference's goldens on CPU)."""
+    kw = dict(image_size=224, patch_size=16, embed_dim=768, num_layers=12, num_heads=12,
+              mlp_dim=3072, dropout=0.0)
+    torch.manual_seed(4)
+    model = vitk.ViTClassifier(num_classes=6, **kw).cuda()
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    x, y = O.synthetic_images(8, 224, seed=9).cuda(), O.synthetic_labels(8).cuda()
+    m = {k: torch.zeros_like(v) for k, v in sd.items()}
+    v2 = {k: torch.zeros_like(v) for k, v in sd.items()}
+    ref_losses = []
+    for step in range(1, 4):
+        params = {k: t.clone().requires_grad_(True) for k, t in sd.items()}
+        _, logits = O.classifier_forward(params, x, 12)
+        loss = O.cross_entropy(logits, y)
+        grads = dict(zip(params, torch.autograd.grad(loss, list(params.values()))))
+        ref_losses.append(loss.item())
+        O.adamw_step(sd, grads, m, v2, step)
+    tuner = vitk.FineTuner(model)
+    got = [tuner.step(x, y)[0].item() for _ in range(3)]
+    print("oracle losses", ref_losses, "vitk losses", got)
+    for a, b in zip(got, ref_losses):
+        assert abs(a - b) < 0.05 * max(1.0, abs(b)), (got, ref_losses)
