@@ -1,10 +1,77 @@
-"""Training path (forward that saves activations + hand-written backward). Filled in below."""
-from ._lib import VitkError
+"""Autograd bridge: `features = backbone(images)` with gradients (reference train.py:831 inside the
+autocast forward of train.py:1441-1444, differentiated by `losses.backward()` at train.py:1455).
+
+The forward runs `vitk_forward_train` (saves activations), the backward receives
+dLoss/d features from PyTorch autograd - whatever loss the caller built on top, e.g. the
+reference's own detection head and Hungarian loss - and runs `vitk_backward_tokens`; parameter
+gradients are handed back to autograd so that any `torch.optim` optimizer works unchanged.
+`FineTuner` (trainer.py) is the fused fast path for the 6-class fine-tune; this bridge is the
+general drop-in.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import check, lib
+from .trainer import TrainState
+
+
+def _state_for(backbone) -> TrainState:
+    st = backbone.__dict__.get("_vitk_train_state")
+    if st is None or st.flat.device != backbone.cls_token.device or not st.owns_params():
+        st = TrainState(backbone, None, backbone._n_prefix, bind_grads=False)
+        backbone.__dict__["_vitk_train_state"] = st
+    return st
+
+
+class _BackboneFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, images, state, *params):
+        if not images.is_cuda:
+            raise _lib.VitkError("images must be a CUDA tensor (no CPU fallback)")
+        images = images.detach().float().contiguous()
+        B = images.shape[0]
+        if state.shadows_stale():
+            state.refresh_shadows()
+        cfg = state.config()
+        saved, saved_bytes, ws, ws_bytes = state.buffers(B)
+        pe = state.backbone.patch_embedding
+        N = pe.n_patches + state.n_prefix
+        tokens = torch.empty((B, N, cfg.embed_dim), dtype=torch.float32, device=images.device)
+        check(lib().vitk_forward_train(C.byref(cfg), C.byref(state.W), images.data_ptr(), B,
+                                       tokens.data_ptr(), saved, saved_bytes, ws, ws_bytes,
+                                       torch.cuda.current_stream().cuda_stream))
+        ctx.state, ctx.batch = state, B
+        return tokens
+
+    @staticmethod
+    def backward(ctx, d_tokens):
+        st, B = ctx.state, ctx.batch
+        d_tokens = d_tokens.float().contiguous()
+        cfg = st.config()
+        saved, _, ws, _ = st.buffers(B)
+        st.grad.zero_()
+        check(lib().vitk_backward_tokens(C.byref(cfg), C.byref(st.W), C.byref(st.T), C.byref(st.G),
+                                         d_tokens.data_ptr(), B, saved, ws,
+                                         torch.cuda.current_stream().cuda_stream))
+        grads = []
+        for name, p in zip(st.names, st.params):
+            o = st.offsets[name]
+            grads.append(st.grad[o:o + p.numel()].view(p.shape).clone() if p.requires_grad else None)
+        return (None, None, *grads)
 
 
 def encoder_forward_train(module, images):
-    raise VitkError("training path is not built yet - wrap inference in torch.no_grad()")
+    """tokens f32 [B, N, D] = backbone(images), differentiable w.r.t. every backbone parameter."""
+    st = _state_for(module)
+    return _BackboneFunction.apply(images, st, *st.params)
 
 
-def classifier_forward_train(module, images):
-    raise VitkError("training path is not built yet - wrap inference in torch.no_grad()")
+def classifier_forward_train(model, images):
+    """ViTClassifier under autograd: backbone through the bridge, the (tiny) head as ordinary
+    autograd ops on the CLS row - the same composition a user-defined head would use."""
+    tokens = encoder_forward_train(model.backbone, images)
+    return torch.nn.functional.linear(tokens[:, 0], model.head.weight, model.head.bias)

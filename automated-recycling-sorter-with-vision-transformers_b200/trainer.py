@@ -31,7 +31,8 @@ def _stream() -> int:
 
 
 class TrainState:
-    def __init__(self, backbone: torch.nn.Module, head: torch.nn.Linear | None, n_prefix: int):
+    def __init__(self, backbone: torch.nn.Module, head: torch.nn.Linear | None, n_prefix: int,
+                 bind_grads: bool = True):
         self.backbone, self.head, self.n_prefix = backbone, head, n_prefix
         named = [("backbone." + n, p) for n, p in backbone.named_parameters()]
         if head is not None:
@@ -55,7 +56,8 @@ class TrainState:
             view = self.flat[o:o + p.numel()].view(p.shape)
             view.copy_(p.detach().contiguous())
             p.data = view
-            p.grad = self.grad[o:o + p.numel()].view(p.shape)
+            if bind_grads:   # FineTuner: .grad aliases the arena; autograd bridge: autograd owns .grad
+                p.grad = self.grad[o:o + p.numel()].view(p.shape)
         # transposed bf16 copies of the four Linear weights of every block
         self._t_jobs = []
         toff = 0
@@ -152,6 +154,11 @@ class TrainState:
         self.refresh_transposes()
         self._versions = [p._version for p in self.params]
 
+    def owns_params(self) -> bool:
+        """False once somebody else re-homed or replaced the module's parameters."""
+        lo, hi = self.flat.data_ptr(), self.flat.data_ptr() + 4 * self.numel
+        return all(lo <= p.data_ptr() < hi for p in self.params)
+
     def shadows_stale(self) -> bool:
         return any(p._version != v for p, v in zip(self.params, self._versions))
 
@@ -209,6 +216,9 @@ class FineTuner:
         images = images.float().contiguous()
         labels = labels.long().contiguous()
         B = images.shape[0]
+        if not st.owns_params():
+            raise _lib.VitkError("the model's parameters were re-homed after this FineTuner was "
+                                 "built (e.g. .to(), load into new tensors, or a second trainer)")
         if st.shadows_stale():
             st.refresh_shadows()
         cfg = st.config()

@@ -84,3 +84,38 @@ def test_no_cpu_fallback(vitk):
     model = vitk.ViTClassifier(num_classes=6, **TINY).eval()
     with pytest.raises(vitk.VitkError), torch.no_grad():
         model(O.synthetic_images(1, 32))
+
+
+def test_vit_l16_width_matches_oracle(vitk):
+    """BASELINE configs[3] geometry (D 1024, 16 heads, MLP 4096) with 3 layers."""
+    kw = dict(image_size=224, patch_size=16, embed_dim=1024, num_layers=3, num_heads=16, mlp_dim=4096)
+    tokens, logits, t_ref, l_ref = _run(vitk, kw, 3, False, seed=5)
+    assert (logits - l_ref).abs().max() < 2e-2
+    assert (tokens - t_ref).abs().max() < 6e-2
+    assert_top1(logits, l_ref)
+
+
+def test_vit_b16_384px_matches_oracle(vitk):
+    """BASELINE configs[4]: 384 px -> 577 tokens (flash attention kernel, ragged GEMM rows)."""
+    kw = dict(image_size=384, patch_size=16, embed_dim=768, num_layers=2, num_heads=12, mlp_dim=3072)
+    tokens, logits, t_ref, l_ref = _run(vitk, kw, 3, True, seed=6)
+    assert tokens.shape[1] == 578
+    assert (logits - l_ref).abs().max() < 2e-2
+    assert (tokens - t_ref).abs().max() < 6e-2
+    assert_top1(logits, l_ref)
+
+
+def test_empty_and_bad_inputs(vitk):
+    model = vitk.ViTClassifier(num_classes=6, **TINY).cuda().eval()
+    with torch.no_grad():
+        with pytest.raises(vitk.VitkError):
+            model(torch.zeros(0, 3, 32, 32, device="cuda"))        # empty batch
+        with pytest.raises(vitk.VitkError):
+            model(torch.zeros(2, 3, 48, 48, device="cuda"))        # wrong resolution
+        with pytest.raises(vitk.VitkError):
+            model(torch.zeros(2, 1, 32, 32, device="cuda"))        # wrong channel count
+        # non-contiguous / fp16 inputs are normalised to contiguous fp32 like `.to(device)` would
+        x = O.synthetic_images(2, 32).cuda()
+        a = model(x)
+        b = model(x.half().float().permute(0, 1, 3, 2).permute(0, 1, 3, 2))
+        assert (a - b).abs().max() < 5e-2
