@@ -3,6 +3,7 @@
 #include "../../include/vitk.h"
 
 #include "common.h"
+#include "fp32_mode.cuh"
 #include "gemm_sm100.cuh"
 #include "rowops.cuh"
 
@@ -154,6 +155,117 @@ int forward_bf16(const VitkConfig* cfg, const VitkWeights* w, const float* image
   return VITK_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// fp32-parity mode (precision = 1): fp32 activations everywhere, every contraction evaluated by
+// the tcgen05 kernel on three-term bf16 splits (K' = 6K), attention in fp32 FMAs, exact erf-GELU.
+// Weight pointers of VitkWeights then address bf16 [out, 6*in] split matrices (vitk_split3).
+// ---------------------------------------------------------------------------------------------
+struct WorkspaceF32 {
+  float* x;      // residual stream [M, D]
+  float* xn;     // LayerNorm output [M, D]
+  float* qkv;    // [M, 3D]
+  float* ctx;    // [M, D]
+  float* h;      // fc1 pre-activation [M, Mlp]
+  float* patch;  // [Mp, Kp]
+  void* a6;      // split activation operand bf16 [M, 6 * max(D, Mlp, Kp)]
+  size_t bytes;
+};
+
+WorkspaceF32 carve_f32(const Dims& d, void* base) {
+  WorkspaceF32 w;
+  size_t off = 0;
+  auto take = [&](size_t n) {
+    void* p = base ? static_cast<char*>(base) + off : nullptr;
+    off += align_up(n, 1024);
+    return p;
+  };
+  int kmax = d.D > d.Mlp ? d.D : d.Mlp;
+  if (d.Kp > kmax) kmax = d.Kp;
+  w.x = static_cast<float*>(take(d.M * d.D * 4));
+  w.xn = static_cast<float*>(take(d.M * d.D * 4));
+  w.qkv = static_cast<float*>(take(d.M * 3 * d.D * 4));
+  w.ctx = static_cast<float*>(take(d.M * d.D * 4));
+  w.h = static_cast<float*>(take(d.M * d.Mlp * 4));
+  w.patch = static_cast<float*>(take(d.Mp * d.Kp * 4));
+  w.a6 = take(d.M * 6 * static_cast<size_t>(kmax) * 2);
+  w.bytes = off;
+  return w;
+}
+
+// out(f32) = epilogue(split(A) * W6^T); A f32 [M, K]; W6 bf16 [N, 6K]
+int linear_f32(const float* A, int K, const void* W6, int M, int N, GemmEpi epi, const float* bias,
+               float* resid_out, float* out, int apply_gelu_to_a, void* a6, cudaStream_t stream) {
+  VITK_TRY(split3(A, K, a6, M, K, 0, apply_gelu_to_a, stream));
+  GemmProblem p;
+  p.A = a6;
+  p.lda = 6 * K;
+  p.B = W6;
+  p.ldb = 6 * K;
+  p.M = M;
+  p.N = N;
+  p.K = 6 * K;
+  p.epi = epi;
+  p.e.bias = bias;
+  p.e.resid = resid_out;
+  p.e.ldr = N;
+  p.e.out = (epi == EPI_RESID_F32) ? resid_out : out;
+  p.e.ldo = N;
+  return gemm_bf16_tn(p, stream);
+}
+
+int forward_f32(const VitkConfig* cfg, const VitkWeights* w, const float* images, const Dims& d,
+                float* tokens_out, float* logits_out, const WorkspaceF32& ws, cudaStream_t stream) {
+  const int M = static_cast<int>(d.M), D = d.D;
+  VITK_TRY(patchify_f32(images, ws.patch, d.B, d.C, d.S, d.p, stream));
+  VITK_TRY(prefix_tokens(ws.x, w->cls_token, w->dist_token, w->pos_embed, d.B, d.N, D, d.prefix,
+                         stream));
+  {
+    VITK_TRY(split3(ws.patch, d.Kp, ws.a6, d.Mp, d.Kp, 0, 0, stream));
+    GemmProblem p;
+    p.A = ws.a6;
+    p.lda = 6 * d.Kp;
+    p.B = w->patch_w;
+    p.ldb = 6 * d.Kp;
+    p.M = static_cast<int>(d.Mp);
+    p.N = D;
+    p.K = 6 * d.Kp;
+    p.epi = EPI_RESID_F32;
+    p.e.bias = w->patch_b;
+    p.e.resid = w->pos_embed;
+    p.e.ldr = D;
+    p.e.out = ws.x;
+    p.e.ldo = D;
+    p.e.rows_per_group = d.P;
+    p.e.group_stride = d.N;
+    p.e.group_offset = d.prefix;
+    VITK_TRY(gemm_bf16_tn(p, stream));
+  }
+  for (int l = 0; l < d.L; ++l) {
+    const VitkBlockWeights& bw = w->blocks[l];
+    VITK_TRY(layernorm_fwd(ws.x, D, bw.ln1_w, bw.ln1_b, ws.xn, 1, D, nullptr, nullptr, M, D,
+                           cfg->ln_eps, stream));
+    VITK_TRY(linear_f32(ws.xn, D, bw.qkv_w, M, 3 * D, EPI_F32, bw.qkv_b, nullptr, ws.qkv, 0, ws.a6,
+                        stream));
+    VITK_TRY(attention_f32(ws.qkv, ws.ctx, d.B, d.N, d.H, d.hd, stream));
+    VITK_TRY(linear_f32(ws.ctx, D, bw.proj_w, M, D, EPI_RESID_F32, bw.proj_b, ws.x, nullptr, 0,
+                        ws.a6, stream));
+    VITK_TRY(layernorm_fwd(ws.x, D, bw.ln2_w, bw.ln2_b, ws.xn, 1, D, nullptr, nullptr, M, D,
+                           cfg->ln_eps, stream));
+    VITK_TRY(linear_f32(ws.xn, D, bw.fc1_w, M, d.Mlp, EPI_F32, bw.fc1_b, nullptr, ws.h, 0, ws.a6,
+                        stream));
+    // exact erf-GELU is applied while splitting the fc2 operand
+    VITK_TRY(linear_f32(ws.h, d.Mlp, bw.fc2_w, M, D, EPI_RESID_F32, bw.fc2_b, ws.x, nullptr, 1,
+                        ws.a6, stream));
+  }
+  if (tokens_out)
+    VITK_TRY(layernorm_fwd(ws.x, D, w->ln_f_w, w->ln_f_b, tokens_out, 1, D, nullptr, nullptr, M, D,
+                           cfg->ln_eps, stream));
+  if (logits_out)
+    VITK_TRY(cls_head(ws.x, static_cast<long long>(d.N) * D, w->ln_f_w, w->ln_f_b, w->head_w,
+                      w->head_b, nullptr, logits_out, d.B, D, cfg->n_classes, cfg->ln_eps, stream));
+  return VITK_OK;
+}
+
 }  // namespace
 }  // namespace vitk
 
@@ -191,7 +303,7 @@ int vitk_workspace_bytes(const VitkConfig* cfg, int batch, size_t* out_bytes) {
   Dims d;
   VITK_TRY(check_config(cfg, batch, &d));
   VITK_REQUIRE(out_bytes != nullptr, "out_bytes is null");
-  *out_bytes = carve(d, nullptr).bytes;
+  *out_bytes = (cfg->precision == 1) ? carve_f32(d, nullptr).bytes : carve(d, nullptr).bytes;
   return VITK_OK;
 }
 
@@ -212,14 +324,28 @@ int vitk_forward(const VitkConfig* cfg, const VitkWeights* w, const float* image
                  "logits requested but no classifier head configured");
   VITK_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0,
                "workspace must be 1024-byte aligned");
+  VITK_REQUIRE(cfg->precision == 0 || cfg->precision == 1, "unknown precision mode %d",
+               cfg->precision);
+  VITK_REQUIRE(d.hd == 64, "head_dim %d unsupported (needs 64)", d.hd);
+  if (cfg->precision == 1) {
+    const WorkspaceF32 wf = carve_f32(d, workspace);
+    if (wf.bytes > workspace_bytes)
+      return set_error(VITK_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", wf.bytes,
+                       workspace_bytes);
+    return forward_f32(cfg, w, images, d, tokens_out, logits_out, wf,
+                       static_cast<cudaStream_t>(stream));
+  }
   const Workspace ws = carve(d, workspace);
   if (ws.bytes > workspace_bytes)
     return set_error(VITK_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", ws.bytes,
                      workspace_bytes);
-  VITK_REQUIRE(cfg->precision == 0, "precision mode %d not available in this build", cfg->precision);
-  VITK_REQUIRE(d.hd == 64, "bf16 path needs head_dim 64 (got %d)", d.hd);
   return forward_bf16(cfg, w, images, d, tokens_out, logits_out, ws,
                       static_cast<cudaStream_t>(stream));
+}
+
+int vitk_split3(const float* in, long long ld_in, void* out_bf16, long long rows, int K,
+                int is_weight, vitk_stream_t stream) {
+  return split3(in, ld_in, out_bf16, rows, K, is_weight, 0, static_cast<cudaStream_t>(stream));
 }
 
 int vitk_gemm(const void* A, int lda, const void* B, int ldb, int M, int N, int K, int epilogue,

@@ -26,6 +26,7 @@ class EncoderEngine:
         self._ws = None
         self._ws_bytes = 0
         self.head: torch.nn.Linear | None = None
+        self.precision = 0       # 0 = bf16 operands, 1 = fp32-parity (three-term bf16 split GEMMs)
 
     # ------------------------------------------------------------------ config
     def config(self, n_classes: int = 0) -> VitkConfig:
@@ -37,7 +38,7 @@ class EncoderEngine:
             in_channels=pe.projection.in_channels, embed_dim=pe.projection.out_channels,
             num_layers=len(m.transformer_blocks), num_heads=blk.attention.num_heads,
             mlp_dim=blk.mlp.linear1.out_features, n_prefix_tokens=self.n_prefix,
-            n_classes=n_classes, precision=0, ln_eps=m.layer_norm.eps,
+            n_classes=n_classes, precision=self.precision, ln_eps=m.layer_norm.eps,
             dropout_p=float(m.dropout.p), seed=0)
 
     # ------------------------------------------------------------------ weights
@@ -49,7 +50,7 @@ class EncoderEngine:
 
     def pack(self, head: torch.nn.Linear | None = None) -> VitkWeights:
         ps = self._params_for_key(head)
-        key = tuple((p.data_ptr(), p._version) for p in ps)
+        key = (self.precision,) + tuple((p.data_ptr(), p._version) for p in ps)
         if key == self._pack_key:
             return self._weights
         m = self.module
@@ -69,7 +70,7 @@ class EncoderEngine:
         def bf16(t: torch.Tensor) -> int:
             # channels_last conv weights etc.: reshape to a dense [out, in] matrix first
             t = t.detach().float().reshape(t.shape[0], -1).contiguous()
-            s = ops.cast_bf16(t)
+            s = ops.split3(t, is_weight=True) if self.precision == 1 else ops.cast_bf16(t)
             keep.append(s)
             return s.data_ptr()
 

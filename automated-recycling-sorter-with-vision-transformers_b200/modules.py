@@ -124,6 +124,15 @@ class _EncoderBase(nn.Module):
             self.__dict__["_vitk_engine"] = eng  # not a sub-module / not in state_dict
         return eng
 
+    def set_precision(self, mode: str):
+        """'bf16' (default): bf16 operands, fp32 accumulation / residual / LayerNorm statistics.
+        'fp32': parity mode - fp32 activations, contractions on three-term bf16 splits (logits
+        within 1e-4 of the fp32 reference); inference only."""
+        if mode not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' or 'fp32'")
+        self._engine().precision = 1 if mode == "fp32" else 0
+        return self
+
     def forward(self, x):
         """images f32 [B,C,S,S] -> all tokens after the final LayerNorm, f32 [B,N,D]."""
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):

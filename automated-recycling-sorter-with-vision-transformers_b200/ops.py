@@ -37,6 +37,17 @@ def cast_bf16(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def split3(x: torch.Tensor, is_weight: bool) -> torch.Tensor:
+    """fp32 [R, K] -> bf16 [R, 6K] three-term split operand of the fp32-parity mode."""
+    _need_cuda(x)
+    assert x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
+    R, K = x.shape
+    out = torch.empty((R, 6 * K), dtype=torch.bfloat16, device=x.device)
+    check(lib().vitk_split3(x.data_ptr(), x.stride(0), out.data_ptr(), R, K, 1 if is_weight else 0,
+                            _stream()))
+    return out
+
+
 def gemm(a: torch.Tensor, b: torch.Tensor, epilogue: int = _lib.EPI_BF16, *, bias=None, resid=None,
          aux=None, out=None, out2=None, alpha: float = 1.0, beta: float = 0.0) -> torch.Tensor:
     """out = epilogue(a @ b.T); a bf16 [M,K], b bf16 [N,K] (nn.Linear weight layout)."""

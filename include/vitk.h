@@ -159,6 +159,14 @@ int vitk_patchify(const float* images, void* patches_bf16, int batch, int channe
 
 int vitk_cast_f32_to_bf16(const float* in, void* out_bf16, long long n, vitk_stream_t stream);
 
+/* fp32-parity mode (VitkConfig.precision = 1, logits within 1e-4 of the fp32 reference): fp32
+ * operands are split into three bf16 terms and contracted by the same tcgen05 kernel with
+ * K' = 6K.  The matrix members of VitkWeights / VitkBlockWeights must then point at split
+ * weights made with this function (is_weight = 1): in f32 [rows, K] (row pitch ld_in elements)
+ * -> out bf16 [rows, 6K].  Forward only. */
+int vitk_split3(const float* in, long long ld_in, void* out_bf16, long long rows, int K,
+                int is_weight, vitk_stream_t stream);
+
 /* =========================== training step (train.py:1441-1460) ===========================
  * forward (saving activations) -> loss -> backward -> AdamW, replacing
  *     outputs = model(images) ; losses.backward() ; optimizer.step()
