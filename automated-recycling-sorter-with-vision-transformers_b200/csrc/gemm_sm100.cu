@@ -37,23 +37,25 @@ constexpr int kAccStages = 2;
 // CTAS == 2: a CTA pair (cluster of 2, same TPC) computes a 256 x BLOCK_N tile with
 //            tcgen05.mma.cta_group::2 (M = 256): each CTA stages its own 128 A rows and HALF of
 //            the B rows, so per-SM L2->SMEM traffic and SMEM read bandwidth per flop drop by 1/3.
-constexpr int kStagingPerWarp = 2 * 4096;  // two 32-row x 128-byte output staging buffers
-constexpr int kStagingBytes = kNumEpiWarps * kStagingPerWarp;
-
-template <int BLOCK_N, int CTAS>
+// Epilogue staging: per warp SLABS 32-row x 128-byte slabs (two alternate for TMA stores; the
+// gelu'-epilogue adds one that receives the pre-activation tile by TMA load).
+template <int BLOCK_N, int CTAS, int SLABS = 2>
 struct Cfg {
+  static constexpr int kStagingPerWarp = SLABS * 4096;
+  static constexpr int kStagingBytes = kNumEpiWarps * kStagingPerWarp;
   static constexpr int kABytes = kBlockM * kBlockK * 2;
   static constexpr int kBRows = BLOCK_N / CTAS;  // B rows staged by this CTA
   static constexpr int kBBytes = kBRows * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kBarBytes = 256;
+  static constexpr int kBarBytes = 384;
   static constexpr int kBudget = 232448 - 1024 - kBarBytes - kStagingBytes;
   static constexpr int kStages = kBudget / kStageBytes > 8 ? 8 : kBudget / kStageBytes;
   static constexpr int kTmemCols = kAccStages * BLOCK_N;  // 512 or 256 (power of two)
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + kBarBytes + 1024;
   static_assert(kStages >= 3, "pipeline too shallow");
   static_assert(kSmemBytes <= 232448, "exceeds 227 KB of shared memory");
-  static_assert(8 * (2 * kStages + 2 * kAccStages) + 4 <= kBarBytes, "barrier block too small");
+  static_assert(8 * (2 * kStages + 2 * kAccStages + 1 + kNumEpiWarps) <= kBarBytes,
+                "barrier block too small");
 };
 
 __device__ __forceinline__ float gelu_erf(float x) {
@@ -81,6 +83,17 @@ __device__ __forceinline__ float gelu_fast_tanh(float x) {
   float t;
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x * p));
   return x * fmaf(0.5f, t, 0.5f);
+}
+// d/dx [x Phi(x)] with the same logistic CDF: Phi + x Phi (1 - Phi) g'(x), g(x) = x (a0 + a1 x^2 +
+// a2 x^4); no extra MUFU beyond the two of Phi.  max |error| 1.8e-4 vs the exact erf derivative.
+__device__ __forceinline__ float gelu_grad_fast(float x) {
+  const float x2 = fminf(x * x, 100.f);
+  const float p = fmaf(x2, fmaf(x2, 9.2473074e-4f, -0.10595751f), -2.3019681f);
+  float e, phi;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * p));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(phi) : "f"(1.f + e));
+  const float gp = fmaf(x2, fmaf(x2, -3.20487363e-3f, 0.22033243f), 1.5956033f);
+  return fmaf(x * phi, (1.f - phi) * gp, phi);
 }
 template <int EPI>
 __device__ __forceinline__ float gelu_for(float x) {
@@ -300,7 +313,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
                const __grid_constant__ CUtensorMap tmap_c,
                const __grid_constant__ CUtensorMap tmap_c2, int M, int N, int K,
                int kb_per_split, int num_splits, const GemmEpilogue e) {
-  using C = Cfg<BLOCK_N, CTAS>;
+  constexpr bool kAuxTma = TMA_EPI && (EPI == EPI_DGELU_BF16);
+  using C = Cfg<BLOCK_N, CTAS, kAuxTma ? 3 : 2>;
+  constexpr int kStagingBytes = C::kStagingBytes;
+  constexpr int kStagingPerWarp = C::kStagingPerWarp;
   constexpr int kTileM = kBlockM * CTAS;  // rows of C per cluster tile
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -315,6 +331,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * C::kStages + kAccStages + a); };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(
       smem + C::kStages * C::kStageBytes + kStagingBytes + 8 * (2 * C::kStages + 2 * kAccStages));
+  auto aux_bar = [&](int w) { return bar_base + 8u * (2 * C::kStages + 2 * kAccStages + 1 + w); };
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -348,6 +365,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), kNumEpiWarps * CTAS);  // leader collects both CTAs' epilogues
     }
+    if constexpr (kAuxTma)
+      for (int w2 = 0; w2 < kNumEpiWarps; ++w2) mbar_init(aux_bar(w2), 1);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -487,10 +506,22 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
     int buf = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
+    [[maybe_unused]] uint32_t aux_phase = 0;
+    [[maybe_unused]] const uint32_t aux_slab = stg + 2u * 4096u;
+    [[maybe_unused]] const uint32_t my_aux_bar = aux_bar(warp - kFirstEpiWarp);
     for (int work = cluster_id; work < num_tiles; work += num_clusters) {
       const int tile = work % num_out_tiles;
       const int m_blk = tile / num_n_tiles;
       const int n_blk = tile - m_blk * num_n_tiles;
+      if constexpr (kAuxTma) {
+        // fetch the first pre-activation slab of this tile while its main loop is still running
+        const int r0 = m_blk * kTileM + slab_row;
+        const int c0 = n_blk * BLOCK_N + half * kColsPerWarp;
+        if (lane == 0 && r0 < M && c0 < N) {
+          mbar_arrive_expect_tx(my_aux_bar, 4096);
+          tma_load_2d(aux_slab, &tmap_c2, my_aux_bar, c0, r0);
+        }
+      }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const int row0 = m_blk * kTileM + slab_row;
@@ -530,6 +561,34 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
               acc_plus_bias<EPI>(v0, n0, N, e, x0);
               acc_plus_bias<EPI>(v1, n0 + 32, N, e, x1);
               uint32_t pk[32];
+              if constexpr (kAuxTma) {
+                // this lane's row of the pre-activation slab (64 bf16), then refill the slab with
+                // the next group's tile while the math below runs
+                mbar_wait(my_aux_bar, aux_phase);
+                aux_phase ^= 1u;
+                uint32_t a[32];
+                const uint32_t arow = aux_slab + static_cast<uint32_t>(lane) * 128u;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
+                               : "=r"(a[4 * j]), "=r"(a[4 * j + 1]), "=r"(a[4 * j + 2]),
+                                 "=r"(a[4 * j + 3])
+                               : "r"(arow + (static_cast<uint32_t>(j ^ (lane & 7)) << 4))
+                               : "memory");
+                __syncwarp();
+                const int n_next = n0 + 64;
+                if (lane == 0 && g + 1 < kColsPerWarp / 64 && n_next < N) {
+                  mbar_arrive_expect_tx(my_aux_bar, 4096);
+                  tma_load_2d(aux_slab, &tmap_c2, my_aux_bar, n_next, row0);
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  x0[2 * j] *= gelu_grad_fast(bf16lo_to_f32(a[j]));
+                  x0[2 * j + 1] *= gelu_grad_fast(bf16hi_to_f32(a[j]));
+                  x1[2 * j] *= gelu_grad_fast(bf16lo_to_f32(a[16 + j]));
+                  x1[2 * j + 1] *= gelu_grad_fast(bf16hi_to_f32(a[16 + j]));
+                }
+              }
               if constexpr (is_gelu_epi<EPI>()) {
                 if (e.out2 != nullptr) {
 #pragma unroll
@@ -599,7 +658,7 @@ int g_force_direct_epi = 0;  // 1 = never use the TMA-store epilogue (tests, A/B
 
 template <int BLOCK_N, int EPI, int CTAS, bool TMA_EPI, bool MN>
 int launch(const GemmProblem& p, cudaStream_t stream) {
-  using C = Cfg<BLOCK_N, CTAS>;
+  using C = Cfg<BLOCK_N, CTAS, (TMA_EPI && EPI == EPI_DGELU_BF16) ? 3 : 2>;
   auto kernel = gemm_tn_kernel<BLOCK_N, EPI, CTAS, TMA_EPI, MN>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
@@ -629,6 +688,9 @@ int launch(const GemmProblem& p, cudaStream_t stream) {
     if (is_gelu_epi<EPI>() && p.e.out2 != nullptr)
       VITK_TRY(make_tmap_2d(&tc2, p.e.out2, eb, (uint64_t)p.N, (uint64_t)p.M,
                             (uint64_t)p.e.ldo * eb, 128 / eb, 32));
+    if (EPI == EPI_DGELU_BF16)   // the pre-activation tile is TMA-loaded, same geometry as out
+      VITK_TRY(make_tmap_2d(&tc2, p.e.aux, 2, (uint64_t)p.N, (uint64_t)p.M, (uint64_t)p.e.ldo * 2,
+                            64, 32));
   } else {
     tc = ta;
     tc2 = ta;
@@ -678,8 +740,10 @@ int dispatch_tile(const GemmProblem& p, cudaStream_t stream) {
   if (ctas == 2)
     return n128 ? launch<128, EPI, 2, TMA_EPI, MN>(p, stream)
                 : launch<256, EPI, 2, TMA_EPI, MN>(p, stream);
-  return n128 ? launch<128, EPI, 1, TMA_EPI, MN>(p, stream)
-              : launch<256, EPI, 1, TMA_EPI, MN>(p, stream);
+  // single-CTA tiles keep the direct epilogue for the gelu' variant (no room for a third slab)
+  constexpr bool kTma1 = TMA_EPI && (EPI != EPI_DGELU_BF16);
+  return n128 ? launch<128, EPI, 1, kTma1, MN>(p, stream)
+              : launch<256, EPI, 1, kTma1, MN>(p, stream);
 }
 
 // The TMA epilogue needs 16-byte aligned output rows and, for the residual form, an in-place
@@ -697,6 +761,7 @@ bool tma_epilogue_ok(const GemmProblem& p, bool honour_force = true) {
     case EPI_RESID_F32:
       return p.e.rows_per_group == 0 && p.e.resid == p.e.out && p.e.ldr == p.e.ldo;
     case EPI_F32: return p.e.beta == 0.f || p.e.beta == 1.f;
+    case EPI_DGELU_BF16: return (reinterpret_cast<uintptr_t>(p.e.aux) & 15) == 0;
     default: return false;
   }
 }
@@ -704,6 +769,7 @@ bool tma_epilogue_ok(const GemmProblem& p, bool honour_force = true) {
 template <int EPI>
 int dispatch(const GemmProblem& p, cudaStream_t stream) {
   if constexpr (EPI == EPI_DGELU_BF16) {
+    if (tma_epilogue_ok(p)) return dispatch_tile<EPI, true, false>(p, stream);
     return dispatch_tile<EPI, false, false>(p, stream);
   } else if constexpr (EPI == EPI_F32) {
     if (p.mn_major) {
