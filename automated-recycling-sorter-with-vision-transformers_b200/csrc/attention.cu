@@ -248,6 +248,7 @@ attn_fwd_hd64_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __res
 
 static int g_attn_impl = 0;  // 0 auto, 1 = mma.sync flash kernel, 2 = tcgen05 single-block kernel
 void attention_force_impl(int impl) { g_attn_impl = impl; }
+int attention_impl() { return g_attn_impl; }
 
 int attention_fwd(const void* qkv, void* ctx, float* lse, int B, int N, int H, int hd,
                   cudaStream_t stream) {

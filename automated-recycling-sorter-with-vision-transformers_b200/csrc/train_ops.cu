@@ -45,10 +45,28 @@ int grid_for(long long work_items, int block, int max_blocks_per_sm = 8) {
 // x feeds both the LN and the skip connection).  Optionally emits a bf16 copy of the result (the
 // A operand of the next dgrad GEMM).
 // ------------------------------------------------------------------------------------------------
-// Kernel A: dx (warp per row, row kept in registers; ~60 registers so that many warps are
-// resident and the kernel runs at HBM speed).
-template <typename DyT>
-__global__ void __launch_bounds__(256)
+// dy row fragments are kept in their storage type between the passes (bf16: 2 registers per 4
+// elements) to stay within the register budget of 3 resident CTAs per SM.
+template <typename T> struct RawVec;
+template <> struct RawVec<float> {
+  using type = float4;
+  static __device__ __forceinline__ type load(const float* p) { return *reinterpret_cast<const float4*>(p); }
+  static __device__ __forceinline__ float4 f4(const type& v) { return v; }
+};
+template <> struct RawVec<__nv_bfloat16> {
+  using type = uint2;
+  static __device__ __forceinline__ type load(const __nv_bfloat16* p) { return *reinterpret_cast<const uint2*>(p); }
+  static __device__ __forceinline__ float4 f4(const type& u) {
+    return make_float4(bf16lo_to_f32(u.x), bf16hi_to_f32(u.x), bf16lo_to_f32(u.y), bf16hi_to_f32(u.y));
+  }
+};
+
+// Kernel A: dx (warp per row). Only the raw row (x, dy) stays in registers between the two
+// passes - NVEC float4 each - so that 4 CTAs of 256 threads are resident per SM; gamma is
+// re-read from L1.  The residual-gradient row is requested before the reductions so that its
+// DRAM round trip overlaps them.
+template <typename DyT, int NVEC>
+__global__ void __launch_bounds__(256, 3)
 layernorm_bwd_dx_kernel(const DyT* __restrict__ dy, long long dy_stride, const float* __restrict__ x,
                         long long x_stride, const float* __restrict__ mean,
                         const float* __restrict__ rstd, const float* __restrict__ gamma,
@@ -60,41 +78,45 @@ layernorm_bwd_dx_kernel(const DyT* __restrict__ dy, long long dy_stride, const f
   if (r >= rows) return;
   const float mu = mean[r], rs = rstd[r];
   const float inv_d = 1.f / static_cast<float>(D);
-  float4 xh[kLnMaxVec], g[kLnMaxVec];
+  using RV = RawVec<DyT>;
+  float4 xv[NVEC], pv[NVEC];
+  typename RV::type dr[NVEC];
   float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-  for (int j = 0; j < kLnMaxVec; ++j) {
+  for (int j = 0; j < NVEC; ++j) {
     const int i = lane + 32 * j;
     if (i < nvec) {
-      const float4 xv = load4(x + r * x_stride + 4 * i);
-      const float4 d = load4(dy + r * dy_stride + 4 * i);
+      xv[j] = load4(x + r * x_stride + 4 * i);
+      dr[j] = RV::load(dy + r * dy_stride + 4 * i);
+      pv[j] = add_resid ? *reinterpret_cast<const float4*>(dx_io + r * dx_stride + 4 * i)
+                        : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < NVEC; ++j) {
+    const int i = lane + 32 * j;
+    if (i < nvec) {
       const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + i);
-      xh[j] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
-      g[j] = make_float4(d.x * gm.x, d.y * gm.y, d.z * gm.z, d.w * gm.w);
-      s1 += (g[j].x + g[j].y) + (g[j].z + g[j].w);
-      s2 += (g[j].x * xh[j].x + g[j].y * xh[j].y) + (g[j].z * xh[j].z + g[j].w * xh[j].w);
+      const float4 dvj = RV::f4(dr[j]);
+      const float g0 = dvj.x * gm.x, g1 = dvj.y * gm.y, g2 = dvj.z * gm.z, g3 = dvj.w * gm.w;
+      s1 += (g0 + g1) + (g2 + g3);
+      s2 += (g0 * (xv[j].x - mu) + g1 * (xv[j].y - mu)) + (g2 * (xv[j].z - mu) + g3 * (xv[j].w - mu));
     }
   }
   s1 = warp_sum(s1) * inv_d;
-  s2 = warp_sum(s2) * inv_d;
+  s2 = warp_sum(s2) * rs * inv_d;  // mean_D(g * xhat)
 #pragma unroll
-  for (int j = 0; j < kLnMaxVec; ++j) {
+  for (int j = 0; j < NVEC; ++j) {
     const int i = lane + 32 * j;
     if (i < nvec) {
+      const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + i);
+      const float4 dvj = RV::f4(dr[j]);
       float4 o;
-      o.x = rs * (g[j].x - s1 - xh[j].x * s2);
-      o.y = rs * (g[j].y - s1 - xh[j].y * s2);
-      o.z = rs * (g[j].z - s1 - xh[j].z * s2);
-      o.w = rs * (g[j].w - s1 - xh[j].w * s2);
-      float* dst = dx_io + r * dx_stride + 4 * i;
-      if (add_resid) {
-        const float4 p = *reinterpret_cast<const float4*>(dst);
-        o.x += p.x;
-        o.y += p.y;
-        o.z += p.z;
-        o.w += p.w;
-      }
-      *reinterpret_cast<float4*>(dst) = o;
+      o.x = rs * (dvj.x * gm.x - s1 - (xv[j].x - mu) * rs * s2) + pv[j].x;
+      o.y = rs * (dvj.y * gm.y - s1 - (xv[j].y - mu) * rs * s2) + pv[j].y;
+      o.z = rs * (dvj.z * gm.z - s1 - (xv[j].z - mu) * rs * s2) + pv[j].z;
+      o.w = rs * (dvj.w * gm.w - s1 - (xv[j].w - mu) * rs * s2) + pv[j].w;
+      *reinterpret_cast<float4*>(dx_io + r * dx_stride + 4 * i) = o;
       if (dx_bf16 != nullptr) {
         uint2 pk;
         pk.x = pack_bf16x2(o.x, o.y);
@@ -171,8 +193,9 @@ colsum_bf16_kernel(const __nv_bfloat16* __restrict__ y, long long ld, int M, int
   const int r_end = min(M, r_begin + rows_per_block);
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (col0 < N) {
+#pragma unroll 4
     for (int r = r_begin + trow; r < r_end; r += 4) {
-      const uint4 u = *reinterpret_cast<const uint4*>(y + r * ld + col0);
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(y + r * ld + col0));
       acc[0] += bf16lo_to_f32(u.x);
       acc[1] += bf16hi_to_f32(u.x);
       acc[2] += bf16lo_to_f32(u.y);
@@ -473,14 +496,24 @@ int layernorm_bwd(const void* dy, int dy_is_f32, long long dy_stride, const floa
     VITK_CHECK_LAUNCH("layernorm_bwd_params_kernel");
   }
   ProfileScope prof(PROF_LN, static_cast<double>(rows) * D * (dy_is_f32 ? 14.0 : 12.0), stream);
-  if (dy_is_f32)
-    layernorm_bwd_dx_kernel<float><<<grid, block, 0, stream>>>(
-        dyf, dy_stride, x, x_stride, mean, rstd, gamma, dx_io, dx_stride, add_resid,
-        static_cast<__nv_bfloat16*>(dx_bf16), dxb_stride, rows, D);
-  else
-    layernorm_bwd_dx_kernel<__nv_bfloat16><<<grid, block, 0, stream>>>(
-        dyb, dy_stride, x, x_stride, mean, rstd, gamma, dx_io, dx_stride, add_resid,
-        static_cast<__nv_bfloat16*>(dx_bf16), dxb_stride, rows, D);
+  __nv_bfloat16* dxb = static_cast<__nv_bfloat16*>(dx_bf16);
+#define VITK_LN_BWD(T, PTR, NV)                                                                  \
+  layernorm_bwd_dx_kernel<T, NV><<<grid, block, 0, stream>>>(PTR, dy_stride, x, x_stride, mean,  \
+                                                             rstd, gamma, dx_io, dx_stride,       \
+                                                             add_resid, dxb, dxb_stride, rows, D)
+  const int nv = (D / 4 + 31) / 32;
+  if (dy_is_f32) {
+    if (nv <= 2) VITK_LN_BWD(float, dyf, 2);
+    else if (nv <= 4) VITK_LN_BWD(float, dyf, 4);
+    else if (nv <= 6) VITK_LN_BWD(float, dyf, 6);
+    else VITK_LN_BWD(float, dyf, 8);
+  } else {
+    if (nv <= 2) VITK_LN_BWD(__nv_bfloat16, dyb, 2);
+    else if (nv <= 4) VITK_LN_BWD(__nv_bfloat16, dyb, 4);
+    else if (nv <= 6) VITK_LN_BWD(__nv_bfloat16, dyb, 6);
+    else VITK_LN_BWD(__nv_bfloat16, dyb, 8);
+  }
+#undef VITK_LN_BWD
   VITK_CHECK_LAUNCH("layernorm_bwd_dx_kernel");
   return VITK_OK;
 }
@@ -488,7 +521,7 @@ int layernorm_bwd(const void* dy, int dy_is_f32, long long dy_stride, const floa
 int colsum_bf16(const void* y, long long ld, int M, int N, float* out, cudaStream_t stream) {
   VITK_REQUIRE(y && out && M > 0 && N > 0 && N % 8 == 0 && ld % 8 == 0, "colsum: bad argument");
   const int strips = (N + 511) / 512;
-  int chunks = (sm_count() * 4 + strips - 1) / strips;
+  int chunks = (sm_count() * 12 + strips - 1) / strips;
   if (chunks > (M + 31) / 32) chunks = (M + 31) / 32;
   if (chunks < 1) chunks = 1;
   const int rows_per_block = (M + chunks - 1) / chunks;

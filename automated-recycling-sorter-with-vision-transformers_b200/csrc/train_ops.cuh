@@ -45,4 +45,8 @@ int adamw_flat(float* p, const float* g, float* m, float* v, void* shadow_bf16, 
 int attention_bwd(const void* qkv, const void* ctx, const void* dctx, const float* lse, void* dqkv,
                   int B, int N, int H, int hd, cudaStream_t stream);
 
+// tcgen05 variant (attention_bwd_tc.cu); attention_bwd dispatches to it for N <= 256.
+int attention_bwd_tc(const void* qkv, const void* ctx, const void* dctx, const float* lse,
+                     void* dqkv, int B, int N, int H, int hd, cudaStream_t stream);
+
 }  // namespace vitk

@@ -29,8 +29,17 @@ def test_layernorm_backward(vitk, rows, D, dy_dtype):
 
 
 @pytest.mark.parametrize("B,N,H", [(2, 197, 12), (1, 5, 1), (3, 17, 2), (2, 64, 3), (1, 198, 4),
-                                   (1, 129, 2), (1, 256, 1)])
-def test_attention_backward(vitk, B, N, H):
+                                   (1, 129, 2), (1, 256, 1), (1, 128, 2), (30, 197, 12)])
+@pytest.mark.parametrize("impl", [1, 2], ids=["mma_sync", "tcgen05"])
+def test_attention_backward(vitk, impl, B, N, H):
+    vitk._lib.set_attention_impl(impl)
+    try:
+        _attention_backward_case(vitk, B, N, H)
+    finally:
+        vitk._lib.set_attention_impl(0)
+
+
+def _attention_backward_case(vitk, B, N, H):
     g = torch.Generator(device="cuda").manual_seed(N)
     D = H * 64
     qkv = torch.randn(B * N, 3 * D, generator=g, device="cuda").bfloat16()
