@@ -61,11 +61,18 @@ def load(script: str = "evaluation"):
     spec = importlib.util.spec_from_file_location(name, REFERENCE_DIR / f"{script}.py")
     mod = importlib.util.module_from_spec(spec)
     sys.modules[name] = mod
+    # train.py:17 calls mp.set_start_method('fork') at import, which raises when a start method is
+    # already fixed (pytest-xdist, torch.distributed tests); neutralise it for the import only.
+    import multiprocessing as _mp
+    orig = _mp.set_start_method
+    _mp.set_start_method = lambda *a, **k: None
     try:
         spec.loader.exec_module(mod)
-    except RuntimeError as e:  # mp.set_start_method raised because a context already exists
-        if "context has already been set" not in str(e):
-            raise
+    except BaseException:
+        sys.modules.pop(name, None)
+        raise
+    finally:
+        _mp.set_start_method = orig
     if script == "train":
         import torch
         torch.set_float32_matmul_precision("highest")
