@@ -25,6 +25,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC",
     "-Xptxas", "-v",
     "--expt-relaxed-constexpr",
+    *os.environ.get("VITK_NVCC_EXTRA", "").split(),   # e.g. -DVITK_ATTN_TRACE (debug builds)
 ]
 
 

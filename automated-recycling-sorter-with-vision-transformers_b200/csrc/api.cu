@@ -286,7 +286,8 @@ int vitk_gemm_set_direct_epilogue(int on) {
   return VITK_OK;
 }
 int vitk_attention_set_impl(int impl) {
-  VITK_REQUIRE(impl >= 0 && impl <= 2, "attention impl must be 0 (auto), 1 (flash) or 2 (tcgen05)");
+  VITK_REQUIRE(impl >= 0 && impl <= 3,
+               "attention impl must be 0 (auto), 1 (flash), 2 (tcgen05) or 3 (unpipelined tcgen05)");
   attention_force_impl(impl);
   return VITK_OK;
 }

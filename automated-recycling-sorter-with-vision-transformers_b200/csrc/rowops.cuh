@@ -32,6 +32,9 @@ int attention_fwd(const void* qkv, void* ctx, float* lse, int B, int N, int H, i
 // tcgen05 variant for N <= 256 (attention_tc.cu); attention_fwd dispatches to it automatically.
 int attention_fwd_tc(const void* qkv, void* ctx, float* lse, int B, int N, int H, int hd,
                      cudaStream_t stream);
+// Item-pipelined tcgen05 variant for N <= 208 (attention_tc2.cu); the default for the 224 px models.
+int attention_fwd_tc2(const void* qkv, void* ctx, float* lse, int B, int N, int H, int hd,
+                      cudaStream_t stream);
 void attention_force_impl(int impl);
 
 }  // namespace vitk

@@ -33,7 +33,7 @@ def test_patchify(vitk, B, C, S, p):
     assert torch.equal(out, ref.bfloat16())  # pure gather + round-to-nearest: bit exact
 
 
-@pytest.fixture(params=[1, 2], ids=["flash", "tcgen05"])
+@pytest.fixture(params=[1, 2, 3], ids=["flash", "tcgen05", "tcgen05-unpipelined"])
 def attn_impl(request, vitk):
     vitk._lib.set_attention_impl(request.param)
     yield request.param
@@ -53,9 +53,10 @@ def _attn_ref(qkv, B, N, H):
 
 @pytest.mark.parametrize("B,N,H", [(2, 197, 12), (1, 5, 1), (3, 17, 2), (2, 64, 3), (1, 198, 12),
                                    (1, 577, 4), (2, 16, 1), (1, 65, 2), (2, 128, 2), (1, 129, 1),
-                                   (1, 256, 2), (40, 197, 12)])
+                                   (1, 256, 2), (40, 197, 12), (7, 224, 3), (5, 225, 2), (64, 100, 12),
+                                   (33, 208, 16), (150, 1, 1)])
 def test_attention(vitk, attn_impl, B, N, H):
-    if attn_impl == 2 and N > 256:
+    if attn_impl >= 2 and N > 256:
         pytest.skip("tcgen05 kernel covers N <= 256")
     g = torch.Generator(device="cuda").manual_seed(N)
     qkv = (torch.randn(B * N, 3 * H * 64, generator=g, device="cuda") * 1.5).bfloat16()
@@ -74,6 +75,27 @@ def test_attention_peaked_softmax(vitk, attn_impl):
     ref, _ = _attn_ref(qkv, B, N, H)
     assert torch.isfinite(ctx.float()).all()
     torch.testing.assert_close(ctx.float(), ref, rtol=3e-2, atol=3e-2)
+
+
+@pytest.mark.parametrize("gap", [40.0, 80.0, 300.0, -300.0])
+def test_attention_late_peak(vitk, attn_impl, gap):
+    """Scores whose maximum sits `gap` (natural-log units) above/below the first key chunk: the
+    pipelined tcgen05 kernel takes its reference exponent from the first 32 keys and must rescale
+    the row when a later chunk exceeds it by more than 2^64."""
+    B, N, H = 2, 197, 2
+    g = torch.Generator(device="cuda").manual_seed(3)
+    qkv = torch.randn(B, N, 3, H, 64, generator=g, device="cuda") * 0.3
+    u = torch.nn.functional.normalize(torch.randn(64, generator=g, device="cuda"), dim=0)
+    qkv[:, :, 0] += 8.0 * u                      # every query has a large component along u
+    amp = gap * 8.0 / 8.0                        # q.k / sqrt(64) ~= 8 * amp / 8 = gap
+    qkv[:, 70:150, 1] += amp * u                 # keys 70..149 score ~gap higher than keys 0..31
+    qkv[:, 190:, 1] += 0.5 * amp * u
+    qkv = qkv.reshape(B * N, 3 * H * 64).bfloat16()
+    ctx, lse = vitk.ops.attention(qkv, B, N, H, return_lse=True)
+    ref, lse_ref = _attn_ref(qkv, B, N, H)
+    assert torch.isfinite(ctx.float()).all()
+    torch.testing.assert_close(ctx.float(), ref, rtol=3e-2, atol=3e-2)
+    torch.testing.assert_close(lse, lse_ref, rtol=1e-3, atol=2e-2)
 
 
 def test_attention_rejects_other_head_dims(vitk):
