@@ -155,14 +155,19 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_q,
   const uint32_t m_base = staging_base + 8u * 4096u;
   const uint32_t l_base = m_base + 8192u;
   const uint32_t bar_base = l_base + 8192u;
-  auto kv_full = [&](int s) { return bar_base + 8u * s; };
-  auto kv_empty = [&](int s) { return bar_base + 8u * (2 + s); };
-  auto s_full = [&](int t) { return bar_base + 8u * (4 + t); };
-  auto p_full = [&](int t) { return bar_base + 8u * (6 + t); };
-  const uint32_t o_full = bar_base + 8u * 8;
-  const uint32_t o_free = bar_base + 8u * 9;
+  // Q/K and V of a stage are tracked separately: Q and K are dead as soon as the score MMAs of the
+  // item have run - a whole item earlier than V - so their reload gets that much more lead time
+  // over the HBM latency.
+  auto qk_full = [&](int s) { return bar_base + 8u * s; };
+  auto qk_empty = [&](int s) { return bar_base + 8u * (2 + s); };
+  auto v_full = [&](int s) { return bar_base + 8u * (4 + s); };
+  auto v_empty = [&](int s) { return bar_base + 8u * (6 + s); };
+  auto s_full = [&](int t) { return bar_base + 8u * (8 + t); };
+  auto p_full = [&](int t) { return bar_base + 8u * (10 + t); };
+  const uint32_t o_full = bar_base + 8u * 12;
+  const uint32_t o_free = bar_base + 8u * 13;
   volatile uint32_t* tmem_slot =
-      reinterpret_cast<volatile uint32_t*>(smem + (bar_base - base) + 8 * 10);
+      reinterpret_cast<volatile uint32_t*>(smem + (bar_base - base) + 8 * 14);
   float* m_smem = reinterpret_cast<float*>(smem + (m_base - base));
   float* l_smem = reinterpret_cast<float*>(smem + (l_base - base));
   auto stat_idx = [](int par, int t, int cq, int row) { return ((par * 2 + t) * 4 + cq) * 128 + row; };
@@ -185,8 +190,10 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_q,
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < 2; ++s) {
-      mbar_init(kv_full(s), 1);
-      mbar_init(kv_empty(s), 1);
+      mbar_init(qk_full(s), 1);
+      mbar_init(qk_empty(s), 1);
+      mbar_init(v_full(s), 1);
+      mbar_init(v_empty(s), 1);
       mbar_init(s_full(s), 1);
       mbar_init(p_full(s), 16);
     }
@@ -215,15 +222,17 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_q,
           const int stage = it & 1;
           const uint32_t phase = (it >> 1) & 1;
           const int b = item / p.H, h = item - b * p.H;
-          mbar_wait(kv_empty(stage), phase ^ 1u);
           const uint32_t sq = base + stage * stage_bytes;
           const uint32_t sk = sq + 2u * kQTile;
           const uint32_t sv = sk + kv_bytes;
-          mbar_arrive_expect_tx(kv_full(stage), q_tiles * kQTile + 2u * kv_bytes);
+          mbar_wait(qk_empty(stage), phase ^ 1u);
+          mbar_arrive_expect_tx(qk_full(stage), q_tiles * kQTile + kv_bytes);
           for (int t = 0; t < q_tiles; ++t)
-            tma_load_3d(sq + t * kQTile, &tm_q, kv_full(stage), h * 64, t * 128, b);
-          tma_load_3d(sk, &tm_kv, kv_full(stage), D + h * 64, 0, b);
-          tma_load_3d(sv, &tm_kv, kv_full(stage), 2 * D + h * 64, 0, b);
+            tma_load_3d(sq + t * kQTile, &tm_q, qk_full(stage), h * 64, t * 128, b);
+          tma_load_3d(sk, &tm_kv, qk_full(stage), D + h * 64, 0, b);
+          mbar_wait(v_empty(stage), phase ^ 1u);
+          mbar_arrive_expect_tx(v_full(stage), kv_bytes);
+          tma_load_3d(sv, &tm_kv, v_full(stage), 2 * D + h * 64, 0, b);
         }
       }
     } else if (warp == 1) {
@@ -241,13 +250,14 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_q,
           for (int k = 0; k < 4; ++k)
             mma_bf16_ss(d_s, q_desc + 2u * k, k_desc + 2u * k, idesc_s, k > 0 ? 1u : 0u);
           mma_commit(s_full(t));
+          if (t == q_tiles - 1) mma_commit(qk_empty(stage));  // last reader of this stage's Q and K
         }
         __syncwarp();
       };
       int it = 0;
       uint32_t oc = 0;  // O tiles produced so far
       if (static_cast<int>(blockIdx.x) < num_items) {
-        mbar_wait(kv_full(0), 0);
+        mbar_wait(qk_full(0), 0);
         tc_fence_after();
         for (int t = 0; t < q_tiles; ++t) issue_scores(0, t);
       }
@@ -259,6 +269,7 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_q,
         // V: rows = keys (128 B each, 8-row swizzle atoms 1024 B apart); 16 keys per MMA
         const uint64_t v_desc = make_desc_sw128(sv, kv_bytes, 1024);
         for (int t = 0; t < q_tiles; ++t) {
+          if (t == 0) mbar_wait(v_full(stage), (it >> 1) & 1);
           mbar_wait(p_full(t), ph);
           TR(0, it, t * 4 + 0);
           mbar_wait(o_free, (oc & 1u) ^ 1u);  // the previous O tile has been read out
@@ -277,14 +288,14 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_q,
                             v_desc + static_cast<uint64_t>(ks) * 128u, idesc_pv, ks > 0 ? 1u : 0u);
             }
             mma_commit(o_full);
-            if (t == q_tiles - 1) mma_commit(kv_empty(stage));  // last reader of this smem stage
+            if (t == q_tiles - 1) mma_commit(v_empty(stage));  // last reader of this stage's V
           }
           __syncwarp();
           TR(0, it, t * 4 + 3);
           ++oc;
           if (has_next) {
             if (t == 0) {
-              mbar_wait(kv_full(stage ^ 1), ((it + 1) >> 1) & 1);
+              mbar_wait(qk_full(stage ^ 1), ((it + 1) >> 1) & 1);
               tc_fence_after();
             }
             issue_scores(stage ^ 1, t);  // overwrites S_t / P_t behind PV_t (in-order tensor pipe)
