@@ -103,6 +103,7 @@ int linear(const void* A, int lda, const void* W, int M, int N, int K, GemmEpi e
 int forward_bf16(const VitkConfig* cfg, const VitkWeights* w, const float* images, const Dims& d,
                  float* tokens_out, float* logits_out, const Workspace& ws, cudaStream_t stream) {
   const int M = static_cast<int>(d.M), D = d.D;
+  SweepAlternation sweep;  // consecutive row-ordered kernels run in opposite directions (L2 reuse)
   // -- patch embedding as a GEMM; epilogue adds bias + position embedding and writes each patch
   //    row at its token slot (evaluation.py:142-149)
   VITK_TRY(patchify(images, ws.patch, d.B, d.C, d.S, d.p, stream));

@@ -42,6 +42,7 @@ constexpr uint32_t kOColumn = 448;
 
 struct Tc2Params {
   int B, N, H, Nk, q_tiles;
+  int descending;  // walk the (image, head) items from the last to the first
   float scale;
   float* lse;
 };
@@ -221,7 +222,8 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_q,
         for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
           const int stage = it & 1;
           const uint32_t phase = (it >> 1) & 1;
-          const int b = item / p.H, h = item - b * p.H;
+          const int item_id = p.descending ? num_items - 1 - item : item;
+          const int b = item_id / p.H, h = item_id - b * p.H;
           const uint32_t sq = base + stage * stage_bytes;
           const uint32_t sk = sq + 2u * kQTile;
           const uint32_t sv = sk + kv_bytes;
@@ -386,7 +388,8 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_q,
     int it = 0;
     if (static_cast<int>(blockIdx.x) < num_items) mbar_wait(p_full(0), 0);
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
-      const int b = item / p.H, h = item - b * p.H;
+      const int item_id = p.descending ? num_items - 1 - item : item;
+          const int b = item_id / p.H, h = item_id - b * p.H;
       const bool has_next = item + static_cast<int>(gridDim.x) < num_items;
       const int par = it & 1;
       for (int t = 0; t < q_tiles; ++t) {
@@ -498,6 +501,7 @@ int attention_fwd_tc2(const void* qkv, void* ctx, float* lse, int B, int N, int 
   prm.q_tiles = (N + 127) / 128;
   prm.scale = 1.0f / sqrtf(static_cast<float>(hd));
   prm.lse = lse;
+  prm.descending = sweep_next();
   int grid = sm_count();
   if (B * H < grid) grid = B * H;
   ProfileScope prof(PROF_ATTN, 4.0 * B * H * static_cast<double>(N) * N * hd, stream);

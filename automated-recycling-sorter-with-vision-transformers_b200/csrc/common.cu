@@ -1,5 +1,7 @@
 #include "common.h"
 
+#include <cstdlib>
+
 #include <cstdarg>
 #include <cstring>
 #include <atomic>
@@ -91,6 +93,21 @@ static void init_dev(int dev) {
   }
   g_dev_init[dev] = true;
 }
+namespace {
+thread_local int t_sweep_depth = 0;
+thread_local int t_sweep_dir = 0;
+}  // namespace
+SweepAlternation::SweepAlternation() {
+  if (t_sweep_depth++ == 0) t_sweep_dir = 0;
+}
+SweepAlternation::~SweepAlternation() { --t_sweep_depth; }
+int sweep_next() {
+  if (t_sweep_depth == 0 || std::getenv("VITK_NO_SWEEP_ALTERNATION") != nullptr) return 0;
+  const int d = t_sweep_dir;
+  t_sweep_dir ^= 1;
+  return d;
+}
+
 int sm_count() {
   int dev = 0;
   cudaGetDevice(&dev);

@@ -64,6 +64,16 @@ struct ProfileScope {
   cudaStream_t stream_;
 };
 
+// Sweep direction of the row-ordered kernels (LayerNorm rows, GEMM row tiles, attention items).
+// Inside a SweepAlternation scope consecutive launches alternate between ascending and descending
+// order, so every kernel starts on the rows its producer wrote LAST - the part of a 77-310 MB
+// intermediate that is still resident in the 126 MB L2.  Outside a scope everything is ascending.
+struct SweepAlternation {
+  SweepAlternation();
+  ~SweepAlternation();
+};
+int sweep_next();  // direction for the kernel being launched: 0 ascending, 1 descending
+
 // Cached per current device.
 int sm_count();
 int device_cc();  // e.g. 100

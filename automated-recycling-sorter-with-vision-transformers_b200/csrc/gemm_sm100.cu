@@ -312,7 +312,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
                const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_c,
                const __grid_constant__ CUtensorMap tmap_c2, int M, int N, int K,
-               int kb_per_split, int num_splits, const GemmEpilogue e) {
+               int kb_per_split, int num_splits, int descending, const GemmEpilogue e) {
   constexpr bool kAuxTma = TMA_EPI && (EPI == EPI_DGELU_BF16);
   using C = Cfg<BLOCK_N, CTAS, kAuxTma ? 3 : 2>;
   constexpr int kStagingBytes = C::kStagingBytes;
@@ -345,6 +345,11 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
   const int num_out_tiles = num_m_tiles * num_n_tiles;
   const int num_tiles = num_out_tiles * num_splits;  // work items: (output tile, K split)
   const int num_kb_total = (K + kBlockK - 1) / kBlockK;
+  // output tile of a work item; `descending` walks the row tiles from the last to the first
+  auto tile_of = [&](int work) {
+    const int tile = work % num_out_tiles;
+    return descending ? num_out_tiles - 1 - tile : tile;
+  };
   auto kb_begin = [&](int work) { return (work / num_out_tiles) * kb_per_split; };
   auto kb_end = [&](int work) {
     const int e2 = (work / num_out_tiles + 1) * kb_per_split;
@@ -389,7 +394,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
       int stage = 0;
       uint32_t phase = 0;
       for (int work = cluster_id; work < num_tiles; work += num_clusters) {
-        const int tile = work % num_out_tiles;
+        const int tile = tile_of(work);
         const int m_blk = tile / num_n_tiles;
         const int n_blk = tile - m_blk * num_n_tiles;
         const int m0 = m_blk * kTileM + static_cast<int>(cta_rank) * kBlockM;
@@ -510,7 +515,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
     [[maybe_unused]] const uint32_t aux_slab = stg + 2u * 4096u;
     [[maybe_unused]] const uint32_t my_aux_bar = aux_bar(warp - kFirstEpiWarp);
     for (int work = cluster_id; work < num_tiles; work += num_clusters) {
-      const int tile = work % num_out_tiles;
+      const int tile = tile_of(work);
       const int m_blk = tile / num_n_tiles;
       const int n_blk = tile - m_blk * num_n_tiles;
       if constexpr (kAuxTma) {
@@ -719,8 +724,9 @@ int launch(const GemmProblem& p, cudaStream_t stream) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   ProfileScope prof(PROF_GEMM, 2.0 * p.M * p.N * p.K, stream);
+  const int descending = sweep_next();
   cudaError_t le = cudaLaunchKernelEx(&cfg, kernel, ta, tb, tc, tc2, p.M, p.N, p.K, kb_per_split,
-                                      splits, p.e);
+                                      splits, descending, p.e);
   if (le != cudaSuccess)
     return set_error(VITK_ERR_CUDA, "launch of gemm_tn_kernel<%d,%d,%d,%d> failed: %s", BLOCK_N,
                      EPI, CTAS, (int)TMA_EPI, cudaGetErrorString(le));
