@@ -72,6 +72,7 @@ _SIGNATURES = {
     "vitk_gemm_set_cta_group": (C.c_int, [C.c_int]),
     "vitk_gemm_set_direct_epilogue": (C.c_int, [C.c_int]),
     "vitk_attention_set_impl": (C.c_int, [C.c_int]),
+    "vitk_reserve_sms": (C.c_int, [C.c_int]),
     "vitk_profile_enable": (C.c_int, [C.c_int]),
     "vitk_profile_collect": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double),
                                        C.POINTER(C.c_longlong), C.c_int]),
@@ -103,6 +104,10 @@ _SIGNATURES = {
                                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                                 C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
                                                 C.c_void_p, C.c_void_p]),
+    "vitk_classifier_loss_backward_ev": (C.c_int, [C.POINTER(VitkConfig), C.POINTER(VitkWeights),
+                                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                                   C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                   C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "vitk_backward_tokens": (C.c_int, [C.POINTER(VitkConfig), C.POINTER(VitkWeights), C.c_void_p,
                                        C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                        C.c_void_p]),

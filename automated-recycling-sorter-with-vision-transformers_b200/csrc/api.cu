@@ -286,6 +286,11 @@ int vitk_gemm_set_direct_epilogue(int on) {
   gemm_force_direct_epilogue(on != 0);
   return VITK_OK;
 }
+int vitk_reserve_sms(int n) {
+  VITK_REQUIRE(n >= 0 && n <= 64, "reserve_sms: 0 <= n <= 64");
+  reserve_sms(n);
+  return VITK_OK;
+}
 int vitk_attention_set_impl(int impl) {
   VITK_REQUIRE(impl >= 0 && impl <= 3,
                "attention impl must be 0 (auto), 1 (flash), 2 (tcgen05) or 3 (unpipelined tcgen05)");

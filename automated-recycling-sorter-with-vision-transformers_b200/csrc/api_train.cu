@@ -275,8 +275,15 @@ int forward_train(const VitkConfig* cfg, const VitkWeights* w, const float* imag
 // Backward through the blocks and the patch embedding. On entry ws.dx (f32) / ws.dxb (bf16) hold
 // the gradient w.r.t. the residual stream after the last block.
 int backward_blocks(const VitkWeights* w, const VitkWeightsT* wt, const VitkGrads* g, const TDims& d,
-                    const Saved& sv, const TrainWs& ws, cudaStream_t stream) {
+                    const Saved& sv, const TrainWs& ws, cudaStream_t stream,
+                    const vitk_event_t* bucket_events = nullptr) {
   const int M = static_cast<int>(d.M), D = d.D, Mlp = d.Mlp;
+  auto bucket_done = [&](int k) -> int {
+    if (bucket_events != nullptr && bucket_events[k] != nullptr)
+      VITK_CHECK_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(bucket_events[k]), stream));
+    return VITK_OK;
+  };
+  VITK_TRY(bucket_done(0));  // final LayerNorm + head gradients were produced by the caller
   for (int l = d.L - 1; l >= 0; --l) {
     const VitkBlockWeights& bw = w->blocks[l];
     const VitkBlockWeightsT& bt = wt->blocks[l];
@@ -297,13 +304,14 @@ int backward_blocks(const VitkWeights* w, const VitkWeightsT* wt, const VitkGrad
     VITK_TRY(linear_wgrad(ws.dqkv, 3 * D, sb.xn1, D, M, bg.qkv_w, bg.qkv_b, stream));
     VITK_TRY(layernorm_bwd(ws.dxn, 0, D, sb.x1, D, sb.mean1, sb.rstd1, bw.ln1_w, ws.dx, D, 1, ws.dxb,
                            D, bg.ln1_w, bg.ln1_b, M, D, stream));
+    VITK_TRY(bucket_done(d.L - l));
   }
   // ---- token assembly + patch embedding                             (evaluation.py:142-149)
   VITK_TRY(token_grads(ws.dx, d.B, d.N, D, d.prefix, g->pos_embed, g->cls_token, g->dist_token,
                        ws.dxp, stream));
   VITK_TRY(linear_wgrad(ws.dxp, D, sv.patches, d.Kp, static_cast<int>(d.Mp), g->patch_w, g->patch_b,
                         stream));
-  return VITK_OK;
+  return bucket_done(d.L + 1);
 }
 
 int check_train_ptrs(const VitkWeights* w, const VitkWeightsT* wt, const VitkGrads* g,
@@ -355,8 +363,20 @@ int vitk_classifier_loss_backward(const VitkConfig* cfg, const VitkWeights* w,
                                   const long long* labels, int batch, float loss_scale,
                                   float* logits_out, float* loss_out, void* saved, void* workspace,
                                   vitk_stream_t stream_) {
+  return vitk_classifier_loss_backward_ev(cfg, w, wt, g, labels, batch, loss_scale, logits_out,
+                                          loss_out, saved, workspace, nullptr, 0, stream_);
+}
+
+int vitk_classifier_loss_backward_ev(const VitkConfig* cfg, const VitkWeights* w,
+                                     const VitkWeightsT* wt, const VitkGrads* g,
+                                     const long long* labels, int batch, float loss_scale,
+                                     float* logits_out, float* loss_out, void* saved,
+                                     void* workspace, const vitk_event_t* bucket_events,
+                                     int n_events, vitk_stream_t stream_) {
   TDims d;
   VITK_TRY(check_train_config(cfg, batch, &d));
+  VITK_REQUIRE(bucket_events == nullptr || n_events == d.L + 2,
+               "bucket_events needs num_layers + 2 = %d entries (got %d)", d.L + 2, n_events);
   VITK_TRY(check_train_ptrs(w, wt, g, d));
   VITK_REQUIRE(labels && saved && workspace, "null argument");
   VITK_REQUIRE(d.ncls > 0 && w->head_w && w->head_b && g->head_w && g->head_b,
@@ -371,7 +391,7 @@ int vitk_classifier_loss_backward(const VitkConfig* cfg, const VitkWeights* w,
                         w->head_b, labels, loss_scale, cfg->ln_eps, d.B, D, d.ncls, logits_out,
                         loss_out, ws.feat, ws.dlogits, ws.dx, ws.dxb, g->ln_f_w, g->ln_f_b,
                         g->head_w, g->head_b, stream));
-  return backward_blocks(w, wt, g, d, sv, ws, stream);
+  return backward_blocks(w, wt, g, d, sv, ws, stream, bucket_events);
 }
 
 int vitk_backward_tokens(const VitkConfig* cfg, const VitkWeights* w, const VitkWeightsT* wt,

@@ -108,11 +108,14 @@ int sweep_next() {
   return d;
 }
 
+static int g_sm_reserve = 0;
+void reserve_sms(int n) { g_sm_reserve = n < 0 ? 0 : n; }
 int sm_count() {
   int dev = 0;
   cudaGetDevice(&dev);
   if (!g_dev_init[dev]) init_dev(dev);
-  return g_sm_count[dev];
+  const int n = g_sm_count[dev] - g_sm_reserve;
+  return n < 2 ? 2 : n;
 }
 int device_cc() {
   int dev = 0;

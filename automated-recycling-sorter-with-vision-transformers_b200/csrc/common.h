@@ -74,8 +74,10 @@ struct SweepAlternation {
 };
 int sweep_next();  // direction for the kernel being launched: 0 ascending, 1 descending
 
-// Cached per current device.
+// Cached per current device, minus the SMs set aside with reserve_sms (persistent kernels size
+// their grids with it: a data-parallel backward leaves a few SMs to the NCCL kernels it overlaps).
 int sm_count();
+void reserve_sms(int n);
 int device_cc();  // e.g. 100
 
 // 2-D bf16 (or any 2-byte / 4-byte element) row-major tensor map: dims {inner, outer},

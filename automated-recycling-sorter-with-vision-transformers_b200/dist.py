@@ -29,18 +29,25 @@ def shard_range(n_items: int, rank: int, world: int) -> tuple[int, int]:
 
 
 def allreduce_slices(flat: torch.Tensor, slices: Sequence[tuple[int, int]], group=None,
-                     comm_stream=None) -> None:
+                     comm_stream=None, ready_events=None) -> None:
     """In-place sum all-reduce of flat[a:b] for every slice, in the given order.  On CUDA the
-    collectives are enqueued on `comm_stream` (after everything already queued on the current
-    stream) and the current stream waits for them at the end."""
+    collectives are enqueued on `comm_stream` and the current stream waits for them at the end.
+    With `ready_events` (one CUDA event per slice, recorded on the compute stream when that slice
+    is final) slice k only waits for its own event, so its reduction overlaps whatever the compute
+    stream still has queued; without, every collective waits for all work queued so far."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return
+    if ready_events is not None and len(ready_events) != len(slices):
+        raise ValueError("ready_events needs one event per slice")
     if flat.is_cuda and comm_stream is not None:
         main = torch.cuda.current_stream(flat.device)
-        comm_stream.wait_stream(main)
+        if ready_events is None:
+            comm_stream.wait_stream(main)
         works = []
         with torch.cuda.stream(comm_stream):
-            for a, b in slices:
+            for k, (a, b) in enumerate(slices):
+                if ready_events is not None:
+                    comm_stream.wait_event(ready_events[k])
                 if b > a:
                     works.append(dist.all_reduce(flat[a:b], group=group, async_op=True))
         for w in works:

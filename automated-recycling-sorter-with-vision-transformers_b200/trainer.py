@@ -197,14 +197,30 @@ class FineTuner:
     """Fused fine-tune step: AdamW(lr=1e-4, weight_decay=1e-4) as train.py:1598-1602."""
 
     def __init__(self, model, lr=1e-4, weight_decay=1e-4, betas=(0.9, 0.999), eps=1e-8,
-                 process_group=None):
+                 process_group=None, overlap_allreduce: bool = True, reserve_sms: int = 0):
+        """overlap_allreduce: start each gradient bucket's all-reduce on a side stream as soon as
+        the backward has produced it (events recorded by vitk_classifier_loss_backward_ev), instead
+        of reducing everything after the backward.  reserve_sms: SMs kept out of the persistent
+        kernels' grids during the backward so that the NCCL kernels do not have to displace them
+        (pair with a communicator limited to as many CTAs: ProcessGroupNCCL.Options.config.max_ctas)."""
         self.model = model
         self.lr, self.wd, self.betas, self.eps = lr, weight_decay, betas, eps
         self.state = TrainState(model.backbone, model.head, model.backbone._n_prefix)
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
-        self._comm_stream = torch.cuda.Stream(device=self.state.device) if self.world > 1 else None
+        self._comm_stream = (torch.cuda.Stream(device=self.state.device, priority=-1)
+                             if self.world > 1 else None)
         self._loss = torch.zeros(1, dtype=torch.float32, device=self.state.device)
+        self.overlap = bool(overlap_allreduce) and self.world > 1
+        self.reserve_sms = int(reserve_sms) if self.overlap else 0
+        self._slices = self.state.bucket_slices()
+        self._events, self._event_arr = None, None
+        if self.overlap:
+            # one event per gradient bucket; torch creates the cudaEvent lazily at the first record
+            self._events = [torch.cuda.Event() for _ in self._slices]
+            for ev in self._events:
+                ev.record()
+            self._event_arr = (C.c_void_p * len(self._events))(*[ev.cuda_event for ev in self._events])
 
     @torch.no_grad()
     def step(self, images: torch.Tensor, labels: torch.Tensor):
@@ -229,9 +245,19 @@ class FineTuner:
         s = _stream()
         check(lib().vitk_forward_train(C.byref(cfg), C.byref(st.W), images.data_ptr(), B, None,
                                        saved, saved_bytes, ws, ws_bytes, s))
-        check(lib().vitk_classifier_loss_backward(
-            C.byref(cfg), C.byref(st.W), C.byref(st.T), C.byref(st.G), labels.data_ptr(), B,
-            1.0 / (B * self.world), logits.data_ptr(), self._loss.data_ptr(), saved, ws, s))
+        if self.overlap:
+            if self.reserve_sms:
+                check(lib().vitk_reserve_sms(self.reserve_sms))
+            check(lib().vitk_classifier_loss_backward_ev(
+                C.byref(cfg), C.byref(st.W), C.byref(st.T), C.byref(st.G), labels.data_ptr(), B,
+                1.0 / (B * self.world), logits.data_ptr(), self._loss.data_ptr(), saved, ws,
+                self._event_arr, len(self._events), s))
+            if self.reserve_sms:
+                check(lib().vitk_reserve_sms(0))
+        else:
+            check(lib().vitk_classifier_loss_backward(
+                C.byref(cfg), C.byref(st.W), C.byref(st.T), C.byref(st.G), labels.data_ptr(), B,
+                1.0 / (B * self.world), logits.data_ptr(), self._loss.data_ptr(), saved, ws, s))
         if self.world > 1:
             self._allreduce_grads()
         st.step_count += 1
@@ -246,4 +272,5 @@ class FineTuner:
         """Sum gradients over the data-parallel group: a few large all-reduces over contiguous
         slices of the flat gradient arena on a side stream (NCCL over NVLink/NVSwitch)."""
         from .dist import allreduce_slices
-        allreduce_slices(self.state.grad, self.state.bucket_slices(), self.pg, self._comm_stream)
+        allreduce_slices(self.state.grad, self._slices, self.pg, self._comm_stream,
+                         ready_events=self._events if self.overlap else None)

@@ -162,7 +162,7 @@ def run_reference(args) -> None:
     val = batch * steps / dt
     sample = (f"reference algorithm restated in oracle/vit_oracle.py (torch CPU fp32, {cores} threads), "
               f"{steps} steps x batch {batch} of the ViT-B/16 workload")
-    print(json.dumps({
+    _emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": max(warm, 1), "ms_per_step": 1e3 * dt / steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -190,7 +190,10 @@ def measure_train_step(vitk, O, dev, world, rank, barrier, steps: int = 8, warmu
     B = TRAIN_BATCH
     torch.manual_seed(0)
     model = vitk.ViTClassifier(num_classes=N_CLASSES, dropout=0.0, **VIT_B16).to(dev)
-    tuner = vitk.FineTuner(model, lr=1e-4, weight_decay=1e-4)
+    overlap = os.environ.get("VITK_DP_OVERLAP", "1") != "0"
+    reserve = int(os.environ.get("VITK_DP_RESERVE_SMS", "0"))
+    tuner = vitk.FineTuner(model, lr=1e-4, weight_decay=1e-4, overlap_allreduce=overlap,
+                           reserve_sms=reserve)
     x = O.synthetic_images(B, VIT_B16["image_size"], seed=99 + rank).to(dev)
     y = O.synthetic_labels(B, N_CLASSES, seed=5 + rank).to(dev)
     for _ in range(warmup):
@@ -218,6 +221,7 @@ def measure_train_step(vitk, O, dev, world, rank, barrier, steps: int = 8, warmu
     ips = world * B * steps / (ms * 1e-3)
     flops = 3.0 * fwd_flops_per_image()
     peaks, _ = measured_peaks()
+    tuner_overlap = tuner.overlap
     del tuner, model
     torch.cuda.empty_cache()
     return {"metric": "vit_b16_224_finetune_images_per_sec", "value": ips, "unit": UNIT,
@@ -227,7 +231,11 @@ def measure_train_step(vitk, O, dev, world, rank, barrier, steps: int = 8, warmu
             "tflops": ips / world * flops / 1e12,
             "frac_of_burst_peak": ips / world * flops / 1e12 / float(peaks["bf16_tflops"]),
             "by_kind_ms_per_step": {k: v["ms"] / 2 for k, v in prof.items() if v["launches"]},
-            "optimizer": "fused AdamW lr 1e-4 wd 1e-4 (train.py:1598-1602), dropout 0"}
+            "optimizer": "fused AdamW lr 1e-4 wd 1e-4 (train.py:1598-1602), dropout 0",
+            "grad_allreduce": ("none (1 GPU)" if world == 1 else
+                               ("NCCL sum over 14 flat fp32 slices, each started when the backward "
+                                "has produced it (overlapped)" if tuner_overlap else
+                                "NCCL sum over 14 flat fp32 slices after the backward"))}
 
 
 def run_vitk(args) -> None:
@@ -245,7 +253,12 @@ def run_vitk(args) -> None:
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        opts = None
+        if int(os.environ.get("VITK_NCCL_MAX_CTAS", "0")) > 0:
+            opts = dist.ProcessGroupNCCL.Options()
+            opts.config.max_ctas = int(os.environ["VITK_NCCL_MAX_CTAS"])
+            opts.config.min_ctas = 1
+        dist.init_process_group("nccl", device_id=dev, pg_options=opts)
     n_gpus = world
 
     B = args.batch
@@ -360,12 +373,25 @@ def run_vitk(args) -> None:
         line["train_step"] = train
     if cpu is not None:
         line["cpu_baseline"] = cpu
-    print(json.dumps(line))
+    _emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
+def _emit(line: str) -> None:
+    """The one JSON line goes to the process's original stdout; anything a library writes to fd 1
+    meanwhile (e.g. NCCL's version banner) was diverted to stderr by main()."""
+    os.write(_REAL_STDOUT, (line + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

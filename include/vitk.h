@@ -107,6 +107,10 @@ int vitk_gemm_set_cta_group(int ctas);
  * store / reduce-add epilogue (tests, A/B timing). */
 int vitk_gemm_set_direct_epilogue(int on);
 
+/* Persistent kernels (GEMM, attention) launch one CTA per SM; keep `n` SMs out of their grids, e.g.
+ * for the NCCL kernels of a gradient all-reduce that overlaps the backward pass. 0 restores all. */
+int vitk_reserve_sms(int n);
+
 /* Attention kernel choice: 0 = automatic (tcgen05 single-key-block kernel when N <= 256, else the
  * flash kernel), 1 = flash (mma.sync, any N), 2 = tcgen05.  Tests and A/B timing. */
 int vitk_attention_set_impl(int impl);
@@ -238,6 +242,20 @@ int vitk_classifier_loss_backward(const VitkConfig* cfg, const VitkWeights* w,
                                   const long long* labels, int batch, float loss_scale,
                                   float* logits_out, float* loss_out, void* saved, void* workspace,
                                   vitk_stream_t stream);
+
+/* Same, for data-parallel training: bucket_events[k] (a cudaEvent_t each, n_events = num_layers + 2)
+ * is recorded on `stream` as soon as gradient bucket k is final, so that the caller can start that
+ * bucket's all-reduce on another stream while the rest of the backward runs (north_star: "gradient
+ * allreduce over NCCL/NVLink overlapped with backward").  Bucket 0 = final LayerNorm + head,
+ * bucket 1 + i = encoder block (num_layers - 1 - i), last bucket = tokens, position and patch
+ * embedding.  bucket_events may be null (then identical to vitk_classifier_loss_backward). */
+typedef void* vitk_event_t;
+int vitk_classifier_loss_backward_ev(const VitkConfig* cfg, const VitkWeights* w,
+                                     const VitkWeightsT* wt, const VitkGrads* g,
+                                     const long long* labels, int batch, float loss_scale,
+                                     float* logits_out, float* loss_out, void* saved,
+                                     void* workspace, const vitk_event_t* bucket_events,
+                                     int n_events, vitk_stream_t stream);
 
 /* After vitk_forward_train with tokens_out: backward from d_tokens = dLoss/d backbone(images)
  * (f32 [B,N,D]) - what autograd hands to the backbone at train.py:1455. */
