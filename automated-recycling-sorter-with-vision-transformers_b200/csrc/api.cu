@@ -141,7 +141,7 @@ int forward_bf16(const VitkConfig* cfg, const VitkWeights* w, const float* image
                     nullptr, D, stream));
     VITK_TRY(layernorm_fwd(ws.x, D, bw.ln2_w, bw.ln2_b, ws.xn, 0, D, nullptr, nullptr, M, D,
                            cfg->ln_eps, stream));
-    VITK_TRY(linear(ws.xn, D, bw.fc1_w, M, d.Mlp, D, EPI_GELU_BF16, bw.fc1_b, nullptr, 0, ws.h,
+    VITK_TRY(linear(ws.xn, D, bw.fc1_w, M, d.Mlp, D, EPI_GELU_TANH_BF16, bw.fc1_b, nullptr, 0, ws.h,
                     nullptr, d.Mlp, stream));
     VITK_TRY(linear(ws.h, d.Mlp, bw.fc2_w, M, D, d.Mlp, EPI_RESID_F32, bw.fc2_b, ws.x, D, ws.x,
                     nullptr, D, stream));

@@ -261,7 +261,7 @@ int forward_train(const VitkConfig* cfg, const VitkWeights* w, const float* imag
                         nullptr, D, stream));
     VITK_TRY(layernorm_fwd(ws.x, D, bw.ln2_w, bw.ln2_b, sb.xn2, 0, D, sb.mean2, sb.rstd2, M, D,
                            cfg->ln_eps, stream, sb.x2));
-    VITK_TRY(linear_fwd(sb.xn2, D, bw.fc1_w, M, d.Mlp, D, EPI_GELU_BF16, bw.fc1_b, nullptr, sb.hact,
+    VITK_TRY(linear_fwd(sb.xn2, D, bw.fc1_w, M, d.Mlp, D, EPI_GELU_TANH_BF16, bw.fc1_b, nullptr, sb.hact,
                         sb.hpre, d.Mlp, stream));
     VITK_TRY(linear_fwd(sb.hact, d.Mlp, bw.fc2_w, M, D, d.Mlp, EPI_RESID_F32, bw.fc2_b, ws.x, ws.x,
                         nullptr, D, stream));
