@@ -5,8 +5,9 @@
 //   for key tile kt (128 keys) / query tile qt (128 queries):
 //     S^T  = K_kt Q_qt^T           A,B from smem (K-major)              -> TMEM [128 x 128]
 //     dP^T = V_kt dO_qt^T          A,B from smem (K-major)              -> TMEM [128 x 128]
-//     warps 4-7 (thread = key row): P^T = exp2(S^T c - lse_q), dS^T = P^T (dP^T - D_q) scale
-//           P^T, dS^T -> TMEM (bf16, over the dead S^T / dP^T columns); dS^T also -> smem
+//     warps 4-11 (thread = key row x half of the query chunks): P^T = exp2(S^T c - lse_q),
+//           dS^T = P^T (dP^T - D_q) scale; P^T, dS^T -> TMEM (bf16, in place at the start of each
+//           32-column chunk of S^T / dP^T); dS^T also -> smem
 //     dV_kt += P^T  dO_qt          A from TMEM, B = dO from smem (MN-major)
 //     dK_kt += dS^T Q_qt           A from TMEM, B = Q  from smem (MN-major)
 //     dQ_qt += dS   K_kt           A = dS^T tile in smem read as an MN-major operand, B = K (MN-major)
@@ -27,7 +28,9 @@ using namespace ptx;
 
 namespace {
 
-constexpr int kThreads = 8 * 32;  // warp 0 TMA, 1 MMA, 2 TMEM alloc, 4-7 softmax-backward / epilogue
+// warp 0 TMA, 1 MMA, 2 TMEM alloc, 2-3 per-row vectors of the next item, 4-11 softmax-backward /
+// epilogue (warps 4-7 own the first half of a block's query chunks, warps 8-11 the second half)
+constexpr int kThreads = 12 * 32;
 constexpr float kLog2e = 1.44269504088896340736f;
 constexpr uint32_t kColS = 0, kColDP = 128, kColDV = 256, kColDK = 320, kColDQ = 384;
 
@@ -53,15 +56,15 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv,   // box {64, Nk,
   const uint32_t tile_bytes = static_cast<uint32_t>(Nk) * 128u;
   const uint32_t sQ = base, sK = sQ + tile_bytes, sV = sK + tile_bytes, sdO = sV + tile_bytes;
   const uint32_t sdS = sdO + tile_bytes;        // 2 chunks x [128 keys x 128 B]
-  const uint32_t sStage = sdS + 32768u;         // 4 warps x 4 KB
-  const uint32_t vec_off = 4u * tile_bytes + 32768u + 16384u;
-  float* sLse = reinterpret_cast<float*>(smem + vec_off);  // [256], pre-multiplied by log2(e)
-  float* sD = sLse + 256;                                  // [256] rowsum(d_ctx * ctx)
-  const uint32_t bar_base = base + vec_off + 2048u;
+  const uint32_t sStage = sdS + 32768u;         // 8 warps x 4 KB
+  const uint32_t vec_off = 4u * tile_bytes + 32768u + 32768u;
+  // two item parities x { lse_q * log2(e) [256], D_q = rowsum(d_ctx * ctx) [256] }
+  float* sVec = reinterpret_cast<float*>(smem + vec_off);
+  const uint32_t bar_base = base + vec_off + 4096u;
   auto bar = [&](int i) { return bar_base + 8u * i; };
   // 0 ld_full, 1 ld_free, 2 s_full, 3 sm_done, 4 ds_free, 5 dkv_full, 6 dkv_free, 7 dq_full,
-  // 8 dq_free, 9 vec_ready
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + vec_off + 2048 + 96);
+  // 8 dq_free, 9-10 vec_full[2], 11-12 vec_free[2]
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + vec_off + 4096 + 120);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_items = p.B * p.H;
@@ -77,13 +80,16 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv,   // box {64, Nk,
     mbar_init(bar(0), 1);
     mbar_init(bar(1), 1);
     mbar_init(bar(2), 1);
-    mbar_init(bar(3), 4);
+    mbar_init(bar(3), 8);
     mbar_init(bar(4), 1);
     mbar_init(bar(5), 1);
-    mbar_init(bar(6), 4);
+    mbar_init(bar(6), 8);
     mbar_init(bar(7), 1);
-    mbar_init(bar(8), 4);
-    mbar_init(bar(9), 4);
+    mbar_init(bar(8), 8);
+    mbar_init(bar(9), 2);
+    mbar_init(bar(10), 2);
+    mbar_init(bar(11), 8);
+    mbar_init(bar(12), 8);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -112,8 +118,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv,   // box {64, Nk,
       }
     }
   } else if (warp == 1) {
-    // ======================= MMA issuer =======================
-    if (lane == 0) {
+    // ============ MMA issuer (whole warp converged, one elected lane issues) ============
+    {
       const uint32_t idesc_mn64 = make_idesc_bf16(128, 64, 0, 1);  // A K-major/TMEM, B MN-major
       const uint32_t idesc_dq = make_idesc_bf16(128, 64, 1, 1);    // A and B MN-major
       int it = 0;
@@ -136,47 +142,91 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv,   // box {64, Nk,
             const uint64_t av = make_desc_sw128(sV + kt * 16384u, 16, 1024);
             const uint64_t bq = make_desc_sw128(sQ + qt * 16384u, 16, 1024);
             const uint64_t bdo = make_desc_sw128(sdO + qt * 16384u, 16, 1024);
+            if (elect_one_sync()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              mma_bf16_ss(tmem_base + kColS, ak + 2u * k, bq + 2u * k, idesc_s, k > 0);
+              for (int k = 0; k < 4; ++k)
+                mma_bf16_ss(tmem_base + kColS, ak + 2u * k, bq + 2u * k, idesc_s, k > 0);
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              mma_bf16_ss(tmem_base + kColDP, av + 2u * k, bdo + 2u * k, idesc_s, k > 0);
-            mma_commit(bar(2));
+              for (int k = 0; k < 4; ++k)
+                mma_bf16_ss(tmem_base + kColDP, av + 2u * k, bdo + 2u * k, idesc_s, k > 0);
+              mma_commit(bar(2));
+            }
+            __syncwarp();
             // ---- wait for P^T / dS^T (TMEM) and dS^T (smem)
             mbar_wait(bar(3), blk & 1);
             tc_fence_after();
             // dV_kt += P^T dO_qt ; dK_kt += dS^T Q_qt      (K = nq queries, 16 per MMA)
             const uint64_t b_do_mn = make_desc_sw128(sdO + qt * 16384u, tile_bytes, 1024);
             const uint64_t b_q_mn = make_desc_sw128(sQ + qt * 16384u, tile_bytes, 1024);
-            for (int ks = 0; ks < nq / 16; ++ks) {
-              mma_bf16_ts(tmem_base + kColDV, tmem_base + kColS + ks * 8,
-                          b_do_mn + static_cast<uint64_t>(ks) * 128u, idesc_mn64,
-                          (qt > 0 || ks > 0) ? 1u : 0u);
-              mma_bf16_ts(tmem_base + kColDK, tmem_base + kColDP + ks * 8,
-                          b_q_mn + static_cast<uint64_t>(ks) * 128u, idesc_mn64,
-                          (qt > 0 || ks > 0) ? 1u : 0u);
-            }
             // dQ_qt += dS K_kt : A = dS^T smem tile as MN-major (2 x 64-query chunks, 16 KB apart),
             // B = K rows of this key tile (MN-major); K = kcount keys
             const uint64_t a_ds = make_desc_sw128(sdS, 16384, 1024);
             const uint64_t b_k_mn = make_desc_sw128(sK + kt * 16384u, tile_bytes, 1024);
-            for (int ks = 0; ks < kcount / 16; ++ks)
-              mma_bf16_ss(tmem_base + kColDQ + qt * 64, a_ds + static_cast<uint64_t>(ks) * 128u,
-                          b_k_mn + static_cast<uint64_t>(ks) * 128u, idesc_dq,
-                          (kt > 0 || ks > 0) ? 1u : 0u);
-            mma_commit(bar(4));  // dS^T smem tile (and P^T / dS^T in TMEM) consumed
+            if (elect_one_sync()) {
+#pragma unroll 1
+              for (int ks = 0; ks < nq / 16; ++ks) {
+                // 16 queries per step: bf16 pairs at the start of their 32-column chunk
+                const uint32_t acol = static_cast<uint32_t>((ks >> 1) * 32 + (ks & 1) * 8);
+                mma_bf16_ts(tmem_base + kColDV, tmem_base + kColS + acol,
+                            b_do_mn + static_cast<uint64_t>(ks) * 128u, idesc_mn64,
+                            (qt > 0 || ks > 0) ? 1u : 0u);
+                mma_bf16_ts(tmem_base + kColDK, tmem_base + kColDP + acol,
+                            b_q_mn + static_cast<uint64_t>(ks) * 128u, idesc_mn64,
+                            (qt > 0 || ks > 0) ? 1u : 0u);
+              }
+#pragma unroll 1
+              for (int ks = 0; ks < kcount / 16; ++ks)
+                mma_bf16_ss(tmem_base + kColDQ + qt * 64, a_ds + static_cast<uint64_t>(ks) * 128u,
+                            b_k_mn + static_cast<uint64_t>(ks) * 128u, idesc_dq,
+                            (kt > 0 || ks > 0) ? 1u : 0u);
+              mma_commit(bar(4));  // dS^T smem tile (and P^T / dS^T in TMEM) consumed
+              if (qt == n_kt - 1) mma_commit(bar(5));  // dV_kt, dK_kt complete
+              if (qt == n_kt - 1 && kt == n_kt - 1) {
+                mma_commit(bar(7));  // dQ complete
+                mma_commit(bar(1));  // operands of this item no longer needed
+              }
+            }
+            __syncwarp();
           }
-          mma_commit(bar(5));    // dV_kt, dK_kt complete
           ++ktc;
         }
-        mma_commit(bar(7));      // dQ complete
-        mma_commit(bar(1));      // operands of this item no longer needed
       }
+    }
+  } else if (warp == 2 || warp == 3) {
+    // ============ per-row vectors, one item ahead: D_q = rowsum(d_ctx * ctx), lse_q * log2(e) ====
+    int it = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+      const int b = item / p.H, h = item - b * p.H;
+      float* vLse = sVec + (it & 1) * 512;
+      float* vD = vLse + 256;
+      mbar_wait(bar(11 + (it & 1)), ((it >> 1) & 1) ^ 1u);
+      const __nv_bfloat16* obase = p.ctx + static_cast<long long>(b) * N * D + h * 64;
+      const __nv_bfloat16* dobase = p.dctx + static_cast<long long>(b) * N * D + h * 64;
+      for (int r = (warp - 2) * 32 + lane; r < 256; r += 64) {
+        float dsum = 0.f, l2 = INFINITY;  // rows >= N: P = 2^(-inf) = 0
+        if (r < N) {
+          const uint4* po = reinterpret_cast<const uint4*>(obase + static_cast<long long>(r) * D);
+          const uint4* pd = reinterpret_cast<const uint4*>(dobase + static_cast<long long>(r) * D);
+#pragma unroll
+          for (int c8 = 0; c8 < 8; ++c8) {
+            const uint4 a = __ldg(po + c8), d = __ldg(pd + c8);
+            dsum += bf16lo_to_f32(a.x) * bf16lo_to_f32(d.x) + bf16hi_to_f32(a.x) * bf16hi_to_f32(d.x);
+            dsum += bf16lo_to_f32(a.y) * bf16lo_to_f32(d.y) + bf16hi_to_f32(a.y) * bf16hi_to_f32(d.y);
+            dsum += bf16lo_to_f32(a.z) * bf16lo_to_f32(d.z) + bf16hi_to_f32(a.z) * bf16hi_to_f32(d.z);
+            dsum += bf16lo_to_f32(a.w) * bf16lo_to_f32(d.w) + bf16hi_to_f32(a.w) * bf16hi_to_f32(d.w);
+          }
+          l2 = p.lse[(static_cast<long long>(b) * p.H + h) * N + r] * kLog2e;
+        }
+        vLse[r] = l2;
+        vD[r] = dsum;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(9 + (it & 1)));
     }
   } else if (warp >= 4) {
     // ======================= softmax backward + output (thread == key row / output row) =========
     const int q4 = warp & 3;
+    const int hf = (warp - 4) >> 2;  // which half of the query chunks / which accumulator to store
     const int row_in_tile = q4 * 32 + lane;
     const float c = p.scale * kLog2e;
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16);
@@ -213,33 +263,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv,   // box {64, Nk,
 
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
       const int b = item / p.H, h = item - b * p.H;
-      // ---- per-row vectors of this item: D_q = rowsum(d_ctx * ctx), lse_q * log2(e)
-      if (it > 0) mbar_wait(bar(1), (it - 1) & 1);  // previous item's readers of sLse/sD are done
-      {
-        const __nv_bfloat16* obase = p.ctx + static_cast<long long>(b) * N * D + h * 64;
-        const __nv_bfloat16* dobase = p.dctx + static_cast<long long>(b) * N * D + h * 64;
-        for (int r = (warp - 4) * 32 + lane; r < 256; r += 128) {
-          float dsum = 0.f, l2 = INFINITY;  // rows >= N: P = 2^(-inf) = 0
-          if (r < N) {
-            const uint4* po = reinterpret_cast<const uint4*>(obase + static_cast<long long>(r) * D);
-            const uint4* pd = reinterpret_cast<const uint4*>(dobase + static_cast<long long>(r) * D);
-#pragma unroll
-            for (int c8 = 0; c8 < 8; ++c8) {
-              const uint4 a = __ldg(po + c8), d = __ldg(pd + c8);
-              dsum += bf16lo_to_f32(a.x) * bf16lo_to_f32(d.x) + bf16hi_to_f32(a.x) * bf16hi_to_f32(d.x);
-              dsum += bf16lo_to_f32(a.y) * bf16lo_to_f32(d.y) + bf16hi_to_f32(a.y) * bf16hi_to_f32(d.y);
-              dsum += bf16lo_to_f32(a.z) * bf16lo_to_f32(d.z) + bf16hi_to_f32(a.z) * bf16hi_to_f32(d.z);
-              dsum += bf16lo_to_f32(a.w) * bf16lo_to_f32(d.w) + bf16hi_to_f32(a.w) * bf16hi_to_f32(d.w);
-            }
-            l2 = p.lse[(static_cast<long long>(b) * p.H + h) * N + r] * kLog2e;
-          }
-          sLse[r] = l2;
-          sD[r] = dsum;
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar(9));
-        mbar_wait(bar(9), it & 1);  // all four warps have published their rows
-      }
+      // ---- per-row vectors of this item (written by warps 2-3 one item ahead)
+      const float* sLse = sVec + (it & 1) * 512;
+      const float* sD = sLse + 256;
+      mbar_wait(bar(9 + (it & 1)), (it >> 1) & 1);
 
       for (int kt = 0; kt < n_kt; ++kt) {
         const int key = kt * 128 + row_in_tile;
@@ -249,7 +276,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv,   // box {64, Nk,
           mbar_wait(bar(2), blk & 1);
           tc_fence_after();
           if (blk > 0) mbar_wait(bar(4), (blk - 1) & 1);  // previous dS^T smem tile consumed
-          for (int ch = 0; ch < nq / 32 + ((nq & 31) ? 1 : 0); ++ch) {
+          const int nch = nq / 32 + ((nq & 31) ? 1 : 0);
+          const int ch_mid = (nch + 1) >> 1;
+          for (int ch = hf == 0 ? 0 : ch_mid; ch < (hf == 0 ? ch_mid : nch); ++ch) {
             // chunks of 32 queries; the last chunk of a ragged tile holds 16
             const bool half_chunk = (ch * 32 + 32 > nq);
             uint32_t s[32], dp[32];
@@ -291,11 +320,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv,   // box {64, Nk,
                 a8[j] = pp[j];
                 b8[j] = ds[j];
               }
-              tmem_st_32x32b_x8(lane_base + kColS + ch * 16, a8);
-              tmem_st_32x32b_x8(lane_base + kColDP + ch * 16, b8);
+              tmem_st_32x32b_x8(lane_base + kColS + ch * 32, a8);
+              tmem_st_32x32b_x8(lane_base + kColDP + ch * 32, b8);
             } else {
-              tmem_st_32x32b_x16(lane_base + kColS + ch * 16, pp);
-              tmem_st_32x32b_x16(lane_base + kColDP + ch * 16, ds);
+              tmem_st_32x32b_x16(lane_base + kColS + ch * 32, pp);
+              tmem_st_32x32b_x16(lane_base + kColDP + ch * 32, ds);
             }
             // dS^T row -> smem: chunk of 64 queries (ch / 2), 16-byte pieces (ch & 1) * 4 .. + 3
             const uint32_t rowa = sdS + static_cast<uint32_t>(ch >> 1) * 16384u +
@@ -318,8 +347,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv,   // box {64, Nk,
         tc_fence_after();
         const int row0 = kt * 128 + q4 * 32;
         if (row0 < N) {
-          store_acc(kColDK, D + h * 64, row0, b);
-          store_acc(kColDV, 2 * D + h * 64, row0, b);
+          if (hf == 0) store_acc(kColDK, D + h * 64, row0, b);
+          else store_acc(kColDV, 2 * D + h * 64, row0, b);
         }
         tc_fence_before();
         __syncwarp();
@@ -329,13 +358,16 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv,   // box {64, Nk,
       // ---- dQ
       mbar_wait(bar(7), it & 1);
       tc_fence_after();
-      for (int qt = 0; qt < n_kt; ++qt) {
+      for (int qt = hf; qt < n_kt; qt += 2) {
         const int row0 = qt * 128 + q4 * 32;
         if (row0 < N) store_acc(kColDQ + qt * 64, h * 64, row0, b);
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar(8));
+      if (lane == 0) {
+        mbar_arrive(bar(8));
+        mbar_arrive(bar(11 + (it & 1)));  // this item's row vectors may be overwritten
+      }
     }
     if (lane == 0) tma_store_wait<0>();
   }
@@ -356,7 +388,7 @@ int attention_bwd_tc(const void* qkv, const void* ctx, const void* dctx, const f
   VITK_REQUIRE(hd == 64 && N >= 1 && N <= 256, "attention_bwd(tc): needs head_dim 64, N <= 256");
   const int Nk = (N + 15) & ~15;
   const int D = H * 64;
-  const size_t smem = 4 * static_cast<size_t>(Nk) * 128 + 32768 + 16384 + 2048 + 128 + 1024;
+  const size_t smem = 4 * static_cast<size_t>(Nk) * 128 + 32768 + 32768 + 4096 + 128 + 1024;
   VITK_REQUIRE(smem <= 232448, "attention_bwd(tc): shared memory budget exceeded");
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;

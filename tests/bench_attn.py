@@ -39,3 +39,14 @@ for impl, name in ((1, "flash mma.sync"), (3, "tcgen05 unpipelined"), (2, "tcgen
     by = B * N * H * 64 * 2 * 4
     print(f"{name:22s} B={B} N={N} H={H}: {ms*1e3:8.1f} us  {fl/ms/1e9:7.1f} TFLOP/s  {by/ms/1e6:7.1f} GB/s")
 vitk._lib.set_attention_impl(0)
+
+# ---- backward (tcgen05 kernel vs the mma.sync one)
+if N <= 256:
+    ctx, lse = vitk.ops.attention(qkv, B, N, H, return_lse=True)
+    dctx = (torch.randn_like(ctx.float()) * 0.1).bfloat16()
+    for impl, name in ((1, "bwd mma.sync"), (2, "bwd tcgen05")):
+        vitk._lib.set_attention_impl(impl)
+        ms = timeit(lambda: vitk.ops.attention_bwd(qkv, ctx, dctx, lse, B, N, H))
+        fl = 10.0 * B * H * N * N * 64
+        print(f"{name:22s} B={B} N={N} H={H}: {ms*1e3:8.1f} us  {fl/ms/1e9:7.1f} TFLOP/s")
+    vitk._lib.set_attention_impl(0)
