@@ -7,6 +7,8 @@
 
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -124,6 +126,117 @@ layernorm_bwd_dx_kernel(const DyT* __restrict__ dy, long long dy_stride, const f
         *reinterpret_cast<uint2*>(dx_bf16 + r * dxb_stride + 4 * i) = pk;
       }
     }
+  }
+}
+
+// Fused variant: dx AND the parameter gradients in one pass over dy / x (the separate column
+// reduction of kernel B re-reads both: +50 % HBM traffic).  Persistent warps walk rows gw, gw + W,
+// ... and keep their dgamma / dbeta partial sums for the 4 * NVEC columns of each lane in
+// registers; one shared-memory reduction across the 8 warps and one global atomic per column and
+// CTA at the end.
+template <typename DyT, int NVEC>
+__global__ void __launch_bounds__(256, 2)
+layernorm_bwd_fused_kernel(const DyT* __restrict__ dy, long long dy_stride,
+                           const float* __restrict__ x, long long x_stride,
+                           const float* __restrict__ mean, const float* __restrict__ rstd,
+                           const float* __restrict__ gamma, float* __restrict__ dx_io,
+                           long long dx_stride, int add_resid, __nv_bfloat16* __restrict__ dx_bf16,
+                           long long dxb_stride, float* __restrict__ dgamma,
+                           float* __restrict__ dbeta, int rows, int D) {
+  __shared__ float s_red[8][128 * NVEC];
+  const int nvec = D >> 2;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long gw = static_cast<long long>(blockIdx.x) * 8 + warp;
+  const long long W = static_cast<long long>(gridDim.x) * 8;
+  const float inv_d = 1.f / static_cast<float>(D);
+  using RV = RawVec<DyT>;
+  float4 ag[NVEC], ab[NVEC];
+#pragma unroll
+  for (int j = 0; j < NVEC; ++j) {
+    ag[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    ab[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (long long r = gw; r < rows; r += W) {
+    const float mu = mean[r], rs = rstd[r];
+    float4 xv[NVEC], pv[NVEC];
+    typename RV::type dr[NVEC];
+#pragma unroll
+    for (int j = 0; j < NVEC; ++j) {
+      const int i = lane + 32 * j;
+      if (i < nvec) {
+        xv[j] = load4(x + r * x_stride + 4 * i);
+        dr[j] = RV::load(dy + r * dy_stride + 4 * i);
+        // requested now so that its DRAM round trip overlaps the reductions
+        pv[j] = add_resid ? *reinterpret_cast<const float4*>(dx_io + r * dx_stride + 4 * i)
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < NVEC; ++j) {
+      const int i = lane + 32 * j;
+      if (i < nvec) {
+        const float4 d = RV::f4(dr[j]);
+        // xhat in place of x; dgamma += dy * xhat, dbeta += dy
+        xv[j].x = (xv[j].x - mu) * rs;
+        xv[j].y = (xv[j].y - mu) * rs;
+        xv[j].z = (xv[j].z - mu) * rs;
+        xv[j].w = (xv[j].w - mu) * rs;
+        ag[j].x = fmaf(d.x, xv[j].x, ag[j].x);
+        ag[j].y = fmaf(d.y, xv[j].y, ag[j].y);
+        ag[j].z = fmaf(d.z, xv[j].z, ag[j].z);
+        ag[j].w = fmaf(d.w, xv[j].w, ag[j].w);
+        ab[j].x += d.x;
+        ab[j].y += d.y;
+        ab[j].z += d.z;
+        ab[j].w += d.w;
+        const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + i);  // L1 resident
+        const float g0 = d.x * gm.x, g1 = d.y * gm.y, g2 = d.z * gm.z, g3 = d.w * gm.w;
+        s1 += (g0 + g1) + (g2 + g3);
+        s2 += (g0 * xv[j].x + g1 * xv[j].y) + (g2 * xv[j].z + g3 * xv[j].w);
+      }
+    }
+    s1 = warp_sum(s1) * inv_d;
+    s2 = warp_sum(s2) * inv_d;  // mean_D(g * xhat)
+#pragma unroll
+    for (int j = 0; j < NVEC; ++j) {
+      const int i = lane + 32 * j;
+      if (i < nvec) {
+        const float4 d = RV::f4(dr[j]);
+        const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + i);
+        float4 o;
+        o.x = rs * (d.x * gm.x - s1 - xv[j].x * s2) + pv[j].x;
+        o.y = rs * (d.y * gm.y - s1 - xv[j].y * s2) + pv[j].y;
+        o.z = rs * (d.z * gm.z - s1 - xv[j].z * s2) + pv[j].z;
+        o.w = rs * (d.w * gm.w - s1 - xv[j].w * s2) + pv[j].w;
+        *reinterpret_cast<float4*>(dx_io + r * dx_stride + 4 * i) = o;
+        if (dx_bf16 != nullptr) {
+          uint2 pk;
+          pk.x = pack_bf16x2(o.x, o.y);
+          pk.y = pack_bf16x2(o.z, o.w);
+          *reinterpret_cast<uint2*>(dx_bf16 + r * dxb_stride + 4 * i) = pk;
+        }
+      }
+    }
+  }
+  // ---- reduce the per-warp partial sums: dgamma, then dbeta through the same buffer
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+    for (int j = 0; j < NVEC; ++j) {
+      const int i = lane + 32 * j;
+      if (i < nvec)
+        *reinterpret_cast<float4*>(&s_red[warp][4 * i]) = pass == 0 ? ag[j] : ab[j];
+    }
+    __syncthreads();
+    float* out = pass == 0 ? dgamma : dbeta;
+    for (int col = threadIdx.x; col < D; col += 256) {
+      float acc = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) acc += s_red[w][col];
+      atomicAdd(out + col, acc);
+    }
+    __syncthreads();
   }
 }
 
@@ -478,6 +591,30 @@ int layernorm_bwd(const void* dy, int dy_is_f32, long long dy_stride, const floa
   const int grid = (rows + 7) / 8;
   const __nv_bfloat16* dyb = static_cast<const __nv_bfloat16*>(dy);
   const float* dyf = static_cast<const float*>(dy);
+  const int nv = (D / 4 + 31) / 32;
+  if (dgamma != nullptr && nv <= 6 && std::getenv("VITK_LN_BWD_SPLIT") == nullptr) {
+    // one pass: dx and the parameter gradients together
+    ProfileScope prof(PROF_LN, static_cast<double>(rows) * D * (dy_is_f32 ? 14.0 : 12.0), stream);
+    int fgrid = sm_count() * 2;
+    if (fgrid > (rows + 7) / 8) fgrid = (rows + 7) / 8;
+    __nv_bfloat16* dxb = static_cast<__nv_bfloat16*>(dx_bf16);
+#define VITK_LN_FUSED(T, PTR, NV)                                                                 \
+  layernorm_bwd_fused_kernel<T, NV><<<fgrid, block, 0, stream>>>(                                  \
+      PTR, dy_stride, x, x_stride, mean, rstd, gamma, dx_io, dx_stride, add_resid, dxb, dxb_stride, \
+      dgamma, dbeta, rows, D)
+    if (dy_is_f32) {
+      if (nv <= 2) VITK_LN_FUSED(float, dyf, 2);
+      else if (nv <= 4) VITK_LN_FUSED(float, dyf, 4);
+      else VITK_LN_FUSED(float, dyf, 6);
+    } else {
+      if (nv <= 2) VITK_LN_FUSED(__nv_bfloat16, dyb, 2);
+      else if (nv <= 4) VITK_LN_FUSED(__nv_bfloat16, dyb, 4);
+      else VITK_LN_FUSED(__nv_bfloat16, dyb, 6);
+    }
+#undef VITK_LN_FUSED
+    VITK_CHECK_LAUNCH("layernorm_bwd_fused_kernel");
+    return VITK_OK;
+  }
   if (dgamma != nullptr) {
     // parameter gradients first: they read dy / x only, before dx_io is updated in place
     const int strips = (D + 255) / 256;
@@ -501,7 +638,6 @@ int layernorm_bwd(const void* dy, int dy_is_f32, long long dy_stride, const floa
   layernorm_bwd_dx_kernel<T, NV><<<grid, block, 0, stream>>>(PTR, dy_stride, x, x_stride, mean,  \
                                                              rstd, gamma, dx_io, dx_stride,       \
                                                              add_resid, dxb, dxb_stride, rows, D)
-  const int nv = (D / 4 + 31) / 32;
   if (dy_is_f32) {
     if (nv <= 2) VITK_LN_BWD(float, dyf, 2);
     else if (nv <= 4) VITK_LN_BWD(float, dyf, 4);
