@@ -36,7 +36,11 @@ class _BackboneFunction(torch.autograd.Function):
         B = images.shape[0]
         if state.shadows_stale():
             state.refresh_shadows()
-        cfg = state.config()
+        # dropout as in the reference: active in train() mode; the mask seed is drawn from torch's
+        # generator so that torch.manual_seed makes runs reproducible
+        training = bool(state.backbone.training) and float(state.backbone.dropout.p) > 0.0
+        seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item()) if training else 0
+        cfg = state.config(training=training, seed=seed)
         saved, saved_bytes, ws, ws_bytes = state.buffers(B)
         pe = state.backbone.patch_embedding
         N = pe.n_patches + state.n_prefix
@@ -44,14 +48,14 @@ class _BackboneFunction(torch.autograd.Function):
         check(lib().vitk_forward_train(C.byref(cfg), C.byref(state.W), images.data_ptr(), B,
                                        tokens.data_ptr(), saved, saved_bytes, ws, ws_bytes,
                                        torch.cuda.current_stream().cuda_stream))
-        ctx.state, ctx.batch = state, B
+        ctx.state, ctx.batch, ctx.training, ctx.seed = state, B, training, seed
         return tokens
 
     @staticmethod
     def backward(ctx, d_tokens):
         st, B = ctx.state, ctx.batch
         d_tokens = d_tokens.float().contiguous()
-        cfg = st.config()
+        cfg = st.config(training=ctx.training, seed=ctx.seed)
         saved, _, ws, _ = st.buffers(B)
         st.grad.zero_()
         check(lib().vitk_backward_tokens(C.byref(cfg), C.byref(st.W), C.byref(st.T), C.byref(st.G),

@@ -30,9 +30,7 @@ int check_train_config(const VitkConfig* cfg, int batch, TDims* d) {
   VITK_REQUIRE(cfg->embed_dim % 8 == 0 && cfg->mlp_dim % 8 == 0 && cfg->num_layers > 0,
                "bad layer sizes");
   VITK_REQUIRE(cfg->precision == 0, "training runs in the bf16 mode only");
-  VITK_REQUIRE(cfg->dropout_p == 0.f,
-               "dropout_p = %g: the fused training path implements the p = 0 semantics only",
-               cfg->dropout_p);
+  VITK_REQUIRE(cfg->dropout_p >= 0.f && cfg->dropout_p < 1.f, "dropout_p must be in [0, 1)");
   d->B = batch;
   d->S = cfg->image_size;
   d->p = cfg->patch_size;
@@ -53,8 +51,17 @@ int check_train_config(const VitkConfig* cfg, int batch, TDims* d) {
   VITK_REQUIRE(d->hd == 64 && d->N <= 256,
                "training path needs head_dim 64 and <= 256 tokens (got %d, %d)", d->hd, d->N);
   VITK_REQUIRE(d->M < (1ll << 31) / 4, "batch too large");
+  VITK_REQUIRE(cfg->dropout_p == 0.f || (d->N <= 208 && d->M * d->Mlp < (1ll << 32)),
+               "dropout_p > 0 needs <= 208 tokens and batch * tokens * mlp_dim < 2^32");
   return VITK_OK;
 }
+
+// Dropout site parameters of one layer (all off when dropout_p == 0).
+struct DropSet {
+  float p;
+  uint32_t seed;
+  DropParams at(int site, int layer) const { return make_drop_params(p, seed, site, layer); }
+};
 
 // Activations kept from the forward pass for one encoder block.
 struct SavedBlock {
@@ -158,8 +165,9 @@ TrainWs carve_ws(const TDims& d, void* base) {
 
 int linear_fwd(const void* A, int lda, const void* W, int M, int N, int K, GemmEpi epi,
                const float* bias, const float* resid, void* out, void* out2, int ldo,
-               cudaStream_t stream) {
+               cudaStream_t stream, const DropParams& drop = DropParams()) {
   GemmProblem p;
+  p.e.drop = drop;
   p.A = A;
   p.lda = lda;
   p.B = W;
@@ -179,8 +187,10 @@ int linear_fwd(const void* A, int lda, const void* W, int M, int N, int K, GemmE
 
 // dX[M, in] = dY[M, out] * W[out, in]  with W^T [in, out] as the K-major B operand.
 int linear_dgrad(const void* dY, int out_f, const void* Wt, int M, int in_f, GemmEpi epi,
-                 const void* aux, void* dX, cudaStream_t stream) {
+                 const void* aux, void* dX, cudaStream_t stream,
+                 const DropParams& drop = DropParams()) {
   GemmProblem p;
+  p.e.drop = drop;
   p.A = dY;
   p.lda = out_f;
   p.B = Wt;
@@ -249,22 +259,26 @@ int forward_train(const VitkConfig* cfg, const VitkWeights* w, const float* imag
     p.e.group_offset = d.prefix;
     VITK_TRY(gemm_bf16_tn(p, stream));
   }
+  const DropSet drop{cfg->dropout_p, static_cast<uint32_t>(cfg->seed)};
+  if (drop.p > 0.f)   // nn.Dropout on tokens + position embedding (train.py:681)
+    VITK_TRY(dropout_f32_inplace(ws.x, d.M * D, drop.at(DROP_EMBED, 0), stream));
   for (int l = 0; l < d.L; ++l) {
     const VitkBlockWeights& bw = w->blocks[l];
     const SavedBlock sb = carve_block(d, sv.blocks + l * sv.block_bytes, nullptr);
+    const DropParams drop_a = drop.at(DROP_ATTN, l);
     VITK_TRY(layernorm_fwd(ws.x, D, bw.ln1_w, bw.ln1_b, sb.xn1, 0, D, sb.mean1, sb.rstd1, M, D,
                            cfg->ln_eps, stream, sb.x1));
     VITK_TRY(linear_fwd(sb.xn1, D, bw.qkv_w, M, 3 * D, D, EPI_BF16, bw.qkv_b, nullptr, sb.qkv,
                         nullptr, 3 * D, stream));
-    VITK_TRY(attention_fwd(sb.qkv, sb.ctx, sb.lse, d.B, d.N, d.H, d.hd, stream));
+    VITK_TRY(attention_fwd(sb.qkv, sb.ctx, sb.lse, d.B, d.N, d.H, d.hd, stream, &drop_a));
     VITK_TRY(linear_fwd(sb.ctx, D, bw.proj_w, M, D, D, EPI_RESID_F32, bw.proj_b, ws.x, ws.x,
-                        nullptr, D, stream));
+                        nullptr, D, stream, drop.at(DROP_PROJ, l)));
     VITK_TRY(layernorm_fwd(ws.x, D, bw.ln2_w, bw.ln2_b, sb.xn2, 0, D, sb.mean2, sb.rstd2, M, D,
                            cfg->ln_eps, stream, sb.x2));
     VITK_TRY(linear_fwd(sb.xn2, D, bw.fc1_w, M, d.Mlp, D, EPI_GELU_TANH_BF16, bw.fc1_b, nullptr, sb.hact,
-                        sb.hpre, d.Mlp, stream));
+                        sb.hpre, d.Mlp, stream, drop.at(DROP_GELU, l)));
     VITK_TRY(linear_fwd(sb.hact, d.Mlp, bw.fc2_w, M, D, d.Mlp, EPI_RESID_F32, bw.fc2_b, ws.x, ws.x,
-                        nullptr, D, stream));
+                        nullptr, D, stream, drop.at(DROP_FC2, l)));
   }
   if (tokens_out)
     VITK_TRY(layernorm_fwd(ws.x, D, w->ln_f_w, w->ln_f_b, tokens_out, 1, D, sv.mean_f, sv.rstd_f, M,
@@ -274,10 +288,11 @@ int forward_train(const VitkConfig* cfg, const VitkWeights* w, const float* imag
 
 // Backward through the blocks and the patch embedding. On entry ws.dx (f32) / ws.dxb (bf16) hold
 // the gradient w.r.t. the residual stream after the last block.
-int backward_blocks(const VitkWeights* w, const VitkWeightsT* wt, const VitkGrads* g, const TDims& d,
-                    const Saved& sv, const TrainWs& ws, cudaStream_t stream,
-                    const vitk_event_t* bucket_events = nullptr) {
+int backward_blocks(const VitkConfig* cfg, const VitkWeights* w, const VitkWeightsT* wt,
+                    const VitkGrads* g, const TDims& d, const Saved& sv, const TrainWs& ws,
+                    cudaStream_t stream, const vitk_event_t* bucket_events = nullptr) {
   const int M = static_cast<int>(d.M), D = d.D, Mlp = d.Mlp;
+  const DropSet drop{cfg->dropout_p, static_cast<uint32_t>(cfg->seed)};
   auto bucket_done = [&](int k) -> int {
     if (bucket_events != nullptr && bucket_events[k] != nullptr)
       VITK_CHECK_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(bucket_events[k]), stream));
@@ -289,17 +304,24 @@ int backward_blocks(const VitkWeights* w, const VitkWeightsT* wt, const VitkGrad
     const VitkBlockWeightsT& bt = wt->blocks[l];
     const VitkBlockGrads& bg = g->blocks[l];
     const SavedBlock sb = carve_block(d, sv.blocks + l * sv.block_bytes, nullptr);
-    // ---- MLP branch: x_out = x2 + fc2(gelu(fc1(LN2(x2))))          (train.py:590-591)
-    VITK_TRY(linear_dgrad(ws.dxb, D, bt.fc2_wt, M, Mlp, EPI_DGELU_BF16, sb.hpre, ws.dh, stream));
+    // ---- MLP branch: x_out = x2 + drop(fc2(drop(gelu(fc1(LN2(x2))))))   (train.py:567-573,590-591)
+    if (drop.p > 0.f)   // gradient entering the dropped linear2 output
+      VITK_TRY(dropout_cast_bf16(ws.dx, ws.dxb, d.M * D, drop.at(DROP_FC2, l), stream));
+    VITK_TRY(linear_dgrad(ws.dxb, D, bt.fc2_wt, M, Mlp, EPI_DGELU_BF16, sb.hpre, ws.dh, stream,
+                          drop.at(DROP_GELU, l)));
     VITK_TRY(linear_wgrad(ws.dxb, D, sb.hact, Mlp, M, bg.fc2_w, bg.fc2_b, stream));
     VITK_TRY(linear_dgrad(ws.dh, Mlp, bt.fc1_wt, M, D, EPI_BF16, nullptr, ws.dxn, stream));
     VITK_TRY(linear_wgrad(ws.dh, Mlp, sb.xn2, D, M, bg.fc1_w, bg.fc1_b, stream));
     VITK_TRY(layernorm_bwd(ws.dxn, 0, D, sb.x2, D, sb.mean2, sb.rstd2, bw.ln2_w, ws.dx, D, 1, ws.dxb,
                            D, bg.ln2_w, bg.ln2_b, M, D, stream));
-    // ---- attention branch: x2 = x1 + proj(attn(qkv(LN1(x1))))      (train.py:586-587)
+    // ---- attention branch: x2 = x1 + drop(proj(attn(qkv(LN1(x1)))))      (train.py:552-553,586-587)
+    if (drop.p > 0.f)
+      VITK_TRY(dropout_cast_bf16(ws.dx, ws.dxb, d.M * D, drop.at(DROP_PROJ, l), stream));
     VITK_TRY(linear_dgrad(ws.dxb, D, bt.proj_wt, M, D, EPI_BF16, nullptr, ws.dctx, stream));
     VITK_TRY(linear_wgrad(ws.dxb, D, sb.ctx, D, M, bg.proj_w, bg.proj_b, stream));
-    VITK_TRY(attention_bwd(sb.qkv, sb.ctx, ws.dctx, sb.lse, ws.dqkv, d.B, d.N, d.H, d.hd, stream));
+    const DropParams drop_a = drop.at(DROP_ATTN, l);
+    VITK_TRY(attention_bwd(sb.qkv, sb.ctx, ws.dctx, sb.lse, ws.dqkv, d.B, d.N, d.H, d.hd, stream,
+                           &drop_a));
     VITK_TRY(linear_dgrad(ws.dqkv, 3 * D, bt.qkv_wt, M, D, EPI_BF16, nullptr, ws.dxn, stream));
     VITK_TRY(linear_wgrad(ws.dqkv, 3 * D, sb.xn1, D, M, bg.qkv_w, bg.qkv_b, stream));
     VITK_TRY(layernorm_bwd(ws.dxn, 0, D, sb.x1, D, sb.mean1, sb.rstd1, bw.ln1_w, ws.dx, D, 1, ws.dxb,
@@ -307,6 +329,8 @@ int backward_blocks(const VitkWeights* w, const VitkWeightsT* wt, const VitkGrad
     VITK_TRY(bucket_done(d.L - l));
   }
   // ---- token assembly + patch embedding                             (evaluation.py:142-149)
+  if (drop.p > 0.f)
+    VITK_TRY(dropout_f32_inplace(ws.dx, d.M * D, drop.at(DROP_EMBED, 0), stream));
   VITK_TRY(token_grads(ws.dx, d.B, d.N, D, d.prefix, g->pos_embed, g->cls_token, g->dist_token,
                        ws.dxp, stream));
   VITK_TRY(linear_wgrad(ws.dxp, D, sv.patches, d.Kp, static_cast<int>(d.Mp), g->patch_w, g->patch_b,
@@ -330,6 +354,13 @@ int check_train_ptrs(const VitkWeights* w, const VitkWeightsT* wt, const VitkGra
 using namespace vitk;
 
 extern "C" {
+
+int vitk_dropout_keep_mask(float p, unsigned int seed, int site, int layer, long long n,
+                           unsigned char* out, vitk_stream_t stream) {
+  VITK_REQUIRE(site >= 0 && site <= 4 && layer >= 0, "bad dropout site / layer");
+  return dropout_keep_mask(out, n, make_drop_params(p, seed, site, layer),
+                           static_cast<cudaStream_t>(stream));
+}
 
 int vitk_train_workspace_bytes(const VitkConfig* cfg, int batch, size_t* saved_bytes,
                                size_t* workspace_bytes) {
@@ -391,7 +422,7 @@ int vitk_classifier_loss_backward_ev(const VitkConfig* cfg, const VitkWeights* w
                         w->head_b, labels, loss_scale, cfg->ln_eps, d.B, D, d.ncls, logits_out,
                         loss_out, ws.feat, ws.dlogits, ws.dx, ws.dxb, g->ln_f_w, g->ln_f_b,
                         g->head_w, g->head_b, stream));
-  return backward_blocks(w, wt, g, d, sv, ws, stream, bucket_events);
+  return backward_blocks(cfg, w, wt, g, d, sv, ws, stream, bucket_events);
 }
 
 int vitk_backward_tokens(const VitkConfig* cfg, const VitkWeights* w, const VitkWeightsT* wt,
@@ -408,7 +439,7 @@ int vitk_backward_tokens(const VitkConfig* cfg, const VitkWeights* w, const Vitk
   // final LayerNorm backward over every token (evaluation.py:156); ws.x still holds its input
   VITK_TRY(layernorm_bwd(d_tokens, 1, D, ws.x, D, sv.mean_f, sv.rstd_f, w->ln_f_w, ws.dx, D, 0,
                          ws.dxb, D, g->ln_f_w, g->ln_f_b, M, D, stream));
-  return backward_blocks(w, wt, g, d, sv, ws, stream);
+  return backward_blocks(cfg, w, wt, g, d, sv, ws, stream);
 }
 
 int vitk_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,

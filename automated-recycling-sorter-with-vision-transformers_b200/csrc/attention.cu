@@ -253,8 +253,14 @@ void attention_force_impl(int impl) { g_attn_impl = impl; }
 int attention_impl() { return g_attn_impl; }
 
 int attention_fwd(const void* qkv, void* ctx, float* lse, int B, int N, int H, int hd,
-                  cudaStream_t stream) {
+                  cudaStream_t stream, const DropParams* drop) {
   VITK_REQUIRE(qkv && ctx, "attention: null operand");
+  if (drop != nullptr && drop->thresh != 0u) {
+    VITK_REQUIRE(hd == 64 && N <= 208 && device_cc() >= 100,
+                 "attention dropout is implemented by the pipelined tcgen05 kernel only "
+                 "(head_dim 64, <= 208 tokens)");
+    return attention_fwd_tc2(qkv, ctx, lse, B, N, H, hd, stream, drop);
+  }
   if (g_attn_impl == 2 || g_attn_impl == 3 ||
       (g_attn_impl == 0 && hd == 64 && N <= 256 && device_cc() >= 100)) {
     if (g_attn_impl != 3 && hd == 64 && N <= 208)

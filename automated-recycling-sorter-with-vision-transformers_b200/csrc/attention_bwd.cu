@@ -263,10 +263,12 @@ attn_bwd_hd64_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16*
 int attention_impl();  // attention.cu: 0 auto, 1 mma.sync kernels, 2 tcgen05 kernels
 
 int attention_bwd(const void* qkv, const void* ctx, const void* dctx, const float* lse, void* dqkv,
-                  int B, int N, int H, int hd, cudaStream_t stream) {
+                  int B, int N, int H, int hd, cudaStream_t stream, const DropParams* drop) {
   VITK_REQUIRE(qkv && ctx && dctx && lse && dqkv, "attention_bwd: null operand");
-  if (attention_impl() != 1 && hd == 64 && N <= 256 && device_cc() >= 100)
-    return attention_bwd_tc(qkv, ctx, dctx, lse, dqkv, B, N, H, hd, stream);
+  const bool dropping = drop != nullptr && drop->thresh != 0u;
+  if ((attention_impl() != 1 || dropping) && hd == 64 && N <= 256 && device_cc() >= 100)
+    return attention_bwd_tc(qkv, ctx, dctx, lse, dqkv, B, N, H, hd, stream, drop);
+  VITK_REQUIRE(!dropping, "attention_bwd: dropout is implemented by the tcgen05 kernel only");
   VITK_REQUIRE(B > 0 && H > 0 && N > 0, "attention_bwd: bad shape");
   VITK_REQUIRE(hd == 64 && N <= 256, "attention_bwd: needs head_dim 64 and N <= 256 (got %d, %d)",
                hd, N);

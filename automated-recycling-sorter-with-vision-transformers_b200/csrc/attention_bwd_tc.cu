@@ -20,6 +20,7 @@
 #include <mutex>
 
 #include "common.h"
+#include "dropout.cuh"
 #include "ptx.cuh"
 #include "train_ops.cuh"
 
@@ -40,6 +41,7 @@ struct BwdParams {
   const __nv_bfloat16* ctx;
   const __nv_bfloat16* dctx;
   const float* lse;
+  DropParams drop;  // attention-probability dropout of the forward (same index space / key)
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -271,6 +273,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv,   // box {64, Nk,
       for (int kt = 0; kt < n_kt; ++kt) {
         const int key = kt * 128 + row_in_tile;
         const bool key_ok = key < N;
+        const uint32_t drop_item_rows = static_cast<uint32_t>(item) * static_cast<uint32_t>(N);
         for (int qt = 0; qt < n_kt; ++qt, ++blk) {
           const int nq = rows_in_tile(qt);
           mbar_wait(bar(2), blk & 1);
@@ -307,8 +310,25 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv,   // box {64, Nk,
               if (key_ok) {
                 p0 = ex2_approx(fmaf(__uint_as_float(s[2 * j]), c, -sLse[q0 + 2 * j]));
                 p1 = ex2_approx(fmaf(__uint_as_float(s[2 * j + 1]), c, -sLse[q0 + 2 * j + 1]));
-                d0 = p0 * (__uint_as_float(dp[2 * j]) - sD[q0 + 2 * j]) * p.scale;
-                d1 = p1 * (__uint_as_float(dp[2 * j + 1]) - sD[q0 + 2 * j + 1]) * p.scale;
+                float g0 = __uint_as_float(dp[2 * j]), g1 = __uint_as_float(dp[2 * j + 1]);
+                float pd0 = p0, pd1 = p1;
+                if (p.drop.thresh != 0u) {
+                  // one hash per element here: the pairs run along the keys, the thread owns one key
+                  const uint32_t half_nk = static_cast<uint32_t>(Nk >> 1);
+                  const uint32_t kp = static_cast<uint32_t>(key >> 1);
+                  const uint32_t b0 = drop_bits((drop_item_rows + q0 + 2 * j) * half_nk + kp, p.drop.key);
+                  const uint32_t b1 = drop_bits((drop_item_rows + q0 + 2 * j + 1) * half_nk + kp, p.drop.key);
+                  const bool k0 = (key & 1) ? drop_keep_hi(b0, p.drop.thresh) : drop_keep_lo(b0, p.drop.thresh);
+                  const bool k1 = (key & 1) ? drop_keep_hi(b1, p.drop.thresh) : drop_keep_lo(b1, p.drop.thresh);
+                  pd0 = k0 ? p0 * p.drop.scale : 0.f;
+                  pd1 = k1 ? p1 * p.drop.scale : 0.f;
+                  g0 = k0 ? g0 * p.drop.scale : 0.f;
+                  g1 = k1 ? g1 * p.drop.scale : 0.f;
+                }
+                d0 = p0 * (g0 - sD[q0 + 2 * j]) * p.scale;
+                d1 = p1 * (g1 - sD[q0 + 2 * j + 1]) * p.scale;
+                p0 = pd0;   // the dV product uses the dropped probabilities
+                p1 = pd1;
               }
               pp[j] = pack_bf16x2(p0, p1);
               ds[j] = pack_bf16x2(d0, d1);
@@ -383,7 +403,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv,   // box {64, Nk,
 }  // namespace
 
 int attention_bwd_tc(const void* qkv, const void* ctx, const void* dctx, const float* lse,
-                     void* dqkv, int B, int N, int H, int hd, cudaStream_t stream) {
+                     void* dqkv, int B, int N, int H, int hd, cudaStream_t stream,
+                     const DropParams* drop) {
   VITK_REQUIRE(qkv && ctx && dctx && lse && dqkv, "attention_bwd: null operand");
   VITK_REQUIRE(hd == 64 && N >= 1 && N <= 256, "attention_bwd(tc): needs head_dim 64, N <= 256");
   const int Nk = (N + 15) & ~15;
@@ -414,6 +435,7 @@ int attention_bwd_tc(const void* qkv, const void* ctx, const void* dctx, const f
   prm.ctx = static_cast<const __nv_bfloat16*>(ctx);
   prm.dctx = static_cast<const __nv_bfloat16*>(dctx);
   prm.lse = lse;
+  if (drop != nullptr) prm.drop = *drop;
   int grid = sm_count();
   if (B * H < grid) grid = B * H;
   ProfileScope prof(PROF_ATTN, 10.0 * B * H * static_cast<double>(N) * N * hd, stream);

@@ -27,6 +27,7 @@
 #include <mutex>
 
 #include "common.h"
+#include "dropout.cuh"
 #include "ptx.cuh"
 #include "rowops.cuh"
 
@@ -43,6 +44,7 @@ constexpr uint32_t kOColumn = 448;
 struct Tc2Params {
   int B, N, H, Nk, q_tiles;
   int descending;  // walk the (image, head) items from the last to the first
+  DropParams drop; // attention-probability dropout (train.py:545); element = ((b H + h) N + i) Nk + j
   float scale;
   float* lse;
 };
@@ -73,9 +75,12 @@ __device__ __forceinline__ void chunk_max(const uint32_t (&v)[COLS], int k0, int
 // Second sweep, one chunk of COLS keys of one row, in place in the registers the TMEM load filled:
 // p = 2^(s c - m c), row sum, P -> TMEM as bf16 pairs at column pcol.  MASKED is only instantiated
 // for the last chunk of a row (keys >= N are TMA zero fill and must not count).
-template <int COLS, bool MASKED>
+// DROP: the probabilities written for the PV product are dropped / rescaled (the row sum keeps the
+// undropped values: dropout follows the softmax normalisation); row_pairs = pair index of key 0.
+template <int COLS, bool MASKED, bool DROP>
 __device__ __forceinline__ void exp_chunk(uint32_t (&v)[COLS], int k0, int N, uint64_t cc,
-                                          uint64_t nmc, uint32_t pcol, uint64_t& la, uint64_t& lb) {
+                                          uint64_t nmc, uint32_t pcol, uint64_t& la, uint64_t& lb,
+                                          const DropParams& drop, uint32_t row_pairs) {
   const int valid = N - k0;  // only read when MASKED
   uint32_t pk[COLS / 2];
 #pragma unroll
@@ -90,6 +95,11 @@ __device__ __forceinline__ void exp_chunk(uint32_t (&v)[COLS], int k0, int N, ui
     }
     const uint64_t e = pack2(__float_as_uint(e0), __float_as_uint(e1));
     if (j & 1) lb = fadd2(lb, e); else la = fadd2(la, e);
+    if constexpr (DROP) {
+      const uint32_t bits = drop_bits(row_pairs + static_cast<uint32_t>(k0 / 2 + j), drop.key);
+      e0 = drop_keep_lo(bits, drop.thresh) ? e0 * drop.scale : 0.f;
+      e1 = drop_keep_hi(bits, drop.thresh) ? e1 * drop.scale : 0.f;
+    }
     pk[j] = pack_bf16x2(e0, e1);
   }
   if constexpr (COLS == 32) tmem_st_32x32b_x16(pcol, pk);
@@ -99,9 +109,15 @@ __device__ __forceinline__ void exp_chunk(uint32_t (&v)[COLS], int k0, int N, ui
 template <int COLS>
 __device__ __forceinline__ void exp_chunk_any(uint32_t (&v)[COLS], int k0, int N, uint64_t cc,
                                               uint64_t nmc, uint32_t pcol, uint64_t& la,
-                                              uint64_t& lb) {
-  if (k0 + COLS <= N) exp_chunk<COLS, false>(v, k0, N, cc, nmc, pcol, la, lb);
-  else exp_chunk<COLS, true>(v, k0, N, cc, nmc, pcol, la, lb);
+                                              uint64_t& lb, const DropParams& drop,
+                                              uint32_t row_pairs) {
+  if (drop.thresh == 0u) {
+    if (k0 + COLS <= N) exp_chunk<COLS, false, false>(v, k0, N, cc, nmc, pcol, la, lb, drop, 0u);
+    else exp_chunk<COLS, true, false>(v, k0, N, cc, nmc, pcol, la, lb, drop, 0u);
+  } else {
+    if (k0 + COLS <= N) exp_chunk<COLS, false, true>(v, k0, N, cc, nmc, pcol, la, lb, drop, row_pairs);
+    else exp_chunk<COLS, true, true>(v, k0, N, cc, nmc, pcol, la, lb, drop, row_pairs);
+  }
 }
 
 // Debug aid (build with -DVITK_ATTN_TRACE): CTA 0 records SM-clock timestamps of its first 8 items
@@ -299,8 +315,13 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_q,
     int it = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
       const int par = it & 1;
+      const int item_id = p.descending ? num_items - 1 - item : item;
       for (int t = 0; t < q_tiles; ++t) {
         const bool warp_rows = t * 128 + q * 32 < N;
+        // pair index of key 0 of this thread's row in the dropout index space
+        const uint32_t row_pairs =
+            (static_cast<uint32_t>(item_id) * static_cast<uint32_t>(N) +
+             static_cast<uint32_t>(t * 128 + q * 32 + lane)) * static_cast<uint32_t>(Nk >> 1);
         const uint32_t region =
             tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(t) * kRegion;
         const uint32_t pbase = region + kbeg;  // P of this quarter overwrites its own S columns
@@ -334,12 +355,14 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_q,
           for (int ch = 0; ch < n32; ++ch) {
             tmem_ld_32x32b_x32(region + kbeg + ch * 32, v32);
             tmem_ld_wait();
-            exp_chunk_any<32>(v32, kbeg + ch * 32, N, cc, nmc, pbase + ch * 16, la, lb);
+            exp_chunk_any<32>(v32, kbeg + ch * 32, N, cc, nmc, pbase + ch * 16, la, lb, p.drop,
+                              row_pairs);
           }
           if (tail16) {
             tmem_ld_32x32b_x16(region + kbeg + n32 * 32, v16);
             tmem_ld_wait();
-            exp_chunk_any<16>(v16, kbeg + n32 * 32, N, cc, nmc, pbase + n32 * 16, la, lb);
+            exp_chunk_any<16>(v16, kbeg + n32 * 32, N, cc, nmc, pbase + n32 * 16, la, lb, p.drop,
+                              row_pairs);
           }
           float l0, l1, l2, l3;
           unpack2(la, l0, l1);
@@ -444,7 +467,7 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_q,
 }  // namespace
 
 int attention_fwd_tc2(const void* qkv, void* ctx, float* lse, int B, int N, int H, int hd,
-                      cudaStream_t stream) {
+                      cudaStream_t stream, const DropParams* drop) {
   VITK_REQUIRE(qkv && ctx, "attention: null operand");
   VITK_REQUIRE(hd == 64 && N >= 1 && N <= 208, "attention(tc2): needs head_dim 64 and N <= 208");
   VITK_REQUIRE(B > 0 && H > 0, "attention: bad shape B=%d H=%d", B, H);
@@ -479,6 +502,9 @@ int attention_fwd_tc2(const void* qkv, void* ctx, float* lse, int B, int N, int 
   prm.scale = 1.0f / sqrtf(static_cast<float>(hd));
   prm.lse = lse;
   prm.descending = sweep_next();
+  if (drop != nullptr) prm.drop = *drop;
+  VITK_REQUIRE(prm.drop.thresh == 0u || static_cast<long long>(B) * H * N * Nk < (1ll << 32),
+               "attention: dropout index space exceeds 32 bits");
   int grid = sm_count();
   if (B * H < grid) grid = B * H;
   ProfileScope prof(PROF_ATTN, 4.0 * B * H * static_cast<double>(N) * N * hd, stream);

@@ -203,6 +203,11 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int m, i
     }
   }
 
+  const uint32_t drop_idx0 = static_cast<uint32_t>(m) * static_cast<uint32_t>(N) +
+                             static_cast<uint32_t>(n0);
+  if constexpr (EPI == EPI_RESID_F32 || EPI == EPI_DGELU_BF16) {
+    if (e.drop.thresh != 0u) drop_apply_run<32>(x, drop_idx0, e.drop);
+  }
   if constexpr (EPI == EPI_BF16 || is_gelu_epi<EPI>() || EPI == EPI_DGELU_BF16) {
     const size_t off = static_cast<size_t>(m) * e.ldo + n0;
     __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(e.out) + off;
@@ -226,6 +231,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int m, i
       }
 #pragma unroll
       for (int j = 0; j < 32; ++j) x[j] = gelu_for<EPI>(x[j]);
+      if (e.drop.thresh != 0u) drop_apply_run<32>(x, drop_idx0, e.drop);
     }
     if constexpr (EPI == EPI_DGELU_BF16) {
       const __nv_bfloat16* aux = reinterpret_cast<const __nv_bfloat16*>(e.aux) + off;
@@ -610,6 +616,11 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
             if (row0 < M && n0 < N) {
               float x[32];
               acc_plus_bias<EPI>(v[c & 1], n0, N, e, x);
+              if constexpr (EPI == EPI_RESID_F32) {
+                if (e.drop.thresh != 0u)
+                  drop_apply_run<32>(x, static_cast<uint32_t>(row0 + lane) * static_cast<uint32_t>(N) +
+                                            static_cast<uint32_t>(n0), e.drop);
+              }
               uint32_t pk[32];
 #pragma unroll
               for (int j = 0; j < 32; ++j) pk[j] = __float_as_uint(x[j]);
@@ -629,6 +640,15 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
               acc_plus_bias<EPI>(v0, n0, N, e, x0);
               acc_plus_bias<EPI>(v1, n0 + 32, N, e, x1);
               uint32_t pk[32];
+              [[maybe_unused]] const uint32_t drop_idx0 =
+                  static_cast<uint32_t>(row0 + lane) * static_cast<uint32_t>(N) +
+                  static_cast<uint32_t>(n0);
+              if constexpr (EPI == EPI_DGELU_BF16) {
+                if (e.drop.thresh != 0u) {
+                  drop_apply_run<32>(x0, drop_idx0, e.drop);
+                  drop_apply_run<32>(x1, drop_idx0 + 32u, e.drop);
+                }
+              }
               if constexpr (kAuxTma) {
                 // this lane's row of the pre-activation slab (64 bf16), then refill the slab with
                 // the next group's tile while the math below runs
@@ -677,6 +697,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     gelu_fast_pair(x0[2 * j], x0[2 * j + 1]);
                     gelu_fast_pair(x1[2 * j], x1[2 * j + 1]);
                   }
+                }
+                if (e.drop.thresh != 0u) {
+                  drop_apply_run<32>(x0, drop_idx0, e.drop);
+                  drop_apply_run<32>(x1, drop_idx0 + 32u, e.drop);
                 }
               }
 #pragma unroll
@@ -880,6 +904,11 @@ int gemm_bf16_tn(const GemmProblem& p, cudaStream_t stream) {
                "gemm: split_k > 1 accumulates (beta must be 1, no bias)");
   VITK_REQUIRE(p.N % 8 == 0 && p.e.ldo % 8 == 0, "gemm: N and ldo must be multiples of 8");
   VITK_REQUIRE(device_cc() >= 100, "gemm: requires an sm_100 device (found sm_%d)", device_cc());
+  VITK_REQUIRE(p.e.drop.thresh == 0u ||
+                   ((p.epi == EPI_RESID_F32 || p.epi == EPI_DGELU_BF16 || p.epi == EPI_GELU_BF16 ||
+                     p.epi == EPI_GELU_TANH_BF16) && p.e.rows_per_group == 0 && p.N % 2 == 0 &&
+                    static_cast<long long>(p.M) * p.N < (1ll << 32)),
+               "gemm: dropout needs a residual / GELU / GELU' epilogue without row remap");
   switch (p.epi) {
     case EPI_BF16: return dispatch<EPI_BF16>(p, stream);
     case EPI_GELU_BF16: return dispatch<EPI_GELU_BF16>(p, stream);

@@ -3,6 +3,8 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "dropout.cuh"
+
 namespace vitk {
 
 // Epilogue selector (compile-time variants of one kernel).
@@ -32,6 +34,11 @@ struct GemmEpilogue {
   int group_offset = 0;
   float alpha = 1.f;
   float beta = 0.f;
+  // nn.Dropout on the epilogue's result, element index = row * N + column (dropout.cuh):
+  //   EPI_RESID_F32: out += dropout(acc + bias)          (projection / linear2 output dropout)
+  //   EPI_GELU_*   : out = dropout(gelu(acc + bias))     (out2 keeps the undropped pre-activation)
+  //   EPI_DGELU    : out = dropout_mask(acc) * gelu'(aux) (the backward of the above)
+  DropParams drop;
 };
 
 struct GemmProblem {

@@ -2,6 +2,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include "dropout.cuh"
+
 namespace vitk {
 
 // y[r,:] = LN(x[r,:]) * gamma + beta ; x fp32 rows at `in_stride` elements, y bf16 or fp32 rows at
@@ -26,15 +28,16 @@ int cast_f32_to_bf16(const float* in, void* out, long long n, cudaStream_t strea
 
 // softmax(q k^T / sqrt(hd)) v for every (image, head); qkv bf16 [B*N, 3*D] packed as the reference
 // packs it (column = which*D + h*hd + d); ctx bf16 [B*N, D]; optional lse fp32 [B, H, N].
+// `drop` (training only): dropout on the attention probabilities (train.py:545), N <= 208.
 int attention_fwd(const void* qkv, void* ctx, float* lse, int B, int N, int H, int hd,
-                  cudaStream_t stream);
+                  cudaStream_t stream, const DropParams* drop = nullptr);
 
 // tcgen05 variant for N <= 256 (attention_tc.cu); attention_fwd dispatches to it automatically.
 int attention_fwd_tc(const void* qkv, void* ctx, float* lse, int B, int N, int H, int hd,
                      cudaStream_t stream);
 // Item-pipelined tcgen05 variant for N <= 208 (attention_tc2.cu); the default for the 224 px models.
 int attention_fwd_tc2(const void* qkv, void* ctx, float* lse, int B, int N, int H, int hd,
-                      cudaStream_t stream);
+                      cudaStream_t stream, const DropParams* drop = nullptr);
 void attention_force_impl(int impl);
 
 }  // namespace vitk

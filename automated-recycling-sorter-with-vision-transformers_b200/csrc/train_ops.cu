@@ -577,7 +577,54 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Stand-alone dropout passes (thread = one element pair = one hash).
+// ------------------------------------------------------------------------------------------------
+template <int MODE>  // 0: f32 in place, 1: f32 -> bf16, 2: keep mask bytes
+__global__ void __launch_bounds__(256)
+dropout_kernel(float* __restrict__ x, __nv_bfloat16* __restrict__ out_bf16,
+               unsigned char* __restrict__ out_mask, long long n_pairs, DropParams d) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n_pairs;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const uint32_t bits = drop_bits(static_cast<uint32_t>(i), d.key);
+    const bool k0 = d.thresh == 0u || drop_keep_lo(bits, d.thresh);
+    const bool k1 = d.thresh == 0u || drop_keep_hi(bits, d.thresh);
+    if constexpr (MODE == 2) {
+      out_mask[2 * i] = k0 ? 1 : 0;
+      out_mask[2 * i + 1] = k1 ? 1 : 0;
+    } else {
+      const float2 v = reinterpret_cast<const float2*>(x)[i];
+      const float a = k0 ? v.x * d.scale : 0.f, b = k1 ? v.y * d.scale : 0.f;
+      if constexpr (MODE == 0) reinterpret_cast<float2*>(x)[i] = make_float2(a, b);
+      else reinterpret_cast<uint32_t*>(out_bf16)[i] = pack_bf16x2(a, b);
+    }
+  }
+}
+
 }  // namespace
+
+int dropout_f32_inplace(float* x, long long n, const DropParams& d, cudaStream_t stream) {
+  VITK_REQUIRE(x && n > 0 && n % 2 == 0 && n < (1ll << 32), "dropout: bad argument");
+  ProfileScope prof(PROF_OTHER, static_cast<double>(n) * 8.0, stream);
+  dropout_kernel<0><<<grid_for(n / 2, 256, 16), 256, 0, stream>>>(x, nullptr, nullptr, n / 2, d);
+  VITK_CHECK_LAUNCH("dropout_kernel");
+  return VITK_OK;
+}
+int dropout_cast_bf16(const float* x, void* out_bf16, long long n, const DropParams& d,
+                      cudaStream_t stream) {
+  VITK_REQUIRE(x && out_bf16 && n > 0 && n % 2 == 0 && n < (1ll << 32), "dropout: bad argument");
+  ProfileScope prof(PROF_OTHER, static_cast<double>(n) * 6.0, stream);
+  dropout_kernel<1><<<grid_for(n / 2, 256, 16), 256, 0, stream>>>(
+      const_cast<float*>(x), static_cast<__nv_bfloat16*>(out_bf16), nullptr, n / 2, d);
+  VITK_CHECK_LAUNCH("dropout_kernel");
+  return VITK_OK;
+}
+int dropout_keep_mask(unsigned char* out, long long n, const DropParams& d, cudaStream_t stream) {
+  VITK_REQUIRE(out && n > 0 && n % 2 == 0 && n < (1ll << 32), "dropout: bad argument");
+  dropout_kernel<2><<<grid_for(n / 2, 256, 16), 256, 0, stream>>>(nullptr, nullptr, out, n / 2, d);
+  VITK_CHECK_LAUNCH("dropout_kernel");
+  return VITK_OK;
+}
 
 int layernorm_bwd(const void* dy, int dy_is_f32, long long dy_stride, const float* x,
                   long long x_stride, const float* mean, const float* rstd, const float* gamma,

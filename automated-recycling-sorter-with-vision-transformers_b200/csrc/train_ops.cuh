@@ -2,6 +2,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include "dropout.cuh"
+
 namespace vitk {
 
 // dx_io (+)= LN backward; optional bf16 copy; dgamma/dbeta accumulate (atomics).
@@ -26,6 +28,14 @@ int cls_loss_bwd(const float* x, long long row_stride, const float* gamma, const
 int token_grads(const float* dx, int B, int Ntok, int D, int prefix, float* dpos, float* dcls,
                 float* ddist, void* dxp_bf16, cudaStream_t stream);
 
+// nn.Dropout as stand-alone passes (dropout.cuh): x <- dropout(x) in place (the embedding dropout and
+// its backward), out_bf16 = bf16(dropout(x)) (the gradient entering a branch whose output was
+// dropped), and the keep mask itself (0/1 bytes) for the oracle tests.  n must be even.
+int dropout_f32_inplace(float* x, long long n, const DropParams& d, cudaStream_t stream);
+int dropout_cast_bf16(const float* x, void* out_bf16, long long n, const DropParams& d,
+                      cudaStream_t stream);
+int dropout_keep_mask(unsigned char* out, long long n, const DropParams& d, cudaStream_t stream);
+
 constexpr int kMaxTransposeJobs = 64;
 struct TransposeBatch {
   const void* src[kMaxTransposeJobs];
@@ -43,10 +53,12 @@ int adamw_flat(float* p, const float* g, float* m, float* v, void* shadow_bf16, 
 
 // dqkv = backward of softmax(q k^T / sqrt(hd)) v given d_ctx, using the saved log-sum-exp.
 int attention_bwd(const void* qkv, const void* ctx, const void* dctx, const float* lse, void* dqkv,
-                  int B, int N, int H, int hd, cudaStream_t stream);
+                  int B, int N, int H, int hd, cudaStream_t stream,
+                  const DropParams* drop = nullptr);
 
 // tcgen05 variant (attention_bwd_tc.cu); attention_bwd dispatches to it for N <= 256.
 int attention_bwd_tc(const void* qkv, const void* ctx, const void* dctx, const float* lse,
-                     void* dqkv, int B, int N, int H, int hd, cudaStream_t stream);
+                     void* dqkv, int B, int N, int H, int hd, cudaStream_t stream,
+                     const DropParams* drop = nullptr);
 
 }  // namespace vitk

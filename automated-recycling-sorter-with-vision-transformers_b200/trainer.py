@@ -131,7 +131,10 @@ class TrainState:
         self._t_rows = (C.c_int * n)(*[r for _, r, _, _ in self._t_jobs])
         self._t_cols = (C.c_int * n)(*[c for _, _, c, _ in self._t_jobs])
 
-    def config(self) -> VitkConfig:
+    def config(self, training: bool = False, seed: int = 0) -> VitkConfig:
+        """training=True turns the module's dropout probability on (nn.Dropout is the identity in
+        eval mode); `seed` selects the dropout masks and must be the same for the forward and the
+        backward of one step."""
         m = self.backbone
         pe, blk = m.patch_embedding, m.transformer_blocks[0]
         return VitkConfig(
@@ -140,7 +143,8 @@ class TrainState:
             num_layers=len(m.transformer_blocks), num_heads=blk.attention.num_heads,
             mlp_dim=blk.mlp.linear1.out_features, n_prefix_tokens=self.n_prefix,
             n_classes=self.head.out_features if self.head is not None else 0, precision=0,
-            ln_eps=m.layer_norm.eps, dropout_p=float(m.dropout.p), seed=0)
+            ln_eps=m.layer_norm.eps, dropout_p=float(m.dropout.p) if training else 0.0,
+            seed=int(seed) & 0x7FFFFFFF)
 
     # ------------------------------------------------------------------ shadows
     def refresh_transposes(self):
@@ -197,7 +201,8 @@ class FineTuner:
     """Fused fine-tune step: AdamW(lr=1e-4, weight_decay=1e-4) as train.py:1598-1602."""
 
     def __init__(self, model, lr=1e-4, weight_decay=1e-4, betas=(0.9, 0.999), eps=1e-8,
-                 process_group=None, overlap_allreduce: bool = True, reserve_sms: int = 0):
+                 process_group=None, overlap_allreduce: bool = True, reserve_sms: int = 0,
+                 seed: int = 0):
         """overlap_allreduce: start each gradient bucket's all-reduce on a side stream as soon as
         the backward has produced it (events recorded by vitk_classifier_loss_backward_ev), instead
         of reducing everything after the backward.  reserve_sms: SMs kept out of the persistent
@@ -205,6 +210,8 @@ class FineTuner:
         (pair with a communicator limited to as many CTAs: ProcessGroupNCCL.Options.config.max_ctas)."""
         self.model = model
         self.lr, self.wd, self.betas, self.eps = lr, weight_decay, betas, eps
+        self.seed = int(seed)   # dropout mask stream: step k uses seed + k (same on every rank's
+        #                         shard only if the ranks pass different seeds - they should)
         self.state = TrainState(model.backbone, model.head, model.backbone._n_prefix)
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
@@ -237,7 +244,8 @@ class FineTuner:
                                  "built (e.g. .to(), load into new tensors, or a second trainer)")
         if st.shadows_stale():
             st.refresh_shadows()
-        cfg = st.config()
+        # dropout follows the module's train()/eval() state, as nn.Dropout does in the reference
+        cfg = st.config(training=self.model.training, seed=self.seed + st.step_count)
         saved, saved_bytes, ws, ws_bytes = st.buffers(B)
         logits = torch.empty((B, cfg.n_classes), dtype=torch.float32, device=st.device)
         st.grad.zero_()

@@ -226,6 +226,17 @@ typedef struct VitkGrads {
 int vitk_train_workspace_bytes(const VitkConfig* cfg, int batch, size_t* saved_bytes,
                                size_t* workspace_bytes);
 
+/* Dropout (cfg->dropout_p > 0, training entry points only; reference train.py:528-530,545,553,
+ * 563-572,650,681).  Masks are a pure function of (cfg->seed, site, layer, element index) and are
+ * regenerated by the backward kernels, so forward and backward of one step must be given the same
+ * seed; change the seed every step.  Sites: 0 tokens+position embedding (index = flat [B*N, D]),
+ * 1 attention probabilities (index = ((b*H + h)*N + i)*Nk + j with Nk = N rounded up to 16),
+ * 2 projection output, 3 MLP hidden activation, 4 MLP output (index = row * width + column).
+ * vitk_dropout_keep_mask writes the 0/1 keep decisions of elements [0, n) of one site (n even) -
+ * what the parity tests inject into the oracle.  p is quantised to 1/65536. */
+int vitk_dropout_keep_mask(float p, unsigned int seed, int site, int layer, long long n,
+                           unsigned char* out, vitk_stream_t stream);
+
 /* Forward in training mode: same arithmetic as vitk_forward, every activation the backward needs
  * is written into `saved`; the residual stream stays in `workspace`. tokens_out (f32 [B,N,D],
  * optional) = backbone(images). */

@@ -73,8 +73,18 @@ def patch_embed(images: torch.Tensor, w: torch.Tensor, b: torch.Tensor, p: int) 
     return cols @ w.reshape(w.shape[0], -1).t() + b
 
 
-def attention(x: torch.Tensor, qkv_w, qkv_b, proj_w, proj_b, num_heads: int) -> torch.Tensor:
-    """MultiHeadSelfAttention.forward - train.py:532-555 (dropout = identity)."""
+def _drop(x: torch.Tensor, masks, site: str, layer: int) -> torch.Tensor:
+    """nn.Dropout in training mode with an explicit mask: masks[(site, layer)] holds 0 for a
+    dropped element and 1 / (1 - p) for a kept one (identity when masks is None / site absent)."""
+    if not masks or (site, layer) not in masks:
+        return x
+    return x * masks[(site, layer)].to(x.dtype)
+
+
+def attention(x: torch.Tensor, qkv_w, qkv_b, proj_w, proj_b, num_heads: int, masks=None,
+              layer: int = 0) -> torch.Tensor:
+    """MultiHeadSelfAttention.forward - train.py:532-555 (dropout = identity unless masks given:
+    attention_dropout on the probabilities :545, projection_dropout on the output :553)."""
     B, N, D = x.shape
     hd = D // num_heads
     qkv = x @ qkv_w.t() + qkv_b                                    # :536
@@ -82,25 +92,29 @@ def attention(x: torch.Tensor, qkv_w, qkv_b, proj_w, proj_b, num_heads: int) -> 
     q, k, v = qkv[0], qkv[1], qkv[2]                               # :540
     scores = (q @ k.transpose(-2, -1)) / (hd ** 0.5)               # :543 (divide AFTER the product)
     probs = torch.softmax(scores, dim=-1)                          # :544
+    probs = _drop(probs, masks, "attn", layer)                     # :545
     ctx = probs @ v                                                # :548
     ctx = ctx.transpose(1, 2).reshape(B, N, D)                     # :549
-    return ctx @ proj_w.t() + proj_b                               # :552
+    return _drop(ctx @ proj_w.t() + proj_b, masks, "proj", layer)  # :552-553
 
 
-def mlp(x: torch.Tensor, w1, b1, w2, b2) -> torch.Tensor:
-    """MLPBlock.forward - train.py:567-573."""
-    return gelu_erf(x @ w1.t() + b1) @ w2.t() + b2
+def mlp(x: torch.Tensor, w1, b1, w2, b2, masks=None, layer: int = 0) -> torch.Tensor:
+    """MLPBlock.forward - train.py:567-573 (dropout1 after the GELU :570, dropout2 at the end :572)."""
+    h = _drop(gelu_erf(x @ w1.t() + b1), masks, "gelu", layer)
+    return _drop(h @ w2.t() + b2, masks, "fc2", layer)
 
 
-def encoder_block(x: torch.Tensor, sd: dict, prefix: str, num_heads: int) -> torch.Tensor:
+def encoder_block(x: torch.Tensor, sd: dict, prefix: str, num_heads: int, masks=None,
+                  layer: int = 0) -> torch.Tensor:
     """TransformerBlock.forward - train.py:584-593 (pre-LN residual block)."""
     g = lambda k: sd[prefix + k]
     x = x + attention(layer_norm(x, g("layer_norm1.weight"), g("layer_norm1.bias")),
                       g("attention.qkv.weight"), g("attention.qkv.bias"),
-                      g("attention.projection.weight"), g("attention.projection.bias"), num_heads)
+                      g("attention.projection.weight"), g("attention.projection.bias"), num_heads,
+                      masks, layer)
     x = x + mlp(layer_norm(x, g("layer_norm2.weight"), g("layer_norm2.bias")),
                 g("mlp.linear1.weight"), g("mlp.linear1.bias"),
-                g("mlp.linear2.weight"), g("mlp.linear2.bias"))
+                g("mlp.linear2.weight"), g("mlp.linear2.bias"), masks, layer)
     return x
 
 
@@ -114,9 +128,10 @@ def infer_dims(sd: dict, prefix: str = "") -> dict:
 
 
 def backbone_forward(sd: dict, images: torch.Tensor, num_heads: int, prefix: str = "",
-                     dtype: torch.dtype = torch.float32) -> torch.Tensor:
+                     dtype: torch.dtype = torch.float32, masks=None) -> torch.Tensor:
     """VisionTransformer.forward (evaluation.py:138-157) / DataEfficientImageTransformer.forward
-    (train.py:666-688) in eval mode: returns all tokens after the final LayerNorm."""
+    (train.py:666-688): returns all tokens after the final LayerNorm.  Eval mode unless `masks`
+    (explicit dropout masks keyed by (site, layer), see _drop) is given."""
     sd = {k: v.to(dtype) for k, v in sd.items() if k.startswith(prefix)}
     dims = infer_dims(sd, prefix)
     g = lambda k: sd[prefix + k]
@@ -127,16 +142,17 @@ def backbone_forward(sd: dict, images: torch.Tensor, num_heads: int, prefix: str
     if dims["n_prefix"] == 2:
         toks.append(g("dist_token").expand(B, -1, -1))         # train.py:670-673
     x = torch.cat(toks + [x], dim=1) + g("position_embedding")  # evaluation.py:145-149
+    x = _drop(x, masks, "embed", 0)                              # evaluation.py:150 / train.py:681
     for i in range(dims["num_layers"]):                          # evaluation.py:153-154
-        x = encoder_block(x, sd, f"{prefix}transformer_blocks.{i}.", num_heads)
+        x = encoder_block(x, sd, f"{prefix}transformer_blocks.{i}.", num_heads, masks, i)
     return layer_norm(x, g("layer_norm.weight"), g("layer_norm.bias"))  # evaluation.py:156
 
 
 def classifier_forward(sd: dict, images: torch.Tensor, num_heads: int,
-                       dtype: torch.dtype = torch.float32):
+                       dtype: torch.dtype = torch.float32, masks=None):
     """RefClassifier of SURVEY.md 8c: Linear(D, C)(backbone(images)[:, 0]).
     sd uses the keys of ViTClassifier: 'backbone.*', 'head.weight', 'head.bias'."""
-    tokens = backbone_forward(sd, images, num_heads, prefix="backbone.", dtype=dtype)
+    tokens = backbone_forward(sd, images, num_heads, prefix="backbone.", dtype=dtype, masks=masks)
     logits = tokens[:, 0] @ sd["head.weight"].to(dtype).t() + sd["head.bias"].to(dtype)
     return tokens, logits
 
@@ -168,10 +184,11 @@ def adamw_step(params: dict, grads: dict, m: dict, v: dict, step: int, lr=1e-4, 
 
 
 def train_step(sd: dict, images: torch.Tensor, labels: torch.Tensor, num_heads: int,
-               dtype: torch.dtype = torch.float32, lr=1e-4, weight_decay=1e-4):
-    """One fine-tune step with dropout = 0: returns (loss, grads, new_params)."""
+               dtype: torch.dtype = torch.float32, lr=1e-4, weight_decay=1e-4, masks=None):
+    """One fine-tune step (dropout = 0, or the given explicit masks): returns (loss, grads,
+    new_params)."""
     params = {k: v.detach().to(dtype).clone().requires_grad_(True) for k, v in sd.items()}
-    _, logits = classifier_forward(params, images, num_heads, dtype=dtype)
+    _, logits = classifier_forward(params, images, num_heads, dtype=dtype, masks=masks)
     loss = cross_entropy(logits, labels)
     grads_list = torch.autograd.grad(loss, list(params.values()))
     grads = dict(zip(params.keys(), grads_list))

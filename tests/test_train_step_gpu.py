@@ -77,13 +77,87 @@ def test_second_step_uses_updated_weights(vitk):
     assert (logits.cpu().double() - ref).abs().max() < 2e-2
 
 
-def test_dropout_is_rejected_loudly(vitk):
-    kw = dict(image_size=32, patch_size=16, embed_dim=64, num_layers=1, num_heads=1, mlp_dim=64,
-              dropout=0.1)
-    model = vitk.ViTClassifier(num_classes=6, **kw).cuda()
-    tuner = vitk.FineTuner(model)
+def _library_masks(vitk, p, seed, B, N, D, H, Mlp, L):
+    """The keep masks the kernels regenerate from (seed, site, layer, index), as multipliers
+    (0 or 1 / (1 - p_quantised)) shaped for the oracle."""
+    import ctypes as C
+    thresh = int(p * 65536 + 0.5)
+    scale = 65536.0 / (65536 - thresh)
+    Nk = (N + 15) // 16 * 16
+    st = torch.cuda.current_stream().cuda_stream
+
+    def keep(site, layer, n):
+        out = torch.empty(n, dtype=torch.uint8, device="cuda")
+        vitk._lib.check(vitk._lib.lib().vitk_dropout_keep_mask(
+            C.c_float(p), seed, site, layer, n, out.data_ptr(), st))
+        return out.float() * scale
+
+    masks = {("embed", 0): keep(0, 0, B * N * D).view(B, N, D).cpu()}
+    for l in range(L):
+        masks[("attn", l)] = keep(1, l, B * H * N * Nk).view(B, H, N, Nk)[..., :N].cpu()
+        masks[("proj", l)] = keep(2, l, B * N * D).view(B, N, D).cpu()
+        masks[("gelu", l)] = keep(3, l, B * N * Mlp).view(B, N, Mlp).cpu()
+        masks[("fc2", l)] = keep(4, l, B * N * D).view(B, N, D).cpu()
+    return masks
+
+
+@pytest.mark.parametrize("p,deit", [(0.1, False), (0.25, True)])
+def test_train_step_with_dropout_matches_oracle_given_the_same_masks(vitk, p, deit):
+    """nn.Dropout at all five sites of train.py (embedding, attention probabilities, projection,
+    GELU, linear2): the kernels regenerate their masks from (seed, site, layer, index); injecting
+    the same masks into the oracle must reproduce loss, every gradient and the AdamW update."""
+    kw = dict(image_size=96, patch_size=16, embed_dim=128, num_layers=2, num_heads=2, mlp_dim=256,
+              dropout=p)
+    torch.manual_seed(33)
+    model = vitk.ViTClassifier(num_classes=6, deit=deit, **kw)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    B, N = 5, 36 + (2 if deit else 1)
+    x, y = O.synthetic_images(B, 96, seed=17), O.synthetic_labels(B, 6, seed=4)
+    masks = _library_masks(vitk, p, 77, B, N, 128, 2, 256, 2)
+    keep_rate = masks[("gelu", 0)].ne(0).float().mean().item()
+    assert abs(keep_rate - (1 - p)) < 0.02, keep_rate
+    loss, grads, new = O.train_step(sd, x, y, 2, dtype=torch.float64, masks=masks)
+    loss0, _, _ = O.train_step(sd, x, y, 2, dtype=torch.float64)
+    assert abs(float(loss) - float(loss0)) > 1e-3          # the masks really change the step
+    model = model.cuda().train()
+    tuner = vitk.FineTuner(model, lr=1e-4, weight_decay=1e-4, seed=77)
+    got_loss, _ = tuner.step(x.cuda(), y.cuda())
+    assert abs(got_loss.item() - float(loss)) < 2e-2, (got_loss.item(), float(loss))
+    got = dict(zip(tuner.state.names, [q.grad for q in tuner.state.params]))
+    for k, gr in grads.items():
+        a, b = got[k].detach().cpu().double().reshape(-1), gr.double().reshape(-1)
+        rel = (a - b).norm() / (b.norm() + 1e-12)
+        cos = torch.nn.functional.cosine_similarity(a, b, dim=0)
+        assert rel < 0.08 and cos > 0.995, (k, rel.item(), cos.item())
+
+
+def test_dropout_follows_train_eval_mode_and_the_seed(vitk):
+    kw = dict(image_size=32, patch_size=16, embed_dim=64, num_layers=2, num_heads=1, mlp_dim=128,
+              dropout=0.2)
+    x, y = O.synthetic_images(8, 32).cuda(), O.synthetic_labels(8).cuda()
+
+    def first_loss(mode_train, seed):
+        torch.manual_seed(2)
+        model = vitk.ViTClassifier(num_classes=6, **kw).cuda()
+        model.train(mode_train)
+        return vitk.FineTuner(model, seed=seed).step(x, y)[0].item()
+
+    same = lambda a, b: abs(a - b) < 1e-5     # the loss is summed with float atomics
+    assert same(first_loss(True, 1), first_loss(True, 1))          # deterministic given the seed
+    assert not same(first_loss(True, 1), first_loss(True, 2))      # the seed selects the masks
+    assert same(first_loss(False, 1), first_loss(False, 2))        # eval(): dropout is the identity
+    assert not same(first_loss(False, 1), first_loss(True, 1))
+
+
+def test_dropout_rejects_long_sequences_loudly(vitk):
+    # 16 x 16 patches + CLS = 257 tokens: beyond the training path altogether; 15 x 15 + 1 = 226
+    # tokens train without dropout but not with it (the dropout softmax kernel covers <= 208)
+    kw = dict(image_size=240, patch_size=16, embed_dim=64, num_layers=1, num_heads=1, mlp_dim=64)
+    x, y = O.synthetic_images(2, 240).cuda(), O.synthetic_labels(2).cuda()
+    vitk.FineTuner(vitk.ViTClassifier(num_classes=6, dropout=0.0, **kw).cuda().train()).step(x, y)
+    tuner = vitk.FineTuner(vitk.ViTClassifier(num_classes=6, dropout=0.1, **kw).cuda().train())
     with pytest.raises(vitk.VitkError):
-        tuner.step(O.synthetic_images(2, 32).cuda(), O.synthetic_labels(2).cuda())
+        tuner.step(x, y)
 
 
 def test_vit_b16_three_steps_track_the_oracle(vitk):
