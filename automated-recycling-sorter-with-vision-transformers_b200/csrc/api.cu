@@ -286,6 +286,10 @@ int vitk_gemm_set_direct_epilogue(int on) {
   gemm_force_direct_epilogue(on != 0);
   return VITK_OK;
 }
+int vitk_set_pdl(int on) {
+  set_pdl(on);
+  return VITK_OK;
+}
 int vitk_reserve_sms(int n) {
   VITK_REQUIRE(n >= 0 && n <= 64, "reserve_sms: 0 <= n <= 64");
   reserve_sms(n);

@@ -102,6 +102,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv,   // box {64, Nk,
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_launch_dependents();
 
   auto rows_in_tile = [&](int t) { return min(128, Nk - t * 128); };  // multiple of 16
 
@@ -439,7 +441,11 @@ int attention_bwd_tc(const void* qkv, const void* ctx, const void* dctx, const f
   int grid = sm_count();
   if (B * H < grid) grid = B * H;
   ProfileScope prof(PROF_ATTN, 10.0 * B * H * static_cast<double>(N) * N * hd, stream);
-  attn_bwd_tc_kernel<<<grid, kThreads, smem, stream>>>(tq, tdo, tout, prm);
+  const cudaError_t le = launch_pdl(attn_bwd_tc_kernel, dim3(grid), dim3(kThreads), smem, stream, tq,
+                                    tdo, tout, prm);
+  if (le != cudaSuccess)
+    return set_error(VITK_ERR_CUDA, "launch of attn_bwd_tc_kernel failed: %s",
+                     cudaGetErrorString(le));
   VITK_CHECK_LAUNCH("attn_bwd_tc_kernel");
   return VITK_OK;
 }

@@ -108,6 +108,13 @@ int sweep_next() {
   return d;
 }
 
+static int g_pdl = -1;  // -1: from the environment
+void set_pdl(int on) { g_pdl = on ? 1 : 0; }
+bool pdl_enabled() {
+  if (g_pdl < 0) g_pdl = std::getenv("VITK_PDL") != nullptr ? 1 : 0;
+  return g_pdl != 0;
+}
+
 static int g_sm_reserve = 0;
 void reserve_sms(int n) { g_sm_reserve = n < 0 ? 0 : n; }
 int sm_count() {

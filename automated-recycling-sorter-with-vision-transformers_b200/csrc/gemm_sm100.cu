@@ -456,6 +456,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
   if constexpr (CTAS == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above overlapped the tail of the previous kernel; its results are needed from here
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ======================= TMA producer (every CTA stages its own operand slices) ==========
@@ -810,13 +813,15 @@ int launch(const GemmProblem& p, cudaStream_t stream) {
   cfg.blockDim = dim3(kNumThreads);
   cfg.dynamicSmemBytes = C::kSmemBytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CTAS;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   ProfileScope prof(PROF_GEMM, 2.0 * p.M * p.N * p.K, stream);
   const int descending = sweep_next();
   cudaError_t le = cudaLaunchKernelEx(&cfg, kernel, ta, tb, tc, tc2, p.M, p.N, p.K, kb_per_split,

@@ -34,6 +34,17 @@ __device__ __forceinline__ bool elect_one_sync() {
   return pred != 0;
 }
 
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-serialization
+// attribute (common.h: launch_pdl) may start while its predecessor in the stream is still running;
+// pdl_wait() blocks until the predecessor grid has completed and its memory is visible, so a
+// kernel runs its prologue (barrier init, TMEM allocation, descriptor prefetch) early and calls
+// pdl_wait() before it first touches global memory.  pdl_launch_dependents() lets the successor
+// be scheduled before this grid has finished.  Both are no-ops for ordinary launches.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 // Per-warpgroup register budget (all four warps of the warpgroup execute the same instruction).
 template <int REGS>
 __device__ __forceinline__ void setmaxnreg_inc() {

@@ -43,6 +43,8 @@ layernorm_fwd_kernel(const float* __restrict__ x, long long in_stride,
                      float eps, int descending) {
   int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_wait();
+  pdl_launch_dependents();
   if (warp >= rows) return;
   if (descending) warp = rows - 1 - warp;  // blocks are scheduled in index order
   const float* xr = x + static_cast<long long>(warp) * in_stride;
@@ -233,13 +235,13 @@ int layernorm_fwd(const float* x, long long in_stride, const float* gamma, const
   ProfileScope prof(PROF_LN, static_cast<double>(rows) * D * (4.0 + (y_is_f32 ? 4.0 : 2.0)), stream);
   const int descending = sweep_next();
   if (y_is_f32)
-    layernorm_fwd_kernel<float><<<grid, block, 0, stream>>>(
-        x, in_stride, gamma, beta, static_cast<float*>(y), out_stride, mean_out, rstd_out, x_copy,
-        rows, D, eps, descending);
+    launch_pdl(layernorm_fwd_kernel<float>, dim3(grid), dim3(block), 0, stream, x, in_stride, gamma,
+               beta, static_cast<float*>(y), out_stride, mean_out, rstd_out, x_copy, rows, D, eps,
+               descending);
   else
-    layernorm_fwd_kernel<__nv_bfloat16><<<grid, block, 0, stream>>>(
-        x, in_stride, gamma, beta, static_cast<__nv_bfloat16*>(y), out_stride, mean_out, rstd_out,
-        x_copy, rows, D, eps, descending);
+    launch_pdl(layernorm_fwd_kernel<__nv_bfloat16>, dim3(grid), dim3(block), 0, stream, x, in_stride,
+               gamma, beta, static_cast<__nv_bfloat16*>(y), out_stride, mean_out, rstd_out, x_copy,
+               rows, D, eps, descending);
   VITK_CHECK_LAUNCH("layernorm_fwd_kernel");
   return VITK_OK;
 }

@@ -181,7 +181,8 @@ def run_reference(args) -> None:
 TRAIN_BATCH = 128
 
 
-def measure_train_step(vitk, O, dev, world, rank, barrier, steps: int = 8, warmup: int = 3) -> dict:
+def measure_train_step(vitk, O, dev, world, rank, barrier, steps: int = 8, warmup: int = 3,
+                       dropout: float = 0.1) -> dict:
     """BASELINE.json configs[2]: ViT-B/16 6-class fine-tune step (forward saving activations ->
     cross-entropy -> hand-written backward -> NCCL gradient all-reduce -> fused AdamW), bf16,
     128 images per GPU, data parallel. Reported next to the headline inference metric."""
@@ -189,11 +190,11 @@ def measure_train_step(vitk, O, dev, world, rank, barrier, steps: int = 8, warmu
     import torch.distributed as dist
     B = TRAIN_BATCH
     torch.manual_seed(0)
-    model = vitk.ViTClassifier(num_classes=N_CLASSES, dropout=0.0, **VIT_B16).to(dev)
+    model = vitk.ViTClassifier(num_classes=N_CLASSES, dropout=dropout, **VIT_B16).to(dev).train()
     overlap = os.environ.get("VITK_DP_OVERLAP", "1") != "0"
     reserve = int(os.environ.get("VITK_DP_RESERVE_SMS", "0"))
     tuner = vitk.FineTuner(model, lr=1e-4, weight_decay=1e-4, overlap_allreduce=overlap,
-                           reserve_sms=reserve)
+                           reserve_sms=reserve, seed=1000 * rank)
     x = O.synthetic_images(B, VIT_B16["image_size"], seed=99 + rank).to(dev)
     y = O.synthetic_labels(B, N_CLASSES, seed=5 + rank).to(dev)
     for _ in range(warmup):
@@ -231,7 +232,8 @@ def measure_train_step(vitk, O, dev, world, rank, barrier, steps: int = 8, warmu
             "tflops": ips / world * flops / 1e12,
             "frac_of_burst_peak": ips / world * flops / 1e12 / float(peaks["bf16_tflops"]),
             "by_kind_ms_per_step": {k: v["ms"] / 2 for k, v in prof.items() if v["launches"]},
-            "optimizer": "fused AdamW lr 1e-4 wd 1e-4 (train.py:1598-1602), dropout 0",
+            "optimizer": "fused AdamW lr 1e-4 wd 1e-4 (train.py:1598-1602)",
+            "dropout": dropout,
             "grad_allreduce": ("none (1 GPU)" if world == 1 else
                                ("NCCL sum over 14 flat fp32 slices, each started when the backward "
                                 "has produced it (overlapped)" if tuner_overlap else
@@ -321,7 +323,11 @@ def run_vitk(args) -> None:
         assert n_out == B * args.steps
         e2e_value = n_gpus * B * args.steps / e2e_s
 
+    # the reference trains with dropout 0.1 (train.py:519,559,639); the p = 0 step is the one the
+    # parity tests pin, reported next to it
     train = None if args.no_train else measure_train_step(vitk, O, dev, world, rank, barrier)
+    train0 = None if args.no_train else measure_train_step(vitk, O, dev, world, rank, barrier,
+                                                           steps=5, dropout=0.0)
 
     if rank != 0:
         if world > 1:
@@ -371,6 +377,8 @@ def run_vitk(args) -> None:
     }
     if train is not None:
         line["train_step"] = train
+        line["train_step_no_dropout"] = {k: train0[k] for k in
+                                         ("value", "unit", "ms_per_step", "tflops", "dropout")}
     if cpu is not None:
         line["cpu_baseline"] = cpu
     _emit(json.dumps(line))

@@ -110,6 +110,9 @@ int vitk_gemm_set_direct_epilogue(int on);
 /* Persistent kernels (GEMM, attention) launch one CTA per SM; keep `n` SMs out of their grids, e.g.
  * for the NCCL kernels of a gradient all-reduce that overlaps the backward pass. 0 restores all. */
 int vitk_reserve_sms(int n);
+/* Programmatic dependent launch of the library's kernels (off by default; VITK_PDL=1 or
+ * vitk_set_pdl(1) turns it on; measured neutral on B200, tests/ab_pdl.py). */
+int vitk_set_pdl(int on);
 
 /* Attention kernel choice: 0 = automatic (tcgen05 single-key-block kernel when N <= 256, else the
  * flash kernel), 1 = flash (mma.sync, any N), 2 = tcgen05.  Tests and A/B timing. */
