@@ -142,7 +142,11 @@ layernorm_bwd_fused_kernel(const DyT* __restrict__ dy, long long dy_stride,
                            const float* __restrict__ gamma, float* __restrict__ dx_io,
                            long long dx_stride, int add_resid, __nv_bfloat16* __restrict__ dx_bf16,
                            long long dxb_stride, float* __restrict__ dgamma,
-                           float* __restrict__ dbeta, int rows, int D) {
+                           float* __restrict__ dbeta, float* __restrict__ dx_colsum, int rows,
+                           int D) {
+  // per-warp column buffer: during the row loop it accumulates the column sums of the bf16 result
+  // (dx_colsum: the bias gradient of the Linear whose output gradient this is - saves the separate
+  // column-sum pass over dx_bf16); afterwards it carries the cross-warp reduction of dgamma / dbeta
   __shared__ float s_red[8][128 * NVEC];
   const int nvec = D >> 2;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -157,6 +161,9 @@ layernorm_bwd_fused_kernel(const DyT* __restrict__ dy, long long dy_stride,
   for (int j = 0; j < NVEC; ++j) {
     ag[j] = make_float4(0.f, 0.f, 0.f, 0.f);
     ab[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int i = lane + 32 * j;
+    if (dx_colsum != nullptr && i < nvec)
+      *reinterpret_cast<float4*>(&s_red[warp][4 * i]) = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   for (long long r = gw; r < rows; r += W) {
     const float mu = mean[r], rs = rstd[r];
@@ -217,11 +224,30 @@ layernorm_bwd_fused_kernel(const DyT* __restrict__ dy, long long dy_stride,
           pk.x = pack_bf16x2(o.x, o.y);
           pk.y = pack_bf16x2(o.z, o.w);
           *reinterpret_cast<uint2*>(dx_bf16 + r * dxb_stride + 4 * i) = pk;
+          if (dx_colsum != nullptr) {   // sums of the ROUNDED values, as a pass over dx_bf16 gives
+            float4 acc = *reinterpret_cast<float4*>(&s_red[warp][4 * i]);
+            acc.x += bf16lo_to_f32(pk.x);
+            acc.y += bf16hi_to_f32(pk.x);
+            acc.z += bf16lo_to_f32(pk.y);
+            acc.w += bf16hi_to_f32(pk.y);
+            *reinterpret_cast<float4*>(&s_red[warp][4 * i]) = acc;
+          }
         }
       }
     }
   }
-  // ---- reduce the per-warp partial sums: dgamma, then dbeta through the same buffer
+  // ---- column sums of the result, then the per-warp partial sums of dgamma and dbeta through the
+  //      same buffer
+  if (dx_colsum != nullptr) {
+    __syncthreads();
+    for (int col = threadIdx.x; col < D; col += 256) {
+      float acc = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) acc += s_red[w][col];
+      atomicAdd(dx_colsum + col, acc);
+    }
+    __syncthreads();
+  }
 #pragma unroll
   for (int pass = 0; pass < 2; ++pass) {
 #pragma unroll
@@ -632,7 +658,7 @@ int layernorm_bwd(const void* dy, int dy_is_f32, long long dy_stride, const floa
                   long long x_stride, const float* mean, const float* rstd, const float* gamma,
                   float* dx_io, long long dx_stride, int add_resid, void* dx_bf16,
                   long long dxb_stride, float* dgamma, float* dbeta, int rows, int D,
-                  cudaStream_t stream) {
+                  cudaStream_t stream, float* dx_colsum) {
   VITK_REQUIRE(dy && x && mean && rstd && gamma && dx_io, "layernorm_bwd: null operand");
   VITK_REQUIRE(rows > 0 && D % 4 == 0 && D <= 128 * kLnMaxVec, "layernorm_bwd: bad shape");
   VITK_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), "layernorm_bwd: dgamma/dbeta together");
@@ -641,6 +667,8 @@ int layernorm_bwd(const void* dy, int dy_is_f32, long long dy_stride, const floa
   const __nv_bfloat16* dyb = static_cast<const __nv_bfloat16*>(dy);
   const float* dyf = static_cast<const float*>(dy);
   const int nv = (D / 4 + 31) / 32;
+  VITK_REQUIRE(dx_colsum == nullptr || dx_bf16 != nullptr,
+               "layernorm_bwd: dx_colsum needs the bf16 output");
   if (dgamma != nullptr && nv <= 6 && std::getenv("VITK_LN_BWD_SPLIT") == nullptr) {
     // one pass: dx and the parameter gradients together
     ProfileScope prof(PROF_LN, static_cast<double>(rows) * D * (dy_is_f32 ? 14.0 : 12.0), stream);
@@ -650,7 +678,7 @@ int layernorm_bwd(const void* dy, int dy_is_f32, long long dy_stride, const floa
 #define VITK_LN_FUSED(T, PTR, NV)                                                                 \
   launch_pdl(layernorm_bwd_fused_kernel<T, NV>, dim3(fgrid), dim3(block), 0, stream, PTR, dy_stride, \
              x, x_stride, mean, rstd, gamma, dx_io, dx_stride, add_resid, dxb, dxb_stride, dgamma,  \
-             dbeta, rows, D)
+             dbeta, dx_colsum, rows, D)
     if (dy_is_f32) {
       if (nv <= 2) VITK_LN_FUSED(float, dyf, 2);
       else if (nv <= 4) VITK_LN_FUSED(float, dyf, 4);
@@ -700,6 +728,10 @@ int layernorm_bwd(const void* dy, int dy_is_f32, long long dy_stride, const floa
   }
 #undef VITK_LN_BWD
   VITK_CHECK_LAUNCH("layernorm_bwd_dx_kernel");
+  if (dx_colsum != nullptr) {
+    VITK_REQUIRE(dx_bf16 != nullptr, "layernorm_bwd: dx_colsum needs the bf16 output");
+    return colsum_bf16(dx_bf16, dxb_stride, rows, D, dx_colsum, stream);
+  }
   return VITK_OK;
 }
 

@@ -6,12 +6,14 @@
 
 namespace vitk {
 
-// dx_io (+)= LN backward; optional bf16 copy; dgamma/dbeta accumulate (atomics).
+// dx_io (+)= LN backward; optional bf16 copy; dgamma/dbeta accumulate (atomics).  dx_colsum
+// (optional, [D]) += column sums of the bf16 copy: the bias gradient of the Linear layer whose
+// output gradient dx is, produced here instead of by a separate pass over dx_bf16.
 int layernorm_bwd(const void* dy, int dy_is_f32, long long dy_stride, const float* x,
                   long long x_stride, const float* mean, const float* rstd, const float* gamma,
                   float* dx_io, long long dx_stride, int add_resid, void* dx_bf16,
                   long long dxb_stride, float* dgamma, float* dbeta, int rows, int D,
-                  cudaStream_t stream);
+                  cudaStream_t stream, float* dx_colsum = nullptr);
 
 // out[n] += sum_m y[m, n]   (y bf16)
 int colsum_bf16(const void* y, long long ld, int M, int N, float* out, cudaStream_t stream);
