@@ -100,6 +100,9 @@ _SIGNATURES = {
     # ---- training step
     "vitk_train_workspace_bytes": (C.c_int, [C.POINTER(VitkConfig), C.c_int, C.POINTER(C.c_size_t),
                                              C.POINTER(C.c_size_t)]),
+    "vitk_forward_u8": (C.c_int, [C.POINTER(VitkConfig), C.POINTER(VitkWeights), C.c_void_p,
+                                  C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, C.c_void_p,
+                                  C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "vitk_forward_train": (C.c_int, [C.POINTER(VitkConfig), C.POINTER(VitkWeights), C.c_void_p,
                                      C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p,
                                      C.c_size_t, C.c_void_p]),

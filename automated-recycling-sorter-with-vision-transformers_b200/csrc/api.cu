@@ -100,13 +100,23 @@ int linear(const void* A, int lda, const void* W, int M, int N, int K, GemmEpi e
   return gemm_bf16_tn(p, stream);
 }
 
+struct U8Input {
+  const unsigned char* images_hwc;  // [B, S, S, 3]
+  const float* mean;                // 3 host floats
+  const float* stddev;
+};
+
 int forward_bf16(const VitkConfig* cfg, const VitkWeights* w, const float* images, const Dims& d,
-                 float* tokens_out, float* logits_out, const Workspace& ws, cudaStream_t stream) {
+                 float* tokens_out, float* logits_out, const Workspace& ws, cudaStream_t stream,
+                 const U8Input* u8 = nullptr) {
   const int M = static_cast<int>(d.M), D = d.D;
   SweepAlternation sweep;  // consecutive row-ordered kernels run in opposite directions (L2 reuse)
   // -- patch embedding as a GEMM; epilogue adds bias + position embedding and writes each patch
   //    row at its token slot (evaluation.py:142-149)
-  VITK_TRY(patchify(images, ws.patch, d.B, d.C, d.S, d.p, stream));
+  if (u8 != nullptr)
+    VITK_TRY(patchify_u8(u8->images_hwc, ws.patch, d.B, d.S, d.p, u8->mean, u8->stddev, stream));
+  else
+    VITK_TRY(patchify(images, ws.patch, d.B, d.C, d.S, d.p, stream));
   VITK_TRY(prefix_tokens(ws.x, w->cls_token, w->dist_token, w->pos_embed, d.B, d.N, D, d.prefix,
                          stream));
   {
@@ -352,6 +362,36 @@ int vitk_forward(const VitkConfig* cfg, const VitkWeights* w, const float* image
                      workspace_bytes);
   return forward_bf16(cfg, w, images, d, tokens_out, logits_out, ws,
                       static_cast<cudaStream_t>(stream));
+}
+
+int vitk_forward_u8(const VitkConfig* cfg, const VitkWeights* w, const unsigned char* images_hwc,
+                    const float* mean, const float* stddev, int batch, float* tokens_out,
+                    float* logits_out, void* workspace, size_t workspace_bytes,
+                    vitk_stream_t stream) {
+  Dims d;
+  VITK_TRY(check_config(cfg, batch, &d));
+  VITK_REQUIRE(w != nullptr && images_hwc != nullptr && mean != nullptr && stddev != nullptr &&
+                   workspace != nullptr, "null argument");
+  VITK_REQUIRE(tokens_out != nullptr || logits_out != nullptr,
+               "at least one of tokens_out / logits_out must be non-null");
+  VITK_REQUIRE(w->blocks != nullptr && w->patch_w && w->patch_b && w->cls_token && w->pos_embed &&
+                   w->ln_f_w && w->ln_f_b,
+               "weights struct has null members");
+  VITK_REQUIRE(d.prefix == 1 || w->dist_token != nullptr, "DeiT needs dist_token");
+  if (logits_out)
+    VITK_REQUIRE(cfg->n_classes > 0 && w->head_w && w->head_b,
+                 "logits requested but no classifier head configured");
+  VITK_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0,
+               "workspace must be 1024-byte aligned");
+  VITK_REQUIRE(cfg->precision == 0, "the 8-bit input edge feeds the bf16 path only");
+  VITK_REQUIRE(d.C == 3 && d.hd == 64, "the 8-bit input edge needs RGB images and head_dim 64");
+  const Workspace ws = carve(d, workspace);
+  if (ws.bytes > workspace_bytes)
+    return set_error(VITK_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", ws.bytes,
+                     workspace_bytes);
+  const U8Input u8{images_hwc, mean, stddev};
+  return forward_bf16(cfg, w, nullptr, d, tokens_out, logits_out, ws,
+                      static_cast<cudaStream_t>(stream), &u8);
 }
 
 int vitk_split3(const float* in, long long ld_in, void* out_bf16, long long rows, int K,

@@ -124,6 +124,54 @@ patchify_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, 
   }
 }
 
+// The input edge of the reference's data pipeline fused into the patch gather: 8-bit RGB images in
+// the decoder's layout (HWC, [B, S, S, 3]) -> A.Normalize(mean, std) -> ToTensorV2 (evaluation.py:
+// 362-364, train.py:442-443) -> bf16 patch rows.  The normalisation is evaluated exactly as the
+// reference does it in fp32 - (u / 255 - mean) / std with IEEE divisions - so the patch rows are
+// bit-identical to patchify(normalised f32 image); the host sends 1 byte per value instead of 4.
+// Thread = 8 pixels of one image row: 24-byte read, three 16-byte writes (one per channel plane).
+__global__ void __launch_bounds__(256)
+patchify_u8_kernel(const unsigned char* __restrict__ img, __nv_bfloat16* __restrict__ out, int B,
+                   int S, int p, float m0, float m1, float m2, float s0, float s1, float s2) {
+  const int groups_per_row = S >> 3;
+  const long long total = static_cast<long long>(B) * S * groups_per_row;
+  const int grid_w = S / p;
+  const int P = grid_w * grid_w;
+  const int Kp = 3 * p * p;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int xg = static_cast<int>(idx % groups_per_row);
+    long long t = idx / groups_per_row;
+    const int y = static_cast<int>(t % S);
+    const int b = static_cast<int>(t / S);
+    const uint2* src = reinterpret_cast<const uint2*>(img + idx * 24);
+    const uint2 a = __ldg(src), bb = __ldg(src + 1), cc = __ldg(src + 2);
+    const unsigned int w[6] = {a.x, a.y, bb.x, bb.y, cc.x, cc.y};
+    float v[3][8];
+#pragma unroll
+    for (int k = 0; k < 24; ++k) {
+      const float u = static_cast<float>((w[k >> 2] >> (8 * (k & 3))) & 0xFFu);
+      const int ch = k % 3;
+      const float mean = ch == 0 ? m0 : (ch == 1 ? m1 : m2);
+      const float sd = ch == 0 ? s0 : (ch == 1 ? s1 : s2);
+      v[ch][k / 3] = __fdiv_rn(__fsub_rn(__fdiv_rn(u, 255.0f), mean), sd);
+    }
+    const int x0 = xg * 8;
+    const int px = x0 / p, kw0 = x0 - px * p;
+    const int py = y / p, kh = y - py * p;
+    const long long row = static_cast<long long>(b) * P + py * grid_w + px;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      uint4 pk;
+      pk.x = pack_bf16x2(v[ch][0], v[ch][1]);
+      pk.y = pack_bf16x2(v[ch][2], v[ch][3]);
+      pk.z = pack_bf16x2(v[ch][4], v[ch][5]);
+      pk.w = pack_bf16x2(v[ch][6], v[ch][7]);
+      *reinterpret_cast<uint4*>(out + row * Kp + ch * p * p + kh * p + kw0) = pk;
+    }
+  }
+}
+
 // x[b, t, :] = token[t] + pos[t]  for the n_prefix learned tokens (CLS, and DIST for DeiT)
 // (reference evaluation.py:145-149, train.py:669-680).
 __global__ void prefix_tokens_kernel(float* __restrict__ x, const float* __restrict__ cls,
@@ -255,6 +303,21 @@ int patchify(const float* img, void* out_bf16, int B, int C, int S, int p, cudaS
   patchify_kernel<<<grid_for(work, 256, 16), 256, 0, stream>>>(
       img, static_cast<__nv_bfloat16*>(out_bf16), B, C, S, p);
   VITK_CHECK_LAUNCH("patchify_kernel");
+  return VITK_OK;
+}
+
+int patchify_u8(const unsigned char* img_hwc, void* out_bf16, int B, int S, int p, const float* mean,
+                const float* stddev, cudaStream_t stream) {
+  VITK_REQUIRE(img_hwc && out_bf16 && mean && stddev, "patchify_u8: null operand");
+  VITK_REQUIRE(B > 0 && S > 0 && p > 0 && S % p == 0 && p % 8 == 0,
+               "patchify_u8: need image %% patch == 0 and patch %% 8 == 0");
+  VITK_REQUIRE((reinterpret_cast<uintptr_t>(img_hwc) & 7) == 0, "patchify_u8: images must be 8-byte aligned");
+  const long long work = static_cast<long long>(B) * S * (S / 8);
+  ProfileScope prof(PROF_PATCH, static_cast<double>(B) * 3 * S * S * 3.0, stream);
+  patchify_u8_kernel<<<grid_for(work, 256, 16), 256, 0, stream>>>(
+      img_hwc, static_cast<__nv_bfloat16*>(out_bf16), B, S, p, mean[0], mean[1], mean[2], stddev[0],
+      stddev[1], stddev[2]);
+  VITK_CHECK_LAUNCH("patchify_u8_kernel");
   return VITK_OK;
 }
 

@@ -15,6 +15,11 @@ int layernorm_fwd(const float* x, long long in_stride, const float* gamma, const
 // f32 NCHW images -> bf16 patch rows [B*P, C*p*p] in conv-weight column order.
 int patchify(const float* img, void* out_bf16, int B, int C, int S, int p, cudaStream_t stream);
 
+// u8 HWC images [B, S, S, 3] -> (u / 255 - mean) / std -> bf16 patch rows (the input edge of
+// evaluation.py:362-364 fused into the gather); mean / stddev: 3 host floats.
+int patchify_u8(const unsigned char* img_hwc, void* out_bf16, int B, int S, int p, const float* mean,
+                const float* stddev, cudaStream_t stream);
+
 // Rows of the learned prefix tokens (+ their position embeddings) of the residual stream.
 int prefix_tokens(float* x, const float* cls, const float* dist, const float* pos, int B, int Ntok,
                   int D, int n_prefix, cudaStream_t stream);

@@ -110,17 +110,30 @@ class EncoderEngine:
         return base, self._ws_bytes
 
     # ------------------------------------------------------------------ the model call
+    #: A.Normalize defaults of the reference's pipelines (evaluation.py:363, train.py:442)
+    NORM_MEAN = (0.485, 0.456, 0.406)
+    NORM_STD = (0.229, 0.224, 0.225)
+
     def forward(self, images: torch.Tensor, head: torch.nn.Linear | None = None,
                 want_tokens: bool = True, want_logits: bool = False):
+        """images: f32 NCHW [B, C, S, S] (what `images.to(device)` hands the reference's model,
+        evaluation.py:499), or u8 NHWC [B, S, S, 3] straight from the decoder - then Normalize +
+        ToTensorV2 run on the device inside the patch gather (vitk_forward_u8)."""
         if not images.is_cuda:
             raise _lib.VitkError("images must be a CUDA tensor (no CPU fallback)")
-        if images.dtype != torch.float32:
-            images = images.float()
-        images = images.contiguous()
         m = self.module
         pe = m.patch_embedding
-        if images.dim() != 4 or images.shape[1] != pe.projection.in_channels or \
-                images.shape[2] != pe.image_size or images.shape[3] != pe.image_size:
+        u8 = images.dtype == torch.uint8
+        if u8:
+            if images.dim() != 4 or images.shape[3] != 3 or images.shape[1] != pe.image_size or \
+                    images.shape[2] != pe.image_size or pe.projection.in_channels != 3:
+                raise _lib.VitkError(f"expected u8 images of shape [B, {pe.image_size}, "
+                                     f"{pe.image_size}, 3], got {tuple(images.shape)}")
+        elif images.dtype != torch.float32:
+            images = images.float()
+        images = images.contiguous()
+        if not u8 and (images.dim() != 4 or images.shape[1] != pe.projection.in_channels or
+                       images.shape[2] != pe.image_size or images.shape[3] != pe.image_size):
             raise _lib.VitkError(
                 f"expected images of shape [B, {pe.projection.in_channels}, {pe.image_size}, "
                 f"{pe.image_size}], got {tuple(images.shape)}")
@@ -135,8 +148,15 @@ class EncoderEngine:
             if want_tokens else None
         logits = torch.empty((B, n_classes), dtype=torch.float32, device=images.device) \
             if want_logits else None
-        check(lib().vitk_forward(C.byref(cfg), C.byref(w), images.data_ptr(), B,
-                                 tokens.data_ptr() if tokens is not None else None,
-                                 logits.data_ptr() if logits is not None else None,
-                                 ws, ws_bytes, torch.cuda.current_stream().cuda_stream))
+        if u8:
+            mean, std = (C.c_float * 3)(*self.NORM_MEAN), (C.c_float * 3)(*self.NORM_STD)
+            check(lib().vitk_forward_u8(C.byref(cfg), C.byref(w), images.data_ptr(), mean, std, B,
+                                        tokens.data_ptr() if tokens is not None else None,
+                                        logits.data_ptr() if logits is not None else None,
+                                        ws, ws_bytes, torch.cuda.current_stream().cuda_stream))
+        else:
+            check(lib().vitk_forward(C.byref(cfg), C.byref(w), images.data_ptr(), B,
+                                     tokens.data_ptr() if tokens is not None else None,
+                                     logits.data_ptr() if logits is not None else None,
+                                     ws, ws_bytes, torch.cuda.current_stream().cuda_stream))
         return tokens, logits

@@ -17,26 +17,36 @@ import torch
 
 
 class HostBatchRunner:
-    def __init__(self, model, batch_size: int, device: torch.device | str = "cuda"):
+    def __init__(self, model, batch_size: int, device: torch.device | str = "cuda",
+                 input_dtype: torch.dtype = torch.float32):
+        """input_dtype float32: host batches are normalised f32 NCHW tensors, exactly what the
+        reference copies to the device (evaluation.py:499).  uint8: host batches are raw decoder
+        output, u8 NHWC [B, S, S, 3]; Normalize + ToTensorV2 run on the device (a quarter of the
+        host->device bytes; same logits bit for bit)."""
         self.model = model
         self.device = torch.device(device)
         pe = model.backbone.patch_embedding
-        shape = (batch_size, pe.projection.in_channels, pe.image_size, pe.image_size)
-        self.shape = shape
+        if input_dtype == torch.uint8:
+            shape = (batch_size, pe.image_size, pe.image_size, pe.projection.in_channels)
+        elif input_dtype == torch.float32:
+            shape = (batch_size, pe.projection.in_channels, pe.image_size, pe.image_size)
+        else:
+            raise ValueError("input_dtype must be torch.float32 or torch.uint8")
+        self.shape, self.input_dtype = shape, input_dtype
         self.n_classes = model.head.out_features
-        self._dev_in = [torch.empty(shape, dtype=torch.float32, device=self.device) for _ in range(2)]
+        self._dev_in = [torch.empty(shape, dtype=input_dtype, device=self.device) for _ in range(2)]
         self._host_out = [torch.empty((batch_size, self.n_classes), dtype=torch.float32).pin_memory()
                           for _ in range(2)]
         self._copy_stream = torch.cuda.Stream(device=self.device)
         self._in_ready = [torch.cuda.Event() for _ in range(2)]    # H2D of slot done
         self._in_free = [torch.cuda.Event() for _ in range(2)]     # compute finished reading slot
         self._out_ready = [torch.cuda.Event() for _ in range(2)]   # D2H of slot's logits done
-        self.h2d_bytes_per_step = 4 * shape[0] * shape[1] * shape[2] * shape[3]
+        self.h2d_bytes_per_step = self._dev_in[0].element_size() * self._dev_in[0].numel()
         self.d2h_bytes_per_step = 4 * batch_size * self.n_classes
 
     def _enqueue_copy(self, slot: int, host: torch.Tensor, first_use: bool):
-        if tuple(host.shape) != self.shape or host.dtype != torch.float32 or host.is_cuda:
-            raise ValueError(f"expected a CPU float32 tensor of shape {self.shape}")
+        if tuple(host.shape) != self.shape or host.dtype != self.input_dtype or host.is_cuda:
+            raise ValueError(f"expected a CPU {self.input_dtype} tensor of shape {self.shape}")
         with torch.cuda.stream(self._copy_stream):
             if not first_use:
                 self._copy_stream.wait_event(self._in_free[slot])

@@ -323,6 +323,27 @@ def run_vitk(args) -> None:
         assert n_out == B * args.steps
         e2e_value = n_gpus * B * args.steps / e2e_s
 
+        # ---- the same stream with raw 8-bit images as the host buffers (Normalize + ToTensorV2 of
+        #      evaluation.py:362-364 fused into the patch gather on the device): reported next to
+        #      `e2e`, which keeps the reference's own boundary (normalised f32 NCHW host tensors)
+        g8 = torch.Generator().manual_seed(1234 + rank)
+        u8_host = torch.randint(0, 256, (B, VIT_B16["image_size"], VIT_B16["image_size"], 3),
+                                generator=g8, dtype=torch.uint8).pin_memory()
+        runner8 = vitk.HostBatchRunner(model, B, dev, input_dtype=torch.uint8)
+        for _ in runner8.run([u8_host] * 3):
+            pass
+        barrier()
+        t0 = time.perf_counter()
+        for out in runner8.run([u8_host] * args.steps):
+            pass
+        torch.cuda.synchronize()
+        e2e8_s = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([e2e8_s], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e8_s = float(t.item())
+        e2e8_value = n_gpus * B * args.steps / e2e8_s
+
     # the reference trains with dropout 0.1 (train.py:519,559,639); the p = 0 step is the one the
     # parity tests pin, reported next to it
     train = None if args.no_train else measure_train_step(vitk, O, dev, world, rank, barrier)
@@ -371,7 +392,13 @@ def run_vitk(args) -> None:
         "clocks": clk.summary(),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": runner.h2d_bytes_per_step,
                 "d2h_bytes_per_step": runner.d2h_bytes_per_step,
-                "api": "HostBatchRunner.run (pinned host batches -> host logits)"},
+                "api": "HostBatchRunner.run (pinned f32 NCHW host batches, as evaluation.py:499 "
+                       "copies them -> host logits)"},
+        "e2e_uint8_input": {"value": e2e8_value, "unit": UNIT,
+                            "h2d_bytes_per_step": runner8.h2d_bytes_per_step,
+                            "d2h_bytes_per_step": runner8.d2h_bytes_per_step,
+                            "api": "HostBatchRunner(input_dtype=uint8): raw u8 NHWC host batches, "
+                                   "Normalize + ToTensorV2 on the device (vitk_forward_u8)"},
         "gpu_launches": int(launches),
         "roofline": roofline,
     }

@@ -128,6 +128,17 @@ int vitk_forward(const VitkConfig* cfg, const VitkWeights* w, const float* image
                  float* tokens_out, float* logits_out, void* workspace, size_t workspace_bytes,
                  vitk_stream_t stream);
 
+/* vitk_forward for 8-bit images straight from the decoder (HWC, u8 [batch, S, S, 3], 8-byte
+ * aligned): A.Normalize(mean, std) + ToTensorV2 of the reference's data pipeline
+ * (evaluation.py:362-364, 369-372; train.py:442-443) are fused into the patch gather, evaluated
+ * exactly as the reference does in fp32, (u / 255 - mean) / std, so the result is bit-identical
+ * to vitk_forward on the normalised float image while the host sends a quarter of the bytes.
+ * mean / stddev: 3 HOST floats each.  bf16 mode only. */
+int vitk_forward_u8(const VitkConfig* cfg, const VitkWeights* w, const unsigned char* images_hwc,
+                    const float* mean, const float* stddev, int batch, float* tokens_out,
+                    float* logits_out, void* workspace, size_t workspace_bytes,
+                    vitk_stream_t stream);
+
 /* ---- per-operator entry points (unit-tested individually; same kernels vitk_forward uses) ---- */
 
 /* epilogue ids for vitk_gemm */

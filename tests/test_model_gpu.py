@@ -119,3 +119,28 @@ def test_empty_and_bad_inputs(vitk):
         a = model(x)
         b = model(x.half().float().permute(0, 1, 3, 2).permute(0, 1, 3, 2))
         assert (a - b).abs().max() < 5e-2
+
+
+def test_uint8_input_edge_is_bit_identical_to_the_float_path(vitk):
+    """Normalize + ToTensorV2 (evaluation.py:362-364) fused into the patch gather: u8 NHWC images in,
+    the same logits bit for bit as the f32 NCHW path fed with the CPU-normalised images; also
+    through the host-buffer runner."""
+    kw = dict(image_size=64, patch_size=16, embed_dim=128, num_layers=2, num_heads=2, mlp_dim=256)
+    torch.manual_seed(5)
+    model = vitk.ViTClassifier(num_classes=6, dropout=0.0, **kw).cuda().eval()
+    g = torch.Generator().manual_seed(1234)
+    u8 = torch.randint(0, 256, (6, 64, 64, 3), generator=g, dtype=torch.uint8)
+    x = O.synthetic_images(6, 64, seed=1234)          # the same pixels, normalised on the CPU
+    mean, std = torch.tensor(O.IMAGENET_MEAN), torch.tensor(O.IMAGENET_STD)
+    assert torch.equal(x, ((u8.float() / 255.0 - mean) / std).permute(0, 3, 1, 2))
+    with torch.no_grad():
+        a = model(x.cuda())
+        b = model(u8.cuda())
+        tok_a, tok_b = model.backbone(x.cuda()), model.backbone(u8.cuda())
+    assert torch.equal(a, b) and torch.equal(tok_a, tok_b)
+    runner = vitk.HostBatchRunner(model, 3, input_dtype=torch.uint8)
+    outs = [o.clone() for o in runner.run([u8[:3].pin_memory(), u8[3:].pin_memory()])]
+    assert torch.equal(torch.cat(outs).cuda(), a)
+    assert runner.h2d_bytes_per_step == 3 * 64 * 64 * 3
+    with pytest.raises(vitk.VitkError), torch.no_grad():
+        model(torch.zeros(2, 3, 64, 64, dtype=torch.uint8, device="cuda"))   # NCHW u8 is not the edge
