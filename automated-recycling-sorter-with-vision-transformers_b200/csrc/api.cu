@@ -296,6 +296,12 @@ int vitk_gemm_set_direct_epilogue(int on) {
   gemm_force_direct_epilogue(on != 0);
   return VITK_OK;
 }
+int vitk_postprocess_scores(const float* logits, int rows, int n_classes, int exclude_last,
+                            float* scores_out, long long* labels_out, float* probs_out,
+                            vitk_stream_t stream) {
+  return postprocess_scores(logits, rows, n_classes, exclude_last, scores_out, labels_out, probs_out,
+                            static_cast<cudaStream_t>(stream));
+}
 int vitk_set_pdl(int on) {
   set_pdl(on);
   return VITK_OK;

@@ -321,6 +321,59 @@ int patchify_u8(const unsigned char* img_hwc, void* out_bf16, int B, int S, int 
   return VITK_OK;
 }
 
+// post_process_predictions (evaluation.py:403-404): class_probs = softmax(logits, -1);
+// max_probs, predicted = max(class_probs[:, :-1]) (the last class is "background" for the detector;
+// the 6-class classifier keeps all).  One warp per row; scores / labels leave as f32 / i64.
+__global__ void __launch_bounds__(256)
+postprocess_scores_kernel(const float* __restrict__ logits, int rows, int C, int exclude_last,
+                          float* __restrict__ scores, long long* __restrict__ labels,
+                          float* __restrict__ probs) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* lr = logits + static_cast<long long>(row) * C;
+  float m = -INFINITY;
+  for (int c = lane; c < C; c += 32) m = fmaxf(m, lr[c]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  float sum = 0.f;
+  for (int c = lane; c < C; c += 32) sum += __expf(lr[c] - m);
+  sum = warp_sum(sum);
+  const int Cc = exclude_last ? C - 1 : C;
+  float best = -1.f;
+  int arg = 0;
+  for (int c = lane; c < C; c += 32) {
+    const float pr = __expf(lr[c] - m) / sum;
+    if (probs != nullptr) probs[static_cast<long long>(row) * C + c] = pr;
+    if (c < Cc && pr > best) {
+      best = pr;
+      arg = c;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+    if (ob > best || (ob == best && oa < arg)) {   // first maximum wins, as torch.max does
+      best = ob;
+      arg = oa;
+    }
+  }
+  if (lane == 0) {
+    if (scores != nullptr) scores[row] = best;
+    if (labels != nullptr) labels[row] = arg;
+  }
+}
+
+int postprocess_scores(const float* logits, int rows, int C, int exclude_last, float* scores,
+                       long long* labels, float* probs, cudaStream_t stream) {
+  VITK_REQUIRE(logits && rows > 0 && C > (exclude_last ? 1 : 0), "postprocess_scores: bad argument");
+  postprocess_scores_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(logits, rows, C, exclude_last, scores,
+                                                                labels, probs);
+  VITK_CHECK_LAUNCH("postprocess_scores_kernel");
+  return VITK_OK;
+}
+
 int prefix_tokens(float* x, const float* cls, const float* dist, const float* pos, int B, int Ntok,
                   int D, int n_prefix, cudaStream_t stream) {
   VITK_REQUIRE(x && cls && pos, "prefix_tokens: null operand");

@@ -29,6 +29,12 @@ int cls_head(const float* x, long long row_stride, const float* gamma, const flo
              const float* head_w, const float* head_b, float* feat_out, float* logits, int B, int D,
              int n_classes, float eps, cudaStream_t stream);
 
+// softmax over the last dim, then max / argmax over the classes (optionally without the last,
+// "background", class) - evaluation.py:403-404; scores f32 [rows], labels i64 [rows], probs
+// f32 [rows, C], each optional.
+int postprocess_scores(const float* logits, int rows, int C, int exclude_last, float* scores,
+                       long long* labels, float* probs, cudaStream_t stream);
+
 int cast_f32_to_bf16(const float* in, void* out, long long n, cudaStream_t stream);
 
 // softmax(q k^T / sqrt(hd)) v for every (image, head); qkv bf16 [B*N, 3*D] packed as the reference

@@ -210,3 +210,10 @@ class ViTClassifier(nn.Module):
     def predict(self, images):
         """top-1 class per image (cf. evaluation.py:403-404 argmax over class scores)."""
         return self.forward(images).argmax(dim=-1)
+
+    @torch.no_grad()
+    def predict_with_scores(self, images):
+        """(scores, labels): softmax confidence and class of the top-1 prediction per image - the
+        device-side form of post_process_predictions' softmax / max (evaluation.py:403-404)."""
+        from . import ops
+        return ops.postprocess_scores(self.forward(images))

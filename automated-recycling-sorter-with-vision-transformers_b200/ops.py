@@ -178,3 +178,20 @@ def patchify(images: torch.Tensor, patch_size: int) -> torch.Tensor:
                       device=images.device)
     check(lib().vitk_patchify(images.data_ptr(), out.data_ptr(), B, Cc, S, patch_size, _stream()))
     return out
+
+
+def postprocess_scores(logits: torch.Tensor, exclude_last: bool = False, return_probs: bool = False):
+    """softmax(logits, -1) then max / argmax over the classes (evaluation.py:403-404) in one kernel:
+    returns (scores f32 [...], labels i64 [...]) and optionally the probabilities."""
+    _need_cuda(logits)
+    assert logits.dtype == torch.float32
+    lead, C_ = logits.shape[:-1], logits.shape[-1]
+    flat = logits.reshape(-1, C_).contiguous()
+    rows = flat.shape[0]
+    scores = torch.empty(rows, dtype=torch.float32, device=logits.device)
+    labels = torch.empty(rows, dtype=torch.int64, device=logits.device)
+    probs = torch.empty_like(flat) if return_probs else None
+    check(lib().vitk_postprocess_scores(flat.data_ptr(), rows, C_, 1 if exclude_last else 0,
+                                        scores.data_ptr(), labels.data_ptr(), _ptr(probs), _stream()))
+    out = (scores.reshape(lead), labels.reshape(lead))
+    return out + (probs.reshape(logits.shape),) if return_probs else out

@@ -276,6 +276,69 @@ class FineTuner:
         st.refresh_transposes()
         return self._loss, logits
 
+    # ------------------------------------------------------------------ checkpoints
+    # The reference saves {'epoch', 'model_state_dict', 'optimizer_state_dict', 'val_loss',
+    # 'config'} (train.py:1647-1666) and evaluation.py:375-391 loads 'model_state_dict'.  The
+    # module mirrors keep the reference's state_dict keys; the optimizer state below uses
+    # torch.optim.AdamW's own layout (per-parameter 'step', 'exp_avg', 'exp_avg_sq' in
+    # model.parameters() order), so a checkpoint written by either implementation resumes in the
+    # other.
+    def optimizer_state_dict(self) -> dict:
+        st = self.state
+        state = {}
+        for i, (name, p) in enumerate(zip(st.names, st.params)):
+            o = st.offsets[name]
+            state[i] = {"step": torch.tensor(float(st.step_count)),
+                        "exp_avg": st.exp_avg[o:o + p.numel()].view(p.shape).clone(),
+                        "exp_avg_sq": st.exp_avg_sq[o:o + p.numel()].view(p.shape).clone()}
+        group = {"lr": self.lr, "betas": tuple(self.betas), "eps": self.eps,
+                 "weight_decay": self.wd, "amsgrad": False, "maximize": False, "foreach": None,
+                 "capturable": False, "differentiable": False, "fused": None,
+                 "decoupled_weight_decay": True, "params": list(range(len(st.params)))}
+        return {"state": state if st.step_count > 0 else {}, "param_groups": [group]}
+
+    def load_optimizer_state_dict(self, sd: dict) -> None:
+        st = self.state
+        groups = sd["param_groups"]
+        if len(groups) != 1 or len(groups[0]["params"]) != len(st.params):
+            raise _lib.VitkError("optimizer state does not match this model: expected one parameter "
+                                 f"group with {len(st.params)} parameters (train.py:1598-1602)")
+        g = groups[0]
+        self.lr, self.wd, self.eps = float(g["lr"]), float(g["weight_decay"]), float(g["eps"])
+        self.betas = tuple(float(b) for b in g["betas"])
+        st.exp_avg.zero_()
+        st.exp_avg_sq.zero_()
+        steps = set()
+        for i, (name, p) in enumerate(zip(st.names, st.params)):
+            e = sd["state"].get(g["params"][i])
+            if e is None:
+                continue
+            o = st.offsets[name]
+            st.exp_avg[o:o + p.numel()].view(p.shape).copy_(e["exp_avg"])
+            st.exp_avg_sq[o:o + p.numel()].view(p.shape).copy_(e["exp_avg_sq"])
+            steps.add(int(float(e["step"])))
+        if len(steps) > 1:
+            raise _lib.VitkError(f"per-parameter step counts differ ({sorted(steps)}): the fused "
+                                 "AdamW keeps one step count for the whole arena")
+        st.step_count = steps.pop() if steps else 0
+
+    def save_checkpoint(self, path, epoch: int = 0, val_loss: float = float("nan"), config=None):
+        """Same dictionary as train.py:1647-1654."""
+        torch.save({"epoch": epoch, "model_state_dict": self.model.state_dict(),
+                    "optimizer_state_dict": self.optimizer_state_dict(), "val_loss": val_loss,
+                    "config": dict(config or {})}, path)
+
+    def load_checkpoint(self, path, strict: bool = False) -> dict:
+        """Loads a checkpoint written by save_checkpoint or by the reference's training loop
+        (evaluation.py:375-391 semantics: strict=False on the model)."""
+        ck = torch.load(path, map_location=self.state.device, weights_only=False)
+        sd = ck["model_state_dict"] if "model_state_dict" in ck else ck
+        with torch.no_grad():
+            self.model.load_state_dict(sd, strict=strict)   # copies in place into the arena
+        if isinstance(ck, dict) and "optimizer_state_dict" in ck:
+            self.load_optimizer_state_dict(ck["optimizer_state_dict"])
+        return ck
+
     def _allreduce_grads(self):
         """Sum gradients over the data-parallel group: a few large all-reduces over contiguous
         slices of the flat gradient arena on a side stream (NCCL over NVLink/NVSwitch)."""

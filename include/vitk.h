@@ -107,6 +107,15 @@ int vitk_gemm_set_cta_group(int ctas);
  * store / reduce-add epilogue (tests, A/B timing). */
 int vitk_gemm_set_direct_epilogue(int on);
 
+/* Device side of post_process_predictions (evaluation.py:393-407, lines 403-404): softmax over the
+ * class logits f32 [rows, n_classes], then the maximum probability and its class per row,
+ * optionally ignoring the last ("background") class as the detector does.  scores_out f32 [rows],
+ * labels_out i64 [rows], probs_out f32 [rows, n_classes]; each may be null.  Replaces the
+ * per-image Python loop and its host synchronisations. */
+int vitk_postprocess_scores(const float* logits, int rows, int n_classes, int exclude_last,
+                            float* scores_out, long long* labels_out, float* probs_out,
+                            vitk_stream_t stream);
+
 /* Persistent kernels (GEMM, attention) launch one CTA per SM; keep `n` SMs out of their grids, e.g.
  * for the NCCL kernels of a gradient all-reduce that overlaps the backward pass. 0 restores all. */
 int vitk_reserve_sms(int n);

@@ -185,3 +185,70 @@ def test_vit_b16_three_steps_track_the_oracle(vitk):
     print("oracle losses", ref_losses, "vitk losses", got)
     for a, b in zip(got, ref_losses):
         assert abs(a - b) < 0.05 * max(1.0, abs(b)), (got, ref_losses)
+
+
+def test_checkpoints_round_trip_with_torch_adamw(vitk, tmp_path):
+    """train.py:1647-1654 layout: model_state_dict keys of the reference, optimizer_state_dict in
+    torch.optim.AdamW's format.  (a) a FineTuner resumed from its own checkpoint continues exactly;
+    (b) torch.optim.AdamW accepts the optimizer state and its next step lands on the same weights
+    as the fused kernel's; (c) a checkpoint written with torch.optim.AdamW resumes in FineTuner."""
+    kw = dict(image_size=32, patch_size=16, embed_dim=64, num_layers=2, num_heads=1, mlp_dim=128,
+              dropout=0.0)
+    x, y = O.synthetic_images(8, 32).cuda(), O.synthetic_labels(8).cuda()
+    torch.manual_seed(3)
+    model = vitk.ViTClassifier(num_classes=6, **kw).cuda()
+    tuner = vitk.FineTuner(model, lr=1e-3)
+    for _ in range(2):
+        tuner.step(x, y)
+    path = tmp_path / "ck.pth"
+    tuner.save_checkpoint(path, epoch=1, val_loss=0.5)
+    ck = torch.load(path, weights_only=False)
+    assert set(ck) == {"epoch", "model_state_dict", "optimizer_state_dict", "val_loss", "config"}
+    assert "backbone.transformer_blocks.0.attention.qkv.weight" in ck["model_state_dict"]
+    # (a)
+    model2 = vitk.ViTClassifier(num_classes=6, **kw).cuda()
+    tuner2 = vitk.FineTuner(model2, lr=1e-3)
+    tuner2.load_checkpoint(path)
+    assert tuner2.state.step_count == 2
+    tuner.step(x, y)
+    tuner2.step(x, y)
+    for (k, a), (_, b) in zip(model.state_dict().items(), model2.state_dict().items()):
+        assert (a - b).abs().max() < 1e-6, k
+    # (b) torch's AdamW continues from the same state with the gradients of the fused backward
+    model3 = vitk.ViTClassifier(num_classes=6, **kw).cuda()
+    model3.load_state_dict(ck["model_state_dict"])
+    opt = torch.optim.AdamW(model3.parameters(), lr=1e-3, weight_decay=1e-4)
+    opt.load_state_dict(ck["optimizer_state_dict"])
+    model4 = vitk.ViTClassifier(num_classes=6, **kw).cuda()
+    tuner4 = vitk.FineTuner(model4, lr=1e-3)
+    tuner4.load_checkpoint(path)
+    tuner4.step(x, y)
+    grads = [p.grad.clone() for p in tuner4.state.params]
+    for p, g in zip(model3.parameters(), grads):
+        p.grad = g
+    opt.step()
+    for (k, a), (_, b) in zip(model3.state_dict().items(), model4.state_dict().items()):
+        assert (a - b).abs().max() < 2e-6, k
+    # (c) torch-written optimizer state resumes in the fused trainer
+    path2 = tmp_path / "ref.pth"
+    torch.save({"epoch": 7, "model_state_dict": model3.state_dict(),
+                "optimizer_state_dict": opt.state_dict(), "val_loss": 0.1, "config": {}}, path2)
+    model5 = vitk.ViTClassifier(num_classes=6, **kw).cuda()
+    tuner5 = vitk.FineTuner(model5, lr=5e-4)
+    assert tuner5.load_checkpoint(path2)["epoch"] == 7
+    assert tuner5.state.step_count == 3 and tuner5.lr == 1e-3
+    tuner5.step(x, y)
+
+
+def test_postprocess_scores_matches_the_reference_loop(vitk):
+    """evaluation.py:403-404 on detector-shaped logits [B, Q, C+1] and on classifier logits."""
+    g = torch.Generator(device="cuda").manual_seed(0)
+    logits = torch.randn(3, 100, 7, generator=g, device="cuda") * 3
+    scores, labels, probs = vitk.ops.postprocess_scores(logits, exclude_last=True, return_probs=True)
+    ref = torch.softmax(logits, dim=-1)
+    want_s, want_l = torch.max(ref[..., :-1], dim=-1)
+    torch.testing.assert_close(probs, ref, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(scores, want_s, rtol=1e-5, atol=1e-6)
+    assert torch.equal(labels, want_l)
+    s2, l2 = vitk.ops.postprocess_scores(logits[:, 0, :6].contiguous())
+    assert torch.equal(l2, logits[:, 0, :6].argmax(-1))
