@@ -44,6 +44,9 @@ struct BwdParams {
   DropParams drop;  // attention-probability dropout of the forward (same index space / key)
 };
 
+// DROP: attention-probability dropout compiled in (a separate instantiation, so that the p = 0
+// kernel carries neither the extra registers nor the per-element branch).
+template <bool DROP>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv,   // box {64, Nk, 1} over qkv
                    const __grid_constant__ CUtensorMap tm_do,    // box {64, Nk, 1} over d_ctx
@@ -314,7 +317,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv,   // box {64, Nk,
                 p1 = ex2_approx(fmaf(__uint_as_float(s[2 * j + 1]), c, -sLse[q0 + 2 * j + 1]));
                 float g0 = __uint_as_float(dp[2 * j]), g1 = __uint_as_float(dp[2 * j + 1]);
                 float pd0 = p0, pd1 = p1;
-                if (p.drop.thresh != 0u) {
+                if constexpr (DROP) {
                   // one hash per element here: the pairs run along the keys, the thread owns one key
                   const uint32_t half_nk = static_cast<uint32_t>(Nk >> 1);
                   const uint32_t kp = static_cast<uint32_t>(key >> 1);
@@ -416,8 +419,11 @@ int attention_bwd_tc(const void* qkv, const void* ctx, const void* dctx, const f
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [&] {
-    attr_err = cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    232448);
+    attr_err = cudaFuncSetAttribute(attn_bwd_tc_kernel<false>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(attn_bwd_tc_kernel<true>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
   });
   if (attr_err != cudaSuccess)
     return set_error(VITK_ERR_CUDA, "cudaFuncSetAttribute(attention_bwd tc) failed: %s",
@@ -441,8 +447,12 @@ int attention_bwd_tc(const void* qkv, const void* ctx, const void* dctx, const f
   int grid = sm_count();
   if (B * H < grid) grid = B * H;
   ProfileScope prof(PROF_ATTN, 10.0 * B * H * static_cast<double>(N) * N * hd, stream);
-  const cudaError_t le = launch_pdl(attn_bwd_tc_kernel, dim3(grid), dim3(kThreads), smem, stream, tq,
-                                    tdo, tout, prm);
+  const cudaError_t le =
+      prm.drop.thresh != 0u
+          ? launch_pdl(attn_bwd_tc_kernel<true>, dim3(grid), dim3(kThreads), smem, stream, tq, tdo,
+                       tout, prm)
+          : launch_pdl(attn_bwd_tc_kernel<false>, dim3(grid), dim3(kThreads), smem, stream, tq, tdo,
+                       tout, prm);
   if (le != cudaSuccess)
     return set_error(VITK_ERR_CUDA, "launch of attn_bwd_tc_kernel failed: %s",
                      cudaGetErrorString(le));

@@ -106,18 +106,13 @@ __device__ __forceinline__ void exp_chunk(uint32_t (&v)[COLS], int k0, int N, ui
   else tmem_st_32x32b_x8(pcol, pk);
 }
 
-template <int COLS>
+template <int COLS, bool DROP>
 __device__ __forceinline__ void exp_chunk_any(uint32_t (&v)[COLS], int k0, int N, uint64_t cc,
                                               uint64_t nmc, uint32_t pcol, uint64_t& la,
                                               uint64_t& lb, const DropParams& drop,
                                               uint32_t row_pairs) {
-  if (drop.thresh == 0u) {
-    if (k0 + COLS <= N) exp_chunk<COLS, false, false>(v, k0, N, cc, nmc, pcol, la, lb, drop, 0u);
-    else exp_chunk<COLS, true, false>(v, k0, N, cc, nmc, pcol, la, lb, drop, 0u);
-  } else {
-    if (k0 + COLS <= N) exp_chunk<COLS, false, true>(v, k0, N, cc, nmc, pcol, la, lb, drop, row_pairs);
-    else exp_chunk<COLS, true, true>(v, k0, N, cc, nmc, pcol, la, lb, drop, row_pairs);
-  }
+  if (k0 + COLS <= N) exp_chunk<COLS, false, DROP>(v, k0, N, cc, nmc, pcol, la, lb, drop, row_pairs);
+  else exp_chunk<COLS, true, DROP>(v, k0, N, cc, nmc, pcol, la, lb, drop, row_pairs);
 }
 
 // Debug aid (build with -DVITK_ATTN_TRACE): CTA 0 records SM-clock timestamps of its first 8 items
@@ -132,6 +127,9 @@ __device__ __forceinline__ void exp_chunk_any(uint32_t (&v)[COLS], int k0, int N
 #define TR(role, idx, k) do { } while (0)
 #endif
 
+// DROP: attention-probability dropout compiled in (separate instantiation; the inference kernel
+// carries none of it).
+template <bool DROP>
 __global__ void __launch_bounds__(kThreads2, 1)
 attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_q,
                     const __grid_constant__ CUtensorMap tm_kv,
@@ -357,13 +355,13 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_q,
           for (int ch = 0; ch < n32; ++ch) {
             tmem_ld_32x32b_x32(region + kbeg + ch * 32, v32);
             tmem_ld_wait();
-            exp_chunk_any<32>(v32, kbeg + ch * 32, N, cc, nmc, pbase + ch * 16, la, lb, p.drop,
+            exp_chunk_any<32, DROP>(v32, kbeg + ch * 32, N, cc, nmc, pbase + ch * 16, la, lb, p.drop,
                               row_pairs);
           }
           if (tail16) {
             tmem_ld_32x32b_x16(region + kbeg + n32 * 32, v16);
             tmem_ld_wait();
-            exp_chunk_any<16>(v16, kbeg + n32 * 32, N, cc, nmc, pbase + n32 * 16, la, lb, p.drop,
+            exp_chunk_any<16, DROP>(v16, kbeg + n32 * 32, N, cc, nmc, pbase + n32 * 16, la, lb, p.drop,
                               row_pairs);
           }
           float l0, l1, l2, l3;
@@ -483,8 +481,11 @@ int attention_fwd_tc2(const void* qkv, void* ctx, float* lse, int B, int N, int 
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [&] {
-    attr_err = cudaFuncSetAttribute(attn_fwd_tc2_kernel,
+    attr_err = cudaFuncSetAttribute(attn_fwd_tc2_kernel<false>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(attn_fwd_tc2_kernel<true>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
   });
   if (attr_err != cudaSuccess)
     return set_error(VITK_ERR_CUDA, "cudaFuncSetAttribute(attention tc2) failed: %s",
@@ -510,8 +511,12 @@ int attention_fwd_tc2(const void* qkv, void* ctx, float* lse, int B, int N, int 
   int grid = sm_count();
   if (B * H < grid) grid = B * H;
   ProfileScope prof(PROF_ATTN, 4.0 * B * H * static_cast<double>(N) * N * hd, stream);
-  const cudaError_t le = launch_pdl(attn_fwd_tc2_kernel, dim3(grid), dim3(kThreads2), smem, stream,
-                                    tq, tkv, to, prm);
+  const cudaError_t le =
+      prm.drop.thresh != 0u
+          ? launch_pdl(attn_fwd_tc2_kernel<true>, dim3(grid), dim3(kThreads2), smem, stream, tq, tkv,
+                       to, prm)
+          : launch_pdl(attn_fwd_tc2_kernel<false>, dim3(grid), dim3(kThreads2), smem, stream, tq, tkv,
+                       to, prm);
   if (le != cudaSuccess)
     return set_error(VITK_ERR_CUDA, "launch of attn_fwd_tc2_kernel failed: %s",
                      cudaGetErrorString(le));
