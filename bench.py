@@ -367,8 +367,9 @@ def run_vitk(args) -> None:
         "achieved": gemm_tflops, "peak": peak_tf, "unit": "TFLOP/s",
         "frac": gemm_tflops / peak_tf,
         # dram__bytes_read+write per launch, mean of the four per-block GEMM launches at batch 256
-        # (ncu --set full, profiles/r1_prof_gemm_r1_raw.csv: 259 + 340 + 593 + 333 MB)
-        "traffic": 381e6 if B == 256 else None,
+        # (ncu --set full, profiles/r1c_prof_fwd_raw.csv: QKV 256 + fc1 334 + fc2 595 + proj 329 MB;
+        #  algorithmic 310 + 387 + 620 + 387 MB)
+        "traffic": 378.5e6 if B == 256 else None,
         "peak_source": f"{peak_src} MEASURED_PEAKS.json bf16_tflops_sustained; burst "
                        f"{peaks['bf16_tflops']}",
         "avg_launch_ms": gemm["ms"] / max(gemm["launches"], 1),
