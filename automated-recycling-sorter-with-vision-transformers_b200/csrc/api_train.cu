@@ -326,9 +326,9 @@ int backward_blocks(const VitkConfig* cfg, const VitkWeights* w, const VitkWeigh
                           stream));
     const DropParams drop_a = drop.at(DROP_ATTN, l);
     VITK_TRY(attention_bwd(sb.qkv, sb.ctx, ws.dctx, sb.lse, ws.dqkv, d.B, d.N, d.H, d.hd, stream,
-                           &drop_a));
+                           &drop_a, bg.qkv_b));   // also accumulates the qkv bias gradient
     VITK_TRY(linear_dgrad(ws.dqkv, 3 * D, bt.qkv_wt, M, D, EPI_BF16, nullptr, ws.dxn, stream));
-    VITK_TRY(linear_wgrad(ws.dqkv, 3 * D, sb.xn1, D, M, bg.qkv_w, bg.qkv_b, stream));
+    VITK_TRY(linear_wgrad(ws.dqkv, 3 * D, sb.xn1, D, M, bg.qkv_w, nullptr, stream));
     VITK_TRY(layernorm_bwd(ws.dxn, 0, D, sb.x1, D, sb.mean1, sb.rstd1, bw.ln1_w, ws.dx, D, 1, ws.dxb,
                            D, bg.ln1_w, bg.ln1_b, M, D, stream,
                            (drop.p > 0.f || l == 0) ? nullptr : g->blocks[l - 1].fc2_b));

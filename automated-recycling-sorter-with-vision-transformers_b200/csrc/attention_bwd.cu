@@ -263,11 +263,12 @@ attn_bwd_hd64_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16*
 int attention_impl();  // attention.cu: 0 auto, 1 mma.sync kernels, 2 tcgen05 kernels
 
 int attention_bwd(const void* qkv, const void* ctx, const void* dctx, const float* lse, void* dqkv,
-                  int B, int N, int H, int hd, cudaStream_t stream, const DropParams* drop) {
+                  int B, int N, int H, int hd, cudaStream_t stream, const DropParams* drop,
+                  float* dbias) {
   VITK_REQUIRE(qkv && ctx && dctx && lse && dqkv, "attention_bwd: null operand");
   const bool dropping = drop != nullptr && drop->thresh != 0u;
   if ((attention_impl() != 1 || dropping) && hd == 64 && N <= 256 && device_cc() >= 100)
-    return attention_bwd_tc(qkv, ctx, dctx, lse, dqkv, B, N, H, hd, stream, drop);
+    return attention_bwd_tc(qkv, ctx, dctx, lse, dqkv, B, N, H, hd, stream, drop, dbias);
   VITK_REQUIRE(!dropping, "attention_bwd: dropout is implemented by the tcgen05 kernel only");
   VITK_REQUIRE(B > 0 && H > 0 && N > 0, "attention_bwd: bad shape");
   VITK_REQUIRE(hd == 64 && N <= 256, "attention_bwd: needs head_dim 64 and N <= 256 (got %d, %d)",
@@ -289,6 +290,8 @@ int attention_bwd(const void* qkv, const void* ctx, const void* dctx, const floa
       static_cast<const __nv_bfloat16*>(qkv), static_cast<const __nv_bfloat16*>(ctx),
       static_cast<const __nv_bfloat16*>(dctx), lse, static_cast<__nv_bfloat16*>(dqkv), N, H, scale);
   VITK_CHECK_LAUNCH("attn_bwd_hd64_kernel");
+  if (dbias != nullptr)   // this kernel does not accumulate the bias gradient itself
+    return colsum_bf16(dqkv, 3ll * H * hd, B * N, 3 * H * hd, dbias, stream);
   return VITK_OK;
 }
 

@@ -42,6 +42,7 @@ struct BwdParams {
   const __nv_bfloat16* dctx;
   const float* lse;
   DropParams drop;  // attention-probability dropout of the forward (same index space / key)
+  float* dbias;     // optional [3 D]: += column sums of d_qkv (the qkv bias gradient)
 };
 
 // DROP: attention-probability dropout compiled in (a separate instantiation, so that the p = 0
@@ -70,6 +71,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv,   // box {64, Nk,
   // 0 ld_full, 1 ld_free, 2 s_full, 3 sm_done, 4 ds_free, 5 dkv_full, 6 dkv_free, 7 dq_full,
   // 8 dq_free, 9-10 vec_full[2], 11-12 vec_free[2]
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + vec_off + 4096 + 120);
+  // column sums of everything this CTA stores (bf16-rounded values, as a pass over d_qkv would see
+  // them): the qkv bias gradient without re-reading d_qkv.  One global atomic per column at the end.
+  float* colacc = reinterpret_cast<float*>(smem + vec_off + 4096 + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_items = p.B * p.H;
@@ -101,6 +105,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv,   // box {64, Nk,
     tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), 512);
     tmem_relinquish();
   }
+  if (p.dbias != nullptr)
+    for (int i = threadIdx.x; i < 3 * p.H * 64; i += kThreads) colacc[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -266,6 +272,22 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv,   // box {64, Nk,
         tma_store_3d(&tm_out, slab, gcol, row0, b);
         tma_store_commit();
       }
+      if (p.dbias != nullptr) {
+        // lane sums columns 2*lane, 2*lane+1 over the 32 staged rows (rows >= N are exact zeros)
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r) {
+          uint32_t w;
+          const uint32_t a = slab + static_cast<uint32_t>(r) * 128u +
+                             ((static_cast<uint32_t>(lane >> 2) ^ static_cast<uint32_t>(r & 7)) << 4) +
+                             static_cast<uint32_t>(lane & 3) * 4u;
+          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(a));
+          s0 += bf16lo_to_f32(w);
+          s1 += bf16hi_to_f32(w);
+        }
+        atomicAdd(&colacc[gcol + 2 * lane], s0);
+        atomicAdd(&colacc[gcol + 2 * lane + 1], s1);
+      }
     };
 
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
@@ -403,18 +425,21 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv,   // box {64, Nk,
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
+  if (p.dbias != nullptr)
+    for (int i = threadIdx.x; i < 3 * p.H * 64; i += kThreads) atomicAdd(p.dbias + i, colacc[i]);
 }
 
 }  // namespace
 
 int attention_bwd_tc(const void* qkv, const void* ctx, const void* dctx, const float* lse,
                      void* dqkv, int B, int N, int H, int hd, cudaStream_t stream,
-                     const DropParams* drop) {
+                     const DropParams* drop, float* dbias) {
   VITK_REQUIRE(qkv && ctx && dctx && lse && dqkv, "attention_bwd: null operand");
   VITK_REQUIRE(hd == 64 && N >= 1 && N <= 256, "attention_bwd(tc): needs head_dim 64, N <= 256");
   const int Nk = (N + 15) & ~15;
   const int D = H * 64;
-  const size_t smem = 4 * static_cast<size_t>(Nk) * 128 + 32768 + 32768 + 4096 + 128 + 1024;
+  const size_t smem = 4 * static_cast<size_t>(Nk) * 128 + 32768 + 32768 + 4096 + 256 + 1024 +
+                      (dbias != nullptr ? static_cast<size_t>(3) * D * 4 : 0);
   VITK_REQUIRE(smem <= 232448, "attention_bwd(tc): shared memory budget exceeded");
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
@@ -444,6 +469,7 @@ int attention_bwd_tc(const void* qkv, const void* ctx, const void* dctx, const f
   prm.dctx = static_cast<const __nv_bfloat16*>(dctx);
   prm.lse = lse;
   if (drop != nullptr) prm.drop = *drop;
+  prm.dbias = dbias;
   int grid = sm_count();
   if (B * H < grid) grid = B * H;
   ProfileScope prof(PROF_ATTN, 10.0 * B * H * static_cast<double>(N) * N * hd, stream);

@@ -54,13 +54,14 @@ int adamw_flat(float* p, const float* g, float* m, float* v, void* shadow_bf16, 
                float grad_scale, cudaStream_t stream);
 
 // dqkv = backward of softmax(q k^T / sqrt(hd)) v given d_ctx, using the saved log-sum-exp.
+// dbias (optional, [3 H hd]) += column sums of dqkv: the bias gradient of the qkv Linear.
 int attention_bwd(const void* qkv, const void* ctx, const void* dctx, const float* lse, void* dqkv,
                   int B, int N, int H, int hd, cudaStream_t stream,
-                  const DropParams* drop = nullptr);
+                  const DropParams* drop = nullptr, float* dbias = nullptr);
 
 // tcgen05 variant (attention_bwd_tc.cu); attention_bwd dispatches to it for N <= 256.
 int attention_bwd_tc(const void* qkv, const void* ctx, const void* dctx, const float* lse,
                      void* dqkv, int B, int N, int H, int hd, cudaStream_t stream,
-                     const DropParams* drop = nullptr);
+                     const DropParams* drop = nullptr, float* dbias = nullptr);
 
 }  // namespace vitk
