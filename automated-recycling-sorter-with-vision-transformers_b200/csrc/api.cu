@@ -312,8 +312,9 @@ int vitk_reserve_sms(int n) {
   return VITK_OK;
 }
 int vitk_attention_set_impl(int impl) {
-  VITK_REQUIRE(impl >= 0 && impl <= 3,
-               "attention impl must be 0 (auto), 1 (flash), 2 (tcgen05) or 3 (unpipelined tcgen05)");
+  VITK_REQUIRE(impl >= 0 && impl <= 4,
+               "attention impl must be 0 (auto), 1 (flash), 2 (tcgen05), 3 (unpipelined tcgen05) or "
+               "4 (two-pass long-sequence tcgen05)");
   attention_force_impl(impl);
   return VITK_OK;
 }

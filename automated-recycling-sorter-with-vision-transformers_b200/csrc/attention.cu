@@ -246,8 +246,9 @@ attn_fwd_hd64_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __res
 
 }  // namespace
 
-// 0 auto, 1 = mma.sync flash kernel, 2 = tcgen05 single-block kernels, 3 = the unpipelined tcgen05
-// forward (attention_tc.cu) also where the pipelined one (attention_tc2.cu) applies
+// 0 auto, 1 = mma.sync flash kernel, 2 = tcgen05 kernels, 3 = the unpipelined tcgen05 forward
+// (attention_tc.cu) also where the pipelined one (attention_tc2.cu) applies, 4 = the two-pass
+// long-sequence kernel (attention_tc3.cu) for every N <= 640
 static int g_attn_impl = 0;
 void attention_force_impl(int impl) { g_attn_impl = impl; }
 int attention_impl() { return g_attn_impl; }
@@ -262,11 +263,13 @@ int attention_fwd(const void* qkv, void* ctx, float* lse, int B, int N, int H, i
     return attention_fwd_tc2(qkv, ctx, lse, B, N, H, hd, stream, drop);
   }
   if (g_attn_impl == 2 || g_attn_impl == 3 ||
-      (g_attn_impl == 0 && hd == 64 && N <= 256 && device_cc() >= 100)) {
+      (g_attn_impl == 0 && hd == 64 && N <= 640 && device_cc() >= 100)) {
     if (g_attn_impl != 3 && hd == 64 && N <= 208)
       return attention_fwd_tc2(qkv, ctx, lse, B, N, H, hd, stream);
+    if (N > 256 || g_attn_impl == 4) return attention_fwd_tc3(qkv, ctx, lse, B, N, H, hd, stream);
     return attention_fwd_tc(qkv, ctx, lse, B, N, H, hd, stream);
   }
+  if (g_attn_impl == 4) return attention_fwd_tc3(qkv, ctx, lse, B, N, H, hd, stream);
   VITK_REQUIRE(B > 0 && N > 0 && H > 0, "attention: bad shape B=%d N=%d H=%d", B, N, H);
   VITK_REQUIRE(hd == 64, "attention: head_dim %d unsupported by the bf16 kernel (needs 64)", hd);
   const int Nkv = (N + 15) & ~15;

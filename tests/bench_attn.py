@@ -30,8 +30,9 @@ def timeit(fn, iters=20):
     return t[len(t) // 2]
 
 
-for impl, name in ((1, "flash mma.sync"), (3, "tcgen05 unpipelined"), (2, "tcgen05 pipelined")):
-    if impl != 1 and N > 256:
+for impl, name in ((1, "flash mma.sync"), (3, "tcgen05 unpipelined"), (2, "tcgen05 pipelined"),
+                   (4, "tcgen05 two-pass")):
+    if (impl == 3 and N > 256) or (impl == 4 and N > 640):
         continue
     vitk._lib.set_attention_impl(impl)
     ms = timeit(lambda: vitk.ops.attention(qkv, B, N, H))

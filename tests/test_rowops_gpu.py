@@ -33,7 +33,7 @@ def test_patchify(vitk, B, C, S, p):
     assert torch.equal(out, ref.bfloat16())  # pure gather + round-to-nearest: bit exact
 
 
-@pytest.fixture(params=[1, 2, 3], ids=["flash", "tcgen05", "tcgen05-unpipelined"])
+@pytest.fixture(params=[1, 2, 3, 4], ids=["flash", "tcgen05", "tcgen05-unpipelined", "tcgen05-two-pass"])
 def attn_impl(request, vitk):
     vitk._lib.set_attention_impl(request.param)
     yield request.param
@@ -54,10 +54,11 @@ def _attn_ref(qkv, B, N, H):
 @pytest.mark.parametrize("B,N,H", [(2, 197, 12), (1, 5, 1), (3, 17, 2), (2, 64, 3), (1, 198, 12),
                                    (1, 577, 4), (2, 16, 1), (1, 65, 2), (2, 128, 2), (1, 129, 1),
                                    (1, 256, 2), (40, 197, 12), (7, 224, 3), (5, 225, 2), (64, 100, 12),
-                                   (33, 208, 16), (150, 1, 1)])
+                                   (33, 208, 16), (150, 1, 1), (2, 577, 12), (1, 640, 2), (3, 257, 1),
+                                   (1, 513, 3), (20, 384, 4)])
 def test_attention(vitk, attn_impl, B, N, H):
-    if attn_impl >= 2 and N > 256:
-        pytest.skip("tcgen05 kernel covers N <= 256")
+    if attn_impl == 3 and N > 256:
+        pytest.skip("the unpipelined tcgen05 kernel covers N <= 256")
     g = torch.Generator(device="cuda").manual_seed(N)
     qkv = (torch.randn(B * N, 3 * H * 64, generator=g, device="cuda") * 1.5).bfloat16()
     ctx, lse = vitk.ops.attention(qkv, B, N, H, return_lse=True)
