@@ -526,7 +526,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
   } else if (warp == 1) {
     // ======================= MMA issuer (pair leader only) =======================
-    if (lane == 0 && is_leader) {
+    // The whole warp stays converged and one elected lane issues: the uniform-datapath
+    // instructions (UTCHMMA, UTCBAR) are then emitted without a per-active-lane election loop
+    // and register->uniform-register broadcasts around each of them.
+    if (is_leader) {
       constexpr uint32_t idesc = make_idesc_bf16(kTileM, BLOCK_N, MN ? 1 : 0, MN ? 1 : 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -548,25 +551,31 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
           const uint64_t a_desc = make_desc_sw128(sa, MN ? 8192 : 16, 1024);
           const uint64_t b_desc = make_desc_sw128(sb, MN ? 8192 : 16, 1024);
           constexpr uint32_t kstep = MN ? 128u : 2u;  // descriptor start-address units of 16 B
+          if (elect_one_sync()) {
 #pragma unroll
-          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-            const uint32_t accum = (kb > kb0 || k > 0) ? 1u : 0u;
-            if constexpr (CTAS == 2)
-              mma_bf16_ss_2sm(d_tmem, a_desc + kstep * k, b_desc + kstep * k, idesc, accum);
-            else
-              mma_bf16_ss(d_tmem, a_desc + kstep * k, b_desc + kstep * k, idesc, accum);
+            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+              const uint32_t accum = (kb > kb0 || k > 0) ? 1u : 0u;
+              if constexpr (CTAS == 2)
+                mma_bf16_ss_2sm(d_tmem, a_desc + kstep * k, b_desc + kstep * k, idesc, accum);
+              else
+                mma_bf16_ss(d_tmem, a_desc + kstep * k, b_desc + kstep * k, idesc, accum);
+            }
+            // frees the smem slot (in both CTAs) when these MMAs retire
+            if constexpr (CTAS == 2) mma_commit_2sm_mc(empty_bar(stage), 3);
+            else mma_commit(empty_bar(stage));
           }
-          // frees the smem slot (in both CTAs) when these MMAs retire
-          if constexpr (CTAS == 2) mma_commit_2sm_mc(empty_bar(stage), 3);
-          else mma_commit(empty_bar(stage));
+          __syncwarp();
           if (++stage == C::kStages) {
             stage = 0;
             phase ^= 1u;
           }
         }
         // accumulator complete -> epilogue warps of both CTAs
-        if constexpr (CTAS == 2) mma_commit_2sm_mc(tfull_bar(acc), 3);
-        else mma_commit(tfull_bar(acc));
+        if (elect_one_sync()) {
+          if constexpr (CTAS == 2) mma_commit_2sm_mc(tfull_bar(acc), 3);
+          else mma_commit(tfull_bar(acc));
+        }
+        __syncwarp();
         if (++acc == kAccStages) {
           acc = 0;
           acc_phase ^= 1u;
