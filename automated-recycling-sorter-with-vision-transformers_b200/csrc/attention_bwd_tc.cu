@@ -176,22 +176,27 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv,   // box {64, Nk,
             const uint64_t a_ds = make_desc_sw128(sdS, 16384, 1024);
             const uint64_t b_k_mn = make_desc_sw128(sK + kt * 16384u, tile_bytes, 1024);
             if (elect_one_sync()) {
-#pragma unroll 1
-              for (int ks = 0; ks < nq / 16; ++ks) {
-                // 16 queries per step: bf16 pairs at the start of their 32-column chunk
-                const uint32_t acol = static_cast<uint32_t>((ks >> 1) * 32 + (ks & 1) * 8);
-                mma_bf16_ts(tmem_base + kColDV, tmem_base + kColS + acol,
-                            b_do_mn + static_cast<uint64_t>(ks) * 128u, idesc_mn64,
-                            (qt > 0 || ks > 0) ? 1u : 0u);
-                mma_bf16_ts(tmem_base + kColDK, tmem_base + kColDP + acol,
-                            b_q_mn + static_cast<uint64_t>(ks) * 128u, idesc_mn64,
-                            (qt > 0 || ks > 0) ? 1u : 0u);
+              // fully unrolled, predicated MMA issue (two instructions per MMA instead of a rolled
+              // loop's eight: the issuing warp competes with busy warps for issue slots)
+#pragma unroll
+              for (int ks = 0; ks < 8; ++ks) {
+                if (ks < nq / 16) {
+                  // 16 queries per step: bf16 pairs at the start of their 32-column chunk
+                  const uint32_t acol = static_cast<uint32_t>((ks >> 1) * 32 + (ks & 1) * 8);
+                  mma_bf16_ts(tmem_base + kColDV, tmem_base + kColS + acol,
+                              b_do_mn + static_cast<uint64_t>(ks) * 128u, idesc_mn64,
+                              (qt > 0 || ks > 0) ? 1u : 0u);
+                  mma_bf16_ts(tmem_base + kColDK, tmem_base + kColDP + acol,
+                              b_q_mn + static_cast<uint64_t>(ks) * 128u, idesc_mn64,
+                              (qt > 0 || ks > 0) ? 1u : 0u);
+                }
               }
-#pragma unroll 1
-              for (int ks = 0; ks < kcount / 16; ++ks)
-                mma_bf16_ss(tmem_base + kColDQ + qt * 64, a_ds + static_cast<uint64_t>(ks) * 128u,
-                            b_k_mn + static_cast<uint64_t>(ks) * 128u, idesc_dq,
-                            (kt > 0 || ks > 0) ? 1u : 0u);
+#pragma unroll
+              for (int ks = 0; ks < 8; ++ks)
+                if (ks < kcount / 16)
+                  mma_bf16_ss(tmem_base + kColDQ + qt * 64, a_ds + static_cast<uint64_t>(ks) * 128u,
+                              b_k_mn + static_cast<uint64_t>(ks) * 128u, idesc_dq,
+                              (kt > 0 || ks > 0) ? 1u : 0u);
               mma_commit(bar(4));  // dS^T smem tile (and P^T / dS^T in TMEM) consumed
               if (qt == n_kt - 1) mma_commit(bar(5));  // dV_kt, dK_kt complete
               if (qt == n_kt - 1 && kt == n_kt - 1) {

@@ -272,15 +272,20 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_q,
           tc_fence_after();
           const uint32_t region = tmem_base + static_cast<uint32_t>(t) * kRegion;
           if (elect_one_sync()) {
-            // P of a column quarter starts at the quarter's own first S column
-            int ks = 0;
-#pragma unroll 1
+            // P of a column quarter starts at the quarter's own first S column.  Fully unrolled and
+            // predicated (a quarter holds at most 4 MMA steps): the issuing warp shares its
+            // scheduler with five busy warps, so every instruction of a rolled loop costs several
+            // issue slots of latency - unrolled, an MMA is two instructions instead of eight.
+#pragma unroll
             for (int cq = 0; cq < 4; ++cq) {
-              const int kb = quarter_begin(cq), ke = quarter_begin(cq + 1);
-#pragma unroll 1
-              for (int key = kb; key < ke; key += 16, ++ks)
-                mma_bf16_ts(tmem_base + kOColumn, region + static_cast<uint32_t>(kb + (key - kb) / 2),
-                            v_desc + static_cast<uint64_t>(ks) * 128u, idesc_pv, ks > 0 ? 1u : 0u);
+              const int kb = quarter_begin(cq);
+              const int nsteps = (quarter_begin(cq + 1) - kb) >> 4;
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                if (i < nsteps)
+                  mma_bf16_ts(tmem_base + kOColumn, region + static_cast<uint32_t>(kb + i * 8),
+                              v_desc + static_cast<uint64_t>((kb >> 4) + i) * 128u, idesc_pv,
+                              (cq > 0 || i > 0) ? 1u : 0u);
             }
             mma_commit(o_full);
             if (t == q_tiles - 1) mma_commit(v_empty(stage));  // last reader of this stage's V

@@ -241,13 +241,16 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tm_q,    // box {64, 128
                 const uint64_t v_desc = make_desc_sw128(sV + j * (kKeyBlock * 128u), kv_bytes, 1024);
                 const bool last_of_item = (t == t_end - 1 && j == n_kb - 1);
                 if (elect_one_sync()) {
-#pragma unroll 1
-                  for (int ks = 0; ks < nk / 16; ++ks)
-                    mma_bf16_ts(tmem_base + kOCol3,
-                                tmem_base + r * 128u +
-                                    static_cast<uint32_t>((ks >> 1) * 32 + (ks & 1) * 8),
-                                v_desc + static_cast<uint64_t>(ks) * 128u, idesc_pv,
-                                (j > 0 || ks > 0) ? 1u : 0u);
+                  // fully unrolled and predicated: two instructions per MMA instead of a rolled
+                  // loop's eight (the issuing warp competes with five busy warps for issue slots)
+#pragma unroll
+                  for (int ks = 0; ks < kKeyBlock / 16; ++ks)
+                    if (ks < nk / 16)
+                      mma_bf16_ts(tmem_base + kOCol3,
+                                  tmem_base + r * 128u +
+                                      static_cast<uint32_t>((ks >> 1) * 32 + (ks & 1) * 8),
+                                  v_desc + static_cast<uint64_t>(ks) * 128u, idesc_pv,
+                                  (j > 0 || ks > 0) ? 1u : 0u);
                   mma_commit(bar(kRegFree + r));  // P of this region consumed when these retire
                   if (j == n_kb - 1) mma_commit(bar(kOFull));
                   if (last_of_item) mma_commit(bar(kKvFree));  // last reader of K / V
