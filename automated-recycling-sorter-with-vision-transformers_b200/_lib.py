@@ -12,7 +12,7 @@ from pathlib import Path
 PKG_DIR = Path(__file__).resolve().parent
 LIB_PATH = PKG_DIR / "libvitk.so"
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 EPI_BF16 = 0
 EPI_GELU_BF16 = 1

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define VITK_ABI_VERSION 1
+#define VITK_ABI_VERSION 2
 
 #define VITK_OK 0
 #define VITK_ERR_INVALID 1
