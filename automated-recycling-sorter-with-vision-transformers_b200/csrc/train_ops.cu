@@ -455,21 +455,34 @@ cls_loss_bwd_kernel(const float* __restrict__ x, long long row_stride, const flo
   }
 }
 
-// dW[c, :] = sum_b dlogits[b, c] * feat[b, :] ; db[c] = sum_b dlogits[b, c].  One block per class.
+// dW[c, :] = sum_b dlogits[b, c] * feat[b, :] ; db[c] = sum_b dlogits[b, c].
+// Block = (class, 64 feature columns); 4 thread groups split the batch, unrolled so that the loads
+// of a group are in flight together (the first version walked the batch serially in 6 blocks:
+// 116 us of pure load latency for 0.6 MFLOP).
 __global__ void __launch_bounds__(256)
 head_wgrad_kernel(const float* __restrict__ dlogits, const float* __restrict__ feat, int B, int D,
                   int C, float* __restrict__ dW, float* __restrict__ db) {
+  __shared__ float s_part[4][64];
+  __shared__ float s_db[4];
   const int c = blockIdx.x;
-  for (int i = threadIdx.x; i < D; i += blockDim.x) {
-    float acc = 0.f;
-    for (int b = 0; b < B; ++b) acc = fmaf(dlogits[b * C + c], feat[static_cast<long long>(b) * D + i], acc);
-    dW[static_cast<long long>(c) * D + i] += acc;
+  const int col = blockIdx.y * 64 + (threadIdx.x & 63);
+  const int g = threadIdx.x >> 6;
+  float acc = 0.f, accb = 0.f;
+  if (col < D) {
+#pragma unroll 8
+    for (int b = g; b < B; b += 4) {
+      const float dl = __ldg(dlogits + b * C + c);
+      acc = fmaf(dl, __ldg(feat + static_cast<long long>(b) * D + col), acc);
+      accb += dl;
+    }
   }
-  if (threadIdx.x == 0) {
-    float acc = 0.f;
-    for (int b = 0; b < B; ++b) acc += dlogits[b * C + c];
-    db[c] += acc;
-  }
+  s_part[g][threadIdx.x & 63] = acc;
+  if ((threadIdx.x & 63) == 0) s_db[g] = accb;
+  __syncthreads();
+  if (g == 0 && col < D)
+    dW[static_cast<long long>(c) * D + col] +=
+        (s_part[0][threadIdx.x] + s_part[1][threadIdx.x]) + (s_part[2][threadIdx.x] + s_part[3][threadIdx.x]);
+  if (threadIdx.x == 0 && blockIdx.y == 0) db[c] += (s_db[0] + s_db[1]) + (s_db[2] + s_db[3]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -766,7 +779,8 @@ int cls_loss_bwd(const float* x, long long row_stride, const float* gamma, const
   VITK_CHECK_LAUNCH("cls_loss_bwd_kernel");
   if (dhead_w != nullptr) {
     VITK_REQUIRE(dhead_b != nullptr, "cls_loss_bwd: dhead_b missing");
-    head_wgrad_kernel<<<C, 256, 0, stream>>>(dlogits_ws, feat_ws, B, D, C, dhead_w, dhead_b);
+    head_wgrad_kernel<<<dim3(C, (D + 63) / 64), 256, 0, stream>>>(dlogits_ws, feat_ws, B, D, C,
+                                                                  dhead_w, dhead_b);
     VITK_CHECK_LAUNCH("head_wgrad_kernel");
   }
   return VITK_OK;
