@@ -305,33 +305,34 @@ int backward_blocks(const VitkConfig* cfg, const VitkWeights* w, const VitkWeigh
     const VitkBlockGrads& bg = g->blocks[l];
     const SavedBlock sb = carve_block(d, sv.blocks + l * sv.block_bytes, nullptr);
     // ---- MLP branch: x_out = x2 + drop(fc2(drop(gelu(fc1(LN2(x2))))))   (train.py:567-573,590-591)
-    if (drop.p > 0.f)   // gradient entering the dropped linear2 output
+    // with dropout, ws.dxb already carries the linear2-output mask: applied by the LayerNorm backward
+    // of the block above (below), or here for the top block whose dxb came from the loss
+    if (drop.p > 0.f && l == d.L - 1)
       VITK_TRY(dropout_cast_bf16(ws.dx, ws.dxb, d.M * D, drop.at(DROP_FC2, l), stream));
     VITK_TRY(linear_dgrad(ws.dxb, D, bt.fc2_wt, M, Mlp, EPI_DGELU_BF16, sb.hpre, ws.dh, stream,
                           drop.at(DROP_GELU, l)));
     // the bias gradient (column sums of ws.dxb) was produced together with ws.dxb by the
     // LayerNorm backward of the block above, unless dropout re-masked it or this is the top block
-    VITK_TRY(linear_wgrad(ws.dxb, D, sb.hact, Mlp, M, bg.fc2_w,
-                          (drop.p > 0.f || l == d.L - 1) ? bg.fc2_b : nullptr, stream));
+    VITK_TRY(linear_wgrad(ws.dxb, D, sb.hact, Mlp, M, bg.fc2_w, l == d.L - 1 ? bg.fc2_b : nullptr,
+                          stream));
     VITK_TRY(linear_dgrad(ws.dh, Mlp, bt.fc1_wt, M, D, EPI_BF16, nullptr, ws.dxn, stream));
     VITK_TRY(linear_wgrad(ws.dh, Mlp, sb.xn2, D, M, bg.fc1_w, bg.fc1_b, stream));
+    const DropParams drop_p = drop.at(DROP_PROJ, l);   // ws.dxb enters the dropped projection output
     VITK_TRY(layernorm_bwd(ws.dxn, 0, D, sb.x2, D, sb.mean2, sb.rstd2, bw.ln2_w, ws.dx, D, 1, ws.dxb,
-                           D, bg.ln2_w, bg.ln2_b, M, D, stream,
-                           drop.p > 0.f ? nullptr : bg.proj_b));
+                           D, bg.ln2_w, bg.ln2_b, M, D, stream, bg.proj_b, &drop_p));
     // ---- attention branch: x2 = x1 + drop(proj(attn(qkv(LN1(x1)))))      (train.py:552-553,586-587)
-    if (drop.p > 0.f)
-      VITK_TRY(dropout_cast_bf16(ws.dx, ws.dxb, d.M * D, drop.at(DROP_PROJ, l), stream));
     VITK_TRY(linear_dgrad(ws.dxb, D, bt.proj_wt, M, D, EPI_BF16, nullptr, ws.dctx, stream));
-    VITK_TRY(linear_wgrad(ws.dxb, D, sb.ctx, D, M, bg.proj_w, drop.p > 0.f ? bg.proj_b : nullptr,
-                          stream));
+    VITK_TRY(linear_wgrad(ws.dxb, D, sb.ctx, D, M, bg.proj_w, nullptr, stream));
     const DropParams drop_a = drop.at(DROP_ATTN, l);
     VITK_TRY(attention_bwd(sb.qkv, sb.ctx, ws.dctx, sb.lse, ws.dqkv, d.B, d.N, d.H, d.hd, stream,
                            &drop_a, bg.qkv_b));   // also accumulates the qkv bias gradient
     VITK_TRY(linear_dgrad(ws.dqkv, 3 * D, bt.qkv_wt, M, D, EPI_BF16, nullptr, ws.dxn, stream));
     VITK_TRY(linear_wgrad(ws.dqkv, 3 * D, sb.xn1, D, M, bg.qkv_w, nullptr, stream));
+    // ws.dxb next enters the (dropped) linear2 output of the block below
+    const DropParams drop_f = l > 0 ? drop.at(DROP_FC2, l - 1) : DropParams();
     VITK_TRY(layernorm_bwd(ws.dxn, 0, D, sb.x1, D, sb.mean1, sb.rstd1, bw.ln1_w, ws.dx, D, 1, ws.dxb,
                            D, bg.ln1_w, bg.ln1_b, M, D, stream,
-                           (drop.p > 0.f || l == 0) ? nullptr : g->blocks[l - 1].fc2_b));
+                           l == 0 ? nullptr : g->blocks[l - 1].fc2_b, &drop_f));
     VITK_TRY(bucket_done(d.L - l));
   }
   // ---- token assembly + patch embedding                             (evaluation.py:142-149)

@@ -143,7 +143,7 @@ layernorm_bwd_fused_kernel(const DyT* __restrict__ dy, long long dy_stride,
                            long long dx_stride, int add_resid, __nv_bfloat16* __restrict__ dx_bf16,
                            long long dxb_stride, float* __restrict__ dgamma,
                            float* __restrict__ dbeta, float* __restrict__ dx_colsum, int rows,
-                           int D) {
+                           int D, DropParams drop) {
   // per-warp column buffer: during the row loop it accumulates the column sums of the bf16 result
   // (dx_colsum: the bias gradient of the Linear whose output gradient this is - saves the separate
   // column-sum pass over dx_bf16); afterwards it carries the cross-warp reduction of dgamma / dbeta
@@ -220,9 +220,20 @@ layernorm_bwd_fused_kernel(const DyT* __restrict__ dy, long long dy_stride,
         o.w = rs * (d.w * gm.w - s1 - xv[j].w * s2) + pv[j].w;
         *reinterpret_cast<float4*>(dx_io + r * dx_stride + 4 * i) = o;
         if (dx_bf16 != nullptr) {
+          // the bf16 copy is the gradient entering the next branch; if that branch's output was
+          // dropped in the forward, its mask (element index = row * D + column) is applied here
+          float4 ob = o;
+          if (drop.thresh != 0u) {
+            const uint32_t pair0 = (static_cast<uint32_t>(r) * static_cast<uint32_t>(D) + 4u * i) >> 1;
+            const uint32_t b0 = drop_bits(pair0, drop.key), b1 = drop_bits(pair0 + 1u, drop.key);
+            ob.x = drop_keep_lo(b0, drop.thresh) ? o.x * drop.scale : 0.f;
+            ob.y = drop_keep_hi(b0, drop.thresh) ? o.y * drop.scale : 0.f;
+            ob.z = drop_keep_lo(b1, drop.thresh) ? o.z * drop.scale : 0.f;
+            ob.w = drop_keep_hi(b1, drop.thresh) ? o.w * drop.scale : 0.f;
+          }
           uint2 pk;
-          pk.x = pack_bf16x2(o.x, o.y);
-          pk.y = pack_bf16x2(o.z, o.w);
+          pk.x = pack_bf16x2(ob.x, ob.y);
+          pk.y = pack_bf16x2(ob.z, ob.w);
           *reinterpret_cast<uint2*>(dx_bf16 + r * dxb_stride + 4 * i) = pk;
           if (dx_colsum != nullptr) {   // sums of the ROUNDED values, as a pass over dx_bf16 gives
             float4 acc = *reinterpret_cast<float4*>(&s_red[warp][4 * i]);
@@ -671,8 +682,10 @@ int layernorm_bwd(const void* dy, int dy_is_f32, long long dy_stride, const floa
                   long long x_stride, const float* mean, const float* rstd, const float* gamma,
                   float* dx_io, long long dx_stride, int add_resid, void* dx_bf16,
                   long long dxb_stride, float* dgamma, float* dbeta, int rows, int D,
-                  cudaStream_t stream, float* dx_colsum) {
+                  cudaStream_t stream, float* dx_colsum, const DropParams* drop) {
   VITK_REQUIRE(dy && x && mean && rstd && gamma && dx_io, "layernorm_bwd: null operand");
+  const DropParams dp = drop != nullptr ? *drop : DropParams();
+  const bool dropping = dp.thresh != 0u;
   VITK_REQUIRE(rows > 0 && D % 4 == 0 && D <= 128 * kLnMaxVec, "layernorm_bwd: bad shape");
   VITK_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), "layernorm_bwd: dgamma/dbeta together");
   const int block = 256;
@@ -682,7 +695,10 @@ int layernorm_bwd(const void* dy, int dy_is_f32, long long dy_stride, const floa
   const int nv = (D / 4 + 31) / 32;
   VITK_REQUIRE(dx_colsum == nullptr || dx_bf16 != nullptr,
                "layernorm_bwd: dx_colsum needs the bf16 output");
-  if (dgamma != nullptr && nv <= 6 && std::getenv("VITK_LN_BWD_SPLIT") == nullptr) {
+  VITK_REQUIRE(!dropping || (dx_bf16 != nullptr && dxb_stride == D &&
+                             static_cast<long long>(rows) * D < (1ll << 32)),
+               "layernorm_bwd: the dropout mask applies to a dense bf16 output");
+  if (dgamma != nullptr && nv <= 6 && (dropping || std::getenv("VITK_LN_BWD_SPLIT") == nullptr)) {
     // one pass: dx and the parameter gradients together
     ProfileScope prof(PROF_LN, static_cast<double>(rows) * D * (dy_is_f32 ? 14.0 : 12.0), stream);
     int fgrid = sm_count() * 2;
@@ -691,7 +707,7 @@ int layernorm_bwd(const void* dy, int dy_is_f32, long long dy_stride, const floa
 #define VITK_LN_FUSED(T, PTR, NV)                                                                 \
   launch_pdl(layernorm_bwd_fused_kernel<T, NV>, dim3(fgrid), dim3(block), 0, stream, PTR, dy_stride, \
              x, x_stride, mean, rstd, gamma, dx_io, dx_stride, add_resid, dxb, dxb_stride, dgamma,  \
-             dbeta, dx_colsum, rows, D)
+             dbeta, dx_colsum, rows, D, dp)
     if (dy_is_f32) {
       if (nv <= 2) VITK_LN_FUSED(float, dyf, 2);
       else if (nv <= 4) VITK_LN_FUSED(float, dyf, 4);
@@ -705,6 +721,7 @@ int layernorm_bwd(const void* dy, int dy_is_f32, long long dy_stride, const floa
     VITK_CHECK_LAUNCH("layernorm_bwd_fused_kernel");
     return VITK_OK;
   }
+  VITK_REQUIRE(!dropping, "layernorm_bwd: dropout needs the fused kernel (parameter gradients, D <= 768)");
   if (dgamma != nullptr) {
     // parameter gradients first: they read dy / x only, before dx_io is updated in place
     const int strips = (D + 255) / 256;

@@ -13,7 +13,8 @@ int layernorm_bwd(const void* dy, int dy_is_f32, long long dy_stride, const floa
                   long long x_stride, const float* mean, const float* rstd, const float* gamma,
                   float* dx_io, long long dx_stride, int add_resid, void* dx_bf16,
                   long long dxb_stride, float* dgamma, float* dbeta, int rows, int D,
-                  cudaStream_t stream, float* dx_colsum = nullptr);
+                  cudaStream_t stream, float* dx_colsum = nullptr,
+                  const DropParams* drop = nullptr);  // mask of the branch dx_bf16 enters (dropout.cuh)
 
 // out[n] += sum_m y[m, n]   (y bf16)
 int colsum_bf16(const void* y, long long ld, int M, int N, float* out, cudaStream_t stream);
