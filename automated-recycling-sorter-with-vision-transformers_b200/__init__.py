@@ -9,6 +9,7 @@ from ._lib import VitkError, launch_count  # noqa: F401
 from .modules import (DataEfficientImageTransformer, MLPBlock,  # noqa: F401
                       MultiHeadSelfAttention, PatchEmbedding, TransformerBlock, ViTClassifier,
                       VisionTransformer)
+from .detection import DeiTObjectDetector, ObjectDetectionHead, ViTObjectDetector  # noqa: F401
 
 from .pipeline import HostBatchRunner  # noqa: E402,F401
 from .trainer import FineTuner, TrainState  # noqa: E402,F401
@@ -17,5 +18,6 @@ __all__ = [
     "HostBatchRunner", "FineTuner", "TrainState",
     "PatchEmbedding", "MultiHeadSelfAttention", "MLPBlock", "TransformerBlock",
     "VisionTransformer", "DataEfficientImageTransformer", "ViTClassifier", "VitkError",
+    "ObjectDetectionHead", "ViTObjectDetector", "DeiTObjectDetector",
     "launch_count", "ops",
 ]

@@ -12,13 +12,14 @@ from pathlib import Path
 PKG_DIR = Path(__file__).resolve().parent
 LIB_PATH = PKG_DIR / "libvitk.so"
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 EPI_BF16 = 0
 EPI_GELU_BF16 = 1
 EPI_RESID_F32 = 2
 EPI_F32 = 3
 EPI_DGELU_BF16 = 4
+EPI_RELU_BF16 = 7
 
 
 class VitkError(RuntimeError):
@@ -62,6 +63,25 @@ class VitkWeights(C.Structure):
         ("ln_f_w", C.c_void_p), ("ln_f_b", C.c_void_p),
         ("head_w", C.c_void_p), ("head_b", C.c_void_p),
     ]
+
+
+class VitkDetectionHeadConfig(C.Structure):
+    _fields_ = [("embed_dim", C.c_int), ("num_heads", C.c_int), ("ffn_dim", C.c_int),
+                ("num_layers", C.c_int), ("num_queries", C.c_int), ("num_outputs", C.c_int),
+                ("ln_eps", C.c_float)]
+
+
+class VitkDecoderLayerWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "sa_in_w", "sa_in_b", "sa_out_w", "sa_out_b", "ca_q_w", "ca_q_b", "ca_out_w", "ca_out_b",
+        "ff1_w", "ff1_b", "ff2_w", "ff2_b", "norm1_w", "norm1_b", "norm2_w", "norm2_b", "norm3_w",
+        "norm3_b")]
+
+
+class VitkDetectionHeadWeights(C.Structure):
+    _fields_ = [("object_queries", C.c_void_p), ("layers", C.POINTER(VitkDecoderLayerWeights)),
+                ("ca_kv_w", C.c_void_p), ("ca_kv_b", C.c_void_p), ("class_w", C.c_void_p),
+                ("class_b", C.c_void_p), ("bbox_w", C.c_void_p), ("bbox_b", C.c_void_p)]
 
 
 # name -> (restype, argtypes); must list every symbol include/vitk.h declares.
@@ -131,6 +151,13 @@ _SIGNATURES = {
                                      C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "vitk_colsum_bf16": (C.c_int, [C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p,
                                    C.c_void_p]),
+    # ---- detection head
+    "vitk_detection_head_workspace_bytes": (C.c_int, [C.POINTER(VitkDetectionHeadConfig), C.c_int,
+                                                      C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
+    "vitk_detection_head_forward": (C.c_int, [C.POINTER(VitkDetectionHeadConfig),
+                                              C.POINTER(VitkDetectionHeadWeights), C.c_void_p,
+                                              C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                              C.c_void_p, C.c_size_t, C.c_void_p]),
 }
 
 

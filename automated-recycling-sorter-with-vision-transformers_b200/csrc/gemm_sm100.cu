@@ -160,11 +160,14 @@ __device__ __forceinline__ void gelu_fast_pair(float& a, float& b) {
 }
 template <int EPI>
 __device__ __forceinline__ float gelu_for(float x) {
-  if constexpr (EPI == EPI_GELU_TANH_BF16) return gelu_fast_tanh(x);
+  if constexpr (EPI == EPI_RELU_BF16) return fmaxf(x, 0.f);
+  else if constexpr (EPI == EPI_GELU_TANH_BF16) return gelu_fast_tanh(x);
   else return gelu_fast(x);
 }
 template <int EPI>
-constexpr bool is_gelu_epi() { return EPI == EPI_GELU_BF16 || EPI == EPI_GELU_TANH_BF16; }
+constexpr bool is_gelu_epi() {  // bias + activation -> bf16 (the ReLU of the decoder FFN included)
+  return EPI == EPI_GELU_BF16 || EPI == EPI_GELU_TANH_BF16 || EPI == EPI_RELU_BF16;
+}
 __device__ __forceinline__ float gelu_erf_grad(float x) {
   const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752440f));
   const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
@@ -697,7 +700,13 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
                   }
                   stage_and_store(pk, stg, buf, lane, &tmap_c2, n0, row0, false);
                 }
-                if constexpr (EPI == EPI_GELU_TANH_BF16) {
+                if constexpr (EPI == EPI_RELU_BF16) {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) {
+                    x0[j] = fmaxf(x0[j], 0.f);
+                    x1[j] = fmaxf(x1[j], 0.f);
+                  }
+                } else if constexpr (EPI == EPI_GELU_TANH_BF16) {
 #pragma unroll
                   for (int j = 0; j < 16; ++j) {
                     gelu_fast_tanh_pair(x0[2 * j], x0[2 * j + 1]);
@@ -871,6 +880,7 @@ bool tma_epilogue_ok(const GemmProblem& p, bool honour_force = true) {
     case EPI_BF16: return true;
     case EPI_GELU_BF16:
     case EPI_GELU_TANH_BF16:
+    case EPI_RELU_BF16:
       return p.e.out2 == nullptr || (reinterpret_cast<uintptr_t>(p.e.out2) & 15) == 0;
     case EPI_RESID_F32:
       return p.e.rows_per_group == 0 && p.e.resid == p.e.out && p.e.ldr == p.e.ldo;
@@ -927,6 +937,7 @@ int gemm_bf16_tn(const GemmProblem& p, cudaStream_t stream) {
     case EPI_BF16: return dispatch<EPI_BF16>(p, stream);
     case EPI_GELU_BF16: return dispatch<EPI_GELU_BF16>(p, stream);
     case EPI_GELU_TANH_BF16: return dispatch<EPI_GELU_TANH_BF16>(p, stream);
+    case EPI_RELU_BF16: return dispatch<EPI_RELU_BF16>(p, stream);
     case EPI_RESID_F32:
       VITK_REQUIRE(p.e.resid != nullptr && p.e.ldr % 4 == 0, "gemm: residual epilogue needs resid");
       return dispatch<EPI_RESID_F32>(p, stream);

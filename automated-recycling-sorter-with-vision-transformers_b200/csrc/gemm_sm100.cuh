@@ -15,6 +15,7 @@ enum GemmEpi : int {
   EPI_F32 = 3,         // out_f32 = alpha * acc + bias (+ beta * out_f32)
   EPI_DGELU_BF16 = 4,  // out_bf16 = (acc + bias) * gelu'(aux_bf16)            (fc2 dgrad)
   EPI_GELU_TANH_BF16 = 6,  // as EPI_GELU_BF16 with the tanh.approx form of the normal CDF (A/B)
+  EPI_RELU_BF16 = 7,   // out_bf16 = max(acc + bias, 0)   (decoder feed-forward, evaluation.py:170-176)
 };
 
 struct GemmEpilogue {

@@ -1,0 +1,175 @@
+"""Drop-in mirrors of the reference's detection head and detector wrappers:
+
+    ObjectDetectionHead     evaluation.py:160-200 == train.py:691-731
+    ViTObjectDetector       evaluation.py:203-241
+    DeiTObjectDetector      train.py:798-838 (eval-mode forward)
+
+Constructor arguments, attribute names and `state_dict()` keys are the reference's, so its
+checkpoints (`checkpoint['model_state_dict']`, evaluation.py:375-391) load with `load_state_dict`.
+`self.decoder` is a real `nn.TransformerDecoder` - used ONLY as the parameter container (same
+initialisation and key names as the reference); its `forward` is never called.  The arithmetic is
+`vitk_detection_head_forward` (csrc/detection_head.cu): tcgen05 GEMMs with fused bias / ReLU /
+residual epilogues, fused attention at head_dim D/8, one K/V projection GEMM of the encoder tokens
+for all six layers.  Inference only (eval-mode semantics: dropout is the identity).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from . import _lib, ops
+from ._lib import (VitkDecoderLayerWeights, VitkDetectionHeadConfig, VitkDetectionHeadWeights, check,
+                   lib)
+from .modules import DataEfficientImageTransformer, VisionTransformer
+
+
+class ObjectDetectionHead(nn.Module):
+    def __init__(self, embed_dim=768, num_classes=80, num_queries=100):
+        super().__init__()
+        self.num_classes = num_classes
+        self.num_queries = num_queries
+        self.object_queries = nn.Parameter(torch.randn(num_queries, embed_dim))
+        decoder_layer = nn.TransformerDecoderLayer(d_model=embed_dim, nhead=8, dim_feedforward=2048,
+                                                   dropout=0.1, batch_first=True)
+        self.decoder = nn.TransformerDecoder(decoder_layer, num_layers=6)
+        self.class_head = nn.Linear(embed_dim, num_classes + 1)
+        self.bbox_head = nn.Linear(embed_dim, 4)
+
+    # ------------------------------------------------------------------ weights
+    def _pack(self):
+        ps = list(self.parameters())
+        key = tuple((p.data_ptr(), p._version) for p in ps)
+        st = self.__dict__.get("_vitk_pack")
+        if st is not None and st[0] == key:
+            return st[1], st[2]
+        if self.object_queries.device.type != "cuda":
+            raise _lib.VitkError("the vitk detection head runs on CUDA only - call .to('cuda') "
+                                 "first (no CPU fallback)")
+        keep = []
+
+        def f32(t):
+            t = t.detach()
+            if t.dtype != torch.float32 or not t.is_contiguous():
+                t = t.float().contiguous()
+            keep.append(t)
+            return t.data_ptr()
+
+        def bf16(t):
+            s = ops.cast_bf16(t.detach().float().contiguous())
+            keep.append(s)
+            return s.data_ptr()
+
+        layers = self.decoder.layers
+        L = len(layers)
+        D = self.object_queries.shape[1]
+        arr = (VitkDecoderLayerWeights * L)()
+        kv_w, kv_b = [], []
+        for i, ly in enumerate(layers):
+            a = arr[i]
+            sa, ca = ly.self_attn, ly.multihead_attn
+            a.sa_in_w, a.sa_in_b = bf16(sa.in_proj_weight), f32(sa.in_proj_bias)
+            a.sa_out_w, a.sa_out_b = bf16(sa.out_proj.weight), f32(sa.out_proj.bias)
+            a.ca_q_w, a.ca_q_b = bf16(ca.in_proj_weight[:D]), f32(ca.in_proj_bias[:D])
+            a.ca_out_w, a.ca_out_b = bf16(ca.out_proj.weight), f32(ca.out_proj.bias)
+            a.ff1_w, a.ff1_b = bf16(ly.linear1.weight), f32(ly.linear1.bias)
+            a.ff2_w, a.ff2_b = bf16(ly.linear2.weight), f32(ly.linear2.bias)
+            a.norm1_w, a.norm1_b = f32(ly.norm1.weight), f32(ly.norm1.bias)
+            a.norm2_w, a.norm2_b = f32(ly.norm2.weight), f32(ly.norm2.bias)
+            a.norm3_w, a.norm3_b = f32(ly.norm3.weight), f32(ly.norm3.bias)
+            kv_w.append(ca.in_proj_weight.detach()[D:])
+            kv_b.append(ca.in_proj_bias.detach()[D:])
+        w = VitkDetectionHeadWeights()
+        w.object_queries = f32(self.object_queries)
+        w.layers = C.cast(arr, C.POINTER(VitkDecoderLayerWeights))
+        w.ca_kv_w = bf16(torch.cat(kv_w, dim=0))        # [L*2D, D]: K rows then V rows per layer
+        w.ca_kv_b = f32(torch.cat(kv_b, dim=0))
+        w.class_w, w.class_b = f32(self.class_head.weight), f32(self.class_head.bias)
+        w.bbox_w, w.bbox_b = f32(self.bbox_head.weight), f32(self.bbox_head.bias)
+        ly0 = layers[0]
+        cfg = VitkDetectionHeadConfig(
+            embed_dim=D, num_heads=ly0.self_attn.num_heads, ffn_dim=ly0.linear1.out_features,
+            num_layers=L, num_queries=self.num_queries, num_outputs=self.class_head.out_features,
+            ln_eps=ly0.norm1.eps)
+        self.__dict__["_vitk_pack"] = (key, cfg, (w, arr, keep))
+        return cfg, (w, arr, keep)
+
+    # ------------------------------------------------------------------ the call
+    def decode(self, tokens: torch.Tensor, skip_tokens: int = 0):
+        """tokens f32 [B, N, D] (CUDA); the first `skip_tokens` rows of every image are not part
+        of the memory (`features[:, 1:, :]`, evaluation.py:235, without the copy)."""
+        if torch.is_grad_enabled() and self.training:
+            raise _lib.VitkError("the vitk detection head is inference-only: call .eval() and run "
+                                 "under torch.no_grad()")
+        if not tokens.is_cuda:
+            raise _lib.VitkError("encoder features must be a CUDA tensor (no CPU fallback)")
+        if tokens.dim() != 3 or tokens.shape[2] != self.object_queries.shape[1]:
+            raise _lib.VitkError(f"expected encoder features [B, N, {self.object_queries.shape[1]}], "
+                                 f"got {tuple(tokens.shape)}")
+        tokens = tokens.detach().float().contiguous()
+        B, N, _ = tokens.shape
+        cfg, (w, _, _) = self._pack()
+        need = C.c_size_t(0)
+        check(lib().vitk_detection_head_workspace_bytes(C.byref(cfg), B, N, skip_tokens,
+                                                        C.byref(need)))
+        ws = self.__dict__.get("_vitk_ws")
+        if ws is None or ws.numel() < need.value + 1024 or ws.device != tokens.device:
+            ws = torch.empty(need.value + 1024, dtype=torch.uint8, device=tokens.device)
+            self.__dict__["_vitk_ws"] = ws
+        base = (ws.data_ptr() + 1023) // 1024 * 1024
+        Q = self.num_queries
+        logits = torch.empty((B, Q, cfg.num_outputs), dtype=torch.float32, device=tokens.device)
+        boxes = torch.empty((B, Q, 4), dtype=torch.float32, device=tokens.device)
+        check(lib().vitk_detection_head_forward(
+            C.byref(cfg), C.byref(w), tokens.data_ptr(), B, N, skip_tokens, logits.data_ptr(),
+            boxes.data_ptr(), base, need.value, torch.cuda.current_stream().cuda_stream))
+        return {"class_logits": logits, "bbox_coords": boxes}
+
+    def forward(self, encoder_features):
+        return self.decode(encoder_features, 0)
+
+
+class ViTObjectDetector(nn.Module):
+    """evaluation.py:203-241."""
+
+    def __init__(self, image_size=224, patch_size=16, in_channels=3, embed_dim=768,
+                 num_layers=12, num_heads=12, mlp_dim=3072, dropout=0.1,
+                 num_classes=80, num_queries=100):
+        super().__init__()
+        self.backbone = VisionTransformer(image_size=image_size, patch_size=patch_size,
+                                          in_channels=in_channels, embed_dim=embed_dim,
+                                          num_layers=num_layers, num_heads=num_heads,
+                                          mlp_dim=mlp_dim, dropout=dropout)
+        self.detection_head = ObjectDetectionHead(embed_dim=embed_dim, num_classes=num_classes,
+                                                  num_queries=num_queries)
+        self.num_classes = num_classes
+        self.num_queries = num_queries
+
+    def forward(self, images):
+        features = self.backbone(images)                      # [B, P + 1, D]
+        return self.detection_head.decode(features, 1)       # memory = features[:, 1:, :]
+
+
+class DeiTObjectDetector(nn.Module):
+    """train.py:798-838, eval-mode forward (no triplet features)."""
+
+    def __init__(self, image_size=224, patch_size=16, in_channels=3, embed_dim=768,
+                 num_layers=12, num_heads=12, mlp_dim=3072, dropout=0.1,
+                 num_classes=80, num_queries=100):
+        super().__init__()
+        self.backbone = DataEfficientImageTransformer(
+            image_size=image_size, patch_size=patch_size, in_channels=in_channels,
+            embed_dim=embed_dim, num_layers=num_layers, num_heads=num_heads, mlp_dim=mlp_dim,
+            dropout=dropout)
+        self.detection_head = ObjectDetectionHead(embed_dim=embed_dim, num_classes=num_classes,
+                                                  num_queries=num_queries)
+        self.num_classes = num_classes
+        self.num_queries = num_queries
+        self.triplet_projection = nn.Linear(embed_dim, 256)   # state_dict compatibility
+
+    def forward(self, images, return_features=False):
+        if return_features:
+            raise _lib.VitkError("triplet features are outside the accelerated path")
+        features = self.backbone(images)                      # [B, P + 2, D]
+        return self.detection_head.decode(features, 2)       # drop CLS and DIST (train.py:829)

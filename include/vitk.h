@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define VITK_ABI_VERSION 2
+#define VITK_ABI_VERSION 3
 
 #define VITK_OK 0
 #define VITK_ERR_INVALID 1
@@ -156,6 +156,7 @@ int vitk_forward_u8(const VitkConfig* cfg, const VitkWeights* w, const unsigned 
 #define VITK_EPI_RESID_F32 2 /* out f32  = A B^T + bias + resid f32 */
 #define VITK_EPI_F32 3       /* out f32  = alpha * A B^T + bias + beta * out */
 #define VITK_EPI_DGELU_BF16 4 /* out bf16 = (A B^T + bias) * gelu'(aux bf16) */
+#define VITK_EPI_RELU_BF16 7  /* out bf16 = max(A B^T + bias, 0) (decoder feed-forward) */
 
 /* C[M,N] = A[M,K] * B[N,K]^T (bf16 operands, fp32 accumulate on tcgen05) + fused epilogue.
  * Replaces nn.Linear / F.linear at train.py:527,529,561,564 and the Conv2d at train.py:505. */
@@ -318,6 +319,75 @@ int vitk_attention_bwd(const void* qkv_bf16, const void* ctx_bf16, const void* d
                        const float* lse, void* dqkv_bf16, int batch, int n_tokens, int num_heads,
                        int head_dim, vitk_stream_t stream);
 int vitk_colsum_bf16(const void* y, long long ld, int M, int N, float* out, vitk_stream_t stream);
+
+/* ============ detection head (ObjectDetectionHead, evaluation.py:160-200 == train.py:691-731) ====
+ * The consumer of the backbone's tokens in both reference scripts:
+ *     decoder_output = self.decoder(object_queries, encoder_features)     evaluation.py:189
+ *     class_logits = self.class_head(decoder_output)                      evaluation.py:192
+ *     bbox_coords  = sigmoid(self.bbox_head(decoder_output))              evaluation.py:193-194
+ * with decoder = nn.TransformerDecoder(nn.TransformerDecoderLayer(d_model = D, nhead = 8,
+ * dim_feedforward = 2048, dropout = 0.1, batch_first = True), num_layers = 6): post-LN layers,
+ * ReLU, no final norm.  Eval-mode (inference) forward.  Matrix weights bf16 row-major [out, in],
+ * everything else fp32; member names follow the state_dict keys
+ * detection_head.decoder.layers.{i}.{self_attn.in_proj_weight, self_attn.out_proj, multihead_attn.*,
+ * linear1, linear2, norm1, norm2, norm3}. */
+typedef struct VitkDetectionHeadConfig {
+  int embed_dim;   /* D (768) */
+  int num_heads;   /* 8: head_dim = D / 8 must be 32, 64, 96 or 128 */
+  int ffn_dim;     /* 2048 */
+  int num_layers;  /* 6 */
+  int num_queries; /* 100 */
+  int num_outputs; /* num_classes + 1 (background) */
+  float ln_eps;    /* 1e-5 */
+} VitkDetectionHeadConfig;
+
+typedef struct VitkDecoderLayerWeights {
+  const void* sa_in_w; /* bf16 [3D, D]  self_attn.in_proj_weight */
+  const float* sa_in_b;
+  const void* sa_out_w; /* bf16 [D, D]  self_attn.out_proj.weight */
+  const float* sa_out_b;
+  const void* ca_q_w; /* bf16 [D, D]    multihead_attn.in_proj_weight[:D] */
+  const float* ca_q_b; /*               multihead_attn.in_proj_bias[:D] */
+  const void* ca_out_w; /* bf16 [D, D]  multihead_attn.out_proj.weight */
+  const float* ca_out_b;
+  const void* ff1_w; /* bf16 [F, D]     linear1.weight */
+  const float* ff1_b;
+  const void* ff2_w; /* bf16 [D, F]     linear2.weight */
+  const float* ff2_b;
+  const float* norm1_w;
+  const float* norm1_b;
+  const float* norm2_w;
+  const float* norm2_b;
+  const float* norm3_w;
+  const float* norm3_b;
+} VitkDecoderLayerWeights;
+
+typedef struct VitkDetectionHeadWeights {
+  const float* object_queries;           /* f32 [Q, D] */
+  const VitkDecoderLayerWeights* layers; /* HOST array of num_layers entries */
+  /* K and V projections of the memory for every layer, concatenated so that ONE GEMM projects the
+   * encoder tokens for all layers: rows [l*2D, (l+1)*2D) = layer l's
+   * multihead_attn.in_proj_weight[D:3D] (K rows, then V rows); bias likewise. */
+  const void* ca_kv_w;  /* bf16 [L*2D, D] */
+  const float* ca_kv_b; /* f32 [L*2D] */
+  const float* class_w; /* f32 [num_outputs, D]  class_head.weight */
+  const float* class_b;
+  const float* bbox_w; /* f32 [4, D]  bbox_head.weight */
+  const float* bbox_b;
+} VitkDetectionHeadWeights;
+
+int vitk_detection_head_workspace_bytes(const VitkDetectionHeadConfig* cfg, int batch, int n_tokens,
+                                        int skip_tokens, size_t* out_bytes);
+
+/* tokens: f32 [batch, n_tokens, D] = backbone(images) (vitk_forward's tokens_out); the first
+ * skip_tokens rows of every image (the CLS token, evaluation.py:235 `features[:, 1:, :]`; 2 for
+ * DeiT) are not part of the memory.  class_logits_out f32 [batch, Q, num_outputs];
+ * bbox_out f32 [batch, Q, 4] in (0, 1). */
+int vitk_detection_head_forward(const VitkDetectionHeadConfig* cfg,
+                                const VitkDetectionHeadWeights* w, const float* tokens, int batch,
+                                int n_tokens, int skip_tokens, float* class_logits_out,
+                                float* bbox_out, void* workspace, size_t workspace_bytes,
+                                vitk_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -13,6 +13,8 @@ Fixture kinds
   vitb16_*.npz : ViT-B/16 - only seeds, a SHA-256 of the state_dict and the outputs are stored;
                  the tests rebuild the weights from the seed (our modules reproduce the
                  reference's construction order) and verify the checksum before comparing
+  det_head_*   : the detection head (evaluation.py:160-200) on seeded encoder tokens; parameters are
+                 a pure function of a seed (vit_oracle.randomize_head_state), outputs fp32 / fp64
   trainstep_*  : one fine-tune step (cross-entropy on the 6-class CLS head, AdamW of
                  train.py:1598-1602, dropout 0): loss, per-parameter gradient and updated weights
 """
@@ -132,6 +134,33 @@ def gen_trainstep(name, kind, kw, batch, seed):
     print(f"{name}: loss {float(loss):.6f}")
 
 
+def gen_head(name, embed_dim, num_queries, n_tokens, batch, seed, token_seed, store_tokens):
+    """ObjectDetectionHead of evaluation.py:160-200 run as ViTObjectDetector.forward runs it
+    (evaluation.py:231-238): memory = tokens[:, 1:, :].  Parameters come from
+    O.randomize_head_state (a pure function of the seed and the reference's own state_dict keys /
+    shapes), so the tests rebuild them without the reference; the SHA-256 guards that."""
+    ev = ref_loader.load("evaluation")
+    torch.manual_seed(seed)
+    head = ev.ObjectDetectionHead(embed_dim=embed_dim, num_classes=6, num_queries=num_queries).eval()
+    sd = O.randomize_head_state(head.state_dict(), seed)
+    head.load_state_dict(sd)
+    tokens = torch.randn(batch, n_tokens, embed_dim, generator=torch.Generator().manual_seed(token_seed))
+    import copy
+    with torch.no_grad():
+        o32 = head(tokens[:, 1:, :])
+        o64 = copy.deepcopy(head).double()(tokens[:, 1:, :].double())
+    out = dict(seed=seed, token_seed=token_seed, batch=batch, n_tokens=n_tokens, embed_dim=embed_dim,
+               num_queries=num_queries, num_classes=6, state_sha256=state_sha256(sd),
+               state_keys=np.array(sorted(sd)),
+               class_logits_f32=o32["class_logits"].numpy(), bbox_f32=o32["bbox_coords"].numpy(),
+               class_logits_f64=o64["class_logits"].numpy(), bbox_f64=o64["bbox_coords"].numpy())
+    if store_tokens:
+        out["tokens"] = tokens.numpy()
+    np.savez_compressed(GOLDEN / f"{name}.npz", **out)
+    d = float((o32["class_logits"].double() - o64["class_logits"]).abs().max())
+    print(f"{name}: logits32-64 max diff {d:.2e}, sha {out['state_sha256'][:12]}")
+
+
 def main():
     if not ref_loader.reference_available():
         raise SystemExit("/root/reference is not present - golden vectors can only be generated "
@@ -144,7 +173,17 @@ def main():
     gen_forward("vitb16_deit", "deit", VITB, 8, seed=3, store_weights=False)
     gen_trainstep("trainstep_tiny_vit", "vit", TINY, 4, seed=5)
     gen_trainstep("trainstep_small_deit", "deit", TRAIN_SMALL, 6, seed=6)
+    gen_heads()
+
+
+def gen_heads():
+    gen_head("det_head_small", 256, 10, 17, 3, seed=11, token_seed=12, store_tokens=True)
+    gen_head("det_head_vitb", 768, 100, 197, 2, seed=13, token_seed=14, store_tokens=False)
 
 
 if __name__ == "__main__":
-    main()
+    if "--heads-only" in sys.argv:      # the detection-head fixtures were added after the others
+        GOLDEN.mkdir(parents=True, exist_ok=True)
+        gen_heads()
+    else:
+        main()

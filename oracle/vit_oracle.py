@@ -197,3 +197,89 @@ def train_step(sd: dict, images: torch.Tensor, labels: torch.Tensor, num_heads: 
     vv = {k: torch.zeros_like(v) for k, v in new.items()}
     adamw_step(new, grads, m, vv, step=1, lr=lr, weight_decay=weight_decay)
     return loss.detach(), grads, new
+
+
+# --------------------------------------------------------------------------------------------
+# detection head: ObjectDetectionHead, evaluation.py:160-200 == train.py:691-731
+#
+# The decoder is torch's nn.TransformerDecoder(nn.TransformerDecoderLayer(d_model=D, nhead=8,
+# dim_feedforward=2048, dropout=0.1, batch_first=True), num_layers=6) - third-party code (PyTorch,
+# unpinned by the reference; 2.11.0 here).  Restated from its published definition for the default
+# norm_first=False, activation=relu, no masks, eval mode:
+#     x = norm1(x + self_attn(x, x, x)); x = norm2(x + multihead_attn(x, memory, memory));
+#     x = norm3(x + linear2(relu(linear1(x))))
+# nn.MultiheadAttention: q/k/v = rows [0,D) / [D,2D) / [2D,3D) of in_proj_weight (+ in_proj_bias),
+# heads split along the feature axis, softmax(q k^T / sqrt(head_dim)) v, then out_proj.
+# Pinned by tests/golden/det_head_*.npz (the reference's own class run in the build container).
+# --------------------------------------------------------------------------------------------
+def multihead_attention(q_in: torch.Tensor, kv_in: torch.Tensor, in_w, in_b, out_w, out_b,
+                        num_heads: int) -> torch.Tensor:
+    B, Nq, D = q_in.shape
+    Nk = kv_in.shape[1]
+    hd = D // num_heads
+    q = q_in @ in_w[:D].t() + in_b[:D]
+    k = kv_in @ in_w[D:2 * D].t() + in_b[D:2 * D]
+    v = kv_in @ in_w[2 * D:].t() + in_b[2 * D:]
+    q = q.reshape(B, Nq, num_heads, hd).transpose(1, 2)
+    k = k.reshape(B, Nk, num_heads, hd).transpose(1, 2)
+    v = v.reshape(B, Nk, num_heads, hd).transpose(1, 2)
+    probs = torch.softmax((q @ k.transpose(-2, -1)) / math.sqrt(hd), dim=-1)
+    ctx = (probs @ v).transpose(1, 2).reshape(B, Nq, D)
+    return ctx @ out_w.t() + out_b
+
+
+def decoder_layer(x: torch.Tensor, memory: torch.Tensor, sd: dict, prefix: str,
+                  num_heads: int = 8) -> torch.Tensor:
+    g = lambda k: sd[prefix + k]
+    x = layer_norm(x + multihead_attention(x, x, g("self_attn.in_proj_weight"),
+                                           g("self_attn.in_proj_bias"),
+                                           g("self_attn.out_proj.weight"),
+                                           g("self_attn.out_proj.bias"), num_heads),
+                   g("norm1.weight"), g("norm1.bias"))
+    x = layer_norm(x + multihead_attention(x, memory, g("multihead_attn.in_proj_weight"),
+                                           g("multihead_attn.in_proj_bias"),
+                                           g("multihead_attn.out_proj.weight"),
+                                           g("multihead_attn.out_proj.bias"), num_heads),
+                   g("norm2.weight"), g("norm2.bias"))
+    h = torch.relu(x @ g("linear1.weight").t() + g("linear1.bias"))
+    return layer_norm(x + h @ g("linear2.weight").t() + g("linear2.bias"),
+                      g("norm3.weight"), g("norm3.bias"))
+
+
+def detection_head_forward(sd: dict, encoder_features: torch.Tensor, prefix: str = "",
+                           dtype: torch.dtype = torch.float32, num_heads: int = 8) -> dict:
+    """ObjectDetectionHead.forward - evaluation.py:183-200.  encoder_features [B, P, D] is the
+    memory (the callers strip the CLS / DIST rows first: evaluation.py:235, train.py:829)."""
+    sd = {k: v.to(dtype) for k, v in sd.items() if k.startswith(prefix)}
+    g = lambda k: sd[prefix + k]
+    memory = encoder_features.to(dtype)
+    B = memory.shape[0]
+    x = g("object_queries").unsqueeze(0).expand(B, -1, -1)          # :186
+    n_layers = 1 + max(int(k[len(prefix):].split(".")[2]) for k in sd
+                       if k.startswith(prefix + "decoder.layers."))
+    for i in range(n_layers):                                       # :189
+        x = decoder_layer(x, memory, sd, f"{prefix}decoder.layers.{i}.", num_heads)
+    class_logits = x @ g("class_head.weight").t() + g("class_head.bias")            # :192
+    bbox = torch.sigmoid(x @ g("bbox_head.weight").t() + g("bbox_head.bias"))      # :193-194
+    return {"class_logits": class_logits, "bbox_coords": bbox}
+
+
+def randomize_head_state(sd: dict, seed: int) -> dict:
+    """Deterministic non-degenerate parameters for the head fixtures: torch's constructor clones
+    one decoder layer six times and zero-initialises the attention biases, which would leave the
+    bias paths and per-layer indexing untested.  Matrices ~ N(0, 1/fan_in), biases ~ N(0, 0.1^2),
+    LayerNorm weights 1 + N(0, 0.1^2), queries N(0, 1); keys visited in sorted order."""
+    g = torch.Generator().manual_seed(seed)
+    out = {}
+    for k in sorted(sd):
+        v = sd[k]
+        r = torch.randn(v.shape, generator=g, dtype=torch.float32)
+        if k.endswith("object_queries"):
+            out[k] = r
+        elif ".norm" in k and k.endswith("weight"):
+            out[k] = 1.0 + 0.1 * r
+        elif v.dim() == 2:
+            out[k] = r / math.sqrt(v.shape[1])
+        else:
+            out[k] = 0.1 * r
+    return out

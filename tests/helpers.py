@@ -42,3 +42,24 @@ def build_classifier(vitk, z, cfg, seed_rebuild=False):
         missing = model.load_state_dict(weights(z), strict=True)
         assert not missing.missing_keys and not missing.unexpected_keys
     return model
+
+
+def build_head(vitk, z):
+    """ObjectDetectionHead mirror carrying a det_head_* fixture's parameters: rebuilt from the seed
+    with oracle.randomize_head_state over the mirror's own state_dict keys / shapes (which must be
+    the reference's) and checked against the stored SHA-256."""
+    from oracle import vit_oracle as O
+    head = vitk.ObjectDetectionHead(embed_dim=int(z["embed_dim"]), num_classes=int(z["num_classes"]),
+                                    num_queries=int(z["num_queries"]))
+    assert sorted(head.state_dict()) == [str(k) for k in z["state_keys"]]
+    sd = O.randomize_head_state(head.state_dict(), int(z["seed"]))
+    assert state_sha256(sd) == str(z["state_sha256"]), "rebuilt head weights differ from the fixture"
+    head.load_state_dict(sd)
+    return head.eval(), sd
+
+
+def head_tokens(z):
+    if "tokens" in z.files:
+        return torch.from_numpy(z["tokens"])
+    return torch.randn(int(z["batch"]), int(z["n_tokens"]), int(z["embed_dim"]),
+                       generator=torch.Generator().manual_seed(int(z["token_seed"])))

@@ -1,0 +1,135 @@
+"""Detection head on the GPU, through vitk_detection_head_forward, against
+(1) the committed outputs of the reference's own ObjectDetectionHead (tests/golden/det_head_*.npz)
+and (2) the oracle restatement on further shapes.  bf16 operands with fp32 accumulation: the bar
+is north_star's 2e-2 on the class logits (bbox is a sigmoid output in (0,1): 1e-2)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import vit_oracle as O
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+LOGIT_TOL = 2e-2
+BOX_TOL = 1e-2
+
+
+def _check(out, ref_logits, ref_boxes, logit_tol=LOGIT_TOL, box_tol=BOX_TOL):
+    lg = out["class_logits"].cpu().double()
+    bx = out["bbox_coords"].cpu().double()
+    assert lg.shape == ref_logits.shape and bx.shape == ref_boxes.shape
+    assert torch.isfinite(lg).all() and torch.isfinite(bx).all()
+    e_l = (lg - ref_logits).abs().max().item()
+    e_b = (bx - ref_boxes).abs().max().item()
+    print("max |logit err|", e_l, "max |bbox err|", e_b)
+    assert e_l < logit_tol and e_b < box_tol
+    # post_process_predictions' decision (evaluation.py:403-404): class of the best non-background
+    # probability per query - must agree wherever the reference's margin exceeds the tolerance
+    p_ref = torch.softmax(ref_logits, -1)[..., :-1]
+    top2 = p_ref.topk(2, -1).values
+    clear = (top2[..., 0] - top2[..., 1]) > 0.05
+    got = torch.softmax(lg, -1)[..., :-1].argmax(-1)
+    assert torch.equal(got[clear], p_ref.argmax(-1)[clear])
+
+
+@pytest.mark.parametrize("name", ["det_head_small", "det_head_vitb"])
+def test_head_matches_reference_golden(vitk, name):
+    z = np.load(H.GOLDEN / f"{name}.npz", allow_pickle=True)
+    head, _ = H.build_head(vitk, z)
+    head = head.cuda()
+    tokens = H.head_tokens(z).cuda()
+    with torch.no_grad():
+        out = head.decode(tokens, skip_tokens=1)           # ViTObjectDetector.forward's slicing
+        out2 = head(tokens[:, 1:, :].contiguous())         # ObjectDetectionHead.forward's contract
+    _check(out, torch.from_numpy(z["class_logits_f64"]), torch.from_numpy(z["bbox_f64"]))
+    assert torch.equal(out["class_logits"], out2["class_logits"])
+    assert torch.equal(out["bbox_coords"], out2["bbox_coords"])
+
+
+@pytest.mark.parametrize("D,Q,P,B,skip", [
+    (256, 1, 1, 1, 0),        # one query, one memory token
+    (256, 16, 64, 2, 2),      # DeiT slicing (CLS + DIST dropped), head_dim 32
+    (512, 33, 209, 3, 1),     # head_dim 64; memory longer than one shared-memory segment
+    (768, 100, 576, 2, 1),    # ViT-B at 384 px: 576 memory tokens, head_dim 96, 3 key segments
+    (768, 130, 196, 2, 1),    # more than 112 queries: two query groups per (image, head)
+    (1024, 20, 49, 2, 1),     # ViT-L width: head_dim 128
+])
+def test_head_matches_oracle(vitk, D, Q, P, B, skip):
+    torch.manual_seed(0)
+    head = vitk.ObjectDetectionHead(embed_dim=D, num_classes=6, num_queries=Q).eval()
+    sd = O.randomize_head_state(head.state_dict(), 100 + Q)
+    head.load_state_dict(sd)
+    head = head.cuda()
+    tokens = torch.randn(B, P + skip, D, generator=torch.Generator().manual_seed(9))
+    with torch.no_grad():
+        ref = O.detection_head_forward(sd, tokens[:, skip:, :], dtype=torch.float64)
+        out = head.decode(tokens.cuda(), skip_tokens=skip)
+    _check(out, ref["class_logits"], ref["bbox_coords"])
+
+
+def test_batch_independence_and_determinism(vitk):
+    """Images are independent units: the result for an image does not depend on
+    what else is in the batch, and repeated calls are bit-identical."""
+    torch.manual_seed(0)
+    head = vitk.ObjectDetectionHead(embed_dim=768, num_classes=6, num_queries=100).eval()
+    head.load_state_dict(O.randomize_head_state(head.state_dict(), 5))
+    head = head.cuda()
+    tokens = torch.randn(5, 197, 768, generator=torch.Generator().manual_seed(2)).cuda()
+    with torch.no_grad():
+        a = head.decode(tokens, 1)
+        b = head.decode(tokens, 1)
+        c = head.decode(tokens[3:4].contiguous(), 1)
+    assert torch.equal(a["class_logits"], b["class_logits"])
+    assert torch.equal(a["bbox_coords"], b["bbox_coords"])
+    assert (a["class_logits"][3:4] - c["class_logits"]).abs().max() < 1e-5
+    assert (a["bbox_coords"][3:4] - c["bbox_coords"]).abs().max() < 1e-5
+
+
+def test_detector_end_to_end(vitk):
+    """ViTObjectDetector mirror (evaluation.py:203-241): images -> backbone -> head, against the
+    oracle of both stages; plus the device-side post-processing on the class logits."""
+    kw = dict(image_size=64, patch_size=16, embed_dim=256, num_layers=2, num_heads=4, mlp_dim=512)
+    torch.manual_seed(3)
+    det = vitk.ViTObjectDetector(num_classes=6, num_queries=12, dropout=0.1, **kw).eval()
+    sd = det.state_dict()
+    hsd = O.randomize_head_state({k: v for k, v in sd.items() if k.startswith("detection_head.")}, 8)
+    sd.update(hsd)
+    det.load_state_dict(sd)
+    x = O.synthetic_images(3, 64)
+    with torch.no_grad():
+        toks = O.backbone_forward(sd, x, 4, prefix="backbone.", dtype=torch.float64)
+        ref = O.detection_head_forward(sd, toks[:, 1:, :], prefix="detection_head.",
+                                       dtype=torch.float64)
+        det = det.cuda()
+        out = det(x.cuda())
+        # the head alone, fed the GPU backbone's own tokens, meets the per-stage bar ...
+        mine_toks = det.backbone(x.cuda())
+        ref_stage = O.detection_head_forward(sd, mine_toks[:, 1:, :].cpu(),
+                                             prefix="detection_head.", dtype=torch.float64)
+    _check(out, ref_stage["class_logits"], ref_stage["bbox_coords"])
+    # ... and the two bf16 stages chained (encoder tokens within 6e-2, tests/test_golden_gpu.py,
+    # then six decoder layers) stay within 5e-2 of the all-fp64 pipeline
+    _check(out, ref["class_logits"], ref["bbox_coords"], logit_tol=5e-2, box_tol=2e-2)
+    scores, labels = vitk.ops.postprocess_scores(out["class_logits"].reshape(-1, 7),
+                                                 exclude_last=True)
+    p = torch.softmax(out["class_logits"].reshape(-1, 7), -1)[:, :-1]
+    assert torch.equal(labels.cpu(), p.argmax(-1).cpu())
+    assert (scores - p.max(-1).values).abs().max() < 1e-6
+
+
+def test_head_rejects_bad_arguments(vitk):
+    head = vitk.ObjectDetectionHead(embed_dim=256, num_classes=6, num_queries=4).eval().cuda()
+    with torch.no_grad():
+        with pytest.raises(vitk.VitkError):
+            head(torch.zeros(1, 4, 128, device="cuda"))        # wrong width
+        with pytest.raises(vitk.VitkError):
+            head(torch.zeros(1, 4, 256))                       # CPU tensor: no fallback
+        with pytest.raises(vitk.VitkError):
+            head.decode(torch.zeros(1, 2, 256, device="cuda"), skip_tokens=2)   # empty memory
+    head.train()
+    with pytest.raises(vitk.VitkError):
+        head(torch.zeros(1, 4, 256, device="cuda"))            # training mode is not accelerated
+    bad = vitk.ObjectDetectionHead(embed_dim=64, num_classes=6, num_queries=4).eval().cuda()
+    with torch.no_grad(), pytest.raises(vitk.VitkError):
+        bad(torch.zeros(1, 4, 64, device="cuda"))              # head_dim 8 unsupported

@@ -85,6 +85,42 @@ def test_oracle_matches_live_reference(vitk, kind):
     mine.load_state_dict(ref.state_dict(), strict=True)
 
 
+@pytest.mark.parametrize("name", ["det_head_small", "det_head_vitb"])
+def test_head_oracle_matches_reference_golden(vitk, name):
+    """Detection head restatement vs the outputs of the reference's ObjectDetectionHead."""
+    z = H.np.load(H.GOLDEN / f"{name}.npz", allow_pickle=True)
+    _, sd = H.build_head(vitk, z)          # also: mirror keys == reference keys, SHA-256
+    tokens = H.head_tokens(z)
+    with torch.no_grad():
+        o64 = O.detection_head_forward(sd, tokens[:, 1:, :], dtype=torch.float64)
+        o32 = O.detection_head_forward(sd, tokens[:, 1:, :], dtype=torch.float32)
+    assert (o64["class_logits"] - torch.from_numpy(z["class_logits_f64"])).abs().max() < 1e-10
+    assert (o64["bbox_coords"] - torch.from_numpy(z["bbox_f64"])).abs().max() < 1e-10
+    assert (o32["class_logits"] - torch.from_numpy(z["class_logits_f32"])).abs().max() < 2e-5
+    assert (o32["bbox_coords"] - torch.from_numpy(z["bbox_f32"])).abs().max() < 2e-5
+
+
+@pytest.mark.skipif(not ref_loader.reference_available(), reason="reference only in the build box")
+def test_head_oracle_and_mirror_match_live_reference(vitk):
+    ev = ref_loader.load("evaluation")
+    torch.manual_seed(21)
+    ref = ev.ViTObjectDetector(image_size=32, embed_dim=64, num_layers=1, num_heads=2, mlp_dim=64,
+                               num_classes=6, num_queries=5).eval()
+    torch.manual_seed(21)
+    mine = vitk.ViTObjectDetector(image_size=32, embed_dim=64, num_layers=1, num_heads=2, mlp_dim=64,
+                                  num_classes=6, num_queries=5)
+    assert list(ref.state_dict().keys()) == list(mine.state_dict().keys())
+    for (k, a), b in zip(ref.state_dict().items(), mine.state_dict().values()):
+        assert torch.equal(a, b), k                      # same constructor order, same RNG stream
+    mine.load_state_dict(ref.state_dict(), strict=True)  # a reference checkpoint loads
+    mem = torch.randn(2, 4, 64, generator=torch.Generator().manual_seed(5))
+    with torch.no_grad():
+        want = ref.detection_head(mem)
+        got = O.detection_head_forward(ref.state_dict(), mem, prefix="detection_head.")
+    assert (want["class_logits"] - got["class_logits"]).abs().max() < 2e-5
+    assert (want["bbox_coords"] - got["bbox_coords"]).abs().max() < 2e-5
+
+
 def test_synthetic_inputs_are_deterministic():
     a, b = O.synthetic_images(2, 32), O.synthetic_images(2, 32)
     assert torch.equal(a, b) and a.shape == (2, 3, 32, 32) and a.dtype == torch.float32
