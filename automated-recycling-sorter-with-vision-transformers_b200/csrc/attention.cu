@@ -256,6 +256,16 @@ int attention_impl() { return g_attn_impl; }
 int attention_fwd(const void* qkv, void* ctx, float* lse, int B, int N, int H, int hd,
                   cudaStream_t stream, const DropParams* drop) {
   VITK_REQUIRE(qkv && ctx, "attention: null operand");
+  if (hd != 64) {
+    // other head sizes (32 / 96 / 128): the generic-source kernel on the packed activation
+    VITK_REQUIRE(lse == nullptr && (drop == nullptr || drop->thresh == 0u),
+                 "attention: head_dim %d is inference-only (training needs head_dim 64)", hd);
+    const __nv_bfloat16* p = static_cast<const __nv_bfloat16*>(qkv);
+    const int D = H * hd;
+    const long long img = static_cast<long long>(N) * 3 * D;
+    return attention_x(p, img, 3 * D, p + D, p + 2 * D, img, 3 * D, ctx,
+                       static_cast<long long>(N) * D, D, B, N, N, H, hd, stream);
+  }
   if (drop != nullptr && drop->thresh != 0u) {
     VITK_REQUIRE(hd == 64 && N <= 208 && device_cc() >= 100,
                  "attention dropout is implemented by the pipelined tcgen05 kernel only "

@@ -52,6 +52,13 @@ int attention_fwd_tc2(const void* qkv, void* ctx, float* lse, int B, int N, int 
 // Two-pass tcgen05 variant for long sequences, N <= 640 (attention_tc3.cu): 384 px -> 577 tokens.
 int attention_fwd_tc3(const void* qkv, void* ctx, float* lse, int B, int N, int H, int hd,
                       cudaStream_t stream);
+// Generic-source attention (attention_x.cu): query rows at q + b*q_img + r*ldq + h*hd, keys / values
+// at k|v + b*kv_img + r*ldkv + h*hd, output at ctx + b*ctx_img + r*ldc + h*hd (all bf16, strides
+// in elements); head_dim 32 / 64 / 96 / 128.  Decoder self-/cross-attention and the encoder's
+// attention when head_dim != 64 (inference: no log-sum-exp output).
+int attention_x(const void* q, long long q_img, int ldq, const void* k, const void* v,
+                long long kv_img, int ldkv, void* ctx, long long ctx_img, int ldc, int B, int Nq,
+                int Nk, int H, int hd, cudaStream_t stream);
 void attention_force_impl(int impl);
 
 }  // namespace vitk

@@ -240,6 +240,52 @@ def measure_train_step(vitk, O, dev, world, rank, barrier, steps: int = 8, warmu
                                 "NCCL sum over 14 flat fp32 slices after the backward"))}
 
 
+def measure_detector(vitk, dev, world, barrier, batch: int, steps: int = 6, warmup: int = 3) -> dict:
+    """evaluation.py's real model call, ViTObjectDetector(images) = ViT-B/16
+    backbone + 6-layer detection head (100 queries, 6 + 1 classes), batch-sharded like the
+    headline; device-resident inputs, CUDA events, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    torch.manual_seed(0)
+    det = vitk.ViTObjectDetector(num_classes=N_CLASSES, num_queries=100, **VIT_B16).to(dev).eval()
+    x = torch.randn(batch, 3, VIT_B16["image_size"], VIT_B16["image_size"], device=dev)
+    with torch.no_grad():
+        for _ in range(warmup):
+            out = det(x)
+        toks = det.backbone(x)
+        barrier()
+        n0 = vitk.launch_count()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        ev[0].record()
+        for _ in range(steps):
+            out = det(x)
+        ev[1].record()
+        launches = vitk.launch_count() - n0
+        for _ in range(steps):
+            out = det.detection_head.decode(toks, 1)
+        ev[2].record()
+        barrier()
+    ms, ms_head = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])
+    if world > 1:
+        t = torch.tensor([ms, ms_head], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_head = float(t[0].item()), float(t[1].item())
+    P, D, Q, F, L = 196, 768, 100, 2048, 6
+    head_flops = (2 * (P + 1) * D * L * 2 * D + L * (2 * Q * D * 3 * D + 4 * Q * Q * D + 4 * Q * D * D
+                  + 2 * Q * D * D + 4 * Q * P * D + 4 * Q * D * F) + 2 * Q * D * (N_CLASSES + 5))
+    assert bool(torch.isfinite(out["class_logits"]).all())
+    del det
+    torch.cuda.empty_cache()
+    return {"metric": "vit_b16_224_detector_images_per_sec",
+            "value": world * batch * steps / (ms * 1e-3), "unit": UNIT,
+            "ms_per_step": ms / steps, "head_ms_per_step": ms_head / steps,
+            "head_tflops": batch * head_flops / (ms_head / steps * 1e-3) / 1e12,
+            "head_gflop_per_image": head_flops / 1e9, "batch_per_gpu": batch,
+            "gpu_launches": int(launches), "steps": steps, "warmup": warmup,
+            "api": "ViTObjectDetector.forward (evaluation.py:203-241): vitk_forward + "
+                   "vitk_detection_head_forward"}
+
+
 def run_vitk(args) -> None:
     import torch
     import torch.distributed as dist
@@ -350,6 +396,8 @@ def run_vitk(args) -> None:
     train0 = None if args.no_train else measure_train_step(vitk, O, dev, world, rank, barrier,
                                                            steps=5, dropout=0.0)
 
+    detector = None if args.no_train else measure_detector(vitk, dev, world, barrier, B)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -407,6 +455,8 @@ def run_vitk(args) -> None:
         line["train_step"] = train
         line["train_step_no_dropout"] = {k: train0[k] for k in
                                          ("value", "unit", "ms_per_step", "tflops", "dropout")}
+    if detector is not None:
+        line["detector"] = detector
     if cpu is not None:
         line["cpu_baseline"] = cpu
     _emit(json.dumps(line))

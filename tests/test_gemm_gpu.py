@@ -69,6 +69,16 @@ def test_gemm_gelu_epilogue(vitk, M, N, K):
 
 
 @pytest.mark.parametrize("M,N,K", SHAPES[:5])
+def test_gemm_relu_epilogue(vitk, M, N, K):
+    """linear1 + ReLU of the decoder feed-forward (nn.TransformerDecoderLayer, evaluation.py:170)."""
+    a, b, bias = _mk(M, N, K, seed=7)
+    out = vitk.ops.gemm(a, b, vitk._lib.EPI_RELU_BF16, bias=bias)
+    ref = torch.relu(_ref(a, b) + bias)
+    assert (out >= 0).all()
+    torch.testing.assert_close(out.float(), ref.bfloat16().float(), rtol=1e-2, atol=1e-2)
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES[:5])
 def test_gemm_residual_epilogue_inplace(vitk, M, N, K):
     a, b, bias = _mk(M, N, K, seed=3)
     resid = torch.randn(M, N, device="cuda")

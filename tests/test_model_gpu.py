@@ -51,6 +51,19 @@ def test_small_configs_match_oracle(vitk, kw, B, deit):
     assert_top1(logits, l_ref)
 
 
+@pytest.mark.parametrize("D,H,S,deit", [(128, 4, 64, False),      # head_dim 32
+                                         (192, 2, 224, True),     # head_dim 96, 198 tokens
+                                         (256, 2, 384, False)])   # head_dim 128, 577 tokens
+def test_other_head_sizes_match_oracle(vitk, D, H, S, deit):
+    """head_dim != 64 (every configuration of the reference uses 64): the generic-source attention
+    kernel on the packed qkv activation, inference only."""
+    kw = dict(image_size=S, patch_size=16, embed_dim=D, num_layers=2, num_heads=H, mlp_dim=2 * D)
+    tokens, logits, t_ref, l_ref = _run(vitk, kw, 3, deit)
+    assert (logits - l_ref).abs().max() < 2e-2
+    assert (tokens - t_ref).abs().max() < 6e-2
+    assert_top1(logits, l_ref)
+
+
 def test_vit_b16_matches_oracle(vitk):
     kw = dict(image_size=224, patch_size=16, embed_dim=768, num_layers=12, num_heads=12, mlp_dim=3072)
     tokens, logits, t_ref, l_ref = _run(vitk, kw, 4, False)
