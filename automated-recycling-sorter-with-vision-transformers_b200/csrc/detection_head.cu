@@ -243,8 +243,14 @@ int linear(const void* A, int lda, const void* W, int M, int N, int K, GemmEpi e
 
 int attn_x(const HeadDims& d, int B, const void* q, long long q_img, int ldq, const void* k,
            const void* v, long long kv_img, int ldkv, int Nk, void* ctx, cudaStream_t stream) {
-  return attention_x(q, q_img, ldq, k, v, kv_img, ldkv, ctx, static_cast<long long>(d.Q) * d.D, d.D,
-                     B, d.Q, Nk, d.H, d.hd, stream);
+  const long long ctx_img = static_cast<long long>(d.Q) * d.D;
+  // tcgen05 kernel when the queries are one MMA tile and the keys one block (the reference's 100
+  // queries against 100 / 196 keys); attention impl 1 forces the mma.sync kernel (tests, A/B)
+  if (attention_impl() != 1 && attention_xtc_applicable(q_img, kv_img, B, d.Q, Nk, d.hd))
+    return attention_xtc(q, q_img, ldq, k, v, kv_img, ldkv, ctx, ctx_img, d.D, B, d.Q, Nk, d.H, d.hd,
+                         stream);
+  return attention_x(q, q_img, ldq, k, v, kv_img, ldkv, ctx, ctx_img, d.D, B, d.Q, Nk, d.H, d.hd,
+                     stream);
 }
 
 int head_forward(const VitkDetectionHeadConfig* cfg, const VitkDetectionHeadWeights* w,

@@ -59,6 +59,13 @@ int attention_fwd_tc3(const void* qkv, void* ctx, float* lse, int B, int N, int 
 int attention_x(const void* q, long long q_img, int ldq, const void* k, const void* v,
                 long long kv_img, int ldkv, void* ctx, long long ctx_img, int ldc, int B, int Nq,
                 int Nk, int H, int hd, cudaStream_t stream);
+// tcgen05 form of attention_x for one query tile and one key block (<= 128 queries, <= 256 keys):
+// the decoder layers of the detection head (attention_xtc.cu).
+bool attention_xtc_applicable(long long q_img, long long kv_img, int B, int Nq, int Nk, int hd);
+int attention_xtc(const void* q, long long q_img, int ldq, const void* k, const void* v,
+                  long long kv_img, int ldkv, void* ctx, long long ctx_img, int ldc, int B, int Nq,
+                  int Nk, int H, int hd, cudaStream_t stream);
 void attention_force_impl(int impl);
+int attention_impl();
 
 }  // namespace vitk

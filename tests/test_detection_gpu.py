@@ -33,8 +33,17 @@ def _check(out, ref_logits, ref_boxes, logit_tol=LOGIT_TOL, box_tol=BOX_TOL):
     assert torch.equal(got[clear], p_ref.argmax(-1)[clear])
 
 
+@pytest.fixture(params=[0, 1], ids=["attn-tcgen05", "attn-mma.sync"])
+def attn_impl(request, vitk):
+    """0: the tcgen05 decoder attention wherever it applies (<= 128 queries, <= 256 keys);
+    1: the mma.sync generic-source kernel everywhere."""
+    vitk._lib.set_attention_impl(request.param)
+    yield request.param
+    vitk._lib.set_attention_impl(0)
+
+
 @pytest.mark.parametrize("name", ["det_head_small", "det_head_vitb"])
-def test_head_matches_reference_golden(vitk, name):
+def test_head_matches_reference_golden(vitk, name, attn_impl):
     z = np.load(H.GOLDEN / f"{name}.npz", allow_pickle=True)
     head, _ = H.build_head(vitk, z)
     head = head.cuda()
@@ -54,8 +63,10 @@ def test_head_matches_reference_golden(vitk, name):
     (768, 100, 576, 2, 1),    # ViT-B at 384 px: 576 memory tokens, head_dim 96, 3 key segments
     (768, 130, 196, 2, 1),    # more than 112 queries: two query groups per (image, head)
     (1024, 20, 49, 2, 1),     # ViT-L width: head_dim 128
+    (768, 128, 256, 3, 1),    # the largest shape of the tcgen05 kernel: 128 queries, 256 keys
+    (768, 100, 100, 40, 1),   # more (image, head) items than SMs: several items per persistent CTA
 ])
-def test_head_matches_oracle(vitk, D, Q, P, B, skip):
+def test_head_matches_oracle(vitk, D, Q, P, B, skip, attn_impl):
     torch.manual_seed(0)
     head = vitk.ObjectDetectionHead(embed_dim=D, num_classes=6, num_queries=Q).eval()
     sd = O.randomize_head_state(head.state_dict(), 100 + Q)
