@@ -1,10 +1,12 @@
-"""Host-buffer entry point of the classifier: the evaluation loop of the reference
-(evaluation.py:498-502 - `images.to(device)`; `model(images)`) with the host->device copy of batch
-i+1 overlapped with the kernels of batch i.
+"""Host-buffer entry point of the classifier and of the detector: the evaluation loop of the
+reference (evaluation.py:498-502 - `images.to(device)`; `model(images)`) with the host->device copy
+of batch i+1 overlapped with the kernels of batch i.
 
     runner = HostBatchRunner(model, batch_size)
     for logits in runner.run(host_batches):      # host_batches: pinned f32 [B,3,S,S] CPU tensors
         ...                                      # logits: f32 [B, n_classes] CPU tensor
+    # model = ViTObjectDetector / DeiTObjectDetector: each result is the reference's prediction
+    # dict {'class_logits': [B,Q,C+1], 'bbox_coords': [B,Q,4]} as pinned CPU tensors
 
 Two device input slots and a dedicated copy stream; every step moves its images host->device and
 its logits device->host.  PyTorch is used for streams, events and memory only.
@@ -33,16 +35,23 @@ class HostBatchRunner:
         else:
             raise ValueError("input_dtype must be torch.float32 or torch.uint8")
         self.shape, self.input_dtype = shape, input_dtype
-        self.n_classes = model.head.out_features
+        self.detector = hasattr(model, "detection_head")
+        if self.detector:
+            head = model.detection_head
+            out_shapes = {"class_logits": (batch_size, head.num_queries, head.class_head.out_features),
+                          "bbox_coords": (batch_size, head.num_queries, 4)}
+        else:
+            self.n_classes = model.head.out_features
+            out_shapes = {"logits": (batch_size, self.n_classes)}
         self._dev_in = [torch.empty(shape, dtype=input_dtype, device=self.device) for _ in range(2)]
-        self._host_out = [torch.empty((batch_size, self.n_classes), dtype=torch.float32).pin_memory()
-                          for _ in range(2)]
+        self._host_out = [{k: torch.empty(v, dtype=torch.float32).pin_memory()
+                           for k, v in out_shapes.items()} for _ in range(2)]
         self._copy_stream = torch.cuda.Stream(device=self.device)
         self._in_ready = [torch.cuda.Event() for _ in range(2)]    # H2D of slot done
         self._in_free = [torch.cuda.Event() for _ in range(2)]     # compute finished reading slot
         self._out_ready = [torch.cuda.Event() for _ in range(2)]   # D2H of slot's logits done
         self.h2d_bytes_per_step = self._dev_in[0].element_size() * self._dev_in[0].numel()
-        self.d2h_bytes_per_step = 4 * batch_size * self.n_classes
+        self.d2h_bytes_per_step = sum(4 * t.numel() for t in self._host_out[0].values())
 
     def _enqueue_copy(self, slot: int, host: torch.Tensor, first_use: bool):
         if tuple(host.shape) != self.shape or host.dtype != self.input_dtype or host.is_cuda:
@@ -76,17 +85,23 @@ class HostBatchRunner:
                 self._enqueue_copy(slot ^ 1, after, not used[slot ^ 1])
                 used[slot ^ 1] = True
             main.wait_event(self._in_ready[slot])
-            logits = self.model(self._dev_in[slot])
+            out = self.model(self._dev_in[slot])
             self._in_free[slot].record(main)
             if pending is not None:
-                # the previous step's logits must have left the pinned buffer before its reuse
+                # the previous step's results must have left the pinned buffers before their reuse
                 self._out_ready[pending].synchronize()
-                yield self._host_out[pending]
-            self._host_out[slot].copy_(logits, non_blocking=True)
+                yield self._result(pending)
+            if not self.detector:
+                out = {"logits": out}
+            for k, host in self._host_out[slot].items():
+                host.copy_(out[k], non_blocking=True)
             self._out_ready[slot].record(main)
             pending = slot
             nxt = after
             i += 1
         if pending is not None:
             self._out_ready[pending].synchronize()
-            yield self._host_out[pending]
+            yield self._result(pending)
+
+    def _result(self, slot: int):
+        return self._host_out[slot] if self.detector else self._host_out[slot]["logits"]

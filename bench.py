@@ -270,6 +270,28 @@ def measure_detector(vitk, dev, world, barrier, batch: int, steps: int = 6, warm
         t = torch.tensor([ms, ms_head], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms_head = float(t[0].item()), float(t[1].item())
+    # end to end: pinned host images in, the prediction dict on the host out (evaluation.py:498-502)
+    import time
+    host = torch.randn(batch, 3, VIT_B16["image_size"], VIT_B16["image_size"]).pin_memory()
+    runner = vitk.HostBatchRunner(det, batch, dev)
+    for _ in runner.run([host] * 3):
+        pass
+    barrier()
+    t0 = time.perf_counter()
+    for res in runner.run([host] * steps):
+        pass
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e = {"value": world * batch * steps / e2e_s, "unit": UNIT,
+           "h2d_bytes_per_step": runner.h2d_bytes_per_step,
+           "d2h_bytes_per_step": runner.d2h_bytes_per_step,
+           "api": "HostBatchRunner.run over a ViTObjectDetector (pinned f32 NCHW host batches -> "
+                  "host class_logits + bbox_coords)"}
+    del runner
     P, D, Q, F, L = 196, 768, 100, 2048, 6
     head_flops = (2 * (P + 1) * D * L * 2 * D + L * (2 * Q * D * 3 * D + 4 * Q * Q * D + 4 * Q * D * D
                   + 2 * Q * D * D + 4 * Q * P * D + 4 * Q * D * F) + 2 * Q * D * (N_CLASSES + 5))
@@ -281,7 +303,7 @@ def measure_detector(vitk, dev, world, barrier, batch: int, steps: int = 6, warm
             "ms_per_step": ms / steps, "head_ms_per_step": ms_head / steps,
             "head_tflops": batch * head_flops / (ms_head / steps * 1e-3) / 1e12,
             "head_gflop_per_image": head_flops / 1e9, "batch_per_gpu": batch,
-            "gpu_launches": int(launches), "steps": steps, "warmup": warmup,
+            "gpu_launches": int(launches), "steps": steps, "warmup": warmup, "e2e": e2e,
             "api": "ViTObjectDetector.forward (evaluation.py:203-241): vitk_forward + "
                    "vitk_detection_head_forward"}
 

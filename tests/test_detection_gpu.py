@@ -129,6 +129,29 @@ def test_detector_end_to_end(vitk):
     assert (scores - p.max(-1).values).abs().max() < 1e-6
 
 
+def test_host_batch_runner_over_a_detector(vitk):
+    """evaluation.py:498-502 with host buffers: pinned images in, the prediction dict out; the
+    results equal the direct call, also with raw u8 NHWC images (device-side Normalize)."""
+    kw = dict(image_size=64, patch_size=16, embed_dim=256, num_layers=2, num_heads=4, mlp_dim=512)
+    torch.manual_seed(4)
+    det = vitk.ViTObjectDetector(num_classes=6, num_queries=9, **kw).cuda().eval()
+    g = torch.Generator().manual_seed(77)
+    u8 = torch.randint(0, 256, (6, 64, 64, 3), generator=g, dtype=torch.uint8)
+    mean, std = torch.tensor(O.IMAGENET_MEAN), torch.tensor(O.IMAGENET_STD)
+    x = ((u8.float() / 255.0 - mean) / std).permute(0, 3, 1, 2).contiguous()
+    with torch.no_grad():
+        want = det(x.cuda())
+    for dtype, batches in ((torch.float32, [x[:3].pin_memory(), x[3:].pin_memory()]),
+                           (torch.uint8, [u8[:3].pin_memory(), u8[3:].pin_memory()])):
+        runner = vitk.HostBatchRunner(det, 3, input_dtype=dtype)
+        outs = [{k: v.clone() for k, v in o.items()} for o in runner.run(batches)]
+        assert len(outs) == 2 and not outs[0]["class_logits"].is_cuda
+        for k in ("class_logits", "bbox_coords"):
+            got = torch.cat([o[k] for o in outs])
+            assert torch.equal(got, want[k].cpu()), (dtype, k)
+        assert runner.d2h_bytes_per_step == 4 * 3 * 9 * (7 + 4)
+
+
 def test_head_rejects_bad_arguments(vitk):
     head = vitk.ObjectDetectionHead(embed_dim=256, num_classes=6, num_queries=4).eval().cuda()
     with torch.no_grad():
