@@ -46,6 +46,26 @@ def test_workspace_query_and_config_validation(vitk):
     assert lib.vitk_workspace_bytes(C.byref(cfg), 0, C.byref(need)) == 1   # empty batch
 
 
+def test_detection_head_workspace_and_validation(vitk):
+    lib = vitk._lib.lib()
+    cfg = vitk._lib.VitkDetectionHeadConfig(embed_dim=768, num_heads=8, ffn_dim=2048, num_layers=6,
+                                            num_queries=100, num_outputs=7, ln_eps=1e-5)
+    need = C.c_size_t(0)
+    assert lib.vitk_detection_head_workspace_bytes(C.byref(cfg), 256, 197, 1, C.byref(need)) == 0
+    M, Mm = 256 * 100, 256 * 197
+    expect = (M * 768 * (4 + 2 + 6 + 2) + M * 2048 * 2 + Mm * 768 * 2 + Mm * 6 * 2 * 768 * 2
+              + 100 * 768 * 6)
+    assert expect <= need.value <= expect + 16 * 1024
+    assert lib.vitk_detection_head_workspace_bytes(C.byref(cfg), 256, 197, 197, C.byref(need)) == 1
+    assert b"detection head" in lib.vitk_last_error()          # no memory tokens left
+    cfg.num_heads = 96                                          # head_dim 8
+    assert lib.vitk_detection_head_workspace_bytes(C.byref(cfg), 1, 197, 1, C.byref(need)) == 1
+    assert b"head_dim" in lib.vitk_last_error()
+    cfg.num_heads = 8
+    assert lib.vitk_detection_head_forward(C.byref(cfg), None, None, 1, 197, 1, None, None, None, 0,
+                                           None) != 0           # null weights: reported, no crash
+
+
 def test_null_arguments_are_reported_not_crashed(vitk):
     lib = vitk._lib.lib()
     assert lib.vitk_gemm(None, 0, None, 0, 0, 0, 0, 0, None, None, 0, None, None, None, 0,
