@@ -9,7 +9,8 @@ from ._lib import VitkError, launch_count  # noqa: F401
 from .modules import (DataEfficientImageTransformer, MLPBlock,  # noqa: F401
                       MultiHeadSelfAttention, PatchEmbedding, TransformerBlock, ViTClassifier,
                       VisionTransformer)
-from .detection import DeiTObjectDetector, ObjectDetectionHead, ViTObjectDetector  # noqa: F401
+from .detection import (DeiTObjectDetector, ObjectDetectionHead, ViTObjectDetector,  # noqa: F401
+                        post_process_predictions)
 
 from .pipeline import HostBatchRunner  # noqa: E402,F401
 from .trainer import FineTuner, TrainState  # noqa: E402,F401
@@ -18,6 +19,6 @@ __all__ = [
     "HostBatchRunner", "FineTuner", "TrainState",
     "PatchEmbedding", "MultiHeadSelfAttention", "MLPBlock", "TransformerBlock",
     "VisionTransformer", "DataEfficientImageTransformer", "ViTClassifier", "VitkError",
-    "ObjectDetectionHead", "ViTObjectDetector", "DeiTObjectDetector",
+    "ObjectDetectionHead", "ViTObjectDetector", "DeiTObjectDetector", "post_process_predictions",
     "launch_count", "ops",
 ]

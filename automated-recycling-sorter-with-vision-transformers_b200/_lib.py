@@ -96,6 +96,11 @@ _SIGNATURES = {
     "vitk_set_pdl": (C.c_int, [C.c_int]),
     "vitk_postprocess_scores": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                           C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vitk_postprocess_detections": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                              C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
+                                              C.c_void_p, C.c_void_p]),
+    "vitk_linear_rows": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "vitk_dropout_keep_mask": (C.c_int, [C.c_float, C.c_uint, C.c_int, C.c_int, C.c_longlong,
                                          C.c_void_p, C.c_void_p]),
     "vitk_profile_enable": (C.c_int, [C.c_int]),

@@ -302,6 +302,20 @@ int vitk_postprocess_scores(const float* logits, int rows, int n_classes, int ex
   return postprocess_scores(logits, rows, n_classes, exclude_last, scores_out, labels_out, probs_out,
                             static_cast<cudaStream_t>(stream));
 }
+int vitk_postprocess_detections(const float* class_logits, const float* bbox_coords, int batch,
+                                int num_queries, int num_outputs, float confidence_threshold,
+                                int* counts_out, float* boxes_out, long long* labels_out,
+                                float* scores_out, vitk_stream_t stream) {
+  return postprocess_detections(class_logits, bbox_coords, batch, num_queries, num_outputs,
+                                confidence_threshold, counts_out, boxes_out, labels_out, scores_out,
+                                static_cast<cudaStream_t>(stream));
+}
+int vitk_linear_rows(const float* x, long long row_stride, const float* weight, const float* bias,
+                     float* out, int rows, int in_features, int out_features, int l2_normalize,
+                     vitk_stream_t stream) {
+  return linear_rows(x, row_stride, weight, bias, out, rows, in_features, out_features, l2_normalize,
+                     static_cast<cudaStream_t>(stream));
+}
 int vitk_set_pdl(int on) {
   set_pdl(on);
   return VITK_OK;

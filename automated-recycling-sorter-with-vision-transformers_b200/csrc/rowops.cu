@@ -365,12 +365,152 @@ postprocess_scores_kernel(const float* __restrict__ logits, int rows, int C, int
   }
 }
 
+// post_process_predictions (evaluation.py:393-426) for a whole batch in one launch: per query
+// softmax -> best non-background class (as above), `max_probs > confidence_threshold`, and the
+// boolean-mask compaction `bbox_coords[confident_mask]` etc. - kept queries of image b move to the
+// front of row b of the outputs in query order, counts[b] says how many.  One block per image.
+constexpr int kDetMaxQueries = 1024;
+
+__global__ void __launch_bounds__(128)
+postprocess_detections_kernel(const float* __restrict__ logits, const float* __restrict__ boxes,
+                              int Q, int C, float threshold, int* __restrict__ counts,
+                              float* __restrict__ boxes_out, long long* __restrict__ labels_out,
+                              float* __restrict__ scores_out) {
+  __shared__ float s_score[kDetMaxQueries];
+  __shared__ int s_label[kDetMaxQueries];
+  __shared__ int s_pos[kDetMaxQueries];  // output slot, or -1 when the query is filtered out
+  const int b = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int qi = warp; qi < Q; qi += 4) {
+    const float* lr = logits + (static_cast<long long>(b) * Q + qi) * C;
+    float m = -INFINITY;
+    for (int c = lane; c < C; c += 32) m = fmaxf(m, lr[c]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float sum = 0.f;
+    for (int c = lane; c < C; c += 32) sum += __expf(lr[c] - m);
+    sum = warp_sum(sum);
+    float best = -1.f;
+    int arg = 0;
+    for (int c = lane; c < C - 1; c += 32) {
+      const float pr = __expf(lr[c] - m) / sum;
+      if (pr > best) {
+        best = pr;
+        arg = c;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+      if (ob > best || (ob == best && oa < arg)) {
+        best = ob;
+        arg = oa;
+      }
+    }
+    if (lane == 0) {
+      s_score[qi] = best;
+      s_label[qi] = arg;
+    }
+  }
+  __syncthreads();
+  if (warp == 0) {
+    int base = 0;
+    for (int q0 = 0; q0 < Q; q0 += 32) {
+      const int qi = q0 + lane;
+      const bool keep = qi < Q && s_score[qi] > threshold;
+      const unsigned bal = __ballot_sync(0xffffffffu, keep);
+      if (qi < Q) s_pos[qi] = keep ? base + __popc(bal & ((1u << lane) - 1u)) : -1;
+      base += __popc(bal);
+    }
+    if (lane == 0) counts[b] = base;
+  }
+  __syncthreads();
+  for (int qi = threadIdx.x; qi < Q; qi += blockDim.x) {
+    const int pos = s_pos[qi];
+    if (pos >= 0) {
+      const long long o = static_cast<long long>(b) * Q + pos;
+      scores_out[o] = s_score[qi];
+      labels_out[o] = s_label[qi];
+      reinterpret_cast<float4*>(boxes_out)[o] =
+          reinterpret_cast<const float4*>(boxes)[static_cast<long long>(b) * Q + qi];
+    }
+  }
+}
+
+int postprocess_detections(const float* logits, const float* boxes, int batch, int Q, int C,
+                           float threshold, int* counts, float* boxes_out, long long* labels_out,
+                           float* scores_out, cudaStream_t stream) {
+  VITK_REQUIRE(logits && boxes && counts && boxes_out && labels_out && scores_out,
+               "postprocess_detections: null operand");
+  VITK_REQUIRE(batch > 0 && Q > 0 && Q <= kDetMaxQueries && C > 1,
+               "postprocess_detections: need batch > 0, 1 <= queries <= %d, classes + background > 1",
+               kDetMaxQueries);
+  VITK_REQUIRE(((reinterpret_cast<uintptr_t>(boxes) | reinterpret_cast<uintptr_t>(boxes_out)) & 15) == 0,
+               "postprocess_detections: boxes must be 16-byte aligned");
+  postprocess_detections_kernel<<<batch, 128, 0, stream>>>(logits, boxes, Q, C, threshold, counts,
+                                                           boxes_out, labels_out, scores_out);
+  VITK_CHECK_LAUNCH("postprocess_detections_kernel");
+  return VITK_OK;
+}
+
 int postprocess_scores(const float* logits, int rows, int C, int exclude_last, float* scores,
                        long long* labels, float* probs, cudaStream_t stream) {
   VITK_REQUIRE(logits && rows > 0 && C > (exclude_last ? 1 : 0), "postprocess_scores: bad argument");
   postprocess_scores_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(logits, rows, C, exclude_last, scores,
                                                                 labels, probs);
   VITK_CHECK_LAUNCH("postprocess_scores_kernel");
+  return VITK_OK;
+}
+
+// Linear(D, n_out) on a few fp32 rows (+ optional L2 normalisation of each output row): the CLS
+// consumers of the reference - `triplet_projection` + F.normalize (train.py:833-838).  One block
+// per row; the row is staged in shared memory, each warp owns every 8th output.
+__global__ void __launch_bounds__(256)
+linear_rows_kernel(const float* __restrict__ x, long long row_stride, const float* __restrict__ w,
+                   const float* __restrict__ b, float* __restrict__ out, int D, int n_out,
+                   int l2_normalize) {
+  extern __shared__ float s_lin[];  // D inputs, then n_out outputs, then 8 partial sums
+  float* s_x = s_lin;
+  float* s_y = s_lin + D;
+  float* s_part = s_y + n_out;
+  const int row = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* xr = x + static_cast<long long>(row) * row_stride;
+  for (int i = threadIdx.x; i < D; i += blockDim.x) s_x[i] = xr[i];
+  __syncthreads();
+  for (int o = warp; o < n_out; o += 8) {
+    const float* wr = w + static_cast<long long>(o) * D;
+    float acc = 0.f;
+    for (int i = lane; i < D; i += 32) acc = fmaf(s_x[i], __ldg(wr + i), acc);
+    acc = warp_sum(acc);
+    if (lane == 0) s_y[o] = acc + (b != nullptr ? b[o] : 0.f);
+  }
+  __syncthreads();
+  float scale = 1.f;
+  if (l2_normalize) {
+    float sq = 0.f;
+    for (int o = threadIdx.x; o < n_out; o += blockDim.x) sq += s_y[o] * s_y[o];
+    sq = warp_sum(sq);
+    if (lane == 0) s_part[warp] = sq;
+    __syncthreads();
+    float tot = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tot += s_part[i];
+    scale = 1.f / fmaxf(sqrtf(tot), 1e-12f);  // F.normalize: x / max(||x||, eps)
+  }
+  for (int o = threadIdx.x; o < n_out; o += blockDim.x)
+    out[static_cast<long long>(row) * n_out + o] = s_y[o] * scale;
+}
+
+int linear_rows(const float* x, long long row_stride, const float* w, const float* b, float* out,
+                int rows, int D, int n_out, int l2_normalize, cudaStream_t stream) {
+  VITK_REQUIRE(x && w && out, "linear_rows: null operand");
+  VITK_REQUIRE(rows > 0 && D > 0 && n_out > 0 && D + n_out <= 11000,
+               "linear_rows: bad shape rows=%d D=%d n_out=%d", rows, D, n_out);
+  linear_rows_kernel<<<rows, 256, (D + n_out + 8) * sizeof(float), stream>>>(
+      x, row_stride, w, b, out, D, n_out, l2_normalize);
+  VITK_CHECK_LAUNCH("linear_rows_kernel");
   return VITK_OK;
 }
 

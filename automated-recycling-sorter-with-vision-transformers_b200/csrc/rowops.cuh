@@ -35,6 +35,18 @@ int cls_head(const float* x, long long row_stride, const float* gamma, const flo
 int postprocess_scores(const float* logits, int rows, int C, int exclude_last, float* scores,
                        long long* labels, float* probs, cudaStream_t stream);
 
+// out[r, :] = x[r, :] W^T + b (fp32, W [n_out, D]), optionally divided by max(||.||_2, 1e-12):
+// `triplet_projection` + F.normalize on the CLS rows (train.py:833-838).
+int linear_rows(const float* x, long long row_stride, const float* w, const float* b, float* out,
+                int rows, int D, int n_out, int l2_normalize, cudaStream_t stream);
+
+// Batched post_process_predictions (evaluation.py:393-426): scores / labels as above without the
+// background class, `score > threshold`, kept queries compacted to the front of each image's row
+// of boxes_out [B,Q,4] / labels_out [B,Q] / scores_out [B,Q]; counts [B].
+int postprocess_detections(const float* logits, const float* boxes, int batch, int Q, int C,
+                           float threshold, int* counts, float* boxes_out, long long* labels_out,
+                           float* scores_out, cudaStream_t stream);
+
 int cast_f32_to_bf16(const float* in, void* out, long long n, cudaStream_t stream);
 
 // softmax(q k^T / sqrt(hd)) v for every (image, head); qkv bf16 [B*N, 3*D] packed as the reference

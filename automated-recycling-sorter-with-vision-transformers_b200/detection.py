@@ -152,7 +152,8 @@ class ViTObjectDetector(nn.Module):
 
 
 class DeiTObjectDetector(nn.Module):
-    """train.py:798-838, eval-mode forward (no triplet features)."""
+    """train.py:798-849, eval-mode forward; `return_features=True` also returns the L2-normalised
+    triplet projection of the CLS token, as the reference does (train.py:847-848)."""
 
     def __init__(self, image_size=224, patch_size=16, in_channels=3, embed_dim=768,
                  num_layers=12, num_heads=12, mlp_dim=3072, dropout=0.1,
@@ -169,7 +170,53 @@ class DeiTObjectDetector(nn.Module):
         self.triplet_projection = nn.Linear(embed_dim, 256)   # state_dict compatibility
 
     def forward(self, images, return_features=False):
-        if return_features:
-            raise _lib.VitkError("triplet features are outside the accelerated path")
         features = self.backbone(images)                      # [B, P + 2, D]
-        return self.detection_head.decode(features, 2)       # drop CLS and DIST (train.py:829)
+        predictions = self.detection_head.decode(features, 2)  # drop CLS and DIST (train.py:842)
+        if not return_features:
+            return predictions
+        # triplet_projection on the CLS row + F.normalize (train.py:833-838), read in place
+        feats = features.detach().float().contiguous()
+        B, N, D = feats.shape
+        tp = self.triplet_projection
+        w = tp.weight.detach().float().contiguous()
+        b = tp.bias.detach().float().contiguous()
+        triplet = torch.empty((B, tp.out_features), dtype=torch.float32, device=feats.device)
+        check(lib().vitk_linear_rows(feats.data_ptr(), N * D, w.data_ptr(), b.data_ptr(),
+                                     triplet.data_ptr(), B, D, tp.out_features, 1,
+                                     torch.cuda.current_stream().cuda_stream))
+        return predictions, triplet
+
+
+@torch.no_grad()
+def post_process_predictions(outputs, confidence_threshold=0.5, nms_threshold=0.5):
+    """Drop-in for evaluation.py:393-426: same arguments (nms_threshold is unused there too), same
+    return value - one dict per image with 'boxes' [k,4], 'labels' [k] (int64), 'scores' [k] of
+    the queries whose best non-background probability exceeds the threshold, in query order; an
+    image without detections gets the reference's empty CPU tensors.  One kernel launch and ONE
+    host synchronisation per batch instead of a softmax / max / mask / `.sum() > 0` round trip per
+    image."""
+    logits, boxes = outputs["class_logits"], outputs["bbox_coords"]
+    if not logits.is_cuda:
+        raise _lib.VitkError("post_process_predictions: outputs must be CUDA tensors (no CPU fallback)")
+    logits = logits.detach().float().contiguous()
+    boxes = boxes.detach().float().contiguous()
+    B, Q, n_out = logits.shape
+    dev = logits.device
+    counts = torch.empty(B, dtype=torch.int32, device=dev)
+    boxes_out = torch.empty((B, Q, 4), dtype=torch.float32, device=dev)
+    labels_out = torch.empty((B, Q), dtype=torch.int64, device=dev)
+    scores_out = torch.empty((B, Q), dtype=torch.float32, device=dev)
+    check(lib().vitk_postprocess_detections(
+        logits.data_ptr(), boxes.data_ptr(), B, Q, n_out, float(confidence_threshold),
+        counts.data_ptr(), boxes_out.data_ptr(), labels_out.data_ptr(), scores_out.data_ptr(),
+        torch.cuda.current_stream().cuda_stream))
+    result = []
+    for i, k in enumerate(counts.tolist()):          # the one synchronisation
+        if k > 0:
+            result.append({"boxes": boxes_out[i, :k], "labels": labels_out[i, :k],
+                           "scores": scores_out[i, :k]})
+        else:                                         # evaluation.py:419-424
+            result.append({"boxes": torch.zeros((0, 4)),
+                           "labels": torch.zeros((0,), dtype=torch.long),
+                           "scores": torch.zeros((0,))})
+    return result

@@ -116,6 +116,26 @@ int vitk_postprocess_scores(const float* logits, int rows, int n_classes, int ex
                             float* scores_out, long long* labels_out, float* probs_out,
                             vitk_stream_t stream);
 
+/* post_process_predictions (evaluation.py:393-426) for a whole batch in one launch and without a
+ * host synchronisation per image: class_logits f32 [batch, Q, num_outputs] (last output =
+ * background), bbox_coords f32 [batch, Q, 4].  Per query: softmax, best non-background class and
+ * its probability; a query is kept when that probability > confidence_threshold.  The kept queries
+ * of image b are written, in query order (what boolean-mask indexing yields), to the front of row b
+ * of boxes_out [batch, Q, 4], labels_out i64 [batch, Q], scores_out [batch, Q]; counts_out i32
+ * [batch] holds how many.  Q <= 1024. */
+int vitk_postprocess_detections(const float* class_logits, const float* bbox_coords, int batch,
+                                int num_queries, int num_outputs, float confidence_threshold,
+                                int* counts_out, float* boxes_out, long long* labels_out,
+                                float* scores_out, vitk_stream_t stream);
+
+/* The CLS-row consumers of the reference (DeiTObjectDetector.forward,
+ * train.py:833-838): out[r, :] = x[r, :] W^T + b in fp32 for a few rows (x rows `row_stride`
+ * elements apart, e.g. the CLS row of every image of backbone(images): stride N*D), optionally
+ * followed by F.normalize(p=2, dim=1).  weight fp32 [out_features, in_features]; bias may be null. */
+int vitk_linear_rows(const float* x, long long row_stride, const float* weight, const float* bias,
+                     float* out, int rows, int in_features, int out_features, int l2_normalize,
+                     vitk_stream_t stream);
+
 /* Persistent kernels (GEMM, attention) launch one CTA per SM; keep `n` SMs out of their grids, e.g.
  * for the NCCL kernels of a gradient all-reduce that overlaps the backward pass. 0 restores all. */
 int vitk_reserve_sms(int n);

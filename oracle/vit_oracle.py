@@ -283,3 +283,23 @@ def randomize_head_state(sd: dict, seed: int) -> dict:
         else:
             out[k] = 0.1 * r
     return out
+
+
+def post_process_predictions(outputs: dict, confidence_threshold: float = 0.5) -> list:
+    """evaluation.py:393-426 restated: per image softmax over the class logits (:403), best
+    non-background probability and class (:404), `max_probs > confidence_threshold` (:407),
+    boolean-mask selection of boxes / labels / scores (:410-412), empty tensors otherwise."""
+    res = []
+    for logits, boxes in zip(outputs["class_logits"], outputs["bbox_coords"]):
+        probs = torch.softmax(logits, dim=-1)
+        max_probs, labels = torch.max(probs[:, :-1], dim=-1)
+        keep = max_probs > confidence_threshold
+        res.append({"boxes": boxes[keep], "labels": labels[keep], "scores": max_probs[keep]})
+    return res
+
+
+def triplet_features(cls_tokens: torch.Tensor, w: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """DeiTObjectDetector.forward, train.py:833-838: `triplet_projection` on the CLS row, then
+    F.normalize(p=2, dim=1) (x / max(||x||_2, 1e-12))."""
+    y = cls_tokens @ w.t() + b
+    return y / y.norm(dim=1, keepdim=True).clamp_min(1e-12)

@@ -152,6 +152,58 @@ def test_host_batch_runner_over_a_detector(vitk):
         assert runner.d2h_bytes_per_step == 4 * 3 * 9 * (7 + 4)
 
 
+@pytest.mark.parametrize("thr", [0.0, 0.3, 0.5, 0.999])
+def test_post_process_predictions_matches_reference_loop(vitk, thr):
+    """The batched device post-processing returns what evaluation.py:393-426 returns (restated in
+    the oracle and checked there against the live function): same detections per image, in the
+    same order; images without detections get the reference's empty CPU tensors."""
+    g = torch.Generator().manual_seed(31)
+    out = {"class_logits": torch.randn(9, 100, 7, generator=g) * 2.0,
+           "bbox_coords": torch.rand(9, 100, 4, generator=g)}
+    out["class_logits"][4, :, -1] += 30.0            # image 4: background everywhere
+    want = O.post_process_predictions(out, thr)
+    got = vitk.post_process_predictions({k: v.cuda() for k, v in out.items()}, thr)
+    assert len(got) == len(want) == 9
+    p = torch.softmax(out["class_logits"], -1)[..., :-1].max(-1).values
+    for i, (a, b) in enumerate(zip(got, want)):
+        if ((p[i] - thr).abs() < 1e-6).any():        # a probability exactly at the threshold
+            continue
+        assert a["labels"].dtype == torch.int64 and a["boxes"].shape == b["boxes"].shape, i
+        assert torch.equal(a["labels"].cpu(), b["labels"])
+        assert torch.equal(a["boxes"].cpu(), b["boxes"])
+        if len(b["scores"]):
+            assert (a["scores"].cpu() - b["scores"]).abs().max() < 1e-6
+        else:
+            assert not a["boxes"].is_cuda and a["boxes"].shape == (0, 4)   # evaluation.py:419-424
+    if thr >= 0.3:
+        assert len(got[4]["labels"]) == 0
+
+
+def test_deit_detector_triplet_features(vitk):
+    """DeiTObjectDetector(images, return_features=True) (train.py:829-848): predictions plus the
+    L2-normalised triplet projection of the CLS token."""
+    kw = dict(image_size=64, patch_size=16, embed_dim=256, num_layers=2, num_heads=4, mlp_dim=512)
+    torch.manual_seed(6)
+    det = vitk.DeiTObjectDetector(num_classes=6, num_queries=7, **kw).eval()
+    sd = {k: v.clone() for k, v in det.state_dict().items()}
+    x = O.synthetic_images(4, 64)
+    det = det.cuda()
+    with torch.no_grad():
+        pred, trip = det(x.cuda(), return_features=True)
+        pred_only = det(x.cuda())
+        toks = det.backbone(x.cuda()).cpu().double()
+    ref = O.triplet_features(toks[:, 0], sd["triplet_projection.weight"].double(),
+                             sd["triplet_projection.bias"].double())
+    assert trip.shape == (4, 256)
+    assert (trip.cpu().double() - ref).abs().max() < 1e-5
+    assert (trip.norm(dim=1) - 1).abs().max() < 1e-5
+    assert torch.equal(pred["class_logits"], pred_only["class_logits"])
+    # DeiT slicing: CLS and DIST rows are not part of the memory
+    ref_head = O.detection_head_forward(sd, toks[:, 2:, :].float(), prefix="detection_head.",
+                                        dtype=torch.float64)
+    _check(pred, ref_head["class_logits"], ref_head["bbox_coords"])
+
+
 def test_head_rejects_bad_arguments(vitk):
     head = vitk.ObjectDetectionHead(embed_dim=256, num_classes=6, num_queries=4).eval().cuda()
     with torch.no_grad():

@@ -121,6 +121,30 @@ def test_head_oracle_and_mirror_match_live_reference(vitk):
     assert (want["bbox_coords"] - got["bbox_coords"]).abs().max() < 2e-5
 
 
+@pytest.mark.skipif(not ref_loader.reference_available(), reason="reference only in the build box")
+def test_post_process_and_triplet_oracles_match_live_reference():
+    ev, tr = ref_loader.load("evaluation"), ref_loader.load("train")
+    g = torch.Generator().manual_seed(0)
+    out = {"class_logits": torch.randn(4, 50, 7, generator=g) * 2,
+           "bbox_coords": torch.rand(4, 50, 4, generator=g)}
+    out["class_logits"][2, :, -1] += 30.0
+    for thr in (0.3, 0.5):
+        want, got = ev.post_process_predictions(out, thr), O.post_process_predictions(out, thr)
+        for a, b in zip(want, got):
+            assert a["boxes"].shape == b["boxes"].shape
+            assert torch.equal(a["labels"], b["labels"]) and torch.allclose(a["scores"], b["scores"])
+            assert torch.equal(a["boxes"], b["boxes"])
+    torch.manual_seed(2)
+    det = tr.DeiTObjectDetector(image_size=32, embed_dim=64, num_layers=1, num_heads=2, mlp_dim=64,
+                                num_classes=6, num_queries=3).eval()
+    x = O.synthetic_images(2, 32)
+    with torch.no_grad():
+        _, trip = det(x, return_features=True)
+        toks = det.backbone(x)
+    ref = O.triplet_features(toks[:, 0], det.triplet_projection.weight, det.triplet_projection.bias)
+    assert (trip - ref).abs().max() < 1e-6
+
+
 def test_synthetic_inputs_are_deterministic():
     a, b = O.synthetic_images(2, 32), O.synthetic_images(2, 32)
     assert torch.equal(a, b) and a.shape == (2, 3, 32, 32) and a.dtype == torch.float32
