@@ -3,22 +3,23 @@
 // MMA tile - ViT-B/16 at 384 px has 577 tokens (BASELINE.json configs[4]).
 //
 // One (image, head) per work item, persistent CTAs.  K and V of the item stay in shared memory
-// (<= 2 x 80 KB), the query rows are processed in tiles of 128, the keys in blocks of 128, and the
-// softmax is exact in TWO PASSES over the key blocks of a q-tile:
-//     pass 1:  S_j = Q K_j^T for every key block j          -> row maxima only
-//     pass 2:  S_j again, P_j = exp2((S_j - m) c) -> TMEM (bf16), O += P_j V_j, row sums
-// Recomputing S costs tensor time (the tensor pipe is mostly idle here; the kernel is bound by the
-// exponentials) and saves the running-max rescale of O in TMEM that a one-pass flash kernel needs.
-// Every (q-tile, pass, key block) is a "unit"; unit u uses TMEM score region u % 3, so the score
-// product of unit u+2 is in flight while the softmax warps work on unit u and P V of unit u-1 runs.
+// (<= 2 x 80 KB), the query rows are processed in tiles of 128, the keys in blocks of 128, in ONE
+// pass with a lazily updated reference maximum (no second sweep over the key blocks):
+//     S_j = Q K_j^T;  m_j = row max of block j (exchanged across the four column quarters);
+//     the reference m_ref moves up to m_j only when m_j exceeds it by more than 8 (in the base-2
+//     exponent), and only then O and the partial row sums are rescaled by 2^((m_ref - m_j) c);
+//     P_j = exp2((S_j - m_ref) c) <= 2^8 -> TMEM (bf16), O += P_j V_j, row sums
+// O / l at the end is exact whatever reference was used.  After the first block of a q-tile the
+// reference rarely moves, so the rescale (a TMEM read-modify-write of the 64 output columns that
+// has to wait for the previous block's P V) is off the common path.
+// Every (q-tile, key block) is a "unit"; unit u uses TMEM score region u % 3, so the score product
+// of unit u+2 is in flight while the softmax warps work on unit u and P V of unit u-1 runs.
 //
 //   warp 0       TMA producer: K, V per item; Q tiles double-buffered
 //   warp 1       score-product issuer (one elected lane): keeps up to three score tiles in flight
-//   warp 3       completes units in order: releases the region of a pass-1 unit, issues P V of a
-//                pass-2 unit as soon as its probabilities are written
+//   warp 3       issues P V of a unit as soon as its probabilities are written
 //   warps 4-19   softmax: lane quarter x column quarter of the 128-key block (32 columns = one
-//                tcgen05.ld each), thread == query row; pass 1 keeps a running maximum in registers
-//                and exchanges it across the column quarters once per q-tile
+//                tcgen05.ld each), thread == query row
 //   warps 20-23  output: O / rowsum -> bf16 -> smem slab -> TMA store; log-sum-exp rows
 //
 // TMEM (512 columns): score regions [0,128) [128,256) [256,384) | O [384,448).
@@ -49,15 +50,16 @@ struct Tc3Params {
 };
 
 enum : int {
-  kKvFull = 0, kKvFree = 1,
+  kKFull = 0, kKFree = 1,   // K of the item landed / its last score product retired
+  kVFull = 18, kVFree = 19, // V of the item landed / its last P V retired
   kQFull = 2,    // [2]
   kQFree = 4,    // [2]
   kSFull = 6,    // [3] score tile of region r complete
-  kDone = 9,     // [3] softmax finished with region r (pass 1: read; pass 2: P written), 16 warps
+  kDone = 9,     // [3] softmax finished with region r (P written), 16 warps
   kLReady = 12,  // row sums of a q-tile published (16 warps)
   kOFull = 13, kOFree = 14,
-  kRegFree = 15,  // [3] score region r may be overwritten (unit completed / its P V retired)
-  kNumBars3 = 18
+  kRegFree = 15,  // [3] P V of the unit in region r has retired: region reusable, O up to date
+  kNumBars3 = 20
 };
 
 __device__ __forceinline__ void named_bar_sync3(int id, int threads) {
@@ -91,8 +93,9 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tm_q,    // box {64, 128
   const uint32_t sQ = sV + kv_bytes;                               // 2 x 16 KB
   const uint32_t staging_base = sQ + 2u * kQTile3;                 // 4 warps x 4 KB
   const uint32_t stat_base = staging_base + 4u * 4096u;
-  // float [2 q-tile parities][4 column quarters][128 rows] partial row sums, then the same for
-  // the partial maxima, then [2][128] row maxima for the log-sum-exp
+  // float [2 q-tile parities][4 column quarters][128 rows] partial row sums, then [2 unit
+  // parities][4][128] block maxima of the column quarters, then [2][128] reference maxima for the
+  // log-sum-exp
   float* l_smem = reinterpret_cast<float*>(smem + (stat_base - base));
   float* m_smem = l_smem + 2 * 4 * 128;
   float* mrow_smem = m_smem + 2 * 4 * 128;
@@ -110,8 +113,6 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tm_q,    // box {64, 128
   const int D = p.H * 64;
   const int n_qt = p.n_qt, n_kb = p.n_kb;
   auto qt_begin = [&](int part) { return (n_qt * part) / parts; };
-  const int units_per_qt = 2 * n_kb;
-  const int units_per_item = n_qt * units_per_qt;
   auto block_keys = [&](int j) { return min(kKeyBlock, Nk - j * kKeyBlock); };  // multiple of 16
 
   if (warp == 0 && lane == 0) {
@@ -121,8 +122,10 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tm_q,    // box {64, 128
     prefetch_tmap(&tm_o);
   }
   if (warp == 1 && lane == 0) {
-    mbar_init(bar(kKvFull), 1);
-    mbar_init(bar(kKvFree), 1);
+    mbar_init(bar(kKFull), 1);
+    mbar_init(bar(kKFree), 1);
+    mbar_init(bar(kVFull), 1);
+    mbar_init(bar(kVFree), 1);
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar(kQFull + b), 1);
       mbar_init(bar(kQFree + b), 1);
@@ -158,12 +161,21 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tm_q,    // box {64, 128
         for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
           const int head = item / parts, part = item - head * parts;
           const int b = head / p.H, h = head - b * p.H;
-          mbar_wait(bar(kKvFree), (it & 1) ^ 1u);  // every MMA of the previous item has retired
-          mbar_arrive_expect_tx(bar(kKvFull), 2u * kv_bytes);
+          // K and V have their own barriers: K is free again once the item's last score product
+          // has retired (early - the score issuer runs three units ahead), V once its last P V
+          // has, so the next item's K arrives under this item's last softmax blocks and its V
+          // under the next item's first one
+          mbar_wait(bar(kKFree), (it & 1) ^ 1u);
+          mbar_arrive_expect_tx(bar(kKFull), kv_bytes);
           for (int r0 = 0; r0 < Nk; r0 += 256) {   // TMA boxes hold at most 256 rows
             const CUtensorMap* tm = (Nk - r0 >= 256 || Nk < 256) ? &tm_kv : &tm_kv_tail;
-            tma_load_3d(sK + r0 * 128u, tm, bar(kKvFull), D + h * 64, r0, b);
-            tma_load_3d(sV + r0 * 128u, tm, bar(kKvFull), 2 * D + h * 64, r0, b);
+            tma_load_3d(sK + r0 * 128u, tm, bar(kKFull), D + h * 64, r0, b);
+          }
+          mbar_wait(bar(kVFree), (it & 1) ^ 1u);
+          mbar_arrive_expect_tx(bar(kVFull), kv_bytes);
+          for (int r0 = 0; r0 < Nk; r0 += 256) {
+            const CUtensorMap* tm = (Nk - r0 >= 256 || Nk < 256) ? &tm_kv : &tm_kv_tail;
+            tma_load_3d(sV + r0 * 128u, tm, bar(kVFull), 2 * D + h * 64, r0, b);
           }
           for (int t = qt_begin(part); t < qt_begin(part + 1); ++t, ++qc) {
             const uint32_t buf = qc & 1u;
@@ -183,83 +195,79 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tm_q,    // box {64, 128
       uint32_t u = 0, r = 0, qc = 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
         const int part = item % parts;
-        mbar_wait(bar(kKvFull), it & 1);
+        mbar_wait(bar(kKFull), it & 1);
         tc_fence_after();
-        for (int t = qt_begin(part); t < qt_begin(part + 1); ++t, ++qc) {
+        const int t_end = qt_begin(part + 1);
+        for (int t = qt_begin(part); t < t_end; ++t, ++qc) {
           const uint32_t qbuf = qc & 1u;
           mbar_wait(bar(kQFull + qbuf), (qc >> 1) & 1);  // the Q tile has landed
           tc_fence_after();
           const uint64_t q_desc = make_desc_sw128(sQ + qbuf * kQTile3, 16, 1024);
-          for (int pass = 0; pass < 2; ++pass) {
-            for (int j = 0; j < n_kb; ++j, ++u) {
-              if (u >= 3u) {
-                mbar_wait(bar(kRegFree + r), ((u / 3u) - 1u) & 1u);
-                tc_fence_after();
-              }
-              TR3(2, u, 0);
-              const uint32_t idesc_s = make_idesc_bf16(128, block_keys(j));
-              const uint64_t k_desc = make_desc_sw128(sK + j * (kKeyBlock * 128u), 16, 1024);
-              const bool last_of_qt = (pass == 1 && j == n_kb - 1);
-              if (elect_one_sync()) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  mma_bf16_ss(tmem_base + r * 128u, q_desc + 2u * k, k_desc + 2u * k, idesc_s,
-                              k > 0 ? 1u : 0u);
-                mma_commit(bar(kSFull + r));
-                if (last_of_qt) mma_commit(bar(kQFree + qbuf));  // last reader of this Q tile
-              }
-              __syncwarp();
-              TR3(2, u, 1);
-              r = (r == 2u) ? 0u : r + 1u;
+          for (int j = 0; j < n_kb; ++j, ++u) {
+            if (u >= 3u) {
+              mbar_wait(bar(kRegFree + r), ((u / 3u) - 1u) & 1u);
+              tc_fence_after();
             }
+            TR3(2, u, 0);
+            const uint32_t idesc_s = make_idesc_bf16(128, block_keys(j));
+            const uint64_t k_desc = make_desc_sw128(sK + j * (kKeyBlock * 128u), 16, 1024);
+            const bool last_of_qt = (j == n_kb - 1);
+            if (elect_one_sync()) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                mma_bf16_ss(tmem_base + r * 128u, q_desc + 2u * k, k_desc + 2u * k, idesc_s,
+                            k > 0 ? 1u : 0u);
+              mma_commit(bar(kSFull + r));
+              if (last_of_qt) mma_commit(bar(kQFree + qbuf));  // last reader of this Q tile
+              if (last_of_qt && t == t_end - 1) mma_commit(bar(kKFree));  // last reader of K
+            }
+            __syncwarp();
+            TR3(2, u, 1);
+            r = (r == 2u) ? 0u : r + 1u;
           }
         }
       }
     } else if (warp == 3) {
-      // ============ unit completion + P V issuer ============
+      // ============ P V issuer ============
       const uint32_t idesc_pv = make_idesc_bf16(128, 64, 0, 1);  // B (= V) is MN-major
       uint32_t u = 0, r = 0, qc = 0;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      int it = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
         const int part = item % parts;
         const int t_end = qt_begin(part + 1);
+        mbar_wait(bar(kVFull), it & 1);
         for (int t = qt_begin(part); t < t_end; ++t, ++qc) {
-          for (int pass = 0; pass < 2; ++pass) {
-            for (int j = 0; j < n_kb; ++j, ++u) {
-              mbar_wait(bar(kDone + r), (u / 3u) & 1u);  // softmax finished with this region
-              TR3(0, u, 0);
+          for (int j = 0; j < n_kb; ++j, ++u) {
+            mbar_wait(bar(kDone + r), (u / 3u) & 1u);  // the probabilities of this unit are written
+            TR3(0, u, 0);
+            tc_fence_after();
+            if (j == 0) {
+              mbar_wait(bar(kOFree), (qc & 1u) ^ 1u);  // the previous O tile has been read out
               tc_fence_after();
-              if (pass == 0) {
-                if (elect_one_sync()) mbar_arrive(bar(kRegFree + r));
-              } else {
-                if (j == 0) {
-                  mbar_wait(bar(kOFree), (qc & 1u) ^ 1u);  // the previous O tile has been read out
-                  tc_fence_after();
-                }
-                const int nk = block_keys(j);
-                // V rows of this key block (128 B each, 8-row swizzle atoms 1024 B apart); 16 keys
-                // per MMA; P as bf16 pairs at the start of each 32-column chunk of the region
-                const uint64_t v_desc = make_desc_sw128(sV + j * (kKeyBlock * 128u), kv_bytes, 1024);
-                const bool last_of_item = (t == t_end - 1 && j == n_kb - 1);
-                if (elect_one_sync()) {
-                  // fully unrolled and predicated: two instructions per MMA instead of a rolled
-                  // loop's eight (the issuing warp competes with five busy warps for issue slots)
-#pragma unroll
-                  for (int ks = 0; ks < kKeyBlock / 16; ++ks)
-                    if (ks < nk / 16)
-                      mma_bf16_ts(tmem_base + kOCol3,
-                                  tmem_base + r * 128u +
-                                      static_cast<uint32_t>((ks >> 1) * 32 + (ks & 1) * 8),
-                                  v_desc + static_cast<uint64_t>(ks) * 128u, idesc_pv,
-                                  (j > 0 || ks > 0) ? 1u : 0u);
-                  mma_commit(bar(kRegFree + r));  // P of this region consumed when these retire
-                  if (j == n_kb - 1) mma_commit(bar(kOFull));
-                  if (last_of_item) mma_commit(bar(kKvFree));  // last reader of K / V
-                }
-              }
-              __syncwarp();
-              TR3(0, u, 1);
-              r = (r == 2u) ? 0u : r + 1u;
             }
+            const int nk = block_keys(j);
+            // V rows of this key block (128 B each, 8-row swizzle atoms 1024 B apart); 16 keys
+            // per MMA; P as bf16 pairs at the start of each 32-column chunk of the region
+            const uint64_t v_desc = make_desc_sw128(sV + j * (kKeyBlock * 128u), kv_bytes, 1024);
+            const bool last_of_item = (t == t_end - 1 && j == n_kb - 1);
+            if (elect_one_sync()) {
+              // fully unrolled and predicated: two instructions per MMA instead of a rolled
+              // loop's eight (the issuing warp competes with five busy warps for issue slots)
+#pragma unroll
+              for (int ks = 0; ks < kKeyBlock / 16; ++ks)
+                if (ks < nk / 16)
+                  mma_bf16_ts(tmem_base + kOCol3,
+                              tmem_base + r * 128u +
+                                  static_cast<uint32_t>((ks >> 1) * 32 + (ks & 1) * 8),
+                              v_desc + static_cast<uint64_t>(ks) * 128u, idesc_pv,
+                              (j > 0 || ks > 0) ? 1u : 0u);
+              mma_commit(bar(kRegFree + r));  // P consumed and O up to date when these retire
+              if (j == n_kb - 1) mma_commit(bar(kOFull));
+              if (last_of_item) mma_commit(bar(kVFree));  // last reader of V
+            }
+            __syncwarp();
+            TR3(0, u, 1);
+            r = (r == 2u) ? 0u : r + 1u;
           }
         }
       }
@@ -278,61 +286,76 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tm_q,    // box {64, 128
       for (int t = qt_begin(part); t < qt_begin(part + 1); ++t, ++qc) {
         const int par = qc & 1;
         const bool warp_rows = t * 128 + q * 32 < N;
-        float m_run = -INFINITY;
-        float m_row = 0.f;
+        float m_ref = -INFINITY;  // reference maximum of the exponent (raw score units)
         uint64_t la = 0ull, lb = 0ull;
-        for (int rem = 0; rem < units_per_qt; ++rem, ++u) {
-          const bool pass2 = rem >= n_kb;
-          const int j = pass2 ? rem - n_kb : rem;
-          if (rem == n_kb) {
-            // ---- between the passes: row maximum across the four column quarters
-            if (warp_rows) {
-              m_smem[(par * 4 + cq) * 128 + r_in_tile] = m_run;
-              named_bar_sync3(1 + q, 128);
-              m_row = fmaxf(fmaxf(m_smem[(par * 4 + 0) * 128 + r_in_tile],
-                                  m_smem[(par * 4 + 1) * 128 + r_in_tile]),
-                            fmaxf(m_smem[(par * 4 + 2) * 128 + r_in_tile],
-                                  m_smem[(par * 4 + 3) * 128 + r_in_tile]));
-              if (cq == 0) mrow_smem[par * 128 + r_in_tile] = m_row;
-            }
-          }
+        for (int j = 0; j < n_kb; ++j, ++u) {
           mbar_wait(bar(kSFull + r), (u / 3u) & 1u);
           if (warp == 4 && lane == 0) TR3(1, u, 0);
           tc_fence_after();
           const int nk = block_keys(j);
           const int cw = min(32, nk - 32 * cq);  // 32, 16 or <= 0 columns for this warp
-          if (warp_rows && cw > 0) {
+          if (warp_rows) {
             const int k0 = j * kKeyBlock + cq * 32;  // first key of this thread's columns
             const uint32_t tcol = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + r * 128u +
                                   static_cast<uint32_t>(cq * 32);
+            const int valid = min(cw, N - k0);  // keys >= N are TMA zero fill and must not count
             uint32_t v[32];
             if (cw == 32) {
               tmem_ld_32x32b_x32(tcol, v);
-            } else {
+              tmem_ld_wait();
+            } else if (cw > 0) {
               tmem_ld_32x32b_x16(tcol, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
 #pragma unroll
               for (int i = 16; i < 32; ++i) v[i] = 0u;
+              tmem_ld_wait();
             }
-            tmem_ld_wait();
-            const int valid = min(cw, N - k0);  // keys >= N are TMA zero fill and must not count
-            if (!pass2) {
-              if (valid >= 32) {
-                float a0 = m_run, a1 = -INFINITY, a2 = -INFINITY, a3 = -INFINITY;
+            // ---- block maximum of this thread's columns, then across the four column quarters
+            float mq = -INFINITY;
+            if (valid >= 32) {
+              float a0 = -INFINITY, a1 = -INFINITY, a2 = -INFINITY, a3 = -INFINITY;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  a0 = fmax3(a0, __uint_as_float(v[8 * i]), __uint_as_float(v[8 * i + 1]));
-                  a1 = fmax3(a1, __uint_as_float(v[8 * i + 2]), __uint_as_float(v[8 * i + 3]));
-                  a2 = fmax3(a2, __uint_as_float(v[8 * i + 4]), __uint_as_float(v[8 * i + 5]));
-                  a3 = fmax3(a3, __uint_as_float(v[8 * i + 6]), __uint_as_float(v[8 * i + 7]));
-                }
-                m_run = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
-              } else {
-#pragma unroll
-                for (int i = 0; i < 32; ++i)
-                  if (i < valid) m_run = fmaxf(m_run, __uint_as_float(v[i]));
+              for (int i = 0; i < 4; ++i) {
+                a0 = fmax3(a0, __uint_as_float(v[8 * i]), __uint_as_float(v[8 * i + 1]));
+                a1 = fmax3(a1, __uint_as_float(v[8 * i + 2]), __uint_as_float(v[8 * i + 3]));
+                a2 = fmax3(a2, __uint_as_float(v[8 * i + 4]), __uint_as_float(v[8 * i + 5]));
+                a3 = fmax3(a3, __uint_as_float(v[8 * i + 6]), __uint_as_float(v[8 * i + 7]));
               }
-            } else {
-              const float nm = -m_row * c;
+              mq = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
+            } else if (valid > 0) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (i < valid) mq = fmaxf(mq, __uint_as_float(v[i]));
+            }
+            float* mx = m_smem + ((u & 1u) * 4) * 128;  // slot of this unit's parity
+            mx[cq * 128 + r_in_tile] = mq;
+            named_bar_sync3(1 + q, 128);
+            const float m_blk = fmaxf(fmaxf(mx[0 * 128 + r_in_tile], mx[1 * 128 + r_in_tile]),
+                                      fmaxf(mx[2 * 128 + r_in_tile], mx[3 * 128 + r_in_tile]));
+            // ---- lazy reference update: first block adopts its maximum; later blocks move the
+            //      reference (and rescale what has been accumulated) only past 2^8
+            const bool resc = (j > 0) && ((m_blk - m_ref) * c > 8.f);
+            if (j > 0 && __any_sync(0xffffffffu, resc)) {
+              // O += P V of the previous unit must have retired before O is touched
+              const uint32_t rp = (r == 0u) ? 2u : r - 1u;
+              mbar_wait(bar(kRegFree + rp), ((u - 1u) / 3u) & 1u);
+              tc_fence_after();
+              const float f = resc ? exp2f((m_ref - m_blk) * c) : 1.f;
+              const uint32_t ocol = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + kOCol3 +
+                                    static_cast<uint32_t>(cq * 16);
+              uint32_t o[16];
+              tmem_ld_32x32b_x16(ocol, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+              tmem_st_32x32b_x16(ocol, o);
+              tmem_st_wait();
+              const uint64_t ff = pack2(__float_as_uint(f), __float_as_uint(f));
+              la = fmul2(la, ff);
+              lb = fmul2(lb, ff);
+            }
+            if (j == 0 || resc) m_ref = m_blk;
+            if (cw > 0) {
+              const float nm = -m_ref * c;
               const uint64_t nmc = pack2(__float_as_uint(nm), __float_as_uint(nm));
               uint32_t pk[16];
 #pragma unroll
@@ -360,6 +383,7 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tm_q,    // box {64, 128
           if (lane == 0) mbar_arrive(bar(kDone + r));
           r = (r == 2u) ? 0u : r + 1u;
         }
+        if (warp_rows && cq == 0) mrow_smem[par * 128 + r_in_tile] = m_ref;
         // ---- end of the q-tile: publish this quarter's partial row sums
         if (warp_rows) {
           float l0, l1, l2, l3;

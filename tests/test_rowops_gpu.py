@@ -99,6 +99,32 @@ def test_attention_late_peak(vitk, attn_impl, gap):
     torch.testing.assert_close(lse, lse_ref, rtol=1e-3, atol=2e-2)
 
 
+@pytest.mark.parametrize("N,gap", [(577, 12.0), (577, 60.0), (640, 25.0), (300, 200.0)])
+def test_attention_long_sequence_moving_maximum(vitk, N, gap):
+    """Long-sequence kernel (one pass over 128-key blocks with a lazily updated reference
+    maximum): rows whose block maxima rise by `gap` (natural-log units) from block to block must
+    rescale what they have accumulated, rows whose maxima fall must not, rows in between mix -
+    all inside the same warps."""
+    B, H = 2, 3
+    g = torch.Generator(device="cuda").manual_seed(11)
+    qkv = torch.randn(B, N, 3, H, 64, generator=g, device="cuda") * 0.3
+    u = torch.nn.functional.normalize(torch.randn(64, generator=g, device="cuda"), dim=0)
+    sign = torch.linspace(-1.0, 1.0, N, device="cuda").roll(17)[None, :, None, None]
+    qkv[:, :, 0] += 8.0 * sign * u                # query component along u: -8 .. +8 over the rows
+    blk = (torch.arange(N, device="cuda") // 128).float()[None, :, None, None]
+    qkv[:, :, 1] += gap * blk * u                 # keys of block j score ~ sign * gap * j
+    qkv = qkv.reshape(B * N, 3 * H * 64).bfloat16()
+    vitk._lib.set_attention_impl(4)
+    try:
+        ctx, lse = vitk.ops.attention(qkv, B, N, H, return_lse=True)
+    finally:
+        vitk._lib.set_attention_impl(0)
+    ref, lse_ref = _attn_ref(qkv, B, N, H)
+    assert torch.isfinite(ctx.float()).all() and torch.isfinite(lse).all()
+    torch.testing.assert_close(ctx.float(), ref, rtol=3e-2, atol=3e-2)
+    torch.testing.assert_close(lse, lse_ref, rtol=1e-3, atol=2e-2)
+
+
 def test_attention_rejects_other_head_dims(vitk):
     qkv = torch.zeros(10, 3 * 32, device="cuda").bfloat16()
     with pytest.raises(vitk.VitkError):
