@@ -30,26 +30,28 @@ def timeit(fn, iters=20):
 
 
 def main():
-  for mode in (1, 2):
-      vitk._lib.set_gemm_cta_group(mode)
-      for name, m, n, k, epi in SHAPES:
-          a = torch.randn(m, k, device="cuda").bfloat16()
-          b = torch.randn(n, k, device="cuda").bfloat16()
-          bias = torch.randn(n, device="cuda")
-          f32 = epi == vitk._lib.EPI_RESID_F32
-          out = torch.zeros(m, n, device="cuda", dtype=torch.float32 if f32 else torch.bfloat16)
-          kw = dict(bias=bias, out=out)
-          if f32:
-              kw["resid"] = out
-          ms = timeit(lambda: vitk.ops.gemm(a, b, epi, **kw))
-          print(f"cta{mode} {name:11s} M={m} N={n} K={k}: {ms*1e3:8.1f} us  {2*m*n*k/ms/1e9:8.1f} TFLOP/s")
-      # cuBLAS reference point for the same shape (library baseline, not part of the product)
-  for name, m, n, k, epi in SHAPES[:4]:
-      a = torch.randn(m, k, device="cuda").bfloat16()
-      b = torch.randn(n, k, device="cuda").bfloat16()
-      ms = timeit(lambda: torch.matmul(a, b.t()))
-      print(f"cublas {name:11s}: {ms*1e3:8.1f} us  {2*m*n*k/ms/1e9:8.1f} TFLOP/s")
+    for mode in (1, 2):
+        vitk._lib.set_gemm_cta_group(mode)
+        for name, m, n, k, epi in SHAPES:
+            a = torch.randn(m, k, device="cuda").bfloat16()
+            b = torch.randn(n, k, device="cuda").bfloat16()
+            bias = torch.randn(n, device="cuda")
+            f32 = epi == vitk._lib.EPI_RESID_F32
+            out = torch.zeros(m, n, device="cuda", dtype=torch.float32 if f32 else torch.bfloat16)
+            kw = dict(bias=bias, out=out)
+            if f32:
+                kw["resid"] = out
+            ms = timeit(lambda: vitk.ops.gemm(a, b, epi, **kw))
+            print(f"cta{mode} {name:11s} M={m} N={n} K={k}: {ms*1e3:8.1f} us  "
+                  f"{2*m*n*k/ms/1e9:8.1f} TFLOP/s")
+    vitk._lib.set_gemm_cta_group(0)
+    # cuBLAS reference point for the same shape (library baseline, not part of the product)
+    for name, m, n, k, epi in SHAPES[:4]:
+        a = torch.randn(m, k, device="cuda").bfloat16()
+        b = torch.randn(n, k, device="cuda").bfloat16()
+        ms = timeit(lambda: torch.matmul(a, b.t()))
+        print(f"cublas {name:11s}: {ms*1e3:8.1f} us  {2*m*n*k/ms/1e9:8.1f} TFLOP/s")
 
 
 if __name__ == "__main__":
-  main()
+    main()

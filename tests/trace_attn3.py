@@ -10,7 +10,8 @@ torch.cuda.synchronize()
 tr = lse.flatten()[:1536].view(torch.int64).reshape(3, 64, 4)
 t0 = tr[1, 0, 0].item()
 for u in range(0, 32):
+    # five key blocks (units) per q-tile at N = 577
     print("unit %2d %s  S-issue: start %6d end %6d (%4d) | softmax: s_full %6d done %6d (%5d) | complete: done-seen %6d issued %6d (%5d)" % (
-        u, "P2" if (u % 10) >= 5 else "P1", tr[2, u, 0] - t0, tr[2, u, 1] - t0, tr[2, u, 1] - tr[2, u, 0],
+        u, "kb%d" % (u % 5), tr[2, u, 0] - t0, tr[2, u, 1] - t0, tr[2, u, 1] - tr[2, u, 0],
         tr[1, u, 0] - t0, tr[1, u, 1] - t0, tr[1, u, 1] - tr[1, u, 0],
         tr[0, u, 0] - t0, tr[0, u, 1] - t0, tr[0, u, 1] - tr[0, u, 0]))
