@@ -5,7 +5,7 @@
 // One (image, head) per work item, persistent CTAs.  K and V of the item stay in shared memory
 // (<= 2 x 80 KB), the query rows are processed in tiles of 128, the keys in blocks of 128, in ONE
 // pass with a lazily updated reference maximum (no second sweep over the key blocks):
-//     S_j = Q K_j^T;  m_j = row max of block j (exchanged across the four column quarters);
+//     S_j = Q K_j^T;  m_j = row max of block j;
 //     the reference m_ref moves up to m_j only when m_j exceeds it by more than 8 (in the base-2
 //     exponent), and only then O and the partial row sums are rescaled by 2^((m_ref - m_j) c);
 //     P_j = exp2((S_j - m_ref) c) <= 2^8 -> TMEM (bf16), O += P_j V_j, row sums
@@ -18,9 +18,13 @@
 //   warp 0       TMA producer: K, V per item; Q tiles double-buffered
 //   warp 1       score-product issuer (one elected lane): keeps up to three score tiles in flight
 //   warp 3       issues P V of a unit as soon as its probabilities are written
-//   warps 4-19   softmax: lane quarter x column quarter of the 128-key block (32 columns = one
-//                tcgen05.ld each), thread == query row
-//   warps 20-23  output: O / rowsum -> bf16 -> smem slab -> TMA store; log-sum-exp rows
+//   warps 4-15   softmax: three independent sets of four warps (one per TMEM lane quarter), set s
+//                owns score region s and therefore every third unit; thread == query row over the
+//                whole 128-key block (two sweeps of four tcgen05.ld: block maximum, then
+//                exponentials).  The sets run out of phase, so one set's tcgen05.ld / st latencies
+//                hide under the other two's exponentials; the reference maximum of a row is handed
+//                from the set of unit u to the set of unit u+1 through shared memory + an mbarrier
+//   warps 16-19  output: O / rowsum -> bf16 -> smem slab -> TMA store; log-sum-exp rows
 //
 // TMEM (512 columns): score regions [0,128) [128,256) [256,384) | O [384,448).
 #include <cuda_bf16.h>
@@ -36,7 +40,7 @@ using namespace ptx;
 
 namespace {
 
-constexpr int kThreads3 = 24 * 32;
+constexpr int kThreads3 = 20 * 32;
 constexpr int kQTile3 = 128 * 128;  // bytes of one 128-row x 64-column bf16 Q tile
 constexpr uint32_t kOCol3 = 384;
 constexpr int kKeyBlock = 128;
@@ -55,11 +59,13 @@ enum : int {
   kQFull = 2,    // [2]
   kQFree = 4,    // [2]
   kSFull = 6,    // [3] score tile of region r complete
-  kDone = 9,     // [3] softmax finished with region r (P written), 16 warps
-  kLReady = 12,  // row sums of a q-tile published (16 warps)
+  kDone = 9,     // [3] softmax finished with region r (P written), the 4 warps of set r
+  kLReady = 12,  // row sums of a q-tile published (12 warps)
   kOFull = 13, kOFree = 14,
   kRegFree = 15,  // [3] P V of the unit in region r has retired: region reusable, O up to date
-  kNumBars3 = 20
+  kDec = 20,     // [3 sets][4 lane quarters] reference maximum after this set's unit published
+  kFinal = 32,   // [4 lane quarters] reference maximum of the finished q-tile published
+  kNumBars3 = 36
 };
 
 __device__ __forceinline__ void named_bar_sync3(int id, int threads) {
@@ -93,12 +99,12 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tm_q,    // box {64, 128
   const uint32_t sQ = sV + kv_bytes;                               // 2 x 16 KB
   const uint32_t staging_base = sQ + 2u * kQTile3;                 // 4 warps x 4 KB
   const uint32_t stat_base = staging_base + 4u * 4096u;
-  // float [2 q-tile parities][4 column quarters][128 rows] partial row sums, then [2 unit
-  // parities][4][128] block maxima of the column quarters, then [2][128] reference maxima for the
-  // log-sum-exp
+  // float [2 q-tile parities][4 (3 used) sets][128 rows] partial row sums, then [128] the running
+  // reference maximum of each row (handed from unit to unit), then [2][128] final reference
+  // maxima of a q-tile (row-sum conversion, log-sum-exp)
   float* l_smem = reinterpret_cast<float*>(smem + (stat_base - base));
-  float* m_smem = l_smem + 2 * 4 * 128;
-  float* mrow_smem = m_smem + 2 * 4 * 128;
+  float* mref_smem = l_smem + 2 * 4 * 128;
+  float* mrow_smem = mref_smem + 2 * 4 * 128;  // (spare room after the 128 running maxima)
   const uint32_t bar_base = stat_base + (2 * 4 * 128 * 2 + 2 * 128) * 4u;
   auto bar = [&](int i) { return bar_base + 8u * i; };
   volatile uint32_t* tmem_slot =
@@ -132,10 +138,12 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tm_q,    // box {64, 128
     }
     for (int r = 0; r < 3; ++r) {
       mbar_init(bar(kSFull + r), 1);
-      mbar_init(bar(kDone + r), 16);
+      mbar_init(bar(kDone + r), 4);
       mbar_init(bar(kRegFree + r), 1);
     }
-    mbar_init(bar(kLReady), 16);
+    mbar_init(bar(kLReady), 12);
+    for (int i = 0; i < 12; ++i) mbar_init(bar(kDec + i), 1);
+    for (int i = 0; i < 4; ++i) mbar_init(bar(kFinal + i), 1);
     mbar_init(bar(kOFull), 1);
     mbar_init(bar(kOFree), 4);
     fence_mbar_init();
@@ -272,91 +280,132 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tm_q,    // box {64, 128
         }
       }
     }
-  } else if (warp < 20) {
-    setmaxnreg_inc<88>();
-    // ============ softmax (thread == query row x one 32-column quarter of the key block) =======
-    const int cq = (warp - 4) >> 2;  // column quarter
-    const int q = warp & 3;          // TMEM lane quarter
+  } else if (warp < 16) {
+    setmaxnreg_inc<112>();
+    // ============ softmax: set = score region, thread == query row over the whole key block =====
+    const int set = (warp - 4) >> 2;  // owns region `set` and the units u with u % 3 == set
+    const int q = warp & 3;           // TMEM lane quarter
     const float c = p.scale * 1.44269504088896340736f;
     const uint64_t cc = pack2(__float_as_uint(c), __float_as_uint(c));
     const int r_in_tile = q * 32 + lane;
-    uint32_t u = 0, qc = 0, r = 0;
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const uint32_t treg = tmem_base + lane_off + static_cast<uint32_t>(set) * 128u;
+    const uint32_t prev_set = (set + 2) % 3;
+    uint32_t u = 0, qc = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
       const int part = item % parts;
       for (int t = qt_begin(part); t < qt_begin(part + 1); ++t, ++qc) {
         const int par = qc & 1;
         const bool warp_rows = t * 128 + q * 32 < N;
-        float m_ref = -INFINITY;  // reference maximum of the exponent (raw score units)
+        float m_mine = -INFINITY;  // reference this thread's partial row sum is relative to
         uint64_t la = 0ull, lb = 0ull;
         for (int j = 0; j < n_kb; ++j, ++u) {
-          mbar_wait(bar(kSFull + r), (u / 3u) & 1u);
+          if (u % 3u != static_cast<uint32_t>(set)) continue;
+          mbar_wait(bar(kSFull + set), (u / 3u) & 1u);
           if (warp == 4 && lane == 0) TR3(1, u, 0);
           tc_fence_after();
-          const int nk = block_keys(j);
-          const int cw = min(32, nk - 32 * cq);  // 32, 16 or <= 0 columns for this warp
+          const int nk = block_keys(j);           // multiple of 16
+          const int valid = min(nk, N - j * kKeyBlock);  // keys >= N are TMA zero fill
+          const int n32 = nk >> 5;
+          const bool tail16 = (nk & 31) != 0;
+          // ---- sweep 1: block maximum of the row
+          float m_blk = -INFINITY;
           if (warp_rows) {
-            const int k0 = j * kKeyBlock + cq * 32;  // first key of this thread's columns
-            const uint32_t tcol = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + r * 128u +
-                                  static_cast<uint32_t>(cq * 32);
-            const int valid = min(cw, N - k0);  // keys >= N are TMA zero fill and must not count
-            uint32_t v[32];
-            if (cw == 32) {
-              tmem_ld_32x32b_x32(tcol, v);
+            for (int ch = 0; ch < n32; ++ch) {
+              uint32_t v[32];
+              tmem_ld_32x32b_x32(treg + ch * 32, v);
               tmem_ld_wait();
-            } else if (cw > 0) {
-              tmem_ld_32x32b_x16(tcol, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+              const int k0 = ch * 32;
+              if (k0 + 32 <= valid) {
+                float a0 = m_blk, a1 = -INFINITY, a2 = -INFINITY, a3 = -INFINITY;
 #pragma unroll
-              for (int i = 16; i < 32; ++i) v[i] = 0u;
-              tmem_ld_wait();
-            }
-            // ---- block maximum of this thread's columns, then across the four column quarters
-            float mq = -INFINITY;
-            if (valid >= 32) {
-              float a0 = -INFINITY, a1 = -INFINITY, a2 = -INFINITY, a3 = -INFINITY;
+                for (int i = 0; i < 4; ++i) {
+                  a0 = fmax3(a0, __uint_as_float(v[8 * i]), __uint_as_float(v[8 * i + 1]));
+                  a1 = fmax3(a1, __uint_as_float(v[8 * i + 2]), __uint_as_float(v[8 * i + 3]));
+                  a2 = fmax3(a2, __uint_as_float(v[8 * i + 4]), __uint_as_float(v[8 * i + 5]));
+                  a3 = fmax3(a3, __uint_as_float(v[8 * i + 6]), __uint_as_float(v[8 * i + 7]));
+                }
+                m_blk = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
+              } else {
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                a0 = fmax3(a0, __uint_as_float(v[8 * i]), __uint_as_float(v[8 * i + 1]));
-                a1 = fmax3(a1, __uint_as_float(v[8 * i + 2]), __uint_as_float(v[8 * i + 3]));
-                a2 = fmax3(a2, __uint_as_float(v[8 * i + 4]), __uint_as_float(v[8 * i + 5]));
-                a3 = fmax3(a3, __uint_as_float(v[8 * i + 6]), __uint_as_float(v[8 * i + 7]));
+                for (int i = 0; i < 32; ++i)
+                  if (k0 + i < valid) m_blk = fmaxf(m_blk, __uint_as_float(v[i]));
               }
-              mq = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
-            } else if (valid > 0) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (i < valid) mq = fmaxf(mq, __uint_as_float(v[i]));
             }
-            float* mx = m_smem + ((u & 1u) * 4) * 128;  // slot of this unit's parity
-            mx[cq * 128 + r_in_tile] = mq;
-            named_bar_sync3(1 + q, 128);
-            const float m_blk = fmaxf(fmaxf(mx[0 * 128 + r_in_tile], mx[1 * 128 + r_in_tile]),
-                                      fmaxf(mx[2 * 128 + r_in_tile], mx[3 * 128 + r_in_tile]));
-            // ---- lazy reference update: first block adopts its maximum; later blocks move the
-            //      reference (and rescale what has been accumulated) only past 2^8
-            const bool resc = (j > 0) && ((m_blk - m_ref) * c > 8.f);
-            if (j > 0 && __any_sync(0xffffffffu, resc)) {
+            if (tail16) {
+              uint32_t v[16];
+              tmem_ld_32x32b_x16(treg + n32 * 32, v);
+              tmem_ld_wait();
+              const int k0 = n32 * 32;
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (k0 + i < valid) m_blk = fmaxf(m_blk, __uint_as_float(v[i]));
+            }
+          }
+          // ---- reference maximum: taken over from the previous unit's set, moved lazily
+          float m_ref = m_blk;
+          // (the previous unit's set has finished with mref_smem, also across a q-tile boundary)
+          if (u > 0u) mbar_wait(bar(kDec + prev_set * 4 + q), ((u - 1u) / 3u) & 1u);
+          if (j > 0) {
+            m_ref = mref_smem[r_in_tile];
+            const bool resc = warp_rows && ((m_blk - m_ref) * c > 8.f);
+            if (__any_sync(0xffffffffu, resc)) {
               // O += P V of the previous unit must have retired before O is touched
-              const uint32_t rp = (r == 0u) ? 2u : r - 1u;
-              mbar_wait(bar(kRegFree + rp), ((u - 1u) / 3u) & 1u);
+              mbar_wait(bar(kRegFree + prev_set), ((u - 1u) / 3u) & 1u);
               tc_fence_after();
               const float f = resc ? exp2f((m_ref - m_blk) * c) : 1.f;
-              const uint32_t ocol = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + kOCol3 +
-                                    static_cast<uint32_t>(cq * 16);
-              uint32_t o[16];
-              tmem_ld_32x32b_x16(ocol, o);
-              tmem_ld_wait();
 #pragma unroll
-              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
-              tmem_st_32x32b_x16(ocol, o);
+              for (int h2 = 0; h2 < 2; ++h2) {
+                uint32_t o[32];
+                tmem_ld_32x32b_x32(tmem_base + lane_off + kOCol3 + h2 * 32, o);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+                tmem_st_32x32b_x16(tmem_base + lane_off + kOCol3 + h2 * 32,
+                                   *reinterpret_cast<uint32_t(*)[16]>(&o[0]));
+                tmem_st_32x32b_x16(tmem_base + lane_off + kOCol3 + h2 * 32 + 16,
+                                   *reinterpret_cast<uint32_t(*)[16]>(&o[16]));
+              }
               tmem_st_wait();
+              tc_fence_before();
+            }
+            if (resc) m_ref = m_blk;
+          }
+          mref_smem[r_in_tile] = m_ref;
+          if (j == n_kb - 1) {
+            // Every set has published its row sums of the previous q-tile: with fewer key blocks
+            // than sets a set may have no unit in this q-tile, and without this wait the others
+            // could lap it (kFinal / kLReady arrivals of two q-tiles would mix).
+            if (qc > 0u) mbar_wait(bar(kLReady), (qc - 1u) & 1u);
+            mrow_smem[par * 128 + r_in_tile] = m_ref;
+          }
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(bar(kDec + set * 4 + q));
+            if (j == n_kb - 1) mbar_arrive(bar(kFinal + q));
+          }
+          // ---- this thread's partial row sum follows the reference
+          if (m_mine != m_ref) {
+            if (m_mine == -INFINITY) {
+              la = lb = 0ull;
+            } else {
+              const float f = exp2f((m_mine - m_ref) * c);
               const uint64_t ff = pack2(__float_as_uint(f), __float_as_uint(f));
               la = fmul2(la, ff);
               lb = fmul2(lb, ff);
             }
-            if (j == 0 || resc) m_ref = m_blk;
-            if (cw > 0) {
-              const float nm = -m_ref * c;
-              const uint64_t nmc = pack2(__float_as_uint(nm), __float_as_uint(nm));
+            m_mine = m_ref;
+          }
+          // ---- sweep 2: p = 2^((s - m_ref) c), row sum, P -> TMEM (bf16 pairs at the start of
+          //      each 32-column chunk, where the P V issuer expects them)
+          if (warp_rows) {
+            const float nm = -m_ref * c;
+            const uint64_t nmc = pack2(__float_as_uint(nm), __float_as_uint(nm));
+            for (int ch = 0; ch < n32; ++ch) {
+              uint32_t v[32];
+              tmem_ld_32x32b_x32(treg + ch * 32, v);
+              tmem_ld_wait();
+              const int k0 = ch * 32;
               uint32_t pk[16];
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
@@ -364,32 +413,54 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tm_q,    // box {64, 128
                 unpack2(ffma2(pack2(v[2 * i], v[2 * i + 1]), cc, nmc), t0, t1);
                 float e0 = ex2_approx(t0);
                 float e1 = ex2_approx(t1);
-                if (valid < 32) {
-                  if (2 * i >= valid) e0 = 0.f;
-                  if (2 * i + 1 >= valid) e1 = 0.f;
+                if (k0 + 32 > valid) {
+                  if (k0 + 2 * i >= valid) e0 = 0.f;
+                  if (k0 + 2 * i + 1 >= valid) e1 = 0.f;
                 }
                 const uint64_t e = pack2(__float_as_uint(e0), __float_as_uint(e1));
                 if (i & 1) lb = fadd2(lb, e); else la = fadd2(la, e);
                 pk[i] = pack_bf16x2(e0, e1);
               }
-              if (cw == 32) tmem_st_32x32b_x16(tcol, pk);
-              else tmem_st_32x32b_x8(tcol, *reinterpret_cast<uint32_t(*)[8]>(&pk[0]));
-              tmem_st_wait();
+              tmem_st_32x32b_x16(treg + ch * 32, pk);
             }
+            if (tail16) {
+              uint32_t v[16];
+              tmem_ld_32x32b_x16(treg + n32 * 32, v);
+              tmem_ld_wait();
+              const int k0 = n32 * 32;
+              uint32_t pk[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                float t0, t1;
+                unpack2(ffma2(pack2(v[2 * i], v[2 * i + 1]), cc, nmc), t0, t1);
+                float e0 = ex2_approx(t0);
+                float e1 = ex2_approx(t1);
+                if (k0 + 2 * i >= valid) e0 = 0.f;
+                if (k0 + 2 * i + 1 >= valid) e1 = 0.f;
+                const uint64_t e = pack2(__float_as_uint(e0), __float_as_uint(e1));
+                if (i & 1) lb = fadd2(lb, e); else la = fadd2(la, e);
+                pk[i] = pack_bf16x2(e0, e1);
+              }
+              tmem_st_32x32b_x8(treg + n32 * 32, pk);
+            }
+            tmem_st_wait();
           }
           tc_fence_before();
           __syncwarp();
           if (warp == 4 && lane == 0) TR3(1, u, 1);
-          if (lane == 0) mbar_arrive(bar(kDone + r));
-          r = (r == 2u) ? 0u : r + 1u;
+          if (lane == 0) mbar_arrive(bar(kDone + set));
         }
-        if (warp_rows && cq == 0) mrow_smem[par * 128 + r_in_tile] = m_ref;
-        // ---- end of the q-tile: publish this quarter's partial row sums
-        if (warp_rows) {
+        // ---- end of the q-tile: bring the partial row sum to the final reference and publish it
+        mbar_wait(bar(kFinal + q), qc & 1u);
+        {
+          const float m_fin = mrow_smem[par * 128 + r_in_tile];
           float l0, l1, l2, l3;
           unpack2(la, l0, l1);
           unpack2(lb, l2, l3);
-          l_smem[(par * 4 + cq) * 128 + r_in_tile] = (l0 + l1) + (l2 + l3);
+          float l = (l0 + l1) + (l2 + l3);
+          if (m_mine == -INFINITY) l = 0.f;
+          else if (m_mine != m_fin) l *= exp2f((m_mine - m_fin) * c);
+          l_smem[(par * 4 + set) * 128 + r_in_tile] = l;
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(kLReady));
@@ -400,7 +471,7 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tm_q,    // box {64, 128
     // ======================= output: O / rowsum -> bf16 -> TMA store =======================
     const int q = warp & 3;
     const uint32_t o_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + kOCol3;
-    const uint32_t slab = staging_base + static_cast<uint32_t>(warp - 20) * 4096u;
+    const uint32_t slab = staging_base + static_cast<uint32_t>(warp - 16) * 4096u;
     uint32_t qc = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
       const int head = item / parts, part = item - head * parts;
@@ -417,7 +488,7 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tm_q,    // box {64, 128
         if (rows) {
           const int r = q * 32 + lane;
           l = (l_smem[(par * 4 + 0) * 128 + r] + l_smem[(par * 4 + 1) * 128 + r]) +
-              (l_smem[(par * 4 + 2) * 128 + r] + l_smem[(par * 4 + 3) * 128 + r]);
+              l_smem[(par * 4 + 2) * 128 + r];
           m = mrow_smem[par * 128 + r];
           const float inv_l = 1.f / l;
 #pragma unroll
