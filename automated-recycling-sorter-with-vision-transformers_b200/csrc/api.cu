@@ -328,7 +328,7 @@ int vitk_reserve_sms(int n) {
 int vitk_attention_set_impl(int impl) {
   VITK_REQUIRE(impl >= 0 && impl <= 4,
                "attention impl must be 0 (auto), 1 (flash), 2 (tcgen05), 3 (unpipelined tcgen05) or "
-               "4 (two-pass long-sequence tcgen05)");
+               "4 (long-sequence tcgen05)");
   attention_force_impl(impl);
   return VITK_OK;
 }

@@ -247,7 +247,7 @@ attn_fwd_hd64_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __res
 }  // namespace
 
 // 0 auto, 1 = mma.sync flash kernel, 2 = tcgen05 kernels, 3 = the unpipelined tcgen05 forward
-// (attention_tc.cu) also where the pipelined one (attention_tc2.cu) applies, 4 = the two-pass
+// (attention_tc.cu) also where the pipelined one (attention_tc2.cu) applies, 4 = the key-block
 // long-sequence kernel (attention_tc3.cu) for every N <= 640
 static int g_attn_impl = 0;
 void attention_force_impl(int impl) { g_attn_impl = impl; }

@@ -281,7 +281,7 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tm_q,    // box {64, 128
       }
     }
   } else if (warp < 16) {
-    setmaxnreg_inc<112>();
+    setmaxnreg_inc<120>();
     // ============ softmax: set = score region, thread == query row over the whole key block =====
     const int set = (warp - 4) >> 2;  // owns region `set` and the units u with u % 3 == set
     const int q = warp & 3;           // TMEM lane quarter
@@ -311,25 +311,32 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tm_q,    // box {64, 128
           // ---- sweep 1: block maximum of the row
           float m_blk = -INFINITY;
           if (warp_rows) {
-            for (int ch = 0; ch < n32; ++ch) {
-              uint32_t v[32];
-              tmem_ld_32x32b_x32(treg + ch * 32, v);
+            // two 32-column loads in flight per wait (the wait costs ~100 cycles whatever it covers)
+            for (int ch = 0; ch < n32; ch += 2) {
+              uint32_t v[2][32];
+              const bool two = ch + 1 < n32;
+              tmem_ld_32x32b_x32(treg + ch * 32, v[0]);
+              if (two) tmem_ld_32x32b_x32(treg + (ch + 1) * 32, v[1]);
               tmem_ld_wait();
-              const int k0 = ch * 32;
-              if (k0 + 32 <= valid) {
-                float a0 = m_blk, a1 = -INFINITY, a2 = -INFINITY, a3 = -INFINITY;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  a0 = fmax3(a0, __uint_as_float(v[8 * i]), __uint_as_float(v[8 * i + 1]));
-                  a1 = fmax3(a1, __uint_as_float(v[8 * i + 2]), __uint_as_float(v[8 * i + 3]));
-                  a2 = fmax3(a2, __uint_as_float(v[8 * i + 4]), __uint_as_float(v[8 * i + 5]));
-                  a3 = fmax3(a3, __uint_as_float(v[8 * i + 6]), __uint_as_float(v[8 * i + 7]));
+              for (int hh = 0; hh < 2; ++hh) {
+                if (hh == 1 && !two) break;
+                const int k0 = (ch + hh) * 32;
+                if (k0 + 32 <= valid) {
+                  float a0 = m_blk, a1 = -INFINITY, a2 = -INFINITY, a3 = -INFINITY;
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    a0 = fmax3(a0, __uint_as_float(v[hh][8 * i]), __uint_as_float(v[hh][8 * i + 1]));
+                    a1 = fmax3(a1, __uint_as_float(v[hh][8 * i + 2]), __uint_as_float(v[hh][8 * i + 3]));
+                    a2 = fmax3(a2, __uint_as_float(v[hh][8 * i + 4]), __uint_as_float(v[hh][8 * i + 5]));
+                    a3 = fmax3(a3, __uint_as_float(v[hh][8 * i + 6]), __uint_as_float(v[hh][8 * i + 7]));
+                  }
+                  m_blk = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 32; ++i)
+                    if (k0 + i < valid) m_blk = fmaxf(m_blk, __uint_as_float(v[hh][i]));
                 }
-                m_blk = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
-              } else {
-#pragma unroll
-                for (int i = 0; i < 32; ++i)
-                  if (k0 + i < valid) m_blk = fmaxf(m_blk, __uint_as_float(v[i]));
               }
             }
             if (tail16) {

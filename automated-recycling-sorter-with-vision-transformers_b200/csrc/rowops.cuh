@@ -61,7 +61,7 @@ int attention_fwd_tc(const void* qkv, void* ctx, float* lse, int B, int N, int H
 // Item-pipelined tcgen05 variant for N <= 208 (attention_tc2.cu); the default for the 224 px models.
 int attention_fwd_tc2(const void* qkv, void* ctx, float* lse, int B, int N, int H, int hd,
                       cudaStream_t stream, const DropParams* drop = nullptr);
-// Two-pass tcgen05 variant for long sequences, N <= 640 (attention_tc3.cu): 384 px -> 577 tokens.
+// Key-block tcgen05 variant (online softmax with a lazily moved reference) for long sequences, N <= 640 (attention_tc3.cu): 384 px -> 577 tokens.
 int attention_fwd_tc3(const void* qkv, void* ctx, float* lse, int B, int N, int H, int hd,
                       cudaStream_t stream);
 // Generic-source attention (attention_x.cu): query rows at q + b*q_img + r*ldq + h*hd, keys / values

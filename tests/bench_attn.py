@@ -31,7 +31,7 @@ def timeit(fn, iters=20):
 
 
 for impl, name in ((1, "flash mma.sync"), (3, "tcgen05 unpipelined"), (2, "tcgen05 pipelined"),
-                   (4, "tcgen05 two-pass")):
+                   (4, "tcgen05 long-seq")):
     if (impl == 3 and N > 256) or (impl == 4 and N > 640):
         continue
     vitk._lib.set_attention_impl(impl)

@@ -33,7 +33,7 @@ def test_patchify(vitk, B, C, S, p):
     assert torch.equal(out, ref.bfloat16())  # pure gather + round-to-nearest: bit exact
 
 
-@pytest.fixture(params=[1, 2, 3, 4], ids=["flash", "tcgen05", "tcgen05-unpipelined", "tcgen05-two-pass"])
+@pytest.fixture(params=[1, 2, 3, 4], ids=["flash", "tcgen05", "tcgen05-unpipelined", "tcgen05-long-seq"])
 def attn_impl(request, vitk):
     vitk._lib.set_attention_impl(request.param)
     yield request.param
