@@ -109,6 +109,8 @@ _SIGNATURES = {
     "vitk_workspace_bytes": (C.c_int, [C.POINTER(VitkConfig), C.c_int, C.POINTER(C.c_size_t)]),
     "vitk_forward": (C.c_int, [C.POINTER(VitkConfig), C.POINTER(VitkWeights), C.c_void_p, C.c_int,
                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "vitk_forward_cls": (C.c_int, [C.POINTER(VitkConfig), C.POINTER(VitkWeights), C.c_void_p, C.c_int,
+                                   C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "vitk_gemm": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                             C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                             C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p]),

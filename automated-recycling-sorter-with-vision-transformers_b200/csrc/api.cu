@@ -2,6 +2,8 @@
 // sequence that replaces `self.backbone(images)` (reference evaluation.py:231 / train.py:831).
 #include "../../include/vitk.h"
 
+#include <cuda_bf16.h>
+
 #include "common.h"
 #include "fp32_mode.cuh"
 #include "gemm_sm100.cuh"
@@ -58,6 +60,10 @@ struct Workspace {
   void* ctx;    // bf16 [M, D]
   void* h;      // bf16 [M, Mlp]
   void* patch;  // bf16 [Mp, Kp]
+  // CLS-only tail of the last block (vitk_forward_cls): one row per image
+  float* c_x;   // f32 [B, D]
+  void* c_b;    // bf16 [B, D]  (attention context, then the LayerNorm output)
+  void* c_h;    // bf16 [B, Mlp]
   size_t bytes;
 };
 
@@ -75,6 +81,9 @@ Workspace carve(const Dims& d, void* base) {
   w.ctx = take(d.M * d.D * 2);
   w.h = take(d.M * d.Mlp * 2);
   w.patch = take(d.Mp * d.Kp * 2);
+  w.c_x = static_cast<float*>(take(static_cast<size_t>(d.B) * d.D * 4));
+  w.c_b = take(static_cast<size_t>(d.B) * d.D * 2);
+  w.c_h = take(static_cast<size_t>(d.B) * d.Mlp * 2);
   w.bytes = off;
   return w;
 }
@@ -108,7 +117,7 @@ struct U8Input {
 
 int forward_bf16(const VitkConfig* cfg, const VitkWeights* w, const float* images, const Dims& d,
                  float* tokens_out, float* logits_out, const Workspace& ws, cudaStream_t stream,
-                 const U8Input* u8 = nullptr) {
+                 const U8Input* u8 = nullptr, bool cls_only_tail = false) {
   const int M = static_cast<int>(d.M), D = d.D;
   SweepAlternation sweep;  // consecutive row-ordered kernels run in opposite directions (L2 reuse)
   // -- patch embedding as a GEMM; epilogue adds bias + position embedding and writes each patch
@@ -146,6 +155,30 @@ int forward_bf16(const VitkConfig* cfg, const VitkWeights* w, const float* image
                            cfg->ln_eps, stream));
     VITK_TRY(linear(ws.xn, D, bw.qkv_w, M, 3 * D, D, EPI_BF16, bw.qkv_b, nullptr, 0, ws.qkv,
                     nullptr, 3 * D, stream));
+    if (cls_only_tail && l == d.L - 1) {
+      // The classifier reads only row 0 of the last block's output: its attention needs the keys
+      // and values of every token (computed above) but a single query per image, and everything
+      // after it - projection, LayerNorm, MLP - is row-wise, so it runs on B rows instead of B*N.
+      // Same logits as the full evaluation (nothing that is skipped feeds them).
+      const __nv_bfloat16* qkv = static_cast<const __nv_bfloat16*>(ws.qkv);
+      const long long img = static_cast<long long>(d.N) * 3 * D;
+      if (attention_xtc_applicable(img, img, d.B, 1, d.N, d.hd))
+        VITK_TRY(attention_xtc(qkv, img, 3 * D, qkv + D, qkv + 2 * D, img, 3 * D, ws.c_b, D, D, d.B,
+                               1, d.N, d.H, d.hd, stream));
+      else
+        VITK_TRY(attention_x(qkv, img, 3 * D, qkv + D, qkv + 2 * D, img, 3 * D, ws.c_b, D, D, d.B, 1,
+                             d.N, d.H, d.hd, stream));
+      VITK_TRY(linear(ws.c_b, D, bw.proj_w, d.B, D, D, EPI_RESID_F32, bw.proj_b, ws.x, d.N * D,
+                      ws.c_x, nullptr, D, stream));
+      VITK_TRY(layernorm_fwd(ws.c_x, D, bw.ln2_w, bw.ln2_b, ws.c_b, 0, D, nullptr, nullptr, d.B, D,
+                             cfg->ln_eps, stream));
+      VITK_TRY(linear(ws.c_b, D, bw.fc1_w, d.B, d.Mlp, D, EPI_GELU_TANH_BF16, bw.fc1_b, nullptr, 0,
+                      ws.c_h, nullptr, d.Mlp, stream));
+      VITK_TRY(linear(ws.c_h, d.Mlp, bw.fc2_w, d.B, D, d.Mlp, EPI_RESID_F32, bw.fc2_b, ws.c_x, D,
+                      ws.c_x, nullptr, D, stream));
+      return cls_head(ws.c_x, D, w->ln_f_w, w->ln_f_b, w->head_w, w->head_b, nullptr, logits_out,
+                      d.B, D, cfg->n_classes, cfg->ln_eps, stream);
+    }
     VITK_TRY(attention_fwd(ws.qkv, ws.ctx, nullptr, d.B, d.N, d.H, d.hd, stream));
     VITK_TRY(linear(ws.ctx, D, bw.proj_w, M, D, D, EPI_RESID_F32, bw.proj_b, ws.x, D, ws.x,
                     nullptr, D, stream));
@@ -384,6 +417,31 @@ int vitk_forward(const VitkConfig* cfg, const VitkWeights* w, const float* image
                      workspace_bytes);
   return forward_bf16(cfg, w, images, d, tokens_out, logits_out, ws,
                       static_cast<cudaStream_t>(stream));
+}
+
+int vitk_forward_cls(const VitkConfig* cfg, const VitkWeights* w, const float* images, int batch,
+                     float* logits_out, void* workspace, size_t workspace_bytes,
+                     vitk_stream_t stream) {
+  Dims d;
+  VITK_TRY(check_config(cfg, batch, &d));
+  VITK_REQUIRE(w != nullptr && images != nullptr && workspace != nullptr && logits_out != nullptr,
+               "null argument");
+  VITK_REQUIRE(w->blocks != nullptr && w->patch_w && w->patch_b && w->cls_token && w->pos_embed &&
+                   w->ln_f_w && w->ln_f_b,
+               "weights struct has null members");
+  VITK_REQUIRE(d.prefix == 1 || w->dist_token != nullptr, "DeiT needs dist_token");
+  VITK_REQUIRE(cfg->n_classes > 0 && w->head_w && w->head_b, "no classifier head configured");
+  VITK_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0,
+               "workspace must be 1024-byte aligned");
+  VITK_REQUIRE(cfg->precision == 0, "the CLS-only tail is implemented for the bf16 path");
+  VITK_REQUIRE(d.hd == 32 || d.hd == 64 || d.hd == 96 || d.hd == 128,
+               "head_dim %d unsupported (32, 64, 96 or 128)", d.hd);
+  const Workspace ws = carve(d, workspace);
+  if (ws.bytes > workspace_bytes)
+    return set_error(VITK_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", ws.bytes,
+                     workspace_bytes);
+  return forward_bf16(cfg, w, images, d, nullptr, logits_out, ws, static_cast<cudaStream_t>(stream),
+                      nullptr, true);
 }
 
 int vitk_forward_u8(const VitkConfig* cfg, const VitkWeights* w, const unsigned char* images_hwc,

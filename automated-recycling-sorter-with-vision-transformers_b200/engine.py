@@ -115,7 +115,7 @@ class EncoderEngine:
     NORM_STD = (0.229, 0.224, 0.225)
 
     def forward(self, images: torch.Tensor, head: torch.nn.Linear | None = None,
-                want_tokens: bool = True, want_logits: bool = False):
+                want_tokens: bool = True, want_logits: bool = False, cls_only_tail: bool = False):
         """images: f32 NCHW [B, C, S, S] (what `images.to(device)` hands the reference's model,
         evaluation.py:499), or u8 NHWC [B, S, S, 3] straight from the decoder - then Normalize +
         ToTensorV2 run on the device inside the patch gather (vitk_forward_u8)."""
@@ -148,7 +148,13 @@ class EncoderEngine:
             if want_tokens else None
         logits = torch.empty((B, n_classes), dtype=torch.float32, device=images.device) \
             if want_logits else None
-        if u8:
+        if cls_only_tail:
+            if u8 or want_tokens or not want_logits:
+                raise _lib.VitkError("cls_only_tail: f32 images in, logits only out")
+            check(lib().vitk_forward_cls(C.byref(cfg), C.byref(w), images.data_ptr(), B,
+                                         logits.data_ptr(), ws, ws_bytes,
+                                         torch.cuda.current_stream().cuda_stream))
+        elif u8:
             mean, std = (C.c_float * 3)(*self.NORM_MEAN), (C.c_float * 3)(*self.NORM_STD)
             check(lib().vitk_forward_u8(C.byref(cfg), C.byref(w), images.data_ptr(), mean, std, B,
                                         tokens.data_ptr() if tokens is not None else None,

@@ -141,9 +141,12 @@ class _EncoderBase(nn.Module):
         tokens, _ = self._engine().forward(x, want_tokens=True)
         return tokens
 
-    def classify(self, x, head: nn.Linear):
-        """logits f32 [B, n_classes] = head(LN(tokens)[:, 0]) in one library call."""
-        _, logits = self._engine().forward(x, head=head, want_tokens=False, want_logits=True)
+    def classify(self, x, head: nn.Linear, cls_only_tail: bool = False):
+        """logits f32 [B, n_classes] = head(LN(tokens)[:, 0]) in one library call.
+        cls_only_tail: evaluate the last block for the CLS rows only (vitk_forward_cls) - the same
+        logits, without the 71 % of the last block's work that feeds nothing the head reads."""
+        _, logits = self._engine().forward(x, head=head, want_tokens=False, want_logits=True,
+                                           cls_only_tail=cls_only_tail)
         return logits
 
 
@@ -205,6 +208,12 @@ class ViTClassifier(nn.Module):
             from .autograd import classifier_forward_train
             return classifier_forward_train(self, images)
         return self.backbone.classify(images, self.head)
+
+    @torch.no_grad()
+    def classify_pruned(self, images):
+        """Inference logits with the last encoder block evaluated for the CLS rows only (opt-in;
+        `forward` always evaluates every token, as the reference does)."""
+        return self.backbone.classify(images, self.head, cls_only_tail=True)
 
     @torch.no_grad()
     def predict(self, images):

@@ -157,6 +157,15 @@ int vitk_forward(const VitkConfig* cfg, const VitkWeights* w, const float* image
                  float* tokens_out, float* logits_out, void* workspace, size_t workspace_bytes,
                  vitk_stream_t stream);
 
+/* The classifier call with the last block evaluated for the CLS rows only: logits_out is what
+ * vitk_forward(tokens_out = NULL) returns, but since head(LN(x)[:, 0]) reads a single row per
+ * image, the last block's attention is run for that one query (against the keys / values of all
+ * tokens) and its projection, LayerNorm and MLP on `batch` rows instead of batch * N - 71 % of the
+ * last block's contraction work feeds nothing the classifier returns.  bf16 mode. */
+int vitk_forward_cls(const VitkConfig* cfg, const VitkWeights* w, const float* images, int batch,
+                     float* logits_out, void* workspace, size_t workspace_bytes,
+                     vitk_stream_t stream);
+
 /* vitk_forward for 8-bit images straight from the decoder (HWC, u8 [batch, S, S, 3], 8-byte
  * aligned): A.Normalize(mean, std) + ToTensorV2 of the reference's data pipeline
  * (evaluation.py:362-364, 369-372; train.py:442-443) are fused into the patch gather, evaluated

@@ -35,6 +35,7 @@ def test_workspace_query_and_config_validation(vitk):
     assert lib.vitk_workspace_bytes(C.byref(cfg), 256, C.byref(need)) == 0
     M = 256 * 197
     expect = M * 768 * 4 + M * 768 * 2 + M * 2304 * 2 + M * 768 * 2 + M * 3072 * 2 + 256 * 196 * 768 * 2
+    expect += 256 * (768 * 4 + 768 * 2 + 3072 * 2)     # CLS-only tail of vitk_forward_cls
     assert expect <= need.value <= expect + 16 * 1024
     cfg.image_size = 225   # not a multiple of the patch size
     rc = lib.vitk_workspace_bytes(C.byref(cfg), 256, C.byref(need))

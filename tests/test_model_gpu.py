@@ -64,6 +64,30 @@ def test_other_head_sizes_match_oracle(vitk, D, H, S, deit):
     assert_top1(logits, l_ref)
 
 
+@pytest.mark.parametrize("kw,B,deit", [(TINY, 3, False), (SMALL, 9, True),
+                                       (dict(image_size=224, patch_size=16, embed_dim=768, num_layers=2,
+                                             num_heads=12, mlp_dim=3072), 5, False),
+                                       (dict(image_size=384, patch_size=16, embed_dim=192, num_layers=2,
+                                             num_heads=2, mlp_dim=384), 2, False)])
+def test_cls_only_tail_gives_the_same_logits(vitk, kw, B, deit):
+    """vitk_forward_cls: last block evaluated for the CLS rows only - logits equal to the full
+    evaluation up to the reduction order of the two attention kernels, and within the bar of the
+    oracle."""
+    torch.manual_seed(1)
+    model = vitk.ViTClassifier(num_classes=6, deit=deit, dropout=0.0, **kw)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    x = O.synthetic_images(B, kw["image_size"])
+    with torch.no_grad():
+        _, l_ref = O.classifier_forward(sd, x, kw["num_heads"], dtype=torch.float64)
+    model = model.cuda().eval()
+    with torch.no_grad():
+        full = model(x.cuda())
+        pruned = model.classify_pruned(x.cuda())
+    assert (pruned - full).abs().max() < 4e-3
+    assert (pruned.cpu().double() - l_ref).abs().max() < 2e-2
+    assert_top1(pruned.cpu().double(), l_ref)
+
+
 def test_vit_b16_matches_oracle(vitk):
     kw = dict(image_size=224, patch_size=16, embed_dim=768, num_layers=12, num_heads=12, mlp_dim=3072)
     tokens, logits, t_ref, l_ref = _run(vitk, kw, 4, False)
