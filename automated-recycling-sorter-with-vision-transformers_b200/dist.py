@@ -77,10 +77,10 @@ def gather_rows(local: torch.Tensor, n_total: int, group=None) -> torch.Tensor:
     return torch.cat(out, dim=0)
 
 
-def sharded_apply(fn: Callable[[torch.Tensor], torch.Tensor], batch: torch.Tensor, group=None,
-                  gather: bool = True) -> torch.Tensor:
-    """Batch-sharded inference: apply `fn` (e.g. a ViTClassifier) to this rank's slice of `batch`
-    and, if `gather`, assemble the full result on every rank."""
+def sharded_apply(fn: Callable, batch: torch.Tensor, group=None, gather: bool = True):
+    """Batch-sharded inference: apply `fn` (e.g. a ViTClassifier, or a ViTObjectDetector returning
+    the reference's prediction dict of per-image tensors) to this rank's slice of `batch` and, if
+    `gather`, assemble the full result - a tensor or a dict of tensors - on every rank."""
     world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
     rank = dist.get_rank(group) if world > 1 else 0
     a, b = shard_range(batch.shape[0], rank, world)
@@ -89,5 +89,7 @@ def sharded_apply(fn: Callable[[torch.Tensor], torch.Tensor], batch: torch.Tenso
         return local
     if local is None:   # more ranks than images: contribute an empty shard of the right width
         probe = fn(batch[:1])
-        local = probe[:0]
+        local = {k: v[:0] for k, v in probe.items()} if isinstance(probe, dict) else probe[:0]
+    if isinstance(local, dict):
+        return {k: gather_rows(v, batch.shape[0], group) for k, v in local.items()}
     return gather_rows(local, batch.shape[0], group)

@@ -101,7 +101,25 @@ def job_sharded_inference(rank, world):
     return bool(torch.allclose(out, batch @ w) and local.shape[0] == b - a)
 
 
+def job_sharded_detector(rank, world):
+    """A detector returns the reference's prediction dict; every entry is gathered by image.  Also
+    with more ranks than images."""
+    d = _dist_mod()
+    torch.manual_seed(3)
+    w1, w2 = torch.randn(5, 3 * 7), torch.randn(5, 3 * 4)
+    fn = lambda t: {"class_logits": (t @ w1).reshape(-1, 3, 7),
+                    "bbox_coords": torch.sigmoid(t @ w2).reshape(-1, 3, 4)}
+    ok = True
+    for n in (11, 1):
+        batch = torch.randn(n, 5)
+        out, want = d.sharded_apply(fn, batch), fn(batch)
+        ok = ok and all(torch.allclose(out[k], want[k]) and out[k].shape == want[k].shape
+                        for k in want)
+    return bool(ok)
+
+
 @pytest.mark.parametrize("world", [2, 3])
-@pytest.mark.parametrize("job", ["job_allreduce", "job_data_parallel_mean", "job_sharded_inference"])
+@pytest.mark.parametrize("job", ["job_allreduce", "job_data_parallel_mean", "job_sharded_inference",
+                                 "job_sharded_detector"])
 def test_gloo(world, job):
     assert all(_run(world, job).values())
