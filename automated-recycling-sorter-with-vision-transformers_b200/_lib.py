@@ -9,8 +9,11 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
+import os
+
 PKG_DIR = Path(__file__).resolve().parent
-LIB_PATH = PKG_DIR / "libvitk.so"
+# VITK_LIB: another build of the same library (same ABI), for A/B timing of kernel variants on one box
+LIB_PATH = Path(os.environ["VITK_LIB"]) if os.environ.get("VITK_LIB") else PKG_DIR / "libvitk.so"
 
 ABI_VERSION = 3
 
