@@ -19,6 +19,10 @@ from ._lib import check, lib
 from .trainer import TrainState
 
 
+def _align1k(t: torch.Tensor) -> int:
+    return (t.data_ptr() + 1023) // 1024 * 1024
+
+
 def _state_for(backbone) -> TrainState:
     st = backbone.__dict__.get("_vitk_train_state")
     if st is None or st.flat.device != backbone.cls_token.device or not st.owns_params():
@@ -41,7 +45,9 @@ class _BackboneFunction(torch.autograd.Function):
         training = bool(state.backbone.training) and float(state.backbone.dropout.p) > 0.0
         seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item()) if training else 0
         cfg = state.config(training=training, seed=seed)
-        saved, saved_bytes, ws, ws_bytes = state.buffers(B)
+        # this call's own activation / workspace buffers, kept alive by the autograd context
+        saved_t, saved_bytes, ws_t, ws_bytes = state.new_buffers(B)
+        saved, ws = _align1k(saved_t), _align1k(ws_t)
         pe = state.backbone.patch_embedding
         N = pe.n_patches + state.n_prefix
         tokens = torch.empty((B, N, cfg.embed_dim), dtype=torch.float32, device=images.device)
@@ -49,6 +55,7 @@ class _BackboneFunction(torch.autograd.Function):
                                        tokens.data_ptr(), saved, saved_bytes, ws, ws_bytes,
                                        torch.cuda.current_stream().cuda_stream))
         ctx.state, ctx.batch, ctx.training, ctx.seed = state, B, training, seed
+        ctx.saved_t, ctx.ws_t = saved_t, ws_t
         return tokens
 
     @staticmethod
@@ -56,7 +63,10 @@ class _BackboneFunction(torch.autograd.Function):
         st, B = ctx.state, ctx.batch
         d_tokens = d_tokens.float().contiguous()
         cfg = st.config(training=ctx.training, seed=ctx.seed)
-        saved, _, ws, _ = st.buffers(B)
+        if ctx.saved_t is None:
+            raise _lib.VitkError("backward through the vitk encoder a second time: the saved "
+                                 "activations were released (retain_graph is not supported)")
+        saved, ws = _align1k(ctx.saved_t), _align1k(ctx.ws_t)
         st.grad.zero_()
         check(lib().vitk_backward_tokens(C.byref(cfg), C.byref(st.W), C.byref(st.T), C.byref(st.G),
                                          d_tokens.data_ptr(), B, saved, ws,
@@ -65,6 +75,7 @@ class _BackboneFunction(torch.autograd.Function):
         for name, p in zip(st.names, st.params):
             o = st.offsets[name]
             grads.append(st.grad[o:o + p.numel()].view(p.shape).clone() if p.requires_grad else None)
+        ctx.saved_t = ctx.ws_t = None   # release the activations now, not when ctx is collected
         return (None, None, *grads)
 
 

@@ -64,6 +64,8 @@ struct Workspace {
   float* c_x;   // f32 [B, D]
   void* c_b;    // bf16 [B, D]  (attention context, then the LayerNorm output)
   void* c_h;    // bf16 [B, Mlp]
+  unsigned int* ln_cnt;  // per 128-row block arrival counters of the fused LayerNorm tail
+  size_t ln_cnt_bytes;
   size_t bytes;
 };
 
@@ -84,8 +86,38 @@ Workspace carve(const Dims& d, void* base) {
   w.c_x = static_cast<float*>(take(static_cast<size_t>(d.B) * d.D * 4));
   w.c_b = take(static_cast<size_t>(d.B) * d.D * 2);
   w.c_h = take(static_cast<size_t>(d.B) * d.Mlp * 2);
+  w.ln_cnt_bytes = static_cast<size_t>((d.M + 127) / 128) * 4;
+  w.ln_cnt = static_cast<unsigned int*>(take(w.ln_cnt_bytes));
   w.bytes = off;
   return w;
+}
+
+// x += A W^T + bias, then xn = LN(x) * gamma + beta as bf16 - one launch (gemm_sm100.cu: the
+// residual GEMM's LayerNorm tail).  train.py:586-591.
+int linear_resid_ln(const void* A, int lda, const void* W, int M, int N, int K, const float* bias,
+                    float* x, const float* gamma, const float* beta, float eps, void* xn,
+                    unsigned int* counters, cudaStream_t stream) {
+  GemmProblem p;
+  p.A = A;
+  p.lda = lda;
+  p.B = W;
+  p.ldb = K;
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.epi = EPI_RESID_F32;
+  p.e.bias = bias;
+  p.e.resid = x;
+  p.e.ldr = N;
+  p.e.out = x;
+  p.e.ldo = N;
+  p.e.ln_out = xn;
+  p.e.ln_ldo = N;
+  p.e.ln_gamma = gamma;
+  p.e.ln_beta = beta;
+  p.e.ln_eps = eps;
+  p.e.ln_counters = counters;
+  return gemm_bf16_tn(p, stream);
 }
 
 int linear(const void* A, int lda, const void* W, int M, int N, int K, GemmEpi epi,
@@ -120,6 +152,8 @@ int forward_bf16(const VitkConfig* cfg, const VitkWeights* w, const float* image
                  const U8Input* u8 = nullptr, bool cls_only_tail = false) {
   const int M = static_cast<int>(d.M), D = d.D;
   SweepAlternation sweep;  // consecutive row-ordered kernels run in opposite directions (L2 reuse)
+  // the fused LayerNorm tails leave their counters zero-filled; start from a known state anyway
+  VITK_CHECK_CUDA(cudaMemsetAsync(ws.ln_cnt, 0, ws.ln_cnt_bytes, stream));
   // -- patch embedding as a GEMM; epilogue adds bias + position embedding and writes each patch
   //    row at its token slot (evaluation.py:142-149)
   if (u8 != nullptr)
@@ -149,10 +183,13 @@ int forward_bf16(const VitkConfig* cfg, const VitkWeights* w, const float* image
     VITK_TRY(gemm_bf16_tn(p, stream));
   }
   // -- encoder blocks (train.py:584-593)
+  // LayerNorm 1 of block 0 is the only stand-alone normalisation between blocks: every later one
+  // is the tail of the residual GEMM that produces its input (projection -> LN2, linear2 -> LN1
+  // of the next block)
+  VITK_TRY(layernorm_fwd(ws.x, D, w->blocks[0].ln1_w, w->blocks[0].ln1_b, ws.xn, 0, D, nullptr,
+                         nullptr, M, D, cfg->ln_eps, stream));
   for (int l = 0; l < d.L; ++l) {
     const VitkBlockWeights& bw = w->blocks[l];
-    VITK_TRY(layernorm_fwd(ws.x, D, bw.ln1_w, bw.ln1_b, ws.xn, 0, D, nullptr, nullptr, M, D,
-                           cfg->ln_eps, stream));
     VITK_TRY(linear(ws.xn, D, bw.qkv_w, M, 3 * D, D, EPI_BF16, bw.qkv_b, nullptr, 0, ws.qkv,
                     nullptr, 3 * D, stream));
     if (cls_only_tail && l == d.L - 1) {
@@ -180,14 +217,18 @@ int forward_bf16(const VitkConfig* cfg, const VitkWeights* w, const float* image
                       d.B, D, cfg->n_classes, cfg->ln_eps, stream);
     }
     VITK_TRY(attention_fwd(ws.qkv, ws.ctx, nullptr, d.B, d.N, d.H, d.hd, stream));
-    VITK_TRY(linear(ws.ctx, D, bw.proj_w, M, D, D, EPI_RESID_F32, bw.proj_b, ws.x, D, ws.x,
-                    nullptr, D, stream));
-    VITK_TRY(layernorm_fwd(ws.x, D, bw.ln2_w, bw.ln2_b, ws.xn, 0, D, nullptr, nullptr, M, D,
-                           cfg->ln_eps, stream));
+    VITK_TRY(linear_resid_ln(ws.ctx, D, bw.proj_w, M, D, D, bw.proj_b, ws.x, bw.ln2_w, bw.ln2_b,
+                             cfg->ln_eps, ws.xn, ws.ln_cnt, stream));
     VITK_TRY(linear(ws.xn, D, bw.fc1_w, M, d.Mlp, D, EPI_GELU_TANH_BF16, bw.fc1_b, nullptr, 0, ws.h,
                     nullptr, d.Mlp, stream));
-    VITK_TRY(linear(ws.h, d.Mlp, bw.fc2_w, M, D, d.Mlp, EPI_RESID_F32, bw.fc2_b, ws.x, D, ws.x,
-                    nullptr, D, stream));
+    if (l + 1 < d.L) {
+      const VitkBlockWeights& nx = w->blocks[l + 1];
+      VITK_TRY(linear_resid_ln(ws.h, d.Mlp, bw.fc2_w, M, D, d.Mlp, bw.fc2_b, ws.x, nx.ln1_w,
+                               nx.ln1_b, cfg->ln_eps, ws.xn, ws.ln_cnt, stream));
+    } else {
+      VITK_TRY(linear(ws.h, d.Mlp, bw.fc2_w, M, D, d.Mlp, EPI_RESID_F32, bw.fc2_b, ws.x, D, ws.x,
+                      nullptr, D, stream));
+    }
   }
   // -- final LayerNorm: all tokens for the backbone contract, CLS row only for the classifier
   if (tokens_out)
@@ -327,6 +368,10 @@ int vitk_gemm_set_cta_group(int ctas) {
 }
 int vitk_gemm_set_direct_epilogue(int on) {
   gemm_force_direct_epilogue(on != 0);
+  return VITK_OK;
+}
+int vitk_gemm_set_fused_layernorm(int on) {
+  gemm_set_fused_layernorm(on != 0);
   return VITK_OK;
 }
 int vitk_postprocess_scores(const float* logits, int rows, int n_classes, int exclude_last,
@@ -502,6 +547,36 @@ int vitk_gemm(const void* A, int lda, const void* B, int ldb, int M, int N, int 
   p.e.ldo = ldo;
   p.e.alpha = alpha;
   p.e.beta = beta;
+  return gemm_bf16_tn(p, static_cast<cudaStream_t>(stream));
+}
+
+int vitk_gemm_resid_layernorm(const void* A, int lda, const void* W, int ldb, int M, int N, int K,
+                              const float* bias, float* x_inout, const float* gamma,
+                              const float* beta, float eps, void* ln_out, float* mean_out,
+                              float* rstd_out, unsigned int* counters, vitk_stream_t stream) {
+  VITK_REQUIRE(ln_out != nullptr && x_inout != nullptr, "gemm_resid_layernorm: null output");
+  GemmProblem p;
+  p.A = A;
+  p.lda = lda;
+  p.B = W;
+  p.ldb = ldb;
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.epi = EPI_RESID_F32;
+  p.e.bias = bias;
+  p.e.resid = x_inout;
+  p.e.ldr = N;
+  p.e.out = x_inout;
+  p.e.ldo = N;
+  p.e.ln_out = ln_out;
+  p.e.ln_ldo = N;
+  p.e.ln_gamma = gamma;
+  p.e.ln_beta = beta;
+  p.e.ln_eps = eps;
+  p.e.ln_mean = mean_out;
+  p.e.ln_rstd = rstd_out;
+  p.e.ln_counters = counters;
   return gemm_bf16_tn(p, static_cast<cudaStream_t>(stream));
 }
 

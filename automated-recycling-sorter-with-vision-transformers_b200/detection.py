@@ -172,7 +172,7 @@ class DeiTObjectDetector(nn.Module):
     def forward(self, images, return_features=False):
         features = self.backbone(images)                      # [B, P + 2, D]
         predictions = self.detection_head.decode(features, 2)  # drop CLS and DIST (train.py:842)
-        if not return_features:
+        if not (return_features or self.training):             # train.py:835,847
             return predictions
         # triplet_projection on the CLS row + F.normalize (train.py:833-838), read in place
         feats = features.detach().float().contiguous()

@@ -136,6 +136,10 @@ class _EncoderBase(nn.Module):
     def forward(self, x):
         """images f32 [B,C,S,S] -> all tokens after the final LayerNorm, f32 [B,N,D]."""
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            if self._engine().precision == 1:
+                raise _lib.VitkError("the fp32-parity mode is inference-only: the differentiable "
+                                     "path computes in bf16 (call under torch.no_grad(), or "
+                                     "set_precision('bf16'))")
             from .autograd import encoder_forward_train  # training path (saves activations)
             return encoder_forward_train(self, x)
         tokens, _ = self._engine().forward(x, want_tokens=True)
@@ -205,6 +209,10 @@ class ViTClassifier(nn.Module):
 
     def forward(self, images):
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            if self.backbone._engine().precision == 1:
+                raise _lib.VitkError("the fp32-parity mode is inference-only: the differentiable "
+                                     "path computes in bf16 (call under torch.no_grad(), or "
+                                     "set_precision('bf16'))")
             from .autograd import classifier_forward_train
             return classifier_forward_train(self, images)
         return self.backbone.classify(images, self.head)

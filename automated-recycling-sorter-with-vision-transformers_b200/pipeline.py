@@ -10,6 +10,12 @@ of batch i+1 overlapped with the kernels of batch i.
 
 Two device input slots and a dedicated copy stream; every step moves its images host->device and
 its logits device->host.  PyTorch is used for streams, events and memory only.
+
+A batch may hold fewer images than `batch_size` (the reference's evaluation DataLoader keeps its
+smaller last batch, evaluation.py:555-562: drop_last is False).  Buffer lifetime: every yielded
+result is a view of one of TWO pinned host buffers and is overwritten two steps later - consume it
+(or `.clone()` it) before asking for the batch after the next; `list(runner.run(...))` therefore
+needs `copy_results=True`.
 """
 from __future__ import annotations
 
@@ -20,7 +26,7 @@ import torch
 
 class HostBatchRunner:
     def __init__(self, model, batch_size: int, device: torch.device | str = "cuda",
-                 input_dtype: torch.dtype = torch.float32):
+                 input_dtype: torch.dtype = torch.float32, copy_results: bool = False):
         """input_dtype float32: host batches are normalised f32 NCHW tensors, exactly what the
         reference copies to the device (evaluation.py:499).  uint8: host batches are raw decoder
         output, u8 NHWC [B, S, S, 3]; Normalize + ToTensorV2 run on the device (a quarter of the
@@ -35,6 +41,9 @@ class HostBatchRunner:
         else:
             raise ValueError("input_dtype must be torch.float32 or torch.uint8")
         self.shape, self.input_dtype = shape, input_dtype
+        self.copy_results = bool(copy_results)
+        self._count = [0, 0]       # images in each input slot
+        self._out_count = [0, 0]   # images in each result slot
         self.detector = hasattr(model, "detection_head")
         if self.detector:
             head = model.detection_head
@@ -54,12 +63,16 @@ class HostBatchRunner:
         self.d2h_bytes_per_step = sum(4 * t.numel() for t in self._host_out[0].values())
 
     def _enqueue_copy(self, slot: int, host: torch.Tensor, first_use: bool):
-        if tuple(host.shape) != self.shape or host.dtype != self.input_dtype or host.is_cuda:
-            raise ValueError(f"expected a CPU {self.input_dtype} tensor of shape {self.shape}")
+        n = host.shape[0] if host.dim() == len(self.shape) else -1
+        if tuple(host.shape[1:]) != self.shape[1:] or not 0 < n <= self.shape[0] or \
+                host.dtype != self.input_dtype or host.is_cuda:
+            raise ValueError(f"expected a CPU {self.input_dtype} tensor of shape [1..{self.shape[0]}, "
+                             f"{', '.join(map(str, self.shape[1:]))}], got {tuple(host.shape)}")
+        self._count[slot] = n
         with torch.cuda.stream(self._copy_stream):
             if not first_use:
                 self._copy_stream.wait_event(self._in_free[slot])
-            self._dev_in[slot].copy_(host, non_blocking=True)
+            self._dev_in[slot][:n].copy_(host, non_blocking=True)
             self._in_ready[slot].record(self._copy_stream)
 
     @torch.no_grad()
@@ -85,7 +98,8 @@ class HostBatchRunner:
                 self._enqueue_copy(slot ^ 1, after, not used[slot ^ 1])
                 used[slot ^ 1] = True
             main.wait_event(self._in_ready[slot])
-            out = self.model(self._dev_in[slot])
+            n = self._count[slot]
+            out = self.model(self._dev_in[slot][:n])
             self._in_free[slot].record(main)
             if pending is not None:
                 # the previous step's results must have left the pinned buffers before their reuse
@@ -94,8 +108,9 @@ class HostBatchRunner:
             if not self.detector:
                 out = {"logits": out}
             for k, host in self._host_out[slot].items():
-                host.copy_(out[k], non_blocking=True)
+                host[:n].copy_(out[k], non_blocking=True)
             self._out_ready[slot].record(main)
+            self._out_count[slot] = n
             pending = slot
             nxt = after
             i += 1
@@ -104,4 +119,7 @@ class HostBatchRunner:
             yield self._result(pending)
 
     def _result(self, slot: int):
-        return self._host_out[slot] if self.detector else self._host_out[slot]["logits"]
+        n = self._out_count[slot]
+        res = {k: (v[:n].clone() if self.copy_results else v[:n])
+               for k, v in self._host_out[slot].items()}
+        return res if self.detector else res["logits"]

@@ -49,7 +49,11 @@ class TrainState:
             off += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
         self.numel = off
         z = lambda dt: torch.zeros(self.numel, dtype=dt, device=dev)
-        self.flat, self.grad, self.exp_avg, self.exp_avg_sq = (z(torch.float32) for _ in range(4))
+        self.flat, self.grad = z(torch.float32), z(torch.float32)
+        # Adam moments only where the fused optimizer runs (FineTuner); the autograd bridge hands
+        # gradients to whatever torch.optim optimizer the caller uses
+        self.exp_avg, self.exp_avg_sq = (z(torch.float32), z(torch.float32)) if bind_grads \
+            else (None, None)
         self.shadow = z(torch.bfloat16)
         for n, p in named:                      # re-home parameters into the arena
             o = self.offsets[n]
@@ -167,17 +171,30 @@ class TrainState:
         return any(p._version != v for p, v in zip(self.params, self._versions))
 
     # ------------------------------------------------------------------ buffers
+    def buffer_sizes(self, batch: int) -> tuple[int, int]:
+        cfg = self.config()
+        sv, ws = C.c_size_t(0), C.c_size_t(0)
+        check(lib().vitk_train_workspace_bytes(C.byref(cfg), batch, C.byref(sv), C.byref(ws)))
+        return sv.value, ws.value
+
     def buffers(self, batch: int):
+        """The step-private activation / workspace buffers of FineTuner (one forward in flight)."""
         if self._bufs_batch != batch:
-            cfg = self.config()
-            sv, ws = C.c_size_t(0), C.c_size_t(0)
-            check(lib().vitk_train_workspace_bytes(C.byref(cfg), batch, C.byref(sv), C.byref(ws)))
-            self._saved = torch.empty(sv.value + 1024, dtype=torch.uint8, device=self.device)
-            self._ws = torch.empty(ws.value + 1024, dtype=torch.uint8, device=self.device)
-            self._sizes = (sv.value, ws.value)
+            self._sizes = self.buffer_sizes(batch)
+            self._saved = torch.empty(self._sizes[0] + 1024, dtype=torch.uint8, device=self.device)
+            self._ws = torch.empty(self._sizes[1] + 1024, dtype=torch.uint8, device=self.device)
             self._bufs_batch = batch
         al = lambda t: (t.data_ptr() + 1023) // 1024 * 1024
         return al(self._saved), self._sizes[0], al(self._ws), self._sizes[1]
+
+    def new_buffers(self, batch: int):
+        """Fresh activation / workspace tensors for ONE forward of the autograd bridge: they live on
+        that call's autograd context, so a second forward before the first backward (siamese /
+        triplet pairs, summed micro-batches, other batch sizes) cannot overwrite them.  The
+        caching allocator hands the same blocks back once the backward has released them."""
+        sv, ws = self.buffer_sizes(batch)
+        return (torch.empty(sv + 1024, dtype=torch.uint8, device=self.device), sv,
+                torch.empty(ws + 1024, dtype=torch.uint8, device=self.device), ws)
 
     # ------------------------------------------------------------------ gradient slices
     def bucket_slices(self):
@@ -210,11 +227,15 @@ class FineTuner:
         (pair with a communicator limited to as many CTAs: ProcessGroupNCCL.Options.config.max_ctas)."""
         self.model = model
         self.lr, self.wd, self.betas, self.eps = lr, weight_decay, betas, eps
-        self.seed = int(seed)   # dropout mask stream: step k uses seed + k (same on every rank's
-        #                         shard only if the ranks pass different seeds - they should)
         self.state = TrainState(model.backbone, model.head, model.backbone._n_prefix)
         self.pg = process_group
-        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        ddp = dist.is_available() and dist.is_initialized()
+        self.world = dist.get_world_size(process_group) if ddp else 1
+        rank = dist.get_rank(process_group) if ddp else 0
+        # dropout mask stream: step k uses seed + k; every data-parallel rank draws its own masks
+        # (the same masks on every shard would correlate the ranks' gradients)
+        self.seed = (int(seed) + 0x9E3779B1 * rank) & 0x7FFFFFFF
+        self._ranges_key, self._ranges = None, None
         self._comm_stream = (torch.cuda.Stream(device=self.state.device, priority=-1)
                              if self.world > 1 else None)
         self._loss = torch.zeros(1, dtype=torch.float32, device=self.state.device)
@@ -269,12 +290,42 @@ class FineTuner:
         if self.world > 1:
             self._allreduce_grads()
         st.step_count += 1
-        check(lib().vitk_adamw_step(st.flat.data_ptr(), st.grad.data_ptr(), st.exp_avg.data_ptr(),
-                                    st.exp_avg_sq.data_ptr(), st.shadow.data_ptr(), st.numel,
-                                    self.lr, self.betas[0], self.betas[1], self.eps, self.wd,
-                                    st.step_count, 1.0, s))
+        # torch.optim.AdamW(model.parameters()) skips parameters without a gradient: frozen ones
+        # (requires_grad=False, the usual freeze-the-backbone fine-tune) get neither the Adam
+        # update nor the decoupled weight decay.  One launch per maximal run of trainable
+        # parameters - a single launch over the whole arena when nothing is frozen.
+        for lo, hi in self._trainable_ranges():
+            check(lib().vitk_adamw_step(st.flat.data_ptr() + 4 * lo, st.grad.data_ptr() + 4 * lo,
+                                        st.exp_avg.data_ptr() + 4 * lo,
+                                        st.exp_avg_sq.data_ptr() + 4 * lo,
+                                        st.shadow.data_ptr() + 2 * lo, hi - lo, self.lr,
+                                        self.betas[0], self.betas[1], self.eps, self.wd,
+                                        st.step_count, 1.0, s))
         st.refresh_transposes()
+        # The update went through raw pointers: bump the parameters' version counters so that
+        # everything keyed on them re-reads the weights - the inference engine's packed bf16
+        # copies (engine.py: pack) would otherwise serve the pre-step matrices to the next
+        # validate / predict.  The shadows of THIS state were refreshed by the kernel itself.
+        torch._C._increment_version(st.params)
+        st._versions = [p._version for p in st.params]
         return self._loss, logits
+
+    def _trainable_ranges(self) -> list[tuple[int, int]]:
+        st = self.state
+        key = tuple(p.requires_grad for p in st.params)
+        if key != self._ranges_key:
+            out: list[list[int]] = []
+            for n, p in zip(st.names, st.params):
+                if not p.requires_grad:
+                    continue
+                lo = st.offsets[n]
+                hi = lo + (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+                if out and out[-1][1] == lo:
+                    out[-1][1] = hi
+                else:
+                    out.append([lo, hi])
+            self._ranges_key, self._ranges = key, [(a, b) for a, b in out]
+        return self._ranges
 
     # ------------------------------------------------------------------ checkpoints
     # The reference saves {'epoch', 'model_state_dict', 'optimizer_state_dict', 'val_loss',

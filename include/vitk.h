@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define VITK_ABI_VERSION 3
+#define VITK_ABI_VERSION 4
 
 #define VITK_OK 0
 #define VITK_ERR_INVALID 1
@@ -106,6 +106,11 @@ int vitk_gemm_set_cta_group(int ctas);
 /* 1 = write GEMM outputs with per-thread global stores instead of the smem-staged TMA
  * store / reduce-add epilogue (tests, A/B timing). */
 int vitk_gemm_set_direct_epilogue(int on);
+/* LayerNorm after a residual GEMM (vitk_gemm_resid_layernorm and the encoder's projection /
+ * linear2 launches): 0 (default) = a separate LayerNorm launch, 1 = LayerNorm warps inside the
+ * GEMM kernel (one launch; measured slower on B200, kept for A/B - DESIGN.md section 6).  Same
+ * bits either way.  Initial value from the environment variable VITK_FUSED_LN. */
+int vitk_gemm_set_fused_layernorm(int on);
 
 /* Device side of post_process_predictions (evaluation.py:393-407, lines 403-404): softmax over the
  * class logits f32 [rows, n_classes], then the maximum probability and its class per row,
@@ -192,6 +197,19 @@ int vitk_forward_u8(const VitkConfig* cfg, const VitkWeights* w, const unsigned 
 int vitk_gemm(const void* A, int lda, const void* B, int ldb, int M, int N, int K, int epilogue,
               const float* bias, const float* resid, int ldr, const void* aux, void* out, void* out2,
               int ldo, float alpha, float beta, vitk_stream_t stream);
+
+/* Residual update and the LayerNorm that follows it (train.py:586-591: x = x + f(..), then
+ * layer_norm(x) feeds the next Linear): x[M,N] f32 += A[M,K] W[N,K]^T + bias (TMA reduce-add
+ * epilogue) and ln_out bf16 [M,N] = LN(x) * gamma + beta (optionally mean / rstd f32 [M]).
+ * Two launches by default; with vitk_gemm_set_fused_layernorm(1) one: as soon as all column
+ * tiles of a 128-row block have landed, LayerNorm warps of the GEMM kernel fetch those rows from
+ * L2 by bulk copies and normalise them.  counters: zero-filled uint32[ceil(M/128)] scratch for
+ * the fused form, returned zero-filled (may be null: then always two launches).  Bit-identical
+ * to vitk_gemm(VITK_EPI_RESID_F32) followed by vitk_layernorm in both forms. */
+int vitk_gemm_resid_layernorm(const void* A, int lda, const void* W, int ldb, int M, int N, int K,
+                              const float* bias, float* x_inout, const float* gamma,
+                              const float* beta, float eps, void* ln_out, float* mean_out,
+                              float* rstd_out, unsigned int* counters, vitk_stream_t stream);
 
 /* Weight-gradient contraction C[M,N] (+)= A^T B with A stored [K, lda] (M contiguous) and B stored
  * [K, ldb] (N contiguous): dW[out,in] = sum over tokens of dY[token,out] * X[token,in] - the

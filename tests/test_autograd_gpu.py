@@ -52,3 +52,33 @@ def test_reference_style_loop_with_torch_optimizer(vitk):
     _, ref = O.classifier_forward({k: v.cpu() for k, v in model.state_dict().items()}, x.cpu(), 2,
                                   dtype=torch.float64)
     assert (logits.cpu().double() - ref).abs().max() < 2e-2
+
+
+def test_two_forwards_before_backward(vitk):
+    """Siamese / triplet use (and micro-batches whose losses are summed): each forward keeps its
+    own saved activations, also when the batch sizes differ."""
+    torch.manual_seed(3)
+    bb = vitk.VisionTransformer(**KW).cuda().train()
+    xa, xb = O.synthetic_images(3, 64, seed=1).cuda(), O.synthetic_images(5, 64, seed=2).cuda()
+    wa = torch.randn(3, 17, 128, device="cuda")
+    wb = torch.randn(5, 17, 128, device="cuda")
+
+    def grads(losses_fn):
+        for p in bb.parameters():
+            p.grad = None
+        losses_fn().backward()
+        return [p.grad.clone() for p in bb.parameters()]
+
+    g_a = grads(lambda: (bb(xa) * wa).sum())
+    g_b = grads(lambda: (bb(xb) * wb).sum())
+    g_ab = grads(lambda: (bb(xa) * wa).sum() + (bb(xb) * wb).sum())   # both forwards, then backward
+    for ga, gb, gab in zip(g_a, g_b, g_ab):
+        torch.testing.assert_close(gab, ga + gb, rtol=1e-4, atol=1e-5)
+
+
+def test_fp32_mode_refuses_the_grad_path(vitk):
+    bb = vitk.VisionTransformer(**KW).cuda().eval().set_precision("fp32")
+    with pytest.raises(vitk.VitkError):
+        bb(O.synthetic_images(2, 64).cuda())
+    with torch.no_grad():
+        assert bb(O.synthetic_images(2, 64).cuda()).shape == (2, 17, 128)

@@ -181,3 +181,20 @@ def test_uint8_input_edge_is_bit_identical_to_the_float_path(vitk):
     assert runner.h2d_bytes_per_step == 3 * 64 * 64 * 3
     with pytest.raises(vitk.VitkError), torch.no_grad():
         model(torch.zeros(2, 3, 64, 64, dtype=torch.uint8, device="cuda"))   # NCHW u8 is not the edge
+
+
+def test_host_runner_accepts_a_smaller_last_batch(vitk):
+    """The reference's evaluation DataLoader keeps its short last batch (drop_last=False,
+    evaluation.py:555-562); copy_results=True makes list(runner.run(...)) safe."""
+    kw = dict(image_size=64, patch_size=16, embed_dim=128, num_layers=2, num_heads=2, mlp_dim=256)
+    torch.manual_seed(6)
+    model = vitk.ViTClassifier(num_classes=6, dropout=0.0, **kw).cuda().eval()
+    x = O.synthetic_images(8, 64, seed=3)
+    with torch.no_grad():
+        want = model(x.cuda()).cpu()
+    runner = vitk.HostBatchRunner(model, 3, copy_results=True)
+    outs = list(runner.run([x[:3].pin_memory(), x[3:6].pin_memory(), x[6:].pin_memory()]))
+    assert [o.shape[0] for o in outs] == [3, 3, 2]
+    assert torch.equal(torch.cat(outs), want)
+    with pytest.raises(ValueError):
+        list(runner.run([x[:4].pin_memory()]))     # more images than the runner was sized for

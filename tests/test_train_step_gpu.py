@@ -252,3 +252,47 @@ def test_postprocess_scores_matches_the_reference_loop(vitk):
     assert torch.equal(labels, want_l)
     s2, l2 = vitk.ops.postprocess_scores(logits[:, 0, :6].contiguous())
     assert torch.equal(l2, logits[:, 0, :6].argmax(-1))
+
+
+def test_eval_between_steps_sees_every_update(vitk):
+    """train -> validate -> train -> validate (train.py:1619-1631): the inference engine packs its
+    bf16 weight copies at the first validate; the fused optimizer updates the arena through raw
+    pointers, so every later validate must still see the CURRENT weights."""
+    kw = dict(image_size=32, patch_size=16, embed_dim=64, num_layers=2, num_heads=1, mlp_dim=128,
+              dropout=0.0)
+    torch.manual_seed(5)
+    model = vitk.ViTClassifier(num_classes=6, **kw).cuda()
+    tuner = vitk.FineTuner(model, lr=3e-3)
+    x, y = O.synthetic_images(8, 32).cuda(), O.synthetic_labels(8).cuda()
+    for epoch in range(3):
+        model.train()
+        for _ in range(3):
+            tuner.step(x, y)
+        model.eval()
+        with torch.no_grad():
+            logits = model(x)                  # epoch 0 packs; later epochs must repack
+        _, ref = O.classifier_forward({k: v.cpu() for k, v in model.state_dict().items()},
+                                      x.cpu(), 1, dtype=torch.float64)
+        assert (logits.cpu().double() - ref).abs().max() < 2e-2, epoch
+
+
+def test_frozen_parameters_are_left_alone(vitk):
+    """torch.optim.AdamW(model.parameters()) skips parameters without a gradient: with the
+    backbone frozen only the head may move (no Adam update, no weight decay on the rest)."""
+    kw = dict(image_size=32, patch_size=16, embed_dim=64, num_layers=2, num_heads=1, mlp_dim=128,
+              dropout=0.0)
+    torch.manual_seed(6)
+    model = vitk.ViTClassifier(num_classes=6, **kw).cuda()
+    for p in model.backbone.parameters():
+        p.requires_grad_(False)
+    model.backbone.layer_norm.weight.requires_grad_(True)   # a trainable island inside the arena
+    before = {k: v.clone() for k, v in model.state_dict().items()}
+    tuner = vitk.FineTuner(model, lr=1e-2, weight_decay=1e-1)
+    x, y = O.synthetic_images(8, 32).cuda(), O.synthetic_labels(8).cuda()
+    for _ in range(2):
+        tuner.step(x, y)
+    after = model.state_dict()
+    for k in before:
+        moved = not torch.equal(before[k], after[k])
+        trainable = k.startswith("head.") or k == "backbone.layer_norm.weight"
+        assert moved == trainable, k
