@@ -105,6 +105,9 @@ _SIGNATURES = {
                                               C.c_void_p, C.c_void_p]),
     "vitk_linear_rows": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "vitk_linear_rows_backward": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p,
+                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                            C.c_int, C.c_void_p]),
     "vitk_dropout_keep_mask": (C.c_int, [C.c_float, C.c_uint, C.c_int, C.c_int, C.c_longlong,
                                          C.c_void_p, C.c_void_p]),
     "vitk_profile_enable": (C.c_int, [C.c_int]),
@@ -157,6 +160,12 @@ _SIGNATURES = {
     "vitk_adamw_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_longlong, C.c_double, C.c_double, C.c_double, C.c_double,
                                   C.c_double, C.c_int, C.c_float, C.c_void_p]),
+    "vitk_adamw_step_guarded": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_longlong, C.c_double, C.c_double, C.c_double,
+                                          C.c_double, C.c_double, C.c_int, C.c_float, C.c_void_p,
+                                          C.c_void_p]),
+    "vitk_grad_guard_scan": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_int, C.c_void_p]),
+    "vitk_grad_guard_finish": (C.c_int, [C.c_void_p, C.c_void_p]),
     "vitk_transpose_bf16_batched": (C.c_int, [C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                               C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p]),
     "vitk_layernorm_bwd": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -212,6 +221,9 @@ def lib() -> C.CDLL:
         raise VitkError(
             f"{LIB_PATH} not found - build it with `python {PKG_DIR.name}/build.py` "
             "(there is no CPU or PyTorch fallback)")
+    if os.environ.get("VITK_LIB"):
+        import sys
+        print(f"vitk: loading the library named by VITK_LIB: {LIB_PATH}", file=sys.stderr)
     l = C.CDLL(str(LIB_PATH))
     for name, (res, args) in _SIGNATURES.items():
         fn = getattr(l, name)

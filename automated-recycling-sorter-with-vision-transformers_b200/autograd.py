@@ -85,8 +85,36 @@ def encoder_forward_train(module, images):
     return _BackboneFunction.apply(images, st, *st.params)
 
 
+class _HeadFunction(torch.autograd.Function):
+    """Linear(D, n_classes) on the CLS rows: vitk_linear_rows forward, vitk_linear_rows_backward."""
+
+    @staticmethod
+    def forward(ctx, cls_rows, weight, bias):
+        x = cls_rows.detach().float().contiguous()
+        w, b = weight.detach().float().contiguous(), bias.detach().float().contiguous()
+        out = torch.empty((x.shape[0], w.shape[0]), dtype=torch.float32, device=x.device)
+        check(lib().vitk_linear_rows(x.data_ptr(), x.shape[1], w.data_ptr(), b.data_ptr(),
+                                     out.data_ptr(), x.shape[0], x.shape[1], w.shape[0], 0,
+                                     torch.cuda.current_stream().cuda_stream))
+        ctx.save_for_backward(x, w)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dy = dy.float().contiguous()
+        dx, dw = torch.empty_like(x), torch.empty_like(w)
+        db = torch.empty(w.shape[0], dtype=torch.float32, device=x.device)
+        check(lib().vitk_linear_rows_backward(x.data_ptr(), x.shape[1], w.data_ptr(), dy.data_ptr(),
+                                              dx.data_ptr(), dw.data_ptr(), db.data_ptr(),
+                                              x.shape[0], x.shape[1], w.shape[0],
+                                              torch.cuda.current_stream().cuda_stream))
+        return dx, dw, db
+
+
 def classifier_forward_train(model, images):
-    """ViTClassifier under autograd: backbone through the bridge, the (tiny) head as ordinary
-    autograd ops on the CLS row - the same composition a user-defined head would use."""
+    """ViTClassifier under autograd: backbone through the bridge, the head on the CLS rows through
+    the library's row-wise linear kernels (forward and backward) - the same composition a
+    user-defined head would use on `tokens[:, 0]`."""
     tokens = encoder_forward_train(model.backbone, images)
-    return torch.nn.functional.linear(tokens[:, 0], model.head.weight, model.head.bias)
+    return _HeadFunction.apply(tokens[:, 0], model.head.weight, model.head.bias)

@@ -394,6 +394,12 @@ int vitk_linear_rows(const float* x, long long row_stride, const float* weight, 
   return linear_rows(x, row_stride, weight, bias, out, rows, in_features, out_features, l2_normalize,
                      static_cast<cudaStream_t>(stream));
 }
+int vitk_linear_rows_backward(const float* x, long long row_stride, const float* weight,
+                              const float* dy, float* dx, float* dweight, float* dbias, int rows,
+                              int in_features, int out_features, vitk_stream_t stream) {
+  return linear_rows_bwd(x, row_stride, weight, dy, dx, dweight, dbias, rows, in_features,
+                         out_features, static_cast<cudaStream_t>(stream));
+}
 int vitk_set_pdl(int on) {
   set_pdl(on);
   return VITK_OK;

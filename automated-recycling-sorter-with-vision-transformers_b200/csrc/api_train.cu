@@ -457,6 +457,23 @@ int vitk_adamw_step(float* params, const float* grads, float* exp_avg, float* ex
                     weight_decay, step, grad_scale, static_cast<cudaStream_t>(stream));
 }
 
+int vitk_adamw_step_guarded(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                            void* shadow_bf16, long long n, double lr, double beta1, double beta2,
+                            double eps, double weight_decay, int step, float grad_scale,
+                            const int* guard, vitk_stream_t stream) {
+  return adamw_flat(params, grads, exp_avg, exp_avg_sq, shadow_bf16, n, lr, beta1, beta2, eps,
+                    weight_decay, step, grad_scale, static_cast<cudaStream_t>(stream), guard);
+}
+
+int vitk_grad_guard_scan(const float* grads, long long n, int* guard, int reset,
+                         vitk_stream_t stream) {
+  return grad_guard_scan(grads, n, guard, reset, static_cast<cudaStream_t>(stream));
+}
+
+int vitk_grad_guard_finish(int* guard, vitk_stream_t stream) {
+  return grad_guard_finish(guard, static_cast<cudaStream_t>(stream));
+}
+
 int vitk_transpose_bf16_batched(int n, const void* const* src, void* const* dst, const int* rows,
                                 const int* cols, vitk_stream_t stream) {
   VITK_REQUIRE(n > 0 && src && dst && rows && cols, "transpose: bad argument");

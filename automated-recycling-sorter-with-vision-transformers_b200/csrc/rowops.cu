@@ -517,6 +517,56 @@ int linear_rows(const float* x, long long row_stride, const float* w, const floa
   return VITK_OK;
 }
 
+// Backward of out = x W^T + b on a few rows (the head on the CLS rows under the autograd bridge,
+// train.py:833-838,1455): thread = input feature k; dx[r,k] = sum_o dy[r,o] W[o,k],
+// dW[o,k] = sum_r dy[r,o] x[r,k], db[o] = sum_r dy[r,o].  dy is staged in shared memory.
+__global__ void __launch_bounds__(128)
+linear_rows_bwd_kernel(const float* __restrict__ x, long long row_stride,
+                       const float* __restrict__ w, const float* __restrict__ dy,
+                       float* __restrict__ dx, float* __restrict__ dw, float* __restrict__ db,
+                       int rows, int D, int n_out) {
+  extern __shared__ float s_dy[];  // [rows, n_out]
+  for (int i = threadIdx.x; i < rows * n_out; i += blockDim.x) s_dy[i] = dy[i];
+  __syncthreads();
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (blockIdx.x == 0 && db != nullptr)
+    for (int o = threadIdx.x; o < n_out; o += blockDim.x) {
+      float acc = 0.f;
+      for (int r = 0; r < rows; ++r) acc += s_dy[r * n_out + o];
+      db[o] = acc;
+    }
+  if (k >= D) return;
+  if (dx != nullptr)
+    for (int r = 0; r < rows; ++r) {
+      float acc = 0.f;
+      for (int o = 0; o < n_out; ++o) acc = fmaf(s_dy[r * n_out + o], __ldg(w + (long long)o * D + k), acc);
+      dx[static_cast<long long>(r) * D + k] = acc;
+    }
+  if (dw != nullptr)
+    for (int o = 0; o < n_out; ++o) {
+      float acc = 0.f;
+      for (int r = 0; r < rows; ++r)
+        acc = fmaf(s_dy[r * n_out + o], __ldg(x + static_cast<long long>(r) * row_stride + k), acc);
+      dw[static_cast<long long>(o) * D + k] = acc;
+    }
+}
+
+int linear_rows_bwd(const float* x, long long row_stride, const float* w, const float* dy,
+                    float* dx, float* dw, float* db, int rows, int D, int n_out,
+                    cudaStream_t stream) {
+  VITK_REQUIRE(x && w && dy, "linear_rows_bwd: null operand");
+  VITK_REQUIRE(rows > 0 && D > 0 && n_out > 0 && static_cast<long long>(rows) * n_out <= 48 * 1024,
+               "linear_rows_bwd: rows * n_out = %d * %d exceeds the staged 48 K values", rows, n_out);
+  const size_t smem = static_cast<size_t>(rows) * n_out * sizeof(float);
+  if (smem > 48 * 1024)
+    VITK_CHECK_CUDA(cudaFuncSetAttribute(linear_rows_bwd_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 192 * 1024));
+  linear_rows_bwd_kernel<<<(D + 127) / 128, 128, smem, stream>>>(x, row_stride, w, dy, dx, dw, db,
+                                                                 rows, D, n_out);
+  VITK_CHECK_LAUNCH("linear_rows_bwd_kernel");
+  return VITK_OK;
+}
+
 int prefix_tokens(float* x, const float* cls, const float* dist, const float* pos, int B, int Ntok,
                   int D, int n_prefix, cudaStream_t stream) {
   VITK_REQUIRE(x && cls && pos, "prefix_tokens: null operand");

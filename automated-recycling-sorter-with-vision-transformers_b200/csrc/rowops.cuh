@@ -40,6 +40,12 @@ int postprocess_scores(const float* logits, int rows, int C, int exclude_last, f
 int linear_rows(const float* x, long long row_stride, const float* w, const float* b, float* out,
                 int rows, int D, int n_out, int l2_normalize, cudaStream_t stream);
 
+// Backward of linear_rows without the normalisation: dx [rows, D], dw [n_out, D], db [n_out]
+// (each optional, overwritten).
+int linear_rows_bwd(const float* x, long long row_stride, const float* w, const float* dy,
+                    float* dx, float* dw, float* db, int rows, int D, int n_out,
+                    cudaStream_t stream);
+
 // Batched post_process_predictions (evaluation.py:393-426): scores / labels as above without the
 // background class, `score > threshold`, kept queries compacted to the front of each image's row
 // of boxes_out [B,Q,4] / labels_out [B,Q] / scores_out [B,Q]; counts [B].

@@ -579,11 +579,31 @@ transpose_batched_kernel(const TransposeBatch tb) {
 // One launch for all 85.8 M parameters; also refreshes the bf16 shadow the GEMMs read.
 // Traffic: 16 B read + 12 B write (+2 B shadow) per parameter.
 // ------------------------------------------------------------------------------------------------
+// guard (optional): {non-finite flag of this step's gradients, steps skipped so far}.  With the flag
+// set the launch does nothing - the reference's `scaler.step(optimizer)` skips the optimizer step
+// when a gradient is inf / nan (train.py:1456, 1615) - and skipped steps do not advance Adam's
+// step counter, so the bias corrections are evaluated here, per block, for step - skipped.
 __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
              float* __restrict__ v, __nv_bfloat16* __restrict__ shadow, long long n, float decay,
              float b1, float b2, float omb1, float omb2, float step_size, float inv_sqrt_bc2,
-             float eps, float grad_scale) {
+             float eps, float grad_scale, const int* __restrict__ guard, double lr, double beta1,
+             double beta2, int step) {
+  if (guard != nullptr) {
+    if (guard[0] != 0) return;
+    const int skipped = guard[1];
+    if (skipped != 0) {   // uniform across the grid; the common case keeps the host's constants
+      __shared__ float s_fix[2];
+      if (threadIdx.x == 0) {
+        const int t = step - skipped;
+        s_fix[0] = static_cast<float>(lr / (1.0 - pow(beta1, static_cast<double>(t))));
+        s_fix[1] = static_cast<float>(1.0 / sqrt(1.0 - pow(beta2, static_cast<double>(t))));
+      }
+      __syncthreads();
+      step_size = s_fix[0];
+      inv_sqrt_bc2 = s_fix[1];
+    }
+  }
   const long long nvec = n >> 2;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -823,9 +843,47 @@ int transpose_batched(const TransposeBatch& tb, cudaStream_t stream) {
   return VITK_OK;
 }
 
+// guard[0] |= any(!isfinite(g)); 16-byte loads, one atomic per block that saw one.
+__global__ void __launch_bounds__(256)
+nonfinite_scan_kernel(const float* __restrict__ g, long long n, int* __restrict__ guard) {
+  const long long nvec = n >> 2;
+  bool bad = false;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(g)[i];
+    // x - x is 0 for finite x, nan for inf / nan
+    bad |= !(((v.x - v.x) + (v.y - v.y)) + ((v.z - v.z) + (v.w - v.w)) == 0.f);
+  }
+  for (long long i = (nvec << 2) + blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+       i < n; i += static_cast<long long>(gridDim.x) * blockDim.x)
+    bad |= !(g[i] - g[i] == 0.f);
+  if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(guard, 1);
+}
+
+__global__ void guard_finish_kernel(int* guard) {
+  if (guard[0] != 0) guard[1] += 1;
+}
+
+int grad_guard_scan(const float* g, long long n, int* guard, int reset, cudaStream_t stream) {
+  VITK_REQUIRE(g && guard && n > 0, "grad_guard_scan: bad argument");
+  VITK_REQUIRE((reinterpret_cast<uintptr_t>(g) & 15) == 0, "grad_guard_scan: 16-byte alignment");
+  if (reset) VITK_CHECK_CUDA(cudaMemsetAsync(guard, 0, sizeof(int), stream));
+  ProfileScope prof(PROF_OPT, static_cast<double>(n) * 4.0, stream);
+  nonfinite_scan_kernel<<<grid_for(n / 4 + 1, 256, 8), 256, 0, stream>>>(g, n, guard);
+  VITK_CHECK_LAUNCH("nonfinite_scan_kernel");
+  return VITK_OK;
+}
+
+int grad_guard_finish(int* guard, cudaStream_t stream) {
+  VITK_REQUIRE(guard != nullptr, "grad_guard_finish: null guard");
+  guard_finish_kernel<<<1, 1, 0, stream>>>(guard);
+  VITK_CHECK_LAUNCH("guard_finish_kernel");
+  return VITK_OK;
+}
+
 int adamw_flat(float* p, const float* g, float* m, float* v, void* shadow_bf16, long long n,
                double lr, double beta1, double beta2, double eps, double weight_decay, int step,
-               float grad_scale, cudaStream_t stream) {
+               float grad_scale, cudaStream_t stream, const int* guard) {
   VITK_REQUIRE(p && g && m && v && n > 0 && step >= 1, "adamw: bad argument");
   VITK_REQUIRE((reinterpret_cast<uintptr_t>(p) & 15) == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0 &&
                    (reinterpret_cast<uintptr_t>(m) & 15) == 0 && (reinterpret_cast<uintptr_t>(v) & 15) == 0,
@@ -840,7 +898,7 @@ int adamw_flat(float* p, const float* g, float* m, float* v, void* shadow_bf16, 
   adamw_kernel<<<grid_for(n / 4 + 1, 256, 8), 256, 0, stream>>>(
       p, g, m, v, static_cast<__nv_bfloat16*>(shadow_bf16), n, decay, static_cast<float>(beta1),
       static_cast<float>(beta2), static_cast<float>(1.0 - beta1), static_cast<float>(1.0 - beta2),
-      step_size, inv_sqrt_bc2, static_cast<float>(eps), grad_scale);
+      step_size, inv_sqrt_bc2, static_cast<float>(eps), grad_scale, guard, lr, beta1, beta2, step);
   VITK_CHECK_LAUNCH("adamw_kernel");
   return VITK_OK;
 }

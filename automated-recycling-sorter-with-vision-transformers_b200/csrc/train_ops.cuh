@@ -52,7 +52,12 @@ int transpose_batched(const TransposeBatch& tb, cudaStream_t stream);
 
 int adamw_flat(float* p, const float* g, float* m, float* v, void* shadow_bf16, long long n,
                double lr, double beta1, double beta2, double eps, double weight_decay, int step,
-               float grad_scale, cudaStream_t stream);
+               float grad_scale, cudaStream_t stream, const int* guard = nullptr);
+// Skip-on-non-finite guard of the optimizer step (train.py:1456: scaler.step): guard = device
+// int[2] {flag, steps skipped}.  scan: flag |= any(!isfinite(g[0..n))) (reset clears it first);
+// finish: folds the flag into the skipped count once the step's AdamW launches are queued.
+int grad_guard_scan(const float* g, long long n, int* guard, int reset, cudaStream_t stream);
+int grad_guard_finish(int* guard, cudaStream_t stream);
 
 // dqkv = backward of softmax(q k^T / sqrt(hd)) v given d_ctx, using the saved log-sum-exp.
 // dbias (optional, [3 H hd]) += column sums of dqkv: the bias gradient of the qkv Linear.

@@ -29,12 +29,15 @@ def shard_range(n_items: int, rank: int, world: int) -> tuple[int, int]:
 
 
 def allreduce_slices(flat: torch.Tensor, slices: Sequence[tuple[int, int]], group=None,
-                     comm_stream=None, ready_events=None) -> None:
+                     comm_stream=None, ready_events=None, on_slice_done=None) -> None:
     """In-place sum all-reduce of flat[a:b] for every slice, in the given order.  On CUDA the
     collectives are enqueued on `comm_stream` and the current stream waits for them at the end.
     With `ready_events` (one CUDA event per slice, recorded on the compute stream when that slice
     is final) slice k only waits for its own event, so its reduction overlaps whatever the compute
-    stream still has queued; without, every collective waits for all work queued so far."""
+    stream still has queued; without, every collective waits for all work queued so far.
+    `on_slice_done(k, a, b)` is called, in order, once the current stream has been made to wait
+    for slice k's reduction (and for nothing later): whatever it enqueues - the optimizer update
+    of that slice - runs while the remaining slices are still being reduced."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return
     if ready_events is not None and len(ready_events) != len(slices):
@@ -49,14 +52,18 @@ def allreduce_slices(flat: torch.Tensor, slices: Sequence[tuple[int, int]], grou
                 if ready_events is not None:
                     comm_stream.wait_event(ready_events[k])
                 if b > a:
-                    works.append(dist.all_reduce(flat[a:b], group=group, async_op=True))
-        for w in works:
-            w.wait()
+                    works.append((dist.all_reduce(flat[a:b], group=group, async_op=True), k))
+        for w, k in works:
+            w.wait()                       # the current stream waits for this collective only
+            if on_slice_done is not None:
+                on_slice_done(k, *slices[k])
         main.wait_stream(comm_stream)
     else:
-        for a, b in slices:
+        for k, (a, b) in enumerate(slices):
             if b > a:
                 dist.all_reduce(flat[a:b], group=group)
+                if on_slice_done is not None:
+                    on_slice_done(k, a, b)
 
 
 def gather_rows(local: torch.Tensor, n_total: int, group=None) -> torch.Tensor:

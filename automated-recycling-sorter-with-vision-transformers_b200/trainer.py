@@ -219,7 +219,7 @@ class FineTuner:
 
     def __init__(self, model, lr=1e-4, weight_decay=1e-4, betas=(0.9, 0.999), eps=1e-8,
                  process_group=None, overlap_allreduce: bool = True, reserve_sms: int = 0,
-                 seed: int = 0):
+                 seed: int = 0, data_parallel: bool = True, skip_nonfinite: bool = True):
         """overlap_allreduce: start each gradient bucket's all-reduce on a side stream as soon as
         the backward has produced it (events recorded by vitk_classifier_loss_backward_ev), instead
         of reducing everything after the backward.  reserve_sms: SMs kept out of the persistent
@@ -229,13 +229,21 @@ class FineTuner:
         self.lr, self.wd, self.betas, self.eps = lr, weight_decay, betas, eps
         self.state = TrainState(model.backbone, model.head, model.backbone._n_prefix)
         self.pg = process_group
-        ddp = dist.is_available() and dist.is_initialized()
+        # data_parallel=False: a single-process step even inside an initialised process group
+        # (bench.py's dp_check compares it with the data-parallel step on the same weights)
+        ddp = data_parallel and dist.is_available() and dist.is_initialized()
         self.world = dist.get_world_size(process_group) if ddp else 1
         rank = dist.get_rank(process_group) if ddp else 0
         # dropout mask stream: step k uses seed + k; every data-parallel rank draws its own masks
         # (the same masks on every shard would correlate the ranks' gradients)
         self.seed = (int(seed) + 0x9E3779B1 * rank) & 0x7FFFFFFF
         self._ranges_key, self._ranges = None, None
+        # skip_nonfinite: the reference's scaler.step(optimizer) (train.py:1456) skips the update
+        # when a gradient is inf / nan; device int[2] {flag, steps skipped}, never read by the
+        # host inside step().  Off: every gradient slice is updated as soon as its own all-reduce
+        # has finished (the optimizer then runs under the reductions still in flight).
+        self._guard = torch.zeros(2, dtype=torch.int32, device=self.state.device) \
+            if skip_nonfinite else None
         self._comm_stream = (torch.cuda.Stream(device=self.state.device, priority=-1)
                              if self.world > 1 else None)
         self._loss = torch.zeros(1, dtype=torch.float32, device=self.state.device)
@@ -287,20 +295,48 @@ class FineTuner:
             check(lib().vitk_classifier_loss_backward(
                 C.byref(cfg), C.byref(st.W), C.byref(st.T), C.byref(st.G), labels.data_ptr(), B,
                 1.0 / (B * self.world), logits.data_ptr(), self._loss.data_ptr(), saved, ws, s))
-        if self.world > 1:
-            self._allreduce_grads()
         st.step_count += 1
         # torch.optim.AdamW(model.parameters()) skips parameters without a gradient: frozen ones
         # (requires_grad=False, the usual freeze-the-backbone fine-tune) get neither the Adam
         # update nor the decoupled weight decay.  One launch per maximal run of trainable
         # parameters - a single launch over the whole arena when nothing is frozen.
-        for lo, hi in self._trainable_ranges():
-            check(lib().vitk_adamw_step(st.flat.data_ptr() + 4 * lo, st.grad.data_ptr() + 4 * lo,
-                                        st.exp_avg.data_ptr() + 4 * lo,
-                                        st.exp_avg_sq.data_ptr() + 4 * lo,
-                                        st.shadow.data_ptr() + 2 * lo, hi - lo, self.lr,
-                                        self.betas[0], self.betas[1], self.eps, self.wd,
-                                        st.step_count, 1.0, s))
+        ranges = self._trainable_ranges()
+
+        guard = self._guard.data_ptr() if self._guard is not None else None
+
+        def adamw(a: int, b: int):
+            for lo, hi in ranges:
+                lo, hi = max(lo, a), min(hi, b)
+                if hi > lo:
+                    check(lib().vitk_adamw_step_guarded(
+                        st.flat.data_ptr() + 4 * lo, st.grad.data_ptr() + 4 * lo,
+                        st.exp_avg.data_ptr() + 4 * lo, st.exp_avg_sq.data_ptr() + 4 * lo,
+                        st.shadow.data_ptr() + 2 * lo, hi - lo, self.lr, self.betas[0],
+                        self.betas[1], self.eps, self.wd, st.step_count, 1.0, guard, s))
+
+        first = [True]
+
+        def scan(a: int, b: int):     # non-finite check of one (reduced) gradient slice
+            if b > a:
+                check(lib().vitk_grad_guard_scan(st.grad.data_ptr() + 4 * a, b - a, guard,
+                                                 1 if first[0] else 0, s))
+                first[0] = False
+
+        if guard is None:
+            if self.world > 1:
+                self._allreduce_grads(on_slice_done=lambda k, a, b: adamw(a, b))
+            else:
+                adamw(0, st.numel)
+        else:
+            # all of the step's gradients are checked before any parameter moves; in the
+            # data-parallel case slice by slice as the reductions finish (a non-finite value on
+            # one rank reaches every rank through the sum, so all ranks skip together)
+            if self.world > 1:
+                self._allreduce_grads(on_slice_done=lambda k, a, b: scan(a, b))
+            else:
+                scan(0, st.numel)
+            adamw(0, st.numel)
+            check(lib().vitk_grad_guard_finish(guard, s))
         st.refresh_transposes()
         # The update went through raw pointers: bump the parameters' version counters so that
         # everything keyed on them re-reads the weights - the inference engine's packed bf16
@@ -309,6 +345,11 @@ class FineTuner:
         torch._C._increment_version(st.params)
         st._versions = [p._version for p in st.params]
         return self._loss, logits
+
+    @property
+    def skipped_steps(self) -> int:
+        """Optimizer steps skipped because a gradient was inf / nan (synchronises)."""
+        return int(self._guard[1].item()) if self._guard is not None else 0
 
     def _trainable_ranges(self) -> list[tuple[int, int]]:
         st = self.state
@@ -390,9 +431,10 @@ class FineTuner:
             self.load_optimizer_state_dict(ck["optimizer_state_dict"])
         return ck
 
-    def _allreduce_grads(self):
+    def _allreduce_grads(self, on_slice_done=None):
         """Sum gradients over the data-parallel group: a few large all-reduces over contiguous
         slices of the flat gradient arena on a side stream (NCCL over NVLink/NVSwitch)."""
         from .dist import allreduce_slices
         allreduce_slices(self.state.grad, self._slices, self.pg, self._comm_stream,
-                         ready_events=self._events if self.overlap else None)
+                         ready_events=self._events if self.overlap else None,
+                         on_slice_done=on_slice_done)

@@ -8,9 +8,17 @@ LayerNorm + 6-class head) over one batch of 256 synthetic images per GPU.  Print
 For N>1 launch under torchrun (one rank per GPU); the batch shards across ranks with no data-path
 collective (weak scaling); time = max over ranks of the device-timed region.
 
-`--impl reference` times the reference's algorithm on the host CPU cores (the oracle port in
-oracle/vit_oracle.py - /root/reference does not exist on the GPU box) on a bounded sample of the
-same workload.
+Next to the headline the same line carries, each device-timed with its own TFLOP/s and fraction
+of the measured burst peak: the other BASELINE.json configurations (`configs`: ViT-L/16 weak and
+strong sharding, ViT-B/16 at 384 px), the fine-tune step, the detector, a parity check of the
+TIMED batch against the oracle (`parity_check`), the reference's own classes run by PyTorch eager
+on the same GPU under bf16 autocast (`gpu_eager_baseline`) and, for N > 1, a data-parallel
+equivalence check (`dp_check`).
+
+`--impl reference` times the reference's own classes on the host CPU cores - byte-compiled into
+oracle/_ref by oracle/build_ref.py, since /root/reference does not exist on the GPU box (kind
+"reference"; the oracle port, kind "port", only if oracle/_ref is absent) - on a bounded sample of
+the same workload.
 """
 from __future__ import annotations
 
@@ -28,6 +36,9 @@ sys.path.insert(0, str(ROOT))
 
 VIT_B16 = dict(image_size=224, patch_size=16, in_channels=3, embed_dim=768, num_layers=12,
                num_heads=12, mlp_dim=3072)
+VIT_L16 = dict(image_size=224, patch_size=16, in_channels=3, embed_dim=1024, num_layers=24,
+               num_heads=16, mlp_dim=4096)
+VIT_B16_384 = dict(VIT_B16, image_size=384)
 N_CLASSES = 6
 METRIC = "vit_b16_224_inference_images_per_sec"
 UNIT = "images/s"
@@ -111,28 +122,68 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port on the host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_forward_rate(batch: int, budget_s: float, min_iters: int = 1) -> dict:
+def reference_classifier(kw: dict, n_classes: int = N_CLASSES, seed: int = 0, dropout: float = 0.0):
+    """(backbone, head, kind): the reference's own VisionTransformer (evaluation.py:120-157, from
+    oracle/_ref or /root/reference) + the oracle wrapper's nn.Linear head, built
+    under `seed` exactly as vitk.ViTClassifier is - or (None, None, "port") when the reference
+    cannot be loaded here."""
+    import torch
+    try:
+        from oracle import ref_loader
+        if not ref_loader.reference_available():
+            return None, None, "port"
+        ev = ref_loader.load("evaluation")
+    except Exception:
+        return None, None, "port"
+    torch.manual_seed(seed)
+    bb = ev.VisionTransformer(dropout=dropout, **kw)
+    head = torch.nn.Linear(kw["embed_dim"], n_classes)
+    return bb, head, "reference"
+
+
+def _cpu_forward_fn(batch: int):
+    """A closure running one CPU forward of the classifier on `batch` synthetic images, the
+    reference's classes when present, else the oracle port; plus its kind / description."""
     import torch
     from oracle import vit_oracle as O
-    import vitk
+    x = O.synthetic_images(batch, VIT_B16["image_size"])
+    bb, head, kind = reference_classifier(VIT_B16)
+    if bb is not None:
+        bb.eval()
+
+        def run():
+            return head(bb(x)[:, 0])
+        what = ("the reference's VisionTransformer (evaluation.py:120-157, oracle/_ref) + "
+                "Linear(768, 6) on the CLS row, eval(), no_grad, torch CPU fp32")
+    else:
+        import vitk
+        torch.manual_seed(0)
+        model = vitk.ViTClassifier(num_classes=N_CLASSES, dropout=0.0, **VIT_B16)  # parameter container
+        sd = {k: v.detach() for k, v in model.state_dict().items()}
+
+        def run():
+            return O.classifier_forward(sd, x, VIT_B16["num_heads"])[1]
+        what = "reference algorithm restated in oracle/vit_oracle.py, torch CPU fp32"
+    return run, kind, what
+
+
+def cpu_forward_rate(batch: int, budget_s: float, min_iters: int = 1) -> dict:
+    import torch
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    torch.manual_seed(0)
-    model = vitk.ViTClassifier(num_classes=N_CLASSES, dropout=0.0, **VIT_B16)  # parameter container
-    sd = {k: v.detach() for k, v in model.state_dict().items()}
-    x = O.synthetic_images(batch, VIT_B16["image_size"])
+    run, kind, what = _cpu_forward_fn(batch)
     with torch.no_grad():
-        O.classifier_forward(sd, x, VIT_B16["num_heads"])  # warm-up
+        run()  # warm-up
         times = []
         t_end = time.perf_counter() + budget_s
         while len(times) < min_iters or (time.perf_counter() < t_end and len(times) < 50):
             t0 = time.perf_counter()
-            O.classifier_forward(sd, x, VIT_B16["num_heads"])
+            run()
             times.append(time.perf_counter() - t0)
     best = min(times)
-    return {"value": batch / best, "unit": UNIT, "cores": cores, "kind": "port",
+    return {"value": batch / best, "unit": UNIT, "cores": cores, "kind": kind,
             "threads": torch.get_num_threads(),
-            "sample": f"oracle/vit_oracle.py fp32 forward, batch {batch}, best of {len(times)} "
+            "sample": f"{what}; batch {batch}, best of {len(times)} "
                       f"(median {batch / statistics.median(times):.1f} img/s), 1 warm-up"}
 
 
@@ -144,24 +195,18 @@ def run_reference(args) -> None:
     batch = 32  # configs[0]: the reference's own CPU-runnable case
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    from oracle import vit_oracle as O
-    import vitk
-    torch.manual_seed(0)
-    model = vitk.ViTClassifier(num_classes=N_CLASSES, dropout=0.0, **VIT_B16)
-    sd = {k: v.detach() for k, v in model.state_dict().items()}
-    x = O.synthetic_images(batch, VIT_B16["image_size"])
+    run, kind, what = _cpu_forward_fn(batch)
     steps = min(args.steps, 8)   # bounded: a step is ~1-4 s of host time
     warm = min(args.warmup, 1)
     with torch.no_grad():
         for _ in range(max(warm, 1)):
-            O.classifier_forward(sd, x, VIT_B16["num_heads"])
+            run()
         t0 = time.perf_counter()
         for _ in range(steps):
-            O.classifier_forward(sd, x, VIT_B16["num_heads"])
+            run()
         dt = time.perf_counter() - t0
     val = batch * steps / dt
-    sample = (f"reference algorithm restated in oracle/vit_oracle.py (torch CPU fp32, {cores} threads), "
-              f"{steps} steps x batch {batch} of the ViT-B/16 workload")
+    sample = f"{what}, {cores} threads; {steps} steps x batch {batch} of the ViT-B/16 workload"
     _emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": max(warm, 1), "ms_per_step": 1e3 * dt / steps,
@@ -169,7 +214,7 @@ def run_reference(args) -> None:
         "data": "synthetic",
         "config": {"workload": "ViT-B/16 224px 6-class inference", "batch_per_step": batch,
                    "device": "host CPU"},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
@@ -308,6 +353,227 @@ def measure_detector(vitk, dev, world, barrier, batch: int, steps: int = 6, warm
                    "vitk_detection_head_forward"}
 
 
+def _max_over_ranks(vals, dev, world):
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return [float(v) for v in vals]
+    t = torch.tensor([float(v) for v in vals], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(v) for v in t.tolist()]
+
+
+def measure_inference_leg(vitk, O, dev, world, rank, barrier, label: str, kw: dict,
+                          batch_per_gpu: int, scaling: str, steps: int = 8, warmup: int = 3) -> dict:
+    """One more BASELINE.json configuration, measured exactly like the headline: random-init
+    weights, device-resident synthetic images (a different shard per rank), CUDA events around
+    `steps` forwards, max over ranks; then the per-kernel-class times of the same steps."""
+    import torch
+    torch.manual_seed(0)
+    model = vitk.ViTClassifier(num_classes=N_CLASSES, dropout=0.0, **kw).to(dev).eval()
+    x = O.synthetic_images(batch_per_gpu, kw["image_size"], seed=4321 + rank).to(dev)
+    with torch.no_grad():
+        for _ in range(warmup):
+            logits = model(x)
+        barrier()
+        n0 = vitk.launch_count()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(steps):
+            logits = model(x)
+        ev1.record()
+        barrier()
+        launches = vitk.launch_count() - n0
+        (ms,) = _max_over_ranks([ev0.elapsed_time(ev1)], dev, world)
+        vitk._lib.profile_enable(True)
+        for _ in range(2):
+            model(x)
+        torch.cuda.synchronize()
+        prof = vitk._lib.profile_collect()
+        vitk._lib.profile_enable(False)
+    assert bool(torch.isfinite(logits).all())
+    flops = fwd_flops_per_image(kw)
+    peaks, _ = measured_peaks()
+    ips = world * batch_per_gpu * steps / (ms * 1e-3)
+    tf = ips / world * flops / 1e12
+    del model, x
+    torch.cuda.empty_cache()
+    P = (kw["image_size"] // kw["patch_size"]) ** 2
+    return {"workload": label, "value": ips, "unit": UNIT, "ms_per_step": ms / steps,
+            "batch_per_gpu": batch_per_gpu, "global_batch": batch_per_gpu * world,
+            "scaling": scaling, "tokens_per_image": P + 1, "gflop_per_image": flops / 1e9,
+            "tflops_per_gpu": tf, "frac_of_burst_peak": tf / float(peaks["bf16_tflops"]),
+            "frac_of_sustained_peak": tf / float(peaks.get("bf16_tflops_sustained",
+                                                           peaks["bf16_tflops"])),
+            "steps": steps, "warmup": warmup, "gpu_launches": int(launches),
+            "by_kind_ms_per_step": {k: v["ms"] / 2 for k, v in prof.items() if v["launches"]}}
+
+
+def parity_check(model, x_dev, logits_dev, O, n: int = 8, tol: float = 2e-2) -> dict:
+    """Logits of the first `n` images of the TIMED batch against the oracle (fp32, CPU, the same
+    random-init weights): north_star's bar is 2e-2 absolute in bf16 and identical top-1.  Top-1 is
+    compared where the oracle's own top-2 margin exceeds the tolerance (random-init ViT logits
+    barely depend on the image)."""
+    import torch
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    heads = model.backbone.transformer_blocks[0].attention.num_heads
+    with torch.no_grad():
+        _, ref = O.classifier_forward(sd, x_dev[:n].cpu(), heads, dtype=torch.float32)
+    got = logits_dev[:n].float().cpu()
+    err = float((got - ref).abs().max())
+    top2 = ref.topk(2, dim=-1).values
+    decided = (top2[:, 0] - top2[:, 1]) > tol
+    same = bool((got.argmax(-1) == ref.argmax(-1))[decided].all())
+    ok = err < tol and same
+    out = {"images": n, "max_abs_logit_diff": err, "tolerance": tol, "top1_identical": same,
+           "top1_compared": int(decided.sum()), "ok": ok,
+           "against": "oracle.classifier_forward fp32 on the host (pinned to the reference's classes "
+                      "by tests/golden)"}
+    if not ok:
+        raise SystemExit(f"bench.py: parity check of the timed batch FAILED: {out}")
+    return out
+
+
+def gpu_eager_baseline(O, dev, batch: int, train_batch: int, steps: int = 10) -> dict:
+    """The bar SURVEY.md 2.1 names: the reference's own modules run by PyTorch eager (cuBLASLt /
+    ATen kernels) on THIS GPU under torch.autocast('cuda', bfloat16) - train.py:1441 with the
+    dtype made explicit.  Inference at the headline batch and one fine-tune step (cross-entropy on
+    the CLS head, torch.optim.AdamW per train.py:1598-1602).  Outside every timed region of the
+    vitk arm; none of this repository's kernels run here."""
+    import torch
+    import torch.nn.functional as F
+    bb, head, kind = reference_classifier(VIT_B16, dropout=0.1)
+    x = O.synthetic_images(batch, VIT_B16["image_size"], seed=1234).to(dev)
+    if bb is not None:
+        bb, head = bb.to(dev), head.to(dev)
+
+        def fwd(inp):
+            return head(bb(inp)[:, 0])
+        params = list(bb.parameters()) + list(head.parameters())
+        set_train = lambda on: (bb.train(on), head.train(on))
+        what = "the reference's VisionTransformer (oracle/_ref) + Linear head"
+    else:
+        import vitk
+        torch.manual_seed(0)
+        cont = vitk.ViTClassifier(num_classes=N_CLASSES, dropout=0.0, **VIT_B16)
+        sd = {k: v.detach().to(dev).requires_grad_(True) for k, v in cont.state_dict().items()}
+
+        def fwd(inp):
+            return O.classifier_forward(sd, inp, VIT_B16["num_heads"])[1]
+        params = list(sd.values())
+        set_train = lambda on: None
+        what = "oracle.classifier_forward (restatement; no dropout)"
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    set_train(False)
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        for _ in range(3):
+            fwd(x)
+        torch.cuda.synchronize()
+        ev0.record()
+        for _ in range(steps):
+            out = fwd(x)
+        ev1.record()
+        torch.cuda.synchronize()
+    ms_inf = ev0.elapsed_time(ev1) / steps
+    # one fine-tune step
+    set_train(True)
+    xt = x[:train_batch]
+    y = O.synthetic_labels(train_batch, N_CLASSES, seed=5).to(dev)
+    opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=1e-4)
+    tsteps = max(3, steps // 2)
+
+    def step():
+        opt.zero_grad()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            loss = F.cross_entropy(fwd(xt).float(), y)
+        loss.backward()
+        opt.step()
+        return loss
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(tsteps):
+        loss = step()
+    ev1.record()
+    torch.cuda.synchronize()
+    ms_tr = ev0.elapsed_time(ev1) / tsteps
+    flops = fwd_flops_per_image()
+    del opt, params
+    torch.cuda.empty_cache()
+    return {"kind": f"{kind}, cuda eager, autocast bf16", "what": what,
+            "inference": {"value": batch / (ms_inf * 1e-3), "unit": UNIT, "ms_per_step": ms_inf,
+                          "batch": batch, "tflops": batch / (ms_inf * 1e-3) * flops / 1e12},
+            "train_step": {"value": train_batch / (ms_tr * 1e-3), "unit": UNIT,
+                           "ms_per_step": ms_tr, "batch": train_batch, "dropout": 0.1,
+                           "tflops": train_batch / (ms_tr * 1e-3) * 3 * flops / 1e12,
+                           "loss_after": float(loss.item())}}
+
+
+DP_CHECK_KW = dict(VIT_B16, num_layers=2)   # ViT-B/16 width and token count, two blocks
+
+
+def dp_check(vitk, O, dev, world, rank, steps: int = 3, batch: int = 8) -> dict:
+    """Data-parallel equivalence on the hardware (SURVEY.md 4 tier 5): (1) one DP step - every rank
+    on its own shard, NCCL gradient all-reduce - gives the gradients of a single-GPU step on the
+    concatenated batch, within reduction-order tolerance; (2) after `steps` optimisation steps the
+    parameters are bitwise identical on every rank."""
+    import torch
+    import torch.distributed as dist
+    torch.manual_seed(0)
+    model = vitk.ViTClassifier(num_classes=N_CLASSES, dropout=0.0, **DP_CHECK_KW).to(dev).train()
+    sd0 = {k: v.clone() for k, v in model.state_dict().items()}
+    tuner = vitk.FineTuner(model, lr=1e-4, weight_decay=1e-4)
+    x = O.synthetic_images(batch, DP_CHECK_KW["image_size"], seed=777 + rank).to(dev)
+    y = O.synthetic_labels(batch, N_CLASSES, seed=55 + rank).to(dev)
+    loss, _ = tuner.step(x, y)
+    g_dp = tuner.state.grad.clone()            # summed over ranks, already scaled by 1/(B*world)
+    lt = loss.clone()
+    dist.all_reduce(lt)
+    # the single-GPU step on the concatenated batch, from the same initial weights
+    xs = [torch.empty_like(x) for _ in range(world)]
+    ys = [torch.empty_like(y) for _ in range(world)]
+    dist.all_gather(xs, x)
+    dist.all_gather(ys, y)
+    torch.manual_seed(0)
+    solo = vitk.ViTClassifier(num_classes=N_CLASSES, dropout=0.0, **DP_CHECK_KW).to(dev).train()
+    solo.load_state_dict(sd0)
+    solo_tuner = vitk.FineTuner(solo, lr=1e-4, weight_decay=1e-4, data_parallel=False)
+    loss1, _ = solo_tuner.step(torch.cat(xs), torch.cat(ys))
+    g1 = solo_tuner.state.grad
+    rel = float((g_dp - g1).norm() / (g1.norm() + 1e-30))
+    loss_diff = abs(float(lt.item()) - float(loss1.item()))
+    for _ in range(steps - 1):
+        tuner.step(x, y)
+    flat = tuner.state.flat
+    lo, hi = flat.clone(), flat.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    identical = bool(torch.equal(lo, hi))
+    ok = identical and rel < 2e-2 and loss_diff < 1e-3
+    out = {"ok": ok, "params_bitwise_identical_across_ranks": identical, "steps": steps,
+           "grad_rel_l2_vs_single_gpu_concatenated_batch": rel, "grad_tolerance": 2e-2,
+           "loss_abs_diff_vs_single_gpu": loss_diff,
+           "config": f"ViT-B/16 width, 2 blocks, {batch} images per rank x {world} ranks, dropout 0"}
+    del tuner, solo_tuner, model, solo
+    torch.cuda.empty_cache()
+    if not ok:
+        raise SystemExit(f"bench.py: data-parallel check FAILED: {out}")
+    return out
+
+
+def gemm_traffic_per_launch(batch: int):
+    """dram__bytes_read + dram__bytes_write per GEMM launch from the committed ncu capture
+    (profiles/gemm_dram_traffic.json names the .csv it was read from); None off that geometry."""
+    p = ROOT / "profiles" / "gemm_dram_traffic.json"
+    if not p.exists():
+        return None, None
+    d = json.loads(p.read_text())
+    if int(d.get("batch", -1)) != batch:
+        return None, None
+    return float(d["mean_bytes_per_launch"]), f"profiles/gemm_dram_traffic.json <- {d['source']}"
+
+
 def run_vitk(args) -> None:
     import torch
     import torch.distributed as dist
@@ -443,11 +709,34 @@ def run_vitk(args) -> None:
 
     detector = None if args.no_train else measure_detector(vitk, dev, world, barrier, B)
 
+    # ---- the other BASELINE.json configurations, each under the same timing rules
+    legs = []
+    if not args.no_configs:
+        st = min(args.steps, 8)
+        legs.append(measure_inference_leg(
+            vitk, O, dev, world, rank, barrier, "ViT-L/16 224px inference, 256 images per GPU "
+            "(BASELINE.json configs[3], weak)", VIT_L16, 256, "weak", steps=st))
+        if world > 1:
+            legs.append(measure_inference_leg(
+                vitk, O, dev, world, rank, barrier, f"ViT-L/16 224px inference, global batch 256 = "
+                f"{256 // world} images per GPU (BASELINE.json configs[3], strong)", VIT_L16,
+                256 // world, "strong", steps=st))
+        legs.append(measure_inference_leg(
+            vitk, O, dev, world, rank, barrier, "ViT-B/16 384px (577 tokens) inference, 64 images "
+            "per GPU (BASELINE.json configs[4])", VIT_B16_384, 64, "weak", steps=st))
+    dp = dp_check(vitk, O, dev, world, rank) if (world > 1 and not args.no_train) else None
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
+    parity = parity_check(model, x_dev, logits, O)
+    eager = None
+    if n_gpus == 1 and not args.no_eager_baseline:
+        eager = gpu_eager_baseline(O, dev, B, TRAIN_BATCH)
+    h2d, d2h = runner.h2d_bytes_per_step, runner.d2h_bytes_per_step
+    h2d8, d2h8 = runner8.h2d_bytes_per_step, runner8.d2h_bytes_per_step
     peaks, peak_src = measured_peaks()
     flops_img = fwd_flops_per_image()
     gemm = prof["gemm"]
@@ -455,16 +744,18 @@ def run_vitk(args) -> None:
     # the GEMM launches are timed inside a multi-second loop under the power cap -> sustained peak
     peak_tf = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
     total_prof_ms = sum(v["ms"] for v in prof.values()) or 1.0
+    traffic, traffic_src = gemm_traffic_per_launch(B)
     roofline = {
         "bound": "tensor", "kernel": "gemm_tn_kernel (tcgen05, all Linear/Conv2d contractions)",
         "achieved": gemm_tflops, "peak": peak_tf, "unit": "TFLOP/s",
         "frac": gemm_tflops / peak_tf,
-        # dram__bytes_read+write per launch, mean of the four per-block GEMM launches at batch 256
-        # (ncu --set full, profiles/r1c_prof_fwd_raw.csv: QKV 256 + fc1 334 + fc2 595 + proj 329 MB;
-        #  algorithmic 310 + 387 + 620 + 387 MB)
-        "traffic": 378.5e6 if B == 256 else None,
-        "peak_source": f"{peak_src} MEASURED_PEAKS.json bf16_tflops_sustained; burst "
-                       f"{peaks['bf16_tflops']}",
+        "frac_of_burst_peak": gemm_tflops / float(peaks["bf16_tflops"]),
+        # dram__bytes_read + dram__bytes_write per launch (ncu --set full), read from the
+        # committed summary of the capture; algorithmic bytes beside it there
+        "traffic": traffic, "traffic_source": traffic_src,
+        "peak_source": f"{peak_src} MEASURED_PEAKS.json bf16_tflops_sustained (the GEMMs are timed "
+                       f"inside a multi-second loop under the power cap); burst "
+                       f"{peaks['bf16_tflops']} -> frac_of_burst_peak",
         "avg_launch_ms": gemm["ms"] / max(gemm["launches"], 1),
         "flops_per_launch": gemm["work"] / max(gemm["launches"], 1),
         "share_of_step": gemm["ms"] / total_prof_ms,
@@ -484,13 +775,13 @@ def run_vitk(args) -> None:
                    "gflop_per_image": flops_img / 1e9, "parallelism": f"batch-sharded x{n_gpus}",
                    "l2_policy": "per-step working set ~1.0 GB (activations) + 154 MB images > 126 MB L2"},
         "clocks": clk.summary(),
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": runner.h2d_bytes_per_step,
-                "d2h_bytes_per_step": runner.d2h_bytes_per_step,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h,
                 "api": "HostBatchRunner.run (pinned f32 NCHW host batches, as evaluation.py:499 "
                        "copies them -> host logits)"},
         "e2e_uint8_input": {"value": e2e8_value, "unit": UNIT,
-                            "h2d_bytes_per_step": runner8.h2d_bytes_per_step,
-                            "d2h_bytes_per_step": runner8.d2h_bytes_per_step,
+                            "h2d_bytes_per_step": h2d8,
+                            "d2h_bytes_per_step": d2h8,
                             "api": "HostBatchRunner(input_dtype=uint8): raw u8 NHWC host batches, "
                                    "Normalize + ToTensorV2 on the device (vitk_forward_u8)"},
         "gpu_launches": int(launches),
@@ -503,6 +794,17 @@ def run_vitk(args) -> None:
     line["cls_only_tail"] = pruned
     if detector is not None:
         line["detector"] = detector
+    if legs:
+        line["configs"] = legs
+    line["parity_check"] = parity
+    if dp is not None:
+        line["dp_check"] = dp
+    if eager is not None:
+        line["gpu_eager_baseline"] = eager
+        line["gpu_eager_baseline"]["vitk_over_eager_inference"] = value / eager["inference"]["value"]
+        if train is not None:
+            line["gpu_eager_baseline"]["vitk_over_eager_train_step"] = \
+                train["value"] / eager["train_step"]["value"]
     if cpu is not None:
         line["cpu_baseline"] = cpu
     _emit(json.dumps(line))
@@ -533,6 +835,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the fine-tune step measurement")
     ap.add_argument("--train-batch", type=int, default=128, help="images per GPU per train step")
+    ap.add_argument("--no-configs", action="store_true",
+                    help="skip the ViT-L/16 and 384 px legs (BASELINE.json configs[3], configs[4])")
+    ap.add_argument("--no-eager-baseline", action="store_true",
+                    help="skip the PyTorch-eager bf16 run of the reference's classes on this GPU")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

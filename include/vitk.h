@@ -141,6 +141,14 @@ int vitk_linear_rows(const float* x, long long row_stride, const float* weight, 
                      float* out, int rows, int in_features, int out_features, int l2_normalize,
                      vitk_stream_t stream);
 
+/* Backward of vitk_linear_rows (l2_normalize = 0): given dy f32 [rows, out_features] writes
+ * dx f32 [rows, in_features] = dy W, dweight f32 [out, in] = dy^T x and dbias f32 [out] = column
+ * sums of dy (each optional).  The 6-class head on the CLS rows under the autograd bridge
+ * (loss.backward() of train.py:1455 with a user-supplied loss). */
+int vitk_linear_rows_backward(const float* x, long long row_stride, const float* weight,
+                              const float* dy, float* dx, float* dweight, float* dbias, int rows,
+                              int in_features, int out_features, vitk_stream_t stream);
+
 /* Persistent kernels (GEMM, attention) launch one CTA per SM; keep `n` SMs out of their grids, e.g.
  * for the NCCL kernels of a gradient all-reduce that overlaps the backward pass. 0 restores all. */
 int vitk_reserve_sms(int n);
@@ -352,6 +360,23 @@ int vitk_adamw_step(float* params, const float* grads, float* exp_avg, float* ex
                     void* shadow_bf16, long long n, double lr, double beta1, double beta2,
                     double eps, double weight_decay, int step, float grad_scale,
                     vitk_stream_t stream);
+
+/* Skip-on-non-finite guard of the optimizer step: the reference's `scaler.step(optimizer)`
+ * (train.py:1456 with the GradScaler of train.py:1615) leaves the parameters alone when any
+ * gradient is inf / nan.  guard: device int[2] {flag, steps skipped so far}, zero-initialised by
+ * the caller once.  Per step: vitk_grad_guard_scan over the (reduced) gradients - reset = 1 on
+ * the first call of the step clears the flag, several calls may cover the arena slice by slice;
+ * vitk_adamw_step_guarded does nothing while the flag is set and evaluates Adam's bias
+ * corrections for step - skipped (a skipped step does not advance the step counter);
+ * vitk_grad_guard_finish, queued after the step's last AdamW launch, adds the flag to the count.
+ * No host synchronisation anywhere. */
+int vitk_grad_guard_scan(const float* grads, long long n, int* guard, int reset,
+                         vitk_stream_t stream);
+int vitk_adamw_step_guarded(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                            void* shadow_bf16, long long n, double lr, double beta1, double beta2,
+                            double eps, double weight_decay, int step, float grad_scale,
+                            const int* guard, vitk_stream_t stream);
+int vitk_grad_guard_finish(int* guard, vitk_stream_t stream);
 
 /* dst_i [cols_i, rows_i] = src_i [rows_i, cols_i]^T for n bf16 matrices (host pointer arrays). */
 int vitk_transpose_bf16_batched(int n, const void* const* src, void* const* dst, const int* rows,

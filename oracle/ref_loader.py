@@ -1,19 +1,34 @@
-"""Loads the reference's two scripts as modules (build container only; /root/reference does not
-exist on the GPU box).  Third-party imports the scripts make at module top but only use for data
+"""Loads the reference's two scripts as modules: from /root/reference in the build container, from
+the byte-compiled copies oracle/build_ref.py leaves in oracle/_ref/ on the GPU box (where
+/root/reference does not exist).  Third-party imports the scripts make at module top but only use for data
 loading / visualisation (albumentations, pycocotools, matplotlib - absent here) are stubbed in
 sys.modules.  Test/fixture infrastructure only."""
 from __future__ import annotations
 
+import importlib.machinery
 import importlib.util
 import sys
 import types
 from pathlib import Path
 
 REFERENCE_DIR = Path("/root/reference")
+COMPILED_DIR = Path(__file__).resolve().parent / "_ref"
+
+
+def _compiled_ok() -> bool:
+    ver = COMPILED_DIR / "PYTHON_VERSION"
+    return (COMPILED_DIR / "evaluation.pyc.bin").exists() and ver.exists() and \
+        ver.read_text().strip() == "%d.%d" % sys.version_info[:2]
 
 
 def reference_available() -> bool:
-    return (REFERENCE_DIR / "evaluation.py").exists()
+    return (REFERENCE_DIR / "evaluation.py").exists() or _compiled_ok()
+
+
+def reference_origin() -> str:
+    if (REFERENCE_DIR / "evaluation.py").exists():
+        return "source (/root/reference)"
+    return "byte-compiled (oracle/_ref)" if _compiled_ok() else "absent"
 
 
 def _stub(name: str, **attrs):
@@ -58,7 +73,15 @@ def load(script: str = "evaluation"):
     if name in sys.modules:
         return sys.modules[name]
     _install_stubs()
-    spec = importlib.util.spec_from_file_location(name, REFERENCE_DIR / f"{script}.py")
+    if (REFERENCE_DIR / f"{script}.py").exists():
+        spec = importlib.util.spec_from_file_location(name, REFERENCE_DIR / f"{script}.py")
+    elif _compiled_ok():
+        path = str(COMPILED_DIR / f"{script}.pyc.bin")
+        spec = importlib.util.spec_from_loader(
+            name, importlib.machinery.SourcelessFileLoader(name, path), origin=path)
+    else:
+        raise FileNotFoundError("the reference is neither at /root/reference nor in oracle/_ref "
+                                "(python oracle/build_ref.py in the build container)")
     mod = importlib.util.module_from_spec(spec)
     sys.modules[name] = mod
     # train.py:17 calls mp.set_start_method('fork') at import, which raises when a start method is

@@ -25,11 +25,14 @@ def test_backbone_gradients_match_oracle(vitk):
     assert tokens.requires_grad
     (tokens * w.cuda().float()).sum().backward()
     assert abs((tokens.detach().cpu().double() * w).sum().item() - loss_ref.item()) < 0.05 * (1 + abs(loss_ref.item()))
+    worst = 0.0
     for k, p in bb.named_parameters():
         got, want = p.grad.cpu().double().flatten(), g_ref[k].flatten()
         rel = (got - want).norm() / (want.norm() + 1e-12)
         cos = torch.nn.functional.cosine_similarity(got, want, dim=0)
-        assert rel < 0.08 and cos > 0.995, (k, rel.item(), cos.item())
+        worst = max(worst, rel.item())
+        assert rel < 0.012 and cos > 0.999, (k, rel.item(), cos.item())
+    print(f"autograd bridge: worst relative gradient error {worst:.4f}")
 
 
 def test_reference_style_loop_with_torch_optimizer(vitk):

@@ -72,6 +72,25 @@ def job_allreduce(rank, world):
     return torch.allclose(flat, full.sum(0), atol=1e-6)
 
 
+def job_pipelined_optimizer(rank, world):
+    """on_slice_done: the per-slice update callback (FineTuner runs AdamW on a slice as soon as
+    its reduction has finished) sees every non-empty slice once, in order, already summed."""
+    d = _dist_mod()
+    torch.manual_seed(4)
+    full = torch.randn(world, 600)
+    flat = full[rank].clone()
+    p = torch.zeros(600)
+    slices = [(400, 600), (100, 400), (250, 250), (0, 100)]
+    seen = []
+
+    def update(k, a, b):
+        seen.append(k)
+        p[a:b] -= 0.5 * flat[a:b]             # an SGD step on the reduced slice
+
+    d.allreduce_slices(flat, slices, on_slice_done=update)
+    return seen == [0, 1, 3] and torch.allclose(p, -0.5 * full.sum(0), atol=1e-6)
+
+
 def job_data_parallel_mean(rank, world):
     """loss_scale = 1 / global batch + SUM all-reduce == gradient of the global-batch mean."""
     d = _dist_mod()
@@ -119,7 +138,7 @@ def job_sharded_detector(rank, world):
 
 
 @pytest.mark.parametrize("world", [2, 3])
-@pytest.mark.parametrize("job", ["job_allreduce", "job_data_parallel_mean", "job_sharded_inference",
-                                 "job_sharded_detector"])
+@pytest.mark.parametrize("job", ["job_allreduce", "job_pipelined_optimizer", "job_data_parallel_mean",
+                                 "job_sharded_inference", "job_sharded_detector"])
 def test_gloo(world, job):
     assert all(_run(world, job).values())

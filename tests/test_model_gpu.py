@@ -198,3 +198,66 @@ def test_host_runner_accepts_a_smaller_last_batch(vitk):
     assert torch.equal(torch.cat(outs), want)
     with pytest.raises(ValueError):
         list(runner.run([x[:4].pin_memory()]))     # more images than the runner was sized for
+
+
+def test_vit_l16_full_depth_matches_oracle(vitk):
+    """BASELINE configs[3] at its full depth: ViT-L/16, 24 layers, 304 M parameters (oracle in
+    fp32: it is within 3e-7 of fp64 on this path)."""
+    kw = dict(image_size=224, patch_size=16, embed_dim=1024, num_layers=24, num_heads=16, mlp_dim=4096)
+    torch.manual_seed(11)
+    model = vitk.ViTClassifier(num_classes=6, dropout=0.0, **kw)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    x = O.synthetic_images(2, 224, seed=8)
+    with torch.no_grad():
+        t_ref, l_ref = O.classifier_forward(sd, x, 16, dtype=torch.float32)
+        model = model.cuda().eval()
+        logits = model(x.cuda()).cpu()
+        tokens = model.backbone(x.cuda()).cpu()
+    print("ViT-L/16 x24 logits max abs err:", (logits - l_ref).abs().max().item(),
+          "tokens:", (tokens - t_ref).abs().max().item())
+    assert (logits - l_ref).abs().max() < 2e-2
+    assert_top1(logits.double(), l_ref.double())
+
+
+def test_vit_b16_384px_full_depth_matches_oracle(vitk):
+    """BASELINE configs[4] at its full depth: ViT-B/16 at 384 px, 12 layers, 577 tokens (the
+    long-sequence tcgen05 attention kernel in every block)."""
+    kw = dict(image_size=384, patch_size=16, embed_dim=768, num_layers=12, num_heads=12, mlp_dim=3072)
+    torch.manual_seed(12)
+    model = vitk.ViTClassifier(num_classes=6, dropout=0.0, **kw)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    x = O.synthetic_images(2, 384, seed=9)
+    with torch.no_grad():
+        t_ref, l_ref = O.classifier_forward(sd, x, 12, dtype=torch.float32)
+        model = model.cuda().eval()
+        logits = model(x.cuda()).cpu()
+    print("ViT-B/16 384px x12 logits max abs err:", (logits - l_ref).abs().max().item())
+    assert (logits - l_ref).abs().max() < 2e-2
+    assert_top1(logits.double(), l_ref.double())
+
+
+def test_matches_the_reference_classes_directly(vitk):
+    """The CUDA path against the reference's OWN modules (evaluation.VisionTransformer /
+    train.DataEfficientImageTransformer, loaded from /root/reference or the byte-compiled
+    oracle/_ref) carrying the same state_dict: tokens of the backbone call the drop-in replaces
+    (evaluation.py:231, train.py:831)."""
+    from oracle import ref_loader
+    if not ref_loader.reference_available():
+        pytest.skip("reference neither at /root/reference nor byte-compiled in oracle/_ref")
+    kw = dict(image_size=224, patch_size=16, embed_dim=768, num_layers=12, num_heads=12, mlp_dim=3072)
+    for script, cls_name, mine, n_tok in (("evaluation", "VisionTransformer", vitk.VisionTransformer, 197),
+                                          ("train", "DataEfficientImageTransformer",
+                                           vitk.DataEfficientImageTransformer, 198)):
+        ref_cls = getattr(ref_loader.load(script), cls_name)
+        torch.manual_seed(4)
+        ref = ref_cls(dropout=0.0, **kw).eval()
+        bb = mine(dropout=0.0, **kw)
+        bb.load_state_dict(ref.state_dict(), strict=True)     # same keys, same shapes
+        x = O.synthetic_images(2, 224, seed=10)
+        with torch.no_grad():
+            want = ref(x)
+            got = bb.cuda().eval()(x.cuda()).cpu()
+        assert got.shape == want.shape == (2, n_tok, 768)
+        err = (got - want).abs().max().item()
+        print(f"{cls_name}: tokens max abs err vs the reference class: {err:.3e}")
+        assert err < 6e-2

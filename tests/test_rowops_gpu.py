@@ -129,3 +129,23 @@ def test_attention_rejects_other_head_dims(vitk):
     qkv = torch.zeros(10, 3 * 32, device="cuda").bfloat16()
     with pytest.raises(vitk.VitkError):
         vitk.ops.attention(qkv, 1, 10, 2)   # head_dim 16
+
+
+@pytest.mark.parametrize("rows,D,n_out", [(8, 768, 6), (3, 64, 6), (128, 1024, 256)])
+def test_linear_rows_backward(vitk, rows, D, n_out):
+    """vitk_linear_rows_backward against autograd of F.linear (the head on the CLS rows)."""
+    import ctypes as C
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randn(rows, D, generator=g, device="cuda", requires_grad=True)
+    w = (torch.randn(n_out, D, generator=g, device="cuda") / D ** 0.5).requires_grad_(True)
+    b = torch.randn(n_out, generator=g, device="cuda", requires_grad=True)
+    dy = torch.randn(rows, n_out, generator=g, device="cuda")
+    torch.nn.functional.linear(x, w, b).backward(dy)
+    dx, dw = torch.empty_like(x), torch.empty_like(w)
+    db = torch.empty_like(b)
+    vitk._lib.check(vitk._lib.lib().vitk_linear_rows_backward(
+        x.data_ptr(), D, w.data_ptr(), dy.data_ptr(), dx.data_ptr(), dw.data_ptr(), db.data_ptr(),
+        rows, D, n_out, torch.cuda.current_stream().cuda_stream))
+    torch.testing.assert_close(dx, x.grad, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(dw, w.grad, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(db, b.grad, rtol=1e-4, atol=1e-4)

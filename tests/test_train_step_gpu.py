@@ -9,6 +9,12 @@ from tests import helpers as H
 
 pytestmark = pytest.mark.gpu
 
+# Relative L2 error allowed per parameter gradient (bf16 operands, fp32 accumulation), set at about
+# twice the worst value observed on B200 (printed by the tests): 0.0094 over the golden / oracle
+# small configurations, 0.0050 for ViT-B/16 at full width (with and without dropout).
+GRAD_REL_TOL = 0.02
+GRAD_REL_TOL_FULL_WIDTH = 0.012
+
 
 def _check_step(vitk, model, x, y, loss_ref, g_ref, n_ref, lr=1e-4):
     model = model.cuda()
@@ -24,7 +30,7 @@ def _check_step(vitk, model, x, y, loss_ref, g_ref, n_ref, lr=1e-4):
         rel = (got - want).norm() / (want.norm() + 1e-12)
         cos = torch.nn.functional.cosine_similarity(got, want, dim=0)
         worst = max(worst, rel.item())
-        assert rel < 0.08 and cos > 0.995, (k, rel.item(), cos.item())
+        assert rel < GRAD_REL_TOL and cos > 0.999, (k, rel.item(), cos.item())
     print("worst relative gradient error:", worst)
     sd = model.state_dict()
     for k, want in n_ref.items():
@@ -124,11 +130,14 @@ def test_train_step_with_dropout_matches_oracle_given_the_same_masks(vitk, p, de
     got_loss, _ = tuner.step(x.cuda(), y.cuda())
     assert abs(got_loss.item() - float(loss)) < 2e-2, (got_loss.item(), float(loss))
     got = dict(zip(tuner.state.names, [q.grad for q in tuner.state.params]))
+    worst = 0.0
     for k, gr in grads.items():
         a, b = got[k].detach().cpu().double().reshape(-1), gr.double().reshape(-1)
         rel = (a - b).norm() / (b.norm() + 1e-12)
         cos = torch.nn.functional.cosine_similarity(a, b, dim=0)
-        assert rel < 0.08 and cos > 0.995, (k, rel.item(), cos.item())
+        worst = max(worst, rel.item())
+        assert rel < GRAD_REL_TOL and cos > 0.999, (k, rel.item(), cos.item())
+    print(f"dropout {p}: worst relative gradient error {worst:.4f}")
 
 
 def test_dropout_follows_train_eval_mode_and_the_seed(vitk):
@@ -296,3 +305,72 @@ def test_frozen_parameters_are_left_alone(vitk):
         moved = not torch.equal(before[k], after[k])
         trainable = k.startswith("head.") or k == "backbone.layer_norm.weight"
         assert moved == trainable, k
+
+
+@pytest.mark.parametrize("dropout", [0.0, 0.1])
+def test_vit_b16_full_width_gradients_match_oracle(vitk, dropout):
+    """Every parameter gradient of ViT-B/16 (12 layers, 197 tokens, batch 8) against the oracle's
+    autograd in fp32 (evaluated on the GPU to keep the test fast - the same restatement the CPU
+    tests pin to the reference), without dropout and with the reference's 0.1 (the library's masks
+    injected into the oracle)."""
+    kw = dict(image_size=224, patch_size=16, embed_dim=768, num_layers=12, num_heads=12,
+              mlp_dim=3072, dropout=dropout)
+    torch.manual_seed(14)
+    model = vitk.ViTClassifier(num_classes=6, **kw).cuda().train()
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    B = 8
+    x, y = O.synthetic_images(B, 224, seed=19).cuda(), O.synthetic_labels(B, 6, seed=6).cuda()
+    masks = None
+    if dropout > 0:
+        masks = {k: v.cuda() for k, v in
+                 _library_masks(vitk, dropout, 31, B, 197, 768, 12, 3072, 12).items()}
+    params = {k: t.clone().requires_grad_(True) for k, t in sd.items()}
+    _, logits = O.classifier_forward(params, x, 12, masks=masks)
+    loss = O.cross_entropy(logits, y)
+    g_ref = dict(zip(params, torch.autograd.grad(loss, list(params.values()))))
+    tuner = vitk.FineTuner(model, seed=31)
+    got_loss, _ = tuner.step(x, y)
+    assert abs(got_loss.item() - loss.item()) < 2e-2
+    got = dict(zip(tuner.state.names, [q.grad for q in tuner.state.params]))
+    worst, worst_k = 0.0, None
+    for k, gr in g_ref.items():
+        a, b = got[k].detach().double().reshape(-1), gr.double().reshape(-1)
+        rel = ((a - b).norm() / (b.norm() + 1e-30)).item()
+        cos = torch.nn.functional.cosine_similarity(a, b, dim=0).item()
+        if rel > worst:
+            worst, worst_k = rel, k
+        assert rel < GRAD_REL_TOL_FULL_WIDTH and cos > 0.999, (k, rel, cos)
+    print(f"ViT-B/16 dropout {dropout}: worst relative gradient error {worst:.4f} ({worst_k})")
+
+
+def test_nonfinite_gradients_skip_the_step(vitk):
+    """scaler.step(optimizer) of the reference (train.py:1456) skips the update on inf / nan
+    gradients: parameters and Adam moments stay put, the step counter does not advance - the
+    next good step equals the first step of a run that never saw the bad batch."""
+    kw = dict(image_size=32, patch_size=16, embed_dim=64, num_layers=2, num_heads=1, mlp_dim=128,
+              dropout=0.0)
+    x, y = O.synthetic_images(8, 32).cuda(), O.synthetic_labels(8).cuda()
+    bad = x.clone()
+    bad[3, 1, 5, 7] = float("inf")
+
+    def fresh():
+        torch.manual_seed(8)
+        model = vitk.ViTClassifier(num_classes=6, **kw).cuda()
+        return model, vitk.FineTuner(model, lr=1e-3)
+
+    model_a, tuner_a = fresh()
+    before = {k: v.clone() for k, v in model_a.state_dict().items()}
+    tuner_a.step(bad, y)
+    assert tuner_a.skipped_steps == 1
+    assert all(torch.equal(before[k], v) for k, v in model_a.state_dict().items())
+    assert float(tuner_a.state.exp_avg.abs().sum()) == 0.0
+    tuner_a.step(x, y)                              # step counter 2, one skipped -> Adam step 1
+    assert tuner_a.skipped_steps == 1
+    model_b, tuner_b = fresh()
+    tuner_b.step(x, y)
+    for (k, a), b in zip(model_a.state_dict().items(), model_b.state_dict().values()):
+        torch.testing.assert_close(a, b, rtol=0, atol=1e-7, msg=k)
+    # without the guard the same batch poisons the weights
+    model_c, _ = fresh()
+    vitk.FineTuner(model_c, lr=1e-3, skip_nonfinite=False).step(bad, y)
+    assert not all(bool(torch.isfinite(v).all()) for v in model_c.state_dict().values())
