@@ -452,8 +452,8 @@ int vitk_forward(const VitkConfig* cfg, const VitkWeights* w, const float* image
                "workspace must be 1024-byte aligned");
   VITK_REQUIRE(cfg->precision == 0 || cfg->precision == 1, "unknown precision mode %d",
                cfg->precision);
-  VITK_REQUIRE(d.hd == 64 || (cfg->precision == 0 && (d.hd == 32 || d.hd == 96 || d.hd == 128)),
-               "head_dim %d unsupported (bf16: 32, 64, 96, 128; fp32-parity mode: 64)", d.hd);
+  VITK_REQUIRE(d.hd == 64 || (cfg->precision == 0 && d.hd >= 8 && d.hd <= 128 && d.hd % 8 == 0),
+               "head_dim %d unsupported (bf16: 8..128 in steps of 8; fp32-parity mode: 64)", d.hd);
   if (cfg->precision == 1) {
     const WorkspaceF32 wf = carve_f32(d, workspace);
     if (wf.bytes > workspace_bytes)
@@ -516,8 +516,8 @@ int vitk_forward_u8(const VitkConfig* cfg, const VitkWeights* w, const unsigned 
                "workspace must be 1024-byte aligned");
   VITK_REQUIRE(cfg->precision == 0, "the 8-bit input edge feeds the bf16 path only");
   VITK_REQUIRE(d.C == 3, "the 8-bit input edge needs RGB images");
-  VITK_REQUIRE(d.hd == 32 || d.hd == 64 || d.hd == 96 || d.hd == 128,
-               "head_dim %d unsupported (32, 64, 96 or 128)", d.hd);
+  VITK_REQUIRE(d.hd >= 8 && d.hd <= 128 && d.hd % 8 == 0,
+               "head_dim %d unsupported (8..128 in steps of 8)", d.hd);
   const Workspace ws = carve(d, workspace);
   if (ws.bytes > workspace_bytes)
     return set_error(VITK_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", ws.bytes,

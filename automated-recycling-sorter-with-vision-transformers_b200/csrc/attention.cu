@@ -256,21 +256,24 @@ int attention_impl() { return g_attn_impl; }
 int attention_fwd(const void* qkv, void* ctx, float* lse, int B, int N, int H, int hd,
                   cudaStream_t stream, const DropParams* drop) {
   VITK_REQUIRE(qkv && ctx, "attention: null operand");
+  const bool dropping = drop != nullptr && drop->thresh != 0u;
   if (hd != 64) {
-    // other head sizes (32 / 96 / 128): the generic-source kernel on the packed activation
-    VITK_REQUIRE(lse == nullptr && (drop == nullptr || drop->thresh == 0u),
-                 "attention: head_dim %d is inference-only (training needs head_dim 64)", hd);
+    // training (log-sum-exp / dropout) and head sizes the mma.sync kernel has no form for (e.g.
+    // the 16 of train.py's Config): the CUDA-core kernel; inference at 32 / 96 / 128: the
+    // generic-source mma.sync kernel on the packed activation
+    if (lse != nullptr || dropping || !(hd == 32 || hd == 96 || hd == 128))
+      return attention_gen_fwd(qkv, ctx, lse, B, N, H, hd, stream, drop);
     const __nv_bfloat16* p = static_cast<const __nv_bfloat16*>(qkv);
     const int D = H * hd;
     const long long img = static_cast<long long>(N) * 3 * D;
     return attention_x(p, img, 3 * D, p + D, p + 2 * D, img, 3 * D, ctx,
                        static_cast<long long>(N) * D, D, B, N, N, H, hd, stream);
   }
-  if (drop != nullptr && drop->thresh != 0u) {
-    VITK_REQUIRE(hd == 64 && N <= 208 && device_cc() >= 100,
-                 "attention dropout is implemented by the pipelined tcgen05 kernel only "
-                 "(head_dim 64, <= 208 tokens)");
-    return attention_fwd_tc2(qkv, ctx, lse, B, N, H, hd, stream, drop);
+  if (dropping) {
+    // the pipelined tcgen05 kernel regenerates the masks in its softmax warps up to 208 tokens
+    if (N <= 208 && device_cc() >= 100)
+      return attention_fwd_tc2(qkv, ctx, lse, B, N, H, hd, stream, drop);
+    return attention_gen_fwd(qkv, ctx, lse, B, N, H, hd, stream, drop);
   }
   if (g_attn_impl == 2 || g_attn_impl == 3 ||
       (g_attn_impl == 0 && hd == 64 && N <= 640 && device_cc() >= 100)) {

@@ -12,6 +12,7 @@
 
 #include "common.h"
 #include "ptx.cuh"
+#include "rowops.cuh"
 #include "train_ops.cuh"
 
 namespace vitk {
@@ -269,10 +270,10 @@ int attention_bwd(const void* qkv, const void* ctx, const void* dctx, const floa
   const bool dropping = drop != nullptr && drop->thresh != 0u;
   if ((attention_impl() != 1 || dropping) && hd == 64 && N <= 256 && device_cc() >= 100)
     return attention_bwd_tc(qkv, ctx, dctx, lse, dqkv, B, N, H, hd, stream, drop, dbias);
-  VITK_REQUIRE(!dropping, "attention_bwd: dropout is implemented by the tcgen05 kernel only");
+  // other head sizes, longer sequences, dropout without the tcgen05 kernel: CUDA-core kernel
+  if (hd != 64 || N > 256 || dropping)
+    return attention_gen_bwd(qkv, ctx, dctx, lse, dqkv, B, N, H, hd, stream, drop, dbias);
   VITK_REQUIRE(B > 0 && H > 0 && N > 0, "attention_bwd: bad shape");
-  VITK_REQUIRE(hd == 64 && N <= 256, "attention_bwd: needs head_dim 64 and N <= 256 (got %d, %d)",
-               hd, N);
   const int Nkv = (N + 15) & ~15;
   const size_t smem = 4 * static_cast<size_t>(Nkv) * 128 + 2 * 256 * sizeof(float);
   static std::once_flag once;

@@ -83,6 +83,15 @@ bool attention_xtc_applicable(long long q_img, long long kv_img, int B, int Nq, 
 int attention_xtc(const void* q, long long q_img, int ldq, const void* k, const void* v,
                   long long kv_img, int ldkv, void* ctx, long long ctx_img, int ldc, int B, int Nq,
                   int Nk, int H, int hd, cudaStream_t stream);
+// CUDA-core attention for the shapes the tensor-core kernels do not cover (attention_gen.cu):
+// head_dim 8 .. 128 in steps of 8, up to 1024 tokens, optional log-sum-exp output and
+// attention-probability dropout - forward and (train_ops.cuh: attention_bwd) backward.
+bool attention_gen_fits(int N, int hd);
+int attention_gen_fwd(const void* qkv, void* ctx, float* lse, int B, int N, int H, int hd,
+                      cudaStream_t stream, const DropParams* drop = nullptr);
+int attention_gen_bwd(const void* qkv, const void* ctx, const void* dctx, const float* lse,
+                      void* dqkv, int B, int N, int H, int hd, cudaStream_t stream,
+                      const DropParams* drop, float* dbias);
 void attention_force_impl(int impl);
 int attention_impl();
 

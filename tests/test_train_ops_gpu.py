@@ -83,3 +83,32 @@ def test_adamw_matches_torch(vitk, n):
     st = opt.state[ref]
     torch.testing.assert_close(m, st["exp_avg"], rtol=1e-6, atol=1e-9)
     torch.testing.assert_close(v, st["exp_avg_sq"], rtol=1e-6, atol=1e-12)
+
+
+@pytest.mark.parametrize("B,N,H,hd", [(2, 198, 25, 16),    # train.py's Config: D 400, 25 heads, DeiT
+                                       (3, 50, 4, 32),
+                                       (2, 197, 3, 96),
+                                       (1, 197, 2, 128),
+                                       (2, 577, 2, 64),     # 384 px: beyond the tcgen05 backward
+                                       (1, 257, 1, 8)])
+def test_generic_attention_forward_and_backward(vitk, B, N, H, hd):
+    """attention_gen.cu (CUDA-core kernels): context, log-sum-exp and d_qkv against autograd of the
+    reference's formulation (train.py:536-549) for the shapes the tensor-core kernels leave out."""
+    g = torch.Generator(device="cuda").manual_seed(N + hd)
+    D = H * hd
+    qkv = torch.randn(B * N, 3 * D, generator=g, device="cuda").bfloat16()
+    dctx = torch.randn(B * N, D, generator=g, device="cuda").bfloat16()
+    ctx, lse = vitk.ops.attention(qkv, B, N, H, return_lse=True)
+    dqkv = vitk.ops.attention_bwd(qkv, ctx, dctx, lse, B, N, H)
+    ref_in = qkv.float().requires_grad_(True)
+    q, k, v = ref_in.reshape(B, N, 3, H, hd).permute(2, 0, 3, 1, 4)
+    s = (q @ k.transpose(-2, -1)) / hd ** 0.5
+    o = (torch.softmax(s, dim=-1) @ v).transpose(1, 2).reshape(B * N, D)
+    o.backward(dctx.float())
+    assert (ctx.float() - o.detach()).abs().max() < 2e-2
+    torch.testing.assert_close(lse, torch.logsumexp(s.detach(), dim=-1), rtol=1e-4, atol=1e-4)
+    err = (dqkv.float() - ref_in.grad).abs().max().item()
+    scale = ref_in.grad.abs().max().item()
+    assert err < 3e-2 * max(1.0, scale), (err, scale)
+    cos = torch.nn.functional.cosine_similarity(dqkv.float().flatten(), ref_in.grad.flatten(), dim=0)
+    assert cos > 0.999

@@ -158,13 +158,17 @@ def test_dropout_follows_train_eval_mode_and_the_seed(vitk):
     assert not same(first_loss(False, 1), first_loss(True, 1))
 
 
-def test_dropout_rejects_long_sequences_loudly(vitk):
-    # 16 x 16 patches + CLS = 257 tokens: beyond the training path altogether; 15 x 15 + 1 = 226
-    # tokens train without dropout but not with it (the dropout softmax kernel covers <= 208)
+def test_uncovered_shapes_fail_loudly(vitk):
+    """226 tokens with dropout: beyond the 208-token tcgen05 softmax, served by the CUDA-core
+    attention kernels.  What nothing covers raises instead of falling back: a head dimension that
+    is not a multiple of 8."""
     kw = dict(image_size=240, patch_size=16, embed_dim=64, num_layers=1, num_heads=1, mlp_dim=64)
     x, y = O.synthetic_images(2, 240).cuda(), O.synthetic_labels(2).cuda()
-    vitk.FineTuner(vitk.ViTClassifier(num_classes=6, dropout=0.0, **kw).cuda().train()).step(x, y)
-    tuner = vitk.FineTuner(vitk.ViTClassifier(num_classes=6, dropout=0.1, **kw).cuda().train())
+    for p in (0.0, 0.1):
+        loss, _ = vitk.FineTuner(vitk.ViTClassifier(num_classes=6, dropout=p, **kw).cuda().train()).step(x, y)
+        assert bool(torch.isfinite(loss).all())
+    bad = dict(kw, embed_dim=48, num_heads=4)          # head_dim 12
+    tuner = vitk.FineTuner(vitk.ViTClassifier(num_classes=6, dropout=0.0, **bad).cuda().train())
     with pytest.raises(vitk.VitkError):
         tuner.step(x, y)
 
@@ -374,3 +378,60 @@ def test_nonfinite_gradients_skip_the_step(vitk):
     model_c, _ = fresh()
     vitk.FineTuner(model_c, lr=1e-3, skip_nonfinite=False).step(bad, y)
     assert not all(bool(torch.isfinite(v).all()) for v in model_c.state_dict().values())
+
+
+@pytest.mark.parametrize("dropout", [0.0, 0.1])
+def test_reference_config_trains_one_step(vitk, dropout):
+    """The configuration train.py actually ships (train.py:1345-1356): DeiT, D = 400, 25 heads of
+    dimension 16, MLP 1600, 198 tokens - here with 3 of its 12 layers - one fused step against the
+    oracle, with and without the reference's dropout."""
+    kw = dict(image_size=224, patch_size=16, embed_dim=400, num_layers=3, num_heads=25,
+              mlp_dim=1600, dropout=dropout)
+    torch.manual_seed(41)
+    model = vitk.ViTClassifier(num_classes=6, deit=True, **kw)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    B = 4
+    x, y = O.synthetic_images(B, 224, seed=23), O.synthetic_labels(B, 6, seed=9)
+    masks = _library_masks(vitk, dropout, 13, B, 198, 400, 25, 1600, 3) if dropout > 0 else None
+    loss, grads, new = O.train_step(sd, x, y, 25, dtype=torch.float64, masks=masks)
+    model = model.cuda().train()
+    tuner = vitk.FineTuner(model, lr=1e-4, weight_decay=1e-4, seed=13)
+    got_loss, _ = tuner.step(x.cuda(), y.cuda())
+    assert abs(got_loss.item() - float(loss)) < 2e-2, (got_loss.item(), float(loss))
+    got = dict(zip(tuner.state.names, [q.grad for q in tuner.state.params]))
+    worst = 0.0
+    for k, gr in grads.items():
+        a, b = got[k].detach().cpu().double().reshape(-1), gr.double().reshape(-1)
+        rel = ((a - b).norm() / (b.norm() + 1e-12)).item()
+        worst = max(worst, rel)
+        assert rel < GRAD_REL_TOL, (k, rel)
+    print(f"train.py Config dims, dropout {dropout}: worst relative gradient error {worst:.4f}")
+    # inference at head_dim 16 goes through the same CUDA-core attention
+    model.eval()
+    with torch.no_grad():
+        logits = model(x.cuda()).cpu().double()
+    _, ref = O.classifier_forward({k: v.cpu() for k, v in model.state_dict().items()}, x, 25,
+                                  dtype=torch.float64)
+    assert (logits - ref).abs().max() < 2e-2
+
+
+def test_384px_fine_tune_step(vitk):
+    """577 tokens (image_size is a constructor argument of the reference, train.py:638): a training
+    step beyond the 256-token tcgen05 backward, with dropout beyond the 208-token softmax kernel."""
+    kw = dict(image_size=384, patch_size=16, embed_dim=128, num_layers=2, num_heads=2, mlp_dim=256,
+              dropout=0.1)
+    torch.manual_seed(43)
+    model = vitk.ViTClassifier(num_classes=6, **kw)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    B = 2
+    x, y = O.synthetic_images(B, 384, seed=29), O.synthetic_labels(B, 6, seed=2)
+    masks = _library_masks(vitk, 0.1, 17, B, 577, 128, 2, 256, 2)
+    loss, grads, _ = O.train_step(sd, x, y, 2, dtype=torch.float64, masks=masks)
+    tuner = vitk.FineTuner(model.cuda().train(), seed=17)
+    got_loss, _ = tuner.step(x.cuda(), y.cuda())
+    assert abs(got_loss.item() - float(loss)) < 2e-2
+    got = dict(zip(tuner.state.names, [q.grad for q in tuner.state.params]))
+    for k, gr in grads.items():
+        a, b = got[k].detach().cpu().double().reshape(-1), gr.double().reshape(-1)
+        rel = ((a - b).norm() / (b.norm() + 1e-12)).item()
+        assert rel < GRAD_REL_TOL, (k, rel)
