@@ -15,13 +15,14 @@ PKG_DIR = Path(__file__).resolve().parent
 # VITK_LIB: another build of the same library (same ABI), for A/B timing of kernel variants on one box
 LIB_PATH = Path(os.environ["VITK_LIB"]) if os.environ.get("VITK_LIB") else PKG_DIR / "libvitk.so"
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 EPI_BF16 = 0
 EPI_GELU_BF16 = 1
 EPI_RESID_F32 = 2
 EPI_F32 = 3
 EPI_DGELU_BF16 = 4
+EPI_GELU_TANH_BF16 = 6
 EPI_RELU_BF16 = 7
 
 
@@ -55,6 +56,9 @@ class VitkBlockWeights(C.Structure):
         ("ln2_w", C.c_void_p), ("ln2_b", C.c_void_p),
         ("fc1_w", C.c_void_p), ("fc1_b", C.c_void_p),
         ("fc2_w", C.c_void_p), ("fc2_b", C.c_void_p),
+        # optional: LayerNorm folded into qkv / linear1 (vitk_fold_layernorm); NULL = not folded
+        ("qkv_w_ln", C.c_void_p), ("qkv_colsum", C.c_void_p), ("qkv_b_ln", C.c_void_p),
+        ("fc1_w_ln", C.c_void_p), ("fc1_colsum", C.c_void_p), ("fc1_b_ln", C.c_void_p),
     ]
 
 
@@ -95,6 +99,19 @@ _SIGNATURES = {
     "vitk_gemm_set_cta_group": (C.c_int, [C.c_int]),
     "vitk_gemm_set_direct_epilogue": (C.c_int, [C.c_int]),
     "vitk_gemm_set_fused_layernorm": (C.c_int, [C.c_int]),
+    "vitk_set_layernorm_folding": (C.c_int, [C.c_int]),
+    "vitk_fold_layernorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "vitk_stats_parts": (C.c_int, [C.c_int]),
+    "vitk_row_stats": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_void_p,
+                                 C.c_int, C.c_int, C.c_void_p]),
+    "vitk_gemm_resid_stats": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                        C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p]),
+    "vitk_gemm_layernorm_folded": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                             C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                             C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_int,
+                                             C.c_void_p]),
     "vitk_attention_set_impl": (C.c_int, [C.c_int]),
     "vitk_reserve_sms": (C.c_int, [C.c_int]),
     "vitk_set_pdl": (C.c_int, [C.c_int]),
@@ -255,6 +272,12 @@ def set_gemm_fused_layernorm(on: bool) -> None:
     """True = the LayerNorm after a residual GEMM runs inside the GEMM kernel (A/B, tests);
     default False: a separate launch (measured faster).  Same bits either way."""
     check(lib().vitk_gemm_set_fused_layernorm(1 if on else 0))
+
+
+def set_layernorm_folding(on: bool) -> None:
+    """vitk_forward: True (default) = LayerNorm folded into the GEMMs around it when the packed
+    weights carry the folded matrices; False = separate LayerNorm launches (A/B, tests)."""
+    check(lib().vitk_set_layernorm_folding(1 if on else 0))
 
 
 def set_attention_impl(impl: int) -> None:

@@ -4,6 +4,8 @@
 
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "common.h"
 #include "fp32_mode.cuh"
 #include "gemm_sm100.cuh"
@@ -66,6 +68,7 @@ struct Workspace {
   void* c_h;    // bf16 [B, Mlp]
   unsigned int* ln_cnt;  // per 128-row block arrival counters of the fused LayerNorm tail
   size_t ln_cnt_bytes;
+  float2* stats;         // folded LayerNorm: [gemm_stats_parts(D)][M] partial (sum, sum of squares)
   size_t bytes;
 };
 
@@ -88,6 +91,7 @@ Workspace carve(const Dims& d, void* base) {
   w.c_h = take(static_cast<size_t>(d.B) * d.Mlp * 2);
   w.ln_cnt_bytes = static_cast<size_t>((d.M + 127) / 128) * 4;
   w.ln_cnt = static_cast<unsigned int*>(take(w.ln_cnt_bytes));
+  w.stats = static_cast<float2*>(take(static_cast<size_t>(gemm_stats_parts(d.D)) * d.M * 8));
   w.bytes = off;
   return w;
 }
@@ -141,6 +145,96 @@ int linear(const void* A, int lda, const void* W, int M, int N, int K, GemmEpi e
   return gemm_bf16_tn(p, stream);
 }
 
+// x += A W^T + bias in place; xb = bf16(x); partial row statistics of the updated x.
+int linear_resid_stats(const void* A, int lda, const void* W, int M, int N, int K, const float* bias,
+                       float* x, void* xb, float2* stats, cudaStream_t stream) {
+  GemmProblem p;
+  p.A = A;
+  p.lda = lda;
+  p.B = W;
+  p.ldb = K;
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.epi = EPI_RESID_STATS_F32;
+  p.e.bias = bias;
+  p.e.resid = x;
+  p.e.ldr = N;
+  p.e.out = x;
+  p.e.out2 = xb;
+  p.e.ldo = N;
+  p.e.ln_part_out = stats;
+  return gemm_bf16_tn(p, stream);
+}
+
+// out = epilogue(Linear(LayerNorm(x))) from bf16(x), W * gamma and the row statistics.
+int linear_ln(const void* xb, int K, const void* w_ln, int M, int N, GemmEpi epi,
+              const float* colsum, const float* b_ln, const float2* stats, int nparts, float eps,
+              void* out, int ldo, cudaStream_t stream) {
+  GemmProblem p;
+  p.A = xb;
+  p.lda = K;
+  p.B = w_ln;
+  p.ldb = K;
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.epi = epi;
+  p.e.bias = b_ln;
+  p.e.out = out;
+  p.e.ldo = ldo;
+  p.e.ln_part = stats;
+  p.e.ln_colsum = colsum;
+  p.e.ln_nparts = nparts;
+  p.e.ln_dim = K;
+  p.e.ln_eps = eps;
+  return gemm_bf16_tn(p, stream);
+}
+
+// LayerNorm folding in vitk_forward: on when every block carries folded weights, unless
+// VITK_LN_FOLD=0 / vitk_set_layernorm_folding(0) (A/B timing, tests).
+int g_ln_fold = [] {
+  const char* v = getenv("VITK_LN_FOLD");
+  return (v != nullptr && v[0] == '0') ? 0 : 1;
+}();
+
+bool folded_weights_present(const VitkWeights* w, int L) {
+  for (int l = 0; l < L; ++l) {
+    const VitkBlockWeights& b = w->blocks[l];
+    if (!b.qkv_w_ln || !b.qkv_colsum || !b.qkv_b_ln || !b.fc1_w_ln || !b.fc1_colsum || !b.fc1_b_ln)
+      return false;
+  }
+  return true;
+}
+
+// The classifier reads only row 0 of the last block's output: its attention needs the keys and
+// values of every token (ws.qkv, already computed) but a single query per image, and everything
+// after it - projection, LayerNorm, MLP - is row-wise, so it runs on B rows instead of B*N.
+// Same logits as the full evaluation (nothing that is skipped feeds them).
+int cls_tail(const VitkConfig* cfg, const VitkWeights* w, const Dims& d, const Workspace& ws,
+             float* logits_out, cudaStream_t stream) {
+  const int D = d.D;
+  const VitkBlockWeights& bw = w->blocks[d.L - 1];
+  const __nv_bfloat16* qkv = static_cast<const __nv_bfloat16*>(ws.qkv);
+  const long long img = static_cast<long long>(d.N) * 3 * D;
+  if (attention_xtc_applicable(img, img, d.B, 1, d.N, d.hd))
+    VITK_TRY(attention_xtc(qkv, img, 3 * D, qkv + D, qkv + 2 * D, img, 3 * D, ws.c_b, D, D, d.B, 1,
+                           d.N, d.H, d.hd, stream));
+  else
+    VITK_TRY(attention_x(qkv, img, 3 * D, qkv + D, qkv + 2 * D, img, 3 * D, ws.c_b, D, D, d.B, 1,
+                         d.N, d.H, d.hd, stream));
+  VITK_TRY(linear(ws.c_b, D, bw.proj_w, d.B, D, D, EPI_RESID_F32, bw.proj_b, ws.x, d.N * D, ws.c_x,
+                  nullptr, D, stream));
+  VITK_TRY(layernorm_fwd(ws.c_x, D, bw.ln2_w, bw.ln2_b, ws.c_b, 0, D, nullptr, nullptr, d.B, D,
+                         cfg->ln_eps, stream));
+  VITK_TRY(linear(ws.c_b, D, bw.fc1_w, d.B, d.Mlp, D, EPI_GELU_TANH_BF16, bw.fc1_b, nullptr, 0,
+                  ws.c_h, nullptr, d.Mlp, stream));
+  VITK_TRY(linear(ws.c_h, d.Mlp, bw.fc2_w, d.B, D, d.Mlp, EPI_RESID_F32, bw.fc2_b, ws.c_x, D, ws.c_x,
+                  nullptr, D, stream));
+  return cls_head(ws.c_x, D, w->ln_f_w, w->ln_f_b, w->head_w, w->head_b, nullptr, logits_out, d.B,
+                  D, cfg->n_classes, cfg->ln_eps, stream);
+}
+
 struct U8Input {
   const unsigned char* images_hwc;  // [B, S, S, 3]
   const float* mean;                // 3 host floats
@@ -182,6 +276,41 @@ int forward_bf16(const VitkConfig* cfg, const VitkWeights* w, const float* image
     p.e.group_offset = d.prefix;
     VITK_TRY(gemm_bf16_tn(p, stream));
   }
+  if (g_ln_fold && folded_weights_present(w, d.L)) {
+    // -- encoder blocks with every LayerNorm folded into the GEMMs around it: 5 launches per
+    //    block, no pass over the fp32 residual stream other than the residual GEMMs' own update
+    const int parts = gemm_stats_parts(D);
+    VITK_TRY(row_stats(ws.x, D, ws.xn, D, ws.stats, M, D, stream));
+    int nparts = 1;
+    for (int l = 0; l < d.L; ++l) {
+      const VitkBlockWeights& bw = w->blocks[l];
+      const bool last = (l == d.L - 1);
+      VITK_TRY(linear_ln(ws.xn, D, bw.qkv_w_ln, M, 3 * D, EPI_BF16, bw.qkv_colsum, bw.qkv_b_ln,
+                         ws.stats, nparts, cfg->ln_eps, ws.qkv, 3 * D, stream));
+      if (cls_only_tail && last) break;  // the row-wise tail below finishes the block
+      VITK_TRY(attention_fwd(ws.qkv, ws.ctx, nullptr, d.B, d.N, d.H, d.hd, stream));
+      VITK_TRY(linear_resid_stats(ws.ctx, D, bw.proj_w, M, D, D, bw.proj_b, ws.x, ws.xn, ws.stats,
+                                  stream));
+      nparts = parts;
+      VITK_TRY(linear_ln(ws.xn, D, bw.fc1_w_ln, M, d.Mlp, EPI_GELU_TANH_BF16, bw.fc1_colsum,
+                         bw.fc1_b_ln, ws.stats, nparts, cfg->ln_eps, ws.h, d.Mlp, stream));
+      if (!last)
+        VITK_TRY(linear_resid_stats(ws.h, d.Mlp, bw.fc2_w, M, D, d.Mlp, bw.fc2_b, ws.x, ws.xn,
+                                    ws.stats, stream));
+      else
+        VITK_TRY(linear(ws.h, d.Mlp, bw.fc2_w, M, D, d.Mlp, EPI_RESID_F32, bw.fc2_b, ws.x, D, ws.x,
+                        nullptr, D, stream));
+    }
+    if (cls_only_tail)
+      return cls_tail(cfg, w, d, ws, logits_out, stream);
+    if (tokens_out)
+      VITK_TRY(layernorm_fwd(ws.x, D, w->ln_f_w, w->ln_f_b, tokens_out, 1, D, nullptr, nullptr, M, D,
+                             cfg->ln_eps, stream));
+    if (logits_out)
+      VITK_TRY(cls_head(ws.x, static_cast<long long>(d.N) * D, w->ln_f_w, w->ln_f_b, w->head_w,
+                        w->head_b, nullptr, logits_out, d.B, D, cfg->n_classes, cfg->ln_eps, stream));
+    return VITK_OK;
+  }
   // -- encoder blocks (train.py:584-593)
   // LayerNorm 1 of block 0 is the only stand-alone normalisation between blocks: every later one
   // is the tail of the residual GEMM that produces its input (projection -> LN2, linear2 -> LN1
@@ -192,30 +321,7 @@ int forward_bf16(const VitkConfig* cfg, const VitkWeights* w, const float* image
     const VitkBlockWeights& bw = w->blocks[l];
     VITK_TRY(linear(ws.xn, D, bw.qkv_w, M, 3 * D, D, EPI_BF16, bw.qkv_b, nullptr, 0, ws.qkv,
                     nullptr, 3 * D, stream));
-    if (cls_only_tail && l == d.L - 1) {
-      // The classifier reads only row 0 of the last block's output: its attention needs the keys
-      // and values of every token (computed above) but a single query per image, and everything
-      // after it - projection, LayerNorm, MLP - is row-wise, so it runs on B rows instead of B*N.
-      // Same logits as the full evaluation (nothing that is skipped feeds them).
-      const __nv_bfloat16* qkv = static_cast<const __nv_bfloat16*>(ws.qkv);
-      const long long img = static_cast<long long>(d.N) * 3 * D;
-      if (attention_xtc_applicable(img, img, d.B, 1, d.N, d.hd))
-        VITK_TRY(attention_xtc(qkv, img, 3 * D, qkv + D, qkv + 2 * D, img, 3 * D, ws.c_b, D, D, d.B,
-                               1, d.N, d.H, d.hd, stream));
-      else
-        VITK_TRY(attention_x(qkv, img, 3 * D, qkv + D, qkv + 2 * D, img, 3 * D, ws.c_b, D, D, d.B, 1,
-                             d.N, d.H, d.hd, stream));
-      VITK_TRY(linear(ws.c_b, D, bw.proj_w, d.B, D, D, EPI_RESID_F32, bw.proj_b, ws.x, d.N * D,
-                      ws.c_x, nullptr, D, stream));
-      VITK_TRY(layernorm_fwd(ws.c_x, D, bw.ln2_w, bw.ln2_b, ws.c_b, 0, D, nullptr, nullptr, d.B, D,
-                             cfg->ln_eps, stream));
-      VITK_TRY(linear(ws.c_b, D, bw.fc1_w, d.B, d.Mlp, D, EPI_GELU_TANH_BF16, bw.fc1_b, nullptr, 0,
-                      ws.c_h, nullptr, d.Mlp, stream));
-      VITK_TRY(linear(ws.c_h, d.Mlp, bw.fc2_w, d.B, D, d.Mlp, EPI_RESID_F32, bw.fc2_b, ws.c_x, D,
-                      ws.c_x, nullptr, D, stream));
-      return cls_head(ws.c_x, D, w->ln_f_w, w->ln_f_b, w->head_w, w->head_b, nullptr, logits_out,
-                      d.B, D, cfg->n_classes, cfg->ln_eps, stream);
-    }
+    if (cls_only_tail && l == d.L - 1) return cls_tail(cfg, w, d, ws, logits_out, stream);
     VITK_TRY(attention_fwd(ws.qkv, ws.ctx, nullptr, d.B, d.N, d.H, d.hd, stream));
     VITK_TRY(linear_resid_ln(ws.ctx, D, bw.proj_w, M, D, D, bw.proj_b, ws.x, bw.ln2_w, bw.ln2_b,
                              cfg->ln_eps, ws.xn, ws.ln_cnt, stream));
@@ -373,6 +479,68 @@ int vitk_gemm_set_direct_epilogue(int on) {
 int vitk_gemm_set_fused_layernorm(int on) {
   gemm_set_fused_layernorm(on != 0);
   return VITK_OK;
+}
+int vitk_set_layernorm_folding(int on) {
+  g_ln_fold = on != 0;
+  return VITK_OK;
+}
+int vitk_fold_layernorm(const float* weight, const float* gamma, const float* beta,
+                        const float* bias, void* w_ln_bf16, float* colsum, float* b_ln,
+                        int out_features, int in_features, vitk_stream_t stream) {
+  return ln_fold(weight, gamma, beta, bias, w_ln_bf16, colsum, b_ln, out_features, in_features,
+                 static_cast<cudaStream_t>(stream));
+}
+int vitk_stats_parts(int n_features) { return gemm_stats_parts(n_features); }
+int vitk_row_stats(const float* x, long long in_stride, void* x_bf16, long long out_stride,
+                   float* stats, int rows, int D, vitk_stream_t stream) {
+  return row_stats(x, in_stride, x_bf16, out_stride, reinterpret_cast<float2*>(stats), rows, D,
+                   static_cast<cudaStream_t>(stream));
+}
+int vitk_gemm_resid_stats(const void* A, int lda, const void* W, int ldb, int M, int N, int K,
+                          const float* bias, float* x_inout, void* x_bf16, float* stats,
+                          vitk_stream_t stream) {
+  VITK_REQUIRE(x_inout && x_bf16 && stats, "gemm_resid_stats: null output");
+  GemmProblem p;
+  p.A = A;
+  p.lda = lda;
+  p.B = W;
+  p.ldb = ldb;
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.epi = EPI_RESID_STATS_F32;
+  p.e.bias = bias;
+  p.e.resid = x_inout;
+  p.e.ldr = N;
+  p.e.out = x_inout;
+  p.e.out2 = x_bf16;
+  p.e.ldo = N;
+  p.e.ln_part_out = reinterpret_cast<float2*>(stats);
+  return gemm_bf16_tn(p, static_cast<cudaStream_t>(stream));
+}
+int vitk_gemm_layernorm_folded(const void* x_bf16, int lda, const void* w_ln, int ldb, int M, int N,
+                               int K, int epilogue, const float* colsum, const float* b_ln,
+                               const float* stats, int n_parts, float eps, void* out, int ldo,
+                               vitk_stream_t stream) {
+  VITK_REQUIRE(stats != nullptr, "gemm_layernorm_folded: null statistics");
+  GemmProblem p;
+  p.A = x_bf16;
+  p.lda = lda;
+  p.B = w_ln;
+  p.ldb = ldb;
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.epi = static_cast<GemmEpi>(epilogue);
+  p.e.bias = b_ln;
+  p.e.out = out;
+  p.e.ldo = ldo;
+  p.e.ln_part = reinterpret_cast<const float2*>(stats);
+  p.e.ln_colsum = colsum;
+  p.e.ln_nparts = n_parts;
+  p.e.ln_dim = K;
+  p.e.ln_eps = eps;
+  return gemm_bf16_tn(p, static_cast<cudaStream_t>(stream));
 }
 int vitk_postprocess_scores(const float* logits, int rows, int n_classes, int exclude_last,
                             float* scores_out, long long* labels_out, float* probs_out,

@@ -89,7 +89,7 @@ struct Cfg {
   // barriers: operand ring, accumulator stages, TMEM slot, aux slabs, LayerNorm job ring (+ its
   // job ids and two counters)
   static constexpr int kNumBars = 2 * kStages + 2 * kAccStages + 1 + kNumEpiWarps + 2 * kLnJobs +
-                                  kNumLnWarps * kLnSlots;
+                                  kNumLnWarps * kLnSlots + kNumEpiWarps;
   static_assert(8 * kNumBars + 4 * (kLnJobs + 2) <= kBarBytes, "barrier block too small");
 };
 
@@ -383,6 +383,34 @@ __device__ __forceinline__ void acc_plus_bias(const uint32_t (&v)[32], int n0, i
   }
 }
 
+// LayerNorm folded into the GEMM (GemmEpilogue::ln_part): rstd * (acc - mu * colsum[n]) + bias[n]
+// for one 32-column chunk; nmu = -mu of this thread's row.
+__device__ __forceinline__ void acc_ln_bias(const uint32_t (&v)[32], int n0, int N,
+                                            const GemmEpilogue& e, float nmu, float rstd,
+                                            float (&x)[32]) {
+  if (n0 + 32 <= N) {
+    const float4* s4 = reinterpret_cast<const float4*>(e.ln_colsum + n0);
+    const float4* b4 = reinterpret_cast<const float4*>(e.bias + n0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 s = __ldg(s4 + j);
+      const float4 b = __ldg(b4 + j);
+      x[4 * j + 0] = fmaf(rstd, fmaf(nmu, s.x, __uint_as_float(v[4 * j + 0])), b.x);
+      x[4 * j + 1] = fmaf(rstd, fmaf(nmu, s.y, __uint_as_float(v[4 * j + 1])), b.y);
+      x[4 * j + 2] = fmaf(rstd, fmaf(nmu, s.z, __uint_as_float(v[4 * j + 2])), b.z);
+      x[4 * j + 3] = fmaf(rstd, fmaf(nmu, s.w, __uint_as_float(v[4 * j + 3])), b.w);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const bool in = n0 + j < N;
+      const float s = in ? __ldg(e.ln_colsum + n0 + j) : 0.f;
+      const float b = in ? __ldg(e.bias + n0 + j) : 0.f;
+      x[j] = fmaf(rstd, fmaf(nmu, s, __uint_as_float(v[j])), b);
+    }
+  }
+}
+
 // One epilogue warp: stage a 32-row x 128-byte slab (row = lane) in swizzled smem and hand it to
 // the TMA engine.  `pk` holds the lane's 128 output bytes. Two buffers alternate per warp.
 template <int NBUF = 2>
@@ -530,6 +558,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
                const __grid_constant__ CUtensorMap tmap_c2, int M, int N, int K,
                int kb_per_split, int num_splits, int descending, const GemmEpilogue e) {
   constexpr bool kAuxTma = TMA_EPI && (EPI == EPI_DGELU_BF16);
+  constexpr bool kStats = TMA_EPI && (EPI == EPI_RESID_STATS_F32);
+  static_assert(EPI != EPI_RESID_STATS_F32 || TMA_EPI, "the statistics epilogue is TMA-only");
   using C = Cfg<BLOCK_N, CTAS, LNF ? 1 : (kAuxTma ? 3 : 2), LNF ? ln_ring_bytes(CTAS) : 0>;
   constexpr int kStagingBytes = C::kStagingBytes;
   constexpr int kStagingPerWarp = C::kStagingPerWarp;
@@ -556,6 +586,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
   [[maybe_unused]] auto job_empty = [&](int j) { return bar_base + 8u * (kJobBar0 + kLnJobs + j); };
   [[maybe_unused]] auto ln_row_bar = [&](int w, int sl) {
     return bar_base + 8u * (kJobBar0 + 2 * kLnJobs + w * kLnSlots + sl);
+  };
+  // second slab barrier of the statistics epilogue (the first is aux_bar)
+  [[maybe_unused]] auto aux2_bar = [&](int w) {
+    return bar_base + 8u * (kJobBar0 + 2 * kLnJobs + kNumLnWarps * kLnSlots + w);
   };
   [[maybe_unused]] volatile int* ln_job = reinterpret_cast<volatile int*>(
       smem + C::kStages * C::kStageBytes + kStagingBytes + C::kLnRingBytes + 8 * C::kNumBars);
@@ -599,8 +633,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), kNumEpiWarps * CTAS);  // leader collects both CTAs' epilogues
     }
-    if constexpr (kAuxTma)
+    if constexpr (kAuxTma || kStats)
       for (int w2 = 0; w2 < kNumEpiWarps; ++w2) mbar_init(aux_bar(w2), 1);
+    if constexpr (kStats)
+      for (int w2 = 0; w2 < kNumEpiWarps; ++w2) mbar_init(aux2_bar(w2), 1);
     if constexpr (LNF) {
       for (int j = 0; j < kLnJobs; ++j) {
         mbar_init(job_full(j), 1);             // the epilogue lane that queued the job
@@ -769,6 +805,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
     [[maybe_unused]] uint32_t aux_phase = 0;
     [[maybe_unused]] const uint32_t aux_slab = stg + 2u * 4096u;
     [[maybe_unused]] const uint32_t my_aux_bar = aux_bar(warp - kFirstEpiWarp);
+    [[maybe_unused]] const uint32_t my_aux2_bar = aux2_bar(warp - kFirstEpiWarp);
+    [[maybe_unused]] uint32_t x_phase = 0;  // statistics epilogue: parity bit per slab
     // ---- fused LayerNorm tail: bookkeeping done by lane 0 of every epilogue warp
     // queue a 128-row block (or the -1 sentinel) for this CTA's LayerNorm warps
     [[maybe_unused]] auto ln_push = [&](int blk) {
@@ -804,14 +842,125 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
           tma_load_2d(aux_slab, &tmap_c2, my_aux_bar, c0, r0);
         }
       }
+      const int row0 = m_blk * kTileM + slab_row;
+      if constexpr (kStats) {
+        // fetch this warp's first two 32 x 32 tiles of x while the main loop is still running;
+        // both slabs were last the source of the previous tile's stores
+        if (lane == 0 && row0 < M) {
+          tma_store_wait_read<0>();
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const int c0 = n_blk * BLOCK_N + half * kColsPerWarp + 32 * c;
+            if (c0 < N) {
+              const uint32_t xb = c == 0 ? my_aux_bar : my_aux2_bar;
+              mbar_arrive_expect_tx(xb, 4096);
+              tma_load_2d(stg + static_cast<uint32_t>(c) * 4096u, &tmap_c, xb, c0, row0);
+            }
+          }
+        }
+      }
+      // LayerNorm folded into this GEMM: mean / rstd of this thread's row from the partial sums
+      // the producing residual GEMM left (fixed summation order)
+      [[maybe_unused]] float ln_nmu = 0.f, ln_rstd = 1.f;
+      if constexpr (TMA_EPI && (EPI == EPI_BF16 || is_gelu_epi<EPI>())) {
+        if (e.ln_part != nullptr && row0 + lane < M) {
+          float s1 = 0.f, s2 = 0.f;
+          for (int p2 = 0; p2 < e.ln_nparts; ++p2) {
+            const float2 t = __ldg(e.ln_part + static_cast<size_t>(p2) * M + (row0 + lane));
+            s1 += t.x;
+            s2 += t.y;
+          }
+          const float inv_d = 1.f / static_cast<float>(e.ln_dim);
+          const float mean = s1 * inv_d;
+          const float var = fmaxf(fmaf(-mean, mean, s2 * inv_d), 0.f);
+          ln_rstd = rsqrtf(var + e.ln_eps);
+          ln_nmu = -mean;
+        }
+      }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       [[maybe_unused]] int ln_commits = 0;  // bulk groups this warp commits for this tile
-      const int row0 = m_blk * kTileM + slab_row;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                              static_cast<uint32_t>(acc * BLOCK_N + half * kColsPerWarp);
       const int n_base = n_blk * BLOCK_N + half * kColsPerWarp;
-      if constexpr (TMA_EPI) {
+      if constexpr (kStats) {
+        // x (fp32, in place) += acc + bias; bf16 copy; partial row sums.  Thread == row.
+        float sum1 = 0.f, sum2 = 0.f;
+        uint32_t v[2][32];
+        tmem_ld_32x32b_x32(t_row, v[0]);
+#pragma unroll
+        for (int c = 0; c < kColsPerWarp / 32; ++c) {
+          tmem_ld_wait();
+          if (c + 1 < kColsPerWarp / 32) tmem_ld_32x32b_x32(t_row + (c + 1) * 32, v[(c + 1) & 1]);
+          const int n0 = n_base + c * 32;
+          if (row0 < M && n0 < N) {
+            float x[32];
+            acc_plus_bias<EPI>(v[c & 1], n0, N, e, x);
+            const uint32_t slab = stg + static_cast<uint32_t>(c & 1) * 4096u;
+            const uint32_t row = slab + static_cast<uint32_t>(lane) * 128u;
+            mbar_wait((c & 1) ? my_aux2_bar : my_aux_bar, (x_phase >> (c & 1)) & 1u);
+            x_phase ^= 1u << (c & 1);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float r0, r1, r2, r3;
+              asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                           : "=f"(r0), "=f"(r1), "=f"(r2), "=f"(r3)
+                           : "r"(row + (static_cast<uint32_t>(j ^ (lane & 7)) << 4))
+                           : "memory");
+              x[4 * j + 0] += r0;
+              x[4 * j + 1] += r1;
+              x[4 * j + 2] += r2;
+              x[4 * j + 3] += r3;
+            }
+            // (columns >= N hold zeros: zero-filled operands, no bias, zero-filled x)
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              sum1 += x[j];
+              sum2 = fmaf(x[j], x[j], sum2);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              st_shared_v4(row + (static_cast<uint32_t>(j ^ (lane & 7)) << 4),
+                           __float_as_uint(x[4 * j]), __float_as_uint(x[4 * j + 1]),
+                           __float_as_uint(x[4 * j + 2]), __float_as_uint(x[4 * j + 3]));
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmap_c, slab, n0, row0);
+              tma_store_commit();
+            }
+            // bf16 copy of the row segment: 64 contiguous bytes per thread
+            if (row0 + lane < M) {
+              __nv_bfloat16* o2 = reinterpret_cast<__nv_bfloat16*>(e.out2) +
+                                  static_cast<size_t>(row0 + lane) * e.ldo + n0;
+              if (n0 + 32 <= N) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  uint4 pk;
+                  pk.x = pack_bf16x2(x[8 * j + 0], x[8 * j + 1]);
+                  pk.y = pack_bf16x2(x[8 * j + 2], x[8 * j + 3]);
+                  pk.z = pack_bf16x2(x[8 * j + 4], x[8 * j + 5]);
+                  pk.w = pack_bf16x2(x[8 * j + 6], x[8 * j + 7]);
+                  reinterpret_cast<uint4*>(o2)[j] = pk;
+                }
+              } else {
+                _Pragma("unroll") for (int j = 0; j < 32; ++j)
+                  if (n0 + j < N) o2[j] = __float2bfloat16_rn(x[j]);
+              }
+            }
+            // refill this slab with the tile two chunks ahead once the store has read it
+            if (lane == 0 && c + 2 < kColsPerWarp / 32 && n0 + 64 < N) {
+              tma_store_wait_read<0>();
+              const uint32_t xb = (c & 1) ? my_aux2_bar : my_aux_bar;
+              mbar_arrive_expect_tx(xb, 4096);
+              tma_load_2d(slab, &tmap_c, xb, n0 + 64, row0);
+            }
+          }
+        }
+        if (row0 + lane < M && n_base < N)
+          e.ln_part_out[static_cast<size_t>(n_base / kColsPerWarp) * M + (row0 + lane)] =
+              make_float2(sum1, sum2);
+      } else if constexpr (TMA_EPI) {
         constexpr bool kOutF32 = (EPI == EPI_RESID_F32 || EPI == EPI_F32);
         if constexpr (kOutF32) {
           const bool reduce = (EPI == EPI_RESID_F32) || (e.beta != 0.f);
@@ -847,8 +996,13 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
             const int n0 = n_base + g * 64;
             if (row0 < M && n0 < N) {
               float x0[32], x1[32];
-              acc_plus_bias<EPI>(v0, n0, N, e, x0);
-              acc_plus_bias<EPI>(v1, n0 + 32, N, e, x1);
+              if (e.ln_part != nullptr) {
+                acc_ln_bias(v0, n0, N, e, ln_nmu, ln_rstd, x0);
+                acc_ln_bias(v1, n0 + 32, N, e, ln_nmu, ln_rstd, x1);
+              } else {
+                acc_plus_bias<EPI>(v0, n0, N, e, x0);
+                acc_plus_bias<EPI>(v1, n0 + 32, N, e, x1);
+              }
               uint32_t pk[32];
               [[maybe_unused]] const uint32_t drop_idx0 =
                   static_cast<uint32_t>(row0 + lane) * static_cast<uint32_t>(N) +
@@ -1052,7 +1206,8 @@ int launch(const GemmProblem& p, cudaStream_t stream) {
                           C::kBRows));
   }
   if constexpr (TMA_EPI) {
-    constexpr bool kOutF32 = (EPI == EPI_RESID_F32 || EPI == EPI_F32);
+    constexpr bool kOutF32 =
+        (EPI == EPI_RESID_F32 || EPI == EPI_F32 || EPI == EPI_RESID_STATS_F32);
     constexpr int eb = kOutF32 ? 4 : 2;
     VITK_TRY(make_tmap_2d(&tc, p.e.out, eb, (uint64_t)p.N, (uint64_t)p.M, (uint64_t)p.e.ldo * eb,
                           128 / eb, 32));
@@ -1125,7 +1280,7 @@ int dispatch_tile(const GemmProblem& p, cudaStream_t stream) {
 // update without row remapping.
 bool tma_epilogue_ok(const GemmProblem& p, bool honour_force = true) {
   if (honour_force && g_force_direct_epi) return false;
-  const bool f32 = (p.epi == EPI_RESID_F32 || p.epi == EPI_F32);
+  const bool f32 = (p.epi == EPI_RESID_F32 || p.epi == EPI_F32 || p.epi == EPI_RESID_STATS_F32);
   const int eb = f32 ? 4 : 2;
   if ((reinterpret_cast<uintptr_t>(p.e.out) & 15) != 0 || (p.e.ldo * eb) % 16 != 0) return false;
   switch (p.epi) {
@@ -1136,6 +1291,9 @@ bool tma_epilogue_ok(const GemmProblem& p, bool honour_force = true) {
       return p.e.out2 == nullptr || (reinterpret_cast<uintptr_t>(p.e.out2) & 15) == 0;
     case EPI_RESID_F32:
       return p.e.rows_per_group == 0 && p.e.resid == p.e.out && p.e.ldr == p.e.ldo;
+    case EPI_RESID_STATS_F32:
+      return p.e.rows_per_group == 0 && p.e.resid == p.e.out && p.e.ldr == p.e.ldo &&
+             p.e.out2 != nullptr && (reinterpret_cast<uintptr_t>(p.e.out2) & 15) == 0;
     case EPI_F32: return p.e.beta == 0.f || p.e.beta == 1.f;
     case EPI_DGELU_BF16: return (reinterpret_cast<uintptr_t>(p.e.aux) & 15) == 0;
     default: return false;
@@ -1182,6 +1340,14 @@ int dispatch(const GemmProblem& p, cudaStream_t stream) {
 void gemm_force_cta_group(int ctas) { g_force_ctas = ctas; }
 void gemm_force_direct_epilogue(int on) { g_force_direct_epi = on; }
 void gemm_set_fused_layernorm(int on) { g_fused_ln = on; }
+int gemm_stats_parts(int N) {
+  // as dispatch_tile: 256-wide tiles unless they waste more than 128-wide ones; an epilogue warp
+  // owns half a tile's columns
+  const int waste256 = ((N + 255) / 256) * 256 - N;
+  const int waste128 = ((N + 127) / 128) * 128 - N;
+  const int cols = (waste128 < waste256) ? 64 : 128;
+  return (N + cols - 1) / cols;
+}
 
 int gemm_bf16_tn(const GemmProblem& p, cudaStream_t stream) {
   VITK_REQUIRE(p.A && p.B && p.e.out, "gemm: null operand");
@@ -1200,7 +1366,28 @@ int gemm_bf16_tn(const GemmProblem& p, cudaStream_t stream) {
                      p.epi == EPI_GELU_TANH_BF16) && p.e.rows_per_group == 0 && p.N % 2 == 0 &&
                     static_cast<long long>(p.M) * p.N < (1ll << 32)),
                "gemm: dropout needs a residual / GELU / GELU' epilogue without row remap");
+  if (p.e.ln_part != nullptr) {
+    VITK_REQUIRE(p.epi == EPI_BF16 || p.epi == EPI_GELU_BF16 || p.epi == EPI_GELU_TANH_BF16 ||
+                     p.epi == EPI_RELU_BF16,
+                 "gemm: a folded LayerNorm needs a bf16-output epilogue");
+    VITK_REQUIRE(p.e.ln_colsum && p.e.bias && p.e.ln_nparts > 0 && p.e.ln_dim > 0,
+                 "gemm: folded LayerNorm needs column sums, the folded bias and the row statistics");
+    VITK_REQUIRE(tma_epilogue_ok(p, false), "gemm: folded LayerNorm needs 16-byte aligned outputs");
+    switch (p.epi) {
+      case EPI_BF16: return dispatch_tile<EPI_BF16, true, false>(p, stream);
+      case EPI_GELU_BF16: return dispatch_tile<EPI_GELU_BF16, true, false>(p, stream);
+      case EPI_GELU_TANH_BF16: return dispatch_tile<EPI_GELU_TANH_BF16, true, false>(p, stream);
+      default: return dispatch_tile<EPI_RELU_BF16, true, false>(p, stream);
+    }
+  }
   switch (p.epi) {
+    case EPI_RESID_STATS_F32:
+      VITK_REQUIRE(p.e.resid != nullptr && p.e.ln_part_out != nullptr && p.e.drop.thresh == 0u,
+                   "gemm: the statistics epilogue needs resid and ln_part_out (no dropout)");
+      VITK_REQUIRE(tma_epilogue_ok(p, false),
+                   "gemm: the statistics epilogue updates x in place (resid == out, no row remap) "
+                   "and needs 16-byte aligned outputs");
+      return dispatch_tile<EPI_RESID_STATS_F32, true, false>(p, stream);
     case EPI_BF16: return dispatch<EPI_BF16>(p, stream);
     case EPI_GELU_BF16: return dispatch<EPI_GELU_BF16>(p, stream);
     case EPI_GELU_TANH_BF16: return dispatch<EPI_GELU_TANH_BF16>(p, stream);

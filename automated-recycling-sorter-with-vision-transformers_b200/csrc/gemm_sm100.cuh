@@ -16,6 +16,11 @@ enum GemmEpi : int {
   EPI_DGELU_BF16 = 4,  // out_bf16 = (acc + bias) * gelu'(aux_bf16)            (fc2 dgrad)
   EPI_GELU_TANH_BF16 = 6,  // as EPI_GELU_BF16 with the tanh.approx form of the normal CDF (A/B)
   EPI_RELU_BF16 = 7,   // out_bf16 = max(acc + bias, 0)   (decoder feed-forward, evaluation.py:170-176)
+  // x = x + acc + bias in place (out == resid; the tile of x is TMA-loaded into the staging slab,
+  // updated there and TMA-stored back), out2_bf16 = bf16(x) and per-row partial sums (sum x,
+  // sum x^2) of the updated values -> ln_part_out: what the LayerNorm that follows needs, without
+  // a pass of its own over x (train.py:586-591).  TMA epilogue only.
+  EPI_RESID_STATS_F32 = 8,
 };
 
 struct GemmEpilogue {
@@ -58,6 +63,20 @@ struct GemmEpilogue {
   unsigned int* ln_counters = nullptr;
   int ln_ldo = 0;
   float ln_eps = 1e-5f;
+  // ---- LayerNorm folded into the two GEMMs around it (inference).
+  // Producer (EPI_RESID_STATS_F32): every epilogue thread owns a row and 128 (BLOCK_N / 2) of its
+  // columns, so the partial sums need no exchange: ln_part_out[(column group) * M + row] =
+  // (sum x, sum x^2) over that group; gemm_stats_parts(N) groups per row, summed by the consumer
+  // in a fixed order (deterministic, no atomics).
+  float2* ln_part_out = nullptr;
+  // Consumer (EPI_BF16 / EPI_GELU_*): A holds bf16(x) (NOT normalised), B holds bf16(W * gamma);
+  // with mu / rstd of the row from ln_part[0 .. ln_nparts) (rows of `ln_rows` entries, features
+  // ln_dim), out = rstd * (acc - mu * ln_colsum[n]) + bias[n] where ln_colsum[n] = sum_k B[n,k]
+  // and bias[n] = b[n] + sum_k W[n,k] beta[k] (ln_fold, rowops.cuh) == Linear(LayerNorm(x)).
+  const float2* ln_part = nullptr;
+  const float* ln_colsum = nullptr;
+  int ln_nparts = 0;
+  int ln_dim = 0;
 };
 
 struct GemmProblem {
@@ -80,6 +99,8 @@ int gemm_bf16_tn(const GemmProblem& p, cudaStream_t stream);
 void gemm_force_cta_group(int ctas);
 // 1 = always use the register->global epilogue instead of the smem-staged TMA store/reduce.
 void gemm_force_direct_epilogue(int on);
+// Column groups per row of EPI_RESID_STATS_F32's partial sums for an N-column output.
+int gemm_stats_parts(int N);
 // GemmEpilogue::ln_out: 0 (default) = residual GEMM, then a separate layernorm_fwd launch;
 // 1 = the LayerNorm tail inside the GEMM kernel.  Same bits either way.
 void gemm_set_fused_layernorm(int on);

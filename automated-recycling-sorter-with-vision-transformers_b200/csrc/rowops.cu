@@ -263,6 +263,67 @@ cast_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ o
     out[i] = __float2bfloat16_rn(in[i]);
 }
 
+// ---- LayerNorm folded into the GEMMs around it (gemm_sm100.cuh: GemmEpilogue::ln_part) ---------
+// Entry of the chain (block 0, after token assembly): bf16 copy of the rows and their (sum,
+// sum of squares) as a single partial.  One warp per row; reads 4 B, writes 2 B per element.
+__global__ void __launch_bounds__(256, 5)
+row_stats_kernel(const float* __restrict__ x, long long in_stride, __nv_bfloat16* __restrict__ y,
+                 long long out_stride, float2* __restrict__ part, int rows, int D, int descending) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  pdl_wait();
+  pdl_launch_dependents();
+  if (warp >= rows) return;
+  if (descending) warp = rows - 1 - warp;
+  const float* xr = x + static_cast<long long>(warp) * in_stride;
+  __nv_bfloat16* yr = y + static_cast<long long>(warp) * out_stride;
+  const int nvec = D >> 2;
+  float s = 0.f, q = 0.f;
+#pragma unroll
+  for (int j = 0; j < kLnMaxVec; ++j) {
+    const int i = lane + 32 * j;
+    if (i < nvec) {
+      const float4 v = *reinterpret_cast<const float4*>(xr + 4 * i);
+      s += (v.x + v.y) + (v.z + v.w);
+      q += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+      store4(yr + 4 * i, v.x, v.y, v.z, v.w);
+    }
+  }
+  s = warp_sum(s);
+  q = warp_sum(q);
+  if (lane == 0) part[warp] = make_float2(s, q);
+}
+
+// Weights of Linear(LayerNorm(.)) for the folded form: one warp per output feature n.
+//   w_out[n,k] = bf16(W[n,k] * gamma[k]);  colsum[n] = sum_k float(w_out[n,k]) (of the ROUNDED
+//   values: it must cancel the mean term of the bf16 contraction exactly);
+//   bias_out[n] = b[n] + sum_k W[n,k] * beta[k].
+__global__ void __launch_bounds__(256)
+ln_fold_kernel(const float* __restrict__ W, const float* __restrict__ gamma,
+               const float* __restrict__ beta, const float* __restrict__ b,
+               __nv_bfloat16* __restrict__ w_out, float* __restrict__ colsum,
+               float* __restrict__ bias_out, int N, int K) {
+  const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (n >= N) return;
+  const float* wr = W + static_cast<long long>(n) * K;
+  __nv_bfloat16* wo = w_out + static_cast<long long>(n) * K;
+  float s = 0.f, c = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float w = wr[k];
+    const __nv_bfloat16 r = __float2bfloat16_rn(w * gamma[k]);
+    wo[k] = r;
+    s += __bfloat162float(r);
+    c = fmaf(w, beta[k], c);
+  }
+  s = warp_sum(s);
+  c = warp_sum(c);
+  if (lane == 0) {
+    colsum[n] = s;
+    bias_out[n] = (b != nullptr ? b[n] : 0.f) + c;
+  }
+}
+
 int grid_for(long long work_items, int block, int max_blocks_per_sm = 8) {
   long long g = (work_items + block - 1) / block;
   const long long cap = static_cast<long long>(sm_count()) * max_blocks_per_sm;
@@ -294,6 +355,31 @@ int layernorm_fwd(const float* x, long long in_stride, const float* gamma, const
                gamma, beta, static_cast<__nv_bfloat16*>(y), out_stride, mean_out, rstd_out, x_copy,
                rows, D, eps, descending);
   VITK_CHECK_LAUNCH("layernorm_fwd_kernel");
+  return VITK_OK;
+}
+
+int row_stats(const float* x, long long in_stride, void* y_bf16, long long out_stride, float2* part,
+              int rows, int D, cudaStream_t stream) {
+  VITK_REQUIRE(x && y_bf16 && part, "row_stats: null operand");
+  VITK_REQUIRE(rows > 0 && D % 4 == 0 && D <= 128 * kLnMaxVec,
+               "row_stats: need rows > 0, D %% 4 == 0, D <= %d", 128 * kLnMaxVec);
+  VITK_REQUIRE(in_stride % 4 == 0 && out_stride % 4 == 0, "row_stats: strides must be multiples of 4");
+  ProfileScope prof(PROF_LN, static_cast<double>(rows) * D * 6.0, stream);
+  const int descending = sweep_next();
+  launch_pdl(row_stats_kernel, dim3((rows + 7) / 8), dim3(256), 0, stream, x, in_stride,
+             static_cast<__nv_bfloat16*>(y_bf16), out_stride, part, rows, D, descending);
+  VITK_CHECK_LAUNCH("row_stats_kernel");
+  return VITK_OK;
+}
+
+int ln_fold(const float* W, const float* gamma, const float* beta, const float* b, void* w_out_bf16,
+            float* colsum, float* bias_out, int N, int K, cudaStream_t stream) {
+  VITK_REQUIRE(W && gamma && beta && w_out_bf16 && colsum && bias_out, "ln_fold: null operand");
+  VITK_REQUIRE(N > 0 && K > 0, "ln_fold: empty matrix");
+  ln_fold_kernel<<<(N + 7) / 8, 256, 0, stream>>>(W, gamma, beta, b,
+                                                  static_cast<__nv_bfloat16*>(w_out_bf16), colsum,
+                                                  bias_out, N, K);
+  VITK_CHECK_LAUNCH("ln_fold_kernel");
   return VITK_OK;
 }
 

@@ -12,6 +12,14 @@ int layernorm_fwd(const float* x, long long in_stride, const float* gamma, const
                   void* y, int y_is_f32, long long out_stride, float* mean_out, float* rstd_out,
                   int rows, int D, float eps, cudaStream_t stream, float* x_copy = nullptr);
 
+// LayerNorm folded into the neighbouring GEMMs (gemm_sm100.cuh, GemmEpilogue::ln_part):
+// row_stats: y = bf16(x) and part[r] = (sum, sum of squares) of row r - the entry of the chain;
+// ln_fold: w_out = bf16(W * gamma), colsum[n] = sum_k w_out[n,k], bias_out = b + W beta.
+int row_stats(const float* x, long long in_stride, void* y_bf16, long long out_stride, float2* part,
+              int rows, int D, cudaStream_t stream);
+int ln_fold(const float* W, const float* gamma, const float* beta, const float* b, void* w_out_bf16,
+            float* colsum, float* bias_out, int N, int K, cudaStream_t stream);
+
 // f32 NCHW images -> bf16 patch rows [B*P, C*p*p] in conv-weight column order.
 int patchify(const float* img, void* out_bf16, int B, int C, int S, int p, cudaStream_t stream);
 

@@ -85,6 +85,15 @@ class EncoderEngine:
             b.ln2_w, b.ln2_b = f32(blk.layer_norm2.weight), f32(blk.layer_norm2.bias)
             b.fc1_w, b.fc1_b = bf16(blk.mlp.linear1.weight), f32(blk.mlp.linear1.bias)
             b.fc2_w, b.fc2_b = bf16(blk.mlp.linear2.weight), f32(blk.mlp.linear2.bias)
+            if self.precision == 0:
+                # layer_norm1 folded into qkv, layer_norm2 into linear1 (vitk_fold_layernorm):
+                # vitk_forward then runs no LayerNorm pass between the blocks
+                for name, ln, lin in (("qkv", blk.layer_norm1, blk.attention.qkv),
+                                      ("fc1", blk.layer_norm2, blk.mlp.linear1)):
+                    folded = ops.fold_layernorm(lin.weight, ln.weight, ln.bias, lin.bias)
+                    keep.extend(folded)
+                    for suffix, t in zip(("_w_ln", "_colsum", "_b_ln"), folded):
+                        setattr(b, name + suffix, t.data_ptr())
         w = VitkWeights()
         w.patch_w = bf16(m.patch_embedding.projection.weight)
         w.patch_b = f32(m.patch_embedding.projection.bias)

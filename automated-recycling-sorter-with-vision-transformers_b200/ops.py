@@ -93,6 +93,71 @@ def gemm_resid_layernorm(a: torch.Tensor, w: torch.Tensor, x: torch.Tensor, gamm
     return (y, mean, rstd) if return_stats else y
 
 
+def fold_layernorm(weight: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, bias=None):
+    """Linear(LayerNorm(.)) in the folded form (vitk_fold_layernorm): returns
+    (w_ln bf16 [out, in] = weight * gamma, colsum f32 [out], b_ln f32 [out] = bias + weight beta)."""
+    _need_cuda(weight, gamma, beta)
+    weight = weight.detach().float().contiguous()
+    N, K = weight.shape
+    w_ln = torch.empty((N, K), dtype=torch.bfloat16, device=weight.device)
+    colsum = torch.empty(N, dtype=torch.float32, device=weight.device)
+    b_ln = torch.empty(N, dtype=torch.float32, device=weight.device)
+    g, b = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
+    bb = bias.detach().float().contiguous() if bias is not None else None
+    check(lib().vitk_fold_layernorm(weight.data_ptr(), g.data_ptr(), b.data_ptr(), _ptr(bb),
+                                    w_ln.data_ptr(), colsum.data_ptr(), b_ln.data_ptr(), N, K,
+                                    _stream()))
+    return w_ln, colsum, b_ln
+
+
+def row_stats(x: torch.Tensor):
+    """bf16 copy of the fp32 rows and their (sum, sum of squares): ([rows, D] bf16, [1, rows, 2])."""
+    _need_cuda(x)
+    assert x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
+    rows, D = x.shape
+    xb = torch.empty((rows, D), dtype=torch.bfloat16, device=x.device)
+    stats = torch.empty((1, rows, 2), dtype=torch.float32, device=x.device)
+    check(lib().vitk_row_stats(x.data_ptr(), x.stride(0), xb.data_ptr(), D, stats.data_ptr(), rows,
+                               D, _stream()))
+    return xb, stats
+
+
+def gemm_resid_stats(a: torch.Tensor, w: torch.Tensor, x: torch.Tensor, *, bias=None):
+    """x += a @ w.T + bias in place (fp32); returns (bf16(x), stats [parts, M, 2]) - the partial
+    (sum, sum of squares) of every updated row per column group (vitk_gemm_resid_stats)."""
+    _need_cuda(a, w, x)
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and x.dtype == torch.float32
+    assert a.stride(1) == 1 and w.stride(1) == 1 and x.is_contiguous()
+    M, K = a.shape
+    N = w.shape[0]
+    assert x.shape == (M, N)
+    xb = torch.empty((M, N), dtype=torch.bfloat16, device=x.device)
+    parts = lib().vitk_stats_parts(N)
+    stats = torch.empty((parts, M, 2), dtype=torch.float32, device=x.device)
+    check(lib().vitk_gemm_resid_stats(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), M, N, K,
+                                      _ptr(bias), x.data_ptr(), xb.data_ptr(), stats.data_ptr(),
+                                      _stream()))
+    return xb, stats
+
+
+def gemm_layernorm_folded(xb: torch.Tensor, w_ln: torch.Tensor, colsum: torch.Tensor,
+                          b_ln: torch.Tensor, stats: torch.Tensor, *, eps: float = 1e-5,
+                          epilogue: int = _lib.EPI_BF16) -> torch.Tensor:
+    """epilogue(Linear(LayerNorm(x))) from bf16(x), the folded weights and the row statistics."""
+    _need_cuda(xb, w_ln, stats)
+    assert xb.dtype == torch.bfloat16 and w_ln.dtype == torch.bfloat16
+    assert stats.dtype == torch.float32 and stats.is_contiguous() and stats.dim() == 3
+    M, K = xb.shape
+    N = w_ln.shape[0]
+    assert stats.shape[1] == M and stats.shape[2] == 2
+    out = torch.empty((M, N), dtype=torch.bfloat16, device=xb.device)
+    check(lib().vitk_gemm_layernorm_folded(xb.data_ptr(), xb.stride(0), w_ln.data_ptr(),
+                                           w_ln.stride(0), M, N, K, epilogue, colsum.data_ptr(),
+                                           b_ln.data_ptr(), stats.data_ptr(), stats.shape[0], eps,
+                                           out.data_ptr(), out.stride(0), _stream()))
+    return out
+
+
 def gemm_wgrad(dy: torch.Tensor, x: torch.Tensor, out: torch.Tensor | None = None, *,
                alpha: float = 1.0, accumulate: bool = False, split_k: int = 1) -> torch.Tensor:
     """out[o, i] (+)= alpha * sum_t dy[t, o] * x[t, i]; dy bf16 [T, O], x bf16 [T, I], out f32."""

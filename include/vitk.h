@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define VITK_ABI_VERSION 4
+#define VITK_ABI_VERSION 5
 
 #define VITK_OK 0
 #define VITK_ERR_INVALID 1
@@ -72,6 +72,18 @@ typedef struct VitkBlockWeights {
   const float* fc1_b;
   const void* fc2_w; /* bf16 [D, M] */
   const float* fc2_b;
+  /* Optional (inference, bf16 mode): layer_norm1 folded into qkv and layer_norm2 into linear1 by
+   * vitk_fold_layernorm - *_w_ln bf16 [out, D] = W * gamma, *_colsum f32 [out], *_b_ln f32 [out].
+   * When all six are set for every block, vitk_forward runs no LayerNorm pass between the
+   * blocks: the projection / linear2 GEMMs leave the row statistics and a bf16 copy of the
+   * residual stream, the qkv / linear1 GEMMs normalise in their epilogue.  NULL: separate
+   * LayerNorm launches (the training entry points never read these). */
+  const void* qkv_w_ln;
+  const float* qkv_colsum;
+  const float* qkv_b_ln;
+  const void* fc1_w_ln;
+  const float* fc1_colsum;
+  const float* fc1_b_ln;
 } VitkBlockWeights;
 
 typedef struct VitkWeights {
@@ -111,6 +123,10 @@ int vitk_gemm_set_direct_epilogue(int on);
  * GEMM kernel (one launch; measured slower on B200, kept for A/B - DESIGN.md section 6).  Same
  * bits either way.  Initial value from the environment variable VITK_FUSED_LN. */
 int vitk_gemm_set_fused_layernorm(int on);
+/* vitk_forward with VitkBlockWeights::*_ln set: 1 (default) = LayerNorm folded into the GEMMs
+ * around it, 0 = separate LayerNorm launches (A/B timing, tests).  Initial value from the
+ * environment variable VITK_LN_FOLD. */
+int vitk_set_layernorm_folding(int on);
 
 /* Device side of post_process_predictions (evaluation.py:393-407, lines 403-404): softmax over the
  * class logits f32 [rows, n_classes], then the maximum probability and its class per row,
@@ -199,6 +215,7 @@ int vitk_forward_u8(const VitkConfig* cfg, const VitkWeights* w, const unsigned 
 #define VITK_EPI_F32 3       /* out f32  = alpha * A B^T + bias + beta * out */
 #define VITK_EPI_DGELU_BF16 4 /* out bf16 = (A B^T + bias) * gelu'(aux bf16) */
 #define VITK_EPI_RELU_BF16 7  /* out bf16 = max(A B^T + bias, 0) (decoder feed-forward) */
+#define VITK_EPI_GELU_TANH_BF16 6 /* VITK_EPI_GELU_BF16 with the tanh.approx form of the CDF */
 
 /* C[M,N] = A[M,K] * B[N,K]^T (bf16 operands, fp32 accumulate on tcgen05) + fused epilogue.
  * Replaces nn.Linear / F.linear at train.py:527,529,561,564 and the Conv2d at train.py:505. */
@@ -218,6 +235,43 @@ int vitk_gemm_resid_layernorm(const void* A, int lda, const void* W, int ldb, in
                               const float* bias, float* x_inout, const float* gamma,
                               const float* beta, float eps, void* ln_out, float* mean_out,
                               float* rstd_out, unsigned int* counters, vitk_stream_t stream);
+
+/* ---- LayerNorm folded into the two GEMMs around it (train.py:584-591: x = x + f(..);
+ * Linear(layer_norm(x))).  Instead of a LayerNorm pass over the fp32 residual stream between two
+ * GEMMs, the residual GEMM's epilogue (thread == row) leaves per-row partial sums and a bf16 copy
+ * of x, and the next GEMM contracts that copy against W * gamma and normalises in its epilogue:
+ *   Linear(LN(x))[m,n] = rstd_m * (sum_k x[m,k] gamma_k W[n,k] - mu_m * sum_k gamma_k W[n,k])
+ *                        + b[n] + sum_k beta_k W[n,k]. */
+
+/* Weights of the folded form.  weight f32 [out, in], gamma / beta f32 [in], bias f32 [out] or NULL
+ * -> w_ln bf16 [out, in] = weight * gamma, colsum f32 [out] = row sums of the ROUNDED w_ln,
+ * b_ln f32 [out] = bias + weight beta. */
+int vitk_fold_layernorm(const float* weight, const float* gamma, const float* beta,
+                        const float* bias, void* w_ln_bf16, float* colsum, float* b_ln,
+                        int out_features, int in_features, vitk_stream_t stream);
+
+/* Partial sums per row that vitk_gemm_resid_stats writes for an N-column output. */
+int vitk_stats_parts(int n_features);
+
+/* Entry of the chain: x_bf16[rows, D] = bf16(x) and stats[r] = (sum, sum of squares) of row r
+ * (one partial).  stats: f32 pairs [rows]. */
+int vitk_row_stats(const float* x, long long in_stride, void* x_bf16, long long out_stride,
+                   float* stats, int rows, int D, vitk_stream_t stream);
+
+/* x[M,N] f32 += A[M,K] W[N,K]^T + bias in place (the x tile is TMA-loaded into the epilogue's
+ * staging slab, updated there and TMA-stored), x_bf16[M,N] = bf16(x), stats f32 pairs
+ * [vitk_stats_parts(N)][M]: (sum, sum of squares) of the updated row over each column group. */
+int vitk_gemm_resid_stats(const void* A, int lda, const void* W, int ldb, int M, int N, int K,
+                          const float* bias, float* x_inout, void* x_bf16, float* stats,
+                          vitk_stream_t stream);
+
+/* out bf16 [M,N] = epilogue(Linear(LayerNorm(x))) from x_bf16 [M,K], the folded weights and the
+ * row statistics (n_parts partials of M pairs; K features per row).  epilogue: VITK_EPI_BF16,
+ * VITK_EPI_GELU_BF16, VITK_EPI_GELU_TANH_BF16 or VITK_EPI_RELU_BF16. */
+int vitk_gemm_layernorm_folded(const void* x_bf16, int lda, const void* w_ln, int ldb, int M, int N,
+                               int K, int epilogue, const float* colsum, const float* b_ln,
+                               const float* stats, int n_parts, float eps, void* out, int ldo,
+                               vitk_stream_t stream);
 
 /* Weight-gradient contraction C[M,N] (+)= A^T B with A stored [K, lda] (M contiguous) and B stored
  * [K, ldb] (N contiguous): dW[out,in] = sum over tokens of dY[token,out] * X[token,in] - the
