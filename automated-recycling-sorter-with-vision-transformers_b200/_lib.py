@@ -57,8 +57,8 @@ class VitkBlockWeights(C.Structure):
         ("fc1_w", C.c_void_p), ("fc1_b", C.c_void_p),
         ("fc2_w", C.c_void_p), ("fc2_b", C.c_void_p),
         # optional: LayerNorm folded into qkv / linear1 (vitk_fold_layernorm); NULL = not folded
-        ("qkv_w_ln", C.c_void_p), ("qkv_colsum", C.c_void_p), ("qkv_b_ln", C.c_void_p),
-        ("fc1_w_ln", C.c_void_p), ("fc1_colsum", C.c_void_p), ("fc1_b_ln", C.c_void_p),
+        ("qkv_w_ln", C.c_void_p), ("qkv_b_ln", C.c_void_p),
+        ("fc1_w_ln", C.c_void_p), ("fc1_b_ln", C.c_void_p),
     ]
 
 
@@ -110,8 +110,7 @@ _SIGNATURES = {
                                         C.c_void_p]),
     "vitk_gemm_layernorm_folded": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                              C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
-                                             C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_int,
-                                             C.c_void_p]),
+                                             C.c_int, C.c_float, C.c_void_p, C.c_int, C.c_void_p]),
     "vitk_attention_set_impl": (C.c_int, [C.c_int]),
     "vitk_reserve_sms": (C.c_int, [C.c_int]),
     "vitk_set_pdl": (C.c_int, [C.c_int]),

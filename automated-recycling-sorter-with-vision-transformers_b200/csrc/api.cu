@@ -169,8 +169,8 @@ int linear_resid_stats(const void* A, int lda, const void* W, int M, int N, int 
 
 // out = epilogue(Linear(LayerNorm(x))) from bf16(x), W * gamma and the row statistics.
 int linear_ln(const void* xb, int K, const void* w_ln, int M, int N, GemmEpi epi,
-              const float* colsum, const float* b_ln, const float2* stats, int nparts, float eps,
-              void* out, int ldo, cudaStream_t stream) {
+              const float* b_ln, const float2* stats, int nparts, float eps, void* out, int ldo,
+              cudaStream_t stream) {
   GemmProblem p;
   p.A = xb;
   p.lda = K;
@@ -184,7 +184,6 @@ int linear_ln(const void* xb, int K, const void* w_ln, int M, int N, GemmEpi epi
   p.e.out = out;
   p.e.ldo = ldo;
   p.e.ln_part = stats;
-  p.e.ln_colsum = colsum;
   p.e.ln_nparts = nparts;
   p.e.ln_dim = K;
   p.e.ln_eps = eps;
@@ -201,8 +200,7 @@ int g_ln_fold = [] {
 bool folded_weights_present(const VitkWeights* w, int L) {
   for (int l = 0; l < L; ++l) {
     const VitkBlockWeights& b = w->blocks[l];
-    if (!b.qkv_w_ln || !b.qkv_colsum || !b.qkv_b_ln || !b.fc1_w_ln || !b.fc1_colsum || !b.fc1_b_ln)
-      return false;
+    if (!b.qkv_w_ln || !b.qkv_b_ln || !b.fc1_w_ln || !b.fc1_b_ln) return false;
   }
   return true;
 }
@@ -285,15 +283,15 @@ int forward_bf16(const VitkConfig* cfg, const VitkWeights* w, const float* image
     for (int l = 0; l < d.L; ++l) {
       const VitkBlockWeights& bw = w->blocks[l];
       const bool last = (l == d.L - 1);
-      VITK_TRY(linear_ln(ws.xn, D, bw.qkv_w_ln, M, 3 * D, EPI_BF16, bw.qkv_colsum, bw.qkv_b_ln,
-                         ws.stats, nparts, cfg->ln_eps, ws.qkv, 3 * D, stream));
+      VITK_TRY(linear_ln(ws.xn, D, bw.qkv_w_ln, M, 3 * D, EPI_BF16, bw.qkv_b_ln, ws.stats, nparts,
+                         cfg->ln_eps, ws.qkv, 3 * D, stream));
       if (cls_only_tail && last) break;  // the row-wise tail below finishes the block
       VITK_TRY(attention_fwd(ws.qkv, ws.ctx, nullptr, d.B, d.N, d.H, d.hd, stream));
       VITK_TRY(linear_resid_stats(ws.ctx, D, bw.proj_w, M, D, D, bw.proj_b, ws.x, ws.xn, ws.stats,
                                   stream));
       nparts = parts;
-      VITK_TRY(linear_ln(ws.xn, D, bw.fc1_w_ln, M, d.Mlp, EPI_GELU_TANH_BF16, bw.fc1_colsum,
-                         bw.fc1_b_ln, ws.stats, nparts, cfg->ln_eps, ws.h, d.Mlp, stream));
+      VITK_TRY(linear_ln(ws.xn, D, bw.fc1_w_ln, M, d.Mlp, EPI_GELU_TANH_BF16, bw.fc1_b_ln, ws.stats,
+                         nparts, cfg->ln_eps, ws.h, d.Mlp, stream));
       if (!last)
         VITK_TRY(linear_resid_stats(ws.h, d.Mlp, bw.fc2_w, M, D, d.Mlp, bw.fc2_b, ws.x, ws.xn,
                                     ws.stats, stream));
@@ -485,9 +483,10 @@ int vitk_set_layernorm_folding(int on) {
   return VITK_OK;
 }
 int vitk_fold_layernorm(const float* weight, const float* gamma, const float* beta,
-                        const float* bias, void* w_ln_bf16, float* colsum, float* b_ln,
+                        const float* bias, void* w_ln_bf16, float* b_ln, float* rowsum_or_null,
                         int out_features, int in_features, vitk_stream_t stream) {
-  return ln_fold(weight, gamma, beta, bias, w_ln_bf16, colsum, b_ln, out_features, in_features,
+  return ln_fold(weight, gamma, beta, bias, w_ln_bf16, rowsum_or_null, b_ln, out_features,
+                 in_features,
                  static_cast<cudaStream_t>(stream));
 }
 int vitk_stats_parts(int n_features) { return gemm_stats_parts(n_features); }
@@ -519,9 +518,8 @@ int vitk_gemm_resid_stats(const void* A, int lda, const void* W, int ldb, int M,
   return gemm_bf16_tn(p, static_cast<cudaStream_t>(stream));
 }
 int vitk_gemm_layernorm_folded(const void* x_bf16, int lda, const void* w_ln, int ldb, int M, int N,
-                               int K, int epilogue, const float* colsum, const float* b_ln,
-                               const float* stats, int n_parts, float eps, void* out, int ldo,
-                               vitk_stream_t stream) {
+                               int K, int epilogue, const float* b_ln, const float* stats,
+                               int n_parts, float eps, void* out, int ldo, vitk_stream_t stream) {
   VITK_REQUIRE(stats != nullptr, "gemm_layernorm_folded: null statistics");
   GemmProblem p;
   p.A = x_bf16;
@@ -536,7 +534,6 @@ int vitk_gemm_layernorm_folded(const void* x_bf16, int lda, const void* w_ln, in
   p.e.out = out;
   p.e.ldo = ldo;
   p.e.ln_part = reinterpret_cast<const float2*>(stats);
-  p.e.ln_colsum = colsum;
   p.e.ln_nparts = n_parts;
   p.e.ln_dim = K;
   p.e.ln_eps = eps;

@@ -365,10 +365,17 @@ __device__ __forceinline__ void acc_plus_bias(const uint32_t (&v)[32], int n0, i
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float4 b = __ldg(b4 + j);
-        x[4 * j + 0] = fmaf(acc_scale, __uint_as_float(v[4 * j + 0]), b.x);
-        x[4 * j + 1] = fmaf(acc_scale, __uint_as_float(v[4 * j + 1]), b.y);
-        x[4 * j + 2] = fmaf(acc_scale, __uint_as_float(v[4 * j + 2]), b.z);
-        x[4 * j + 3] = fmaf(acc_scale, __uint_as_float(v[4 * j + 3]), b.w);
+        if constexpr (EPI == EPI_F32) {
+          x[4 * j + 0] = fmaf(acc_scale, __uint_as_float(v[4 * j + 0]), b.x);
+          x[4 * j + 1] = fmaf(acc_scale, __uint_as_float(v[4 * j + 1]), b.y);
+          x[4 * j + 2] = fmaf(acc_scale, __uint_as_float(v[4 * j + 2]), b.z);
+          x[4 * j + 3] = fmaf(acc_scale, __uint_as_float(v[4 * j + 3]), b.w);
+        } else {  // packed fp32: one FADD2 per two columns
+          unpack2(fadd2(pack2(v[4 * j + 0], v[4 * j + 1]), pack2f(b.x, b.y)), x[4 * j + 0],
+                  x[4 * j + 1]);
+          unpack2(fadd2(pack2(v[4 * j + 2], v[4 * j + 3]), pack2f(b.z, b.w)), x[4 * j + 2],
+                  x[4 * j + 3]);
+        }
       }
     } else {
 #pragma unroll
@@ -383,30 +390,27 @@ __device__ __forceinline__ void acc_plus_bias(const uint32_t (&v)[32], int n0, i
   }
 }
 
-// LayerNorm folded into the GEMM (GemmEpilogue::ln_part): rstd * (acc - mu * colsum[n]) + bias[n]
-// for one 32-column chunk; nmu = -mu of this thread's row.
-__device__ __forceinline__ void acc_ln_bias(const uint32_t (&v)[32], int n0, int N,
-                                            const GemmEpilogue& e, float nmu, float rstd,
-                                            float (&x)[32]) {
+// LayerNorm folded into the GEMM (GemmEpilogue::ln_part): rstd * acc + bias[n] for one 32-column
+// chunk (the weight rows are centred, so the contraction has already removed the row mean);
+// packed fp32 arithmetic: one FFMA2 per two columns.
+__device__ __forceinline__ void acc_scale_bias(const uint32_t (&v)[32], int n0, int N,
+                                               const GemmEpilogue& e, float rstd, float (&x)[32]) {
   if (n0 + 32 <= N) {
-    const float4* s4 = reinterpret_cast<const float4*>(e.ln_colsum + n0);
     const float4* b4 = reinterpret_cast<const float4*>(e.bias + n0);
+    const uint64_t r2 = pack2f(rstd, rstd);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float4 s = __ldg(s4 + j);
       const float4 b = __ldg(b4 + j);
-      x[4 * j + 0] = fmaf(rstd, fmaf(nmu, s.x, __uint_as_float(v[4 * j + 0])), b.x);
-      x[4 * j + 1] = fmaf(rstd, fmaf(nmu, s.y, __uint_as_float(v[4 * j + 1])), b.y);
-      x[4 * j + 2] = fmaf(rstd, fmaf(nmu, s.z, __uint_as_float(v[4 * j + 2])), b.z);
-      x[4 * j + 3] = fmaf(rstd, fmaf(nmu, s.w, __uint_as_float(v[4 * j + 3])), b.w);
+      unpack2(ffma2(r2, pack2(v[4 * j + 0], v[4 * j + 1]), pack2f(b.x, b.y)), x[4 * j + 0],
+              x[4 * j + 1]);
+      unpack2(ffma2(r2, pack2(v[4 * j + 2], v[4 * j + 3]), pack2f(b.z, b.w)), x[4 * j + 2],
+              x[4 * j + 3]);
     }
   } else {
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-      const bool in = n0 + j < N;
-      const float s = in ? __ldg(e.ln_colsum + n0 + j) : 0.f;
-      const float b = in ? __ldg(e.bias + n0 + j) : 0.f;
-      x[j] = fmaf(rstd, fmaf(nmu, s, __uint_as_float(v[j])), b);
+      const float b = (n0 + j < N) ? __ldg(e.bias + n0 + j) : 0.f;
+      x[j] = fmaf(rstd, __uint_as_float(v[j]), b);
     }
   }
 }
@@ -861,20 +865,40 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
       }
       // LayerNorm folded into this GEMM: mean / rstd of this thread's row from the partial sums
       // the producing residual GEMM left (fixed summation order)
-      [[maybe_unused]] float ln_nmu = 0.f, ln_rstd = 1.f;
+      [[maybe_unused]] float ln_rstd = 1.f;
       if constexpr (TMA_EPI && (EPI == EPI_BF16 || is_gelu_epi<EPI>())) {
-        if (e.ln_part != nullptr && row0 + lane < M) {
+        if (e.ln_part != nullptr) {
+          // up to 8 independent loads in flight (a runtime-bounded loop would serialise them)
           float s1 = 0.f, s2 = 0.f;
-          for (int p2 = 0; p2 < e.ln_nparts; ++p2) {
-            const float2 t = __ldg(e.ln_part + static_cast<size_t>(p2) * M + (row0 + lane));
-            s1 += t.x;
-            s2 += t.y;
+          if (row0 + lane < M) {
+            float2 t[8];
+#pragma unroll
+            for (int p2 = 0; p2 < 8; ++p2)
+              t[p2] = p2 < e.ln_nparts
+                          ? __ldg(e.ln_part + static_cast<size_t>(p2) * M + (row0 + lane))
+                          : make_float2(0.f, 0.f);
+#pragma unroll
+            for (int p2 = 0; p2 < 8; ++p2) {
+              s1 += t[p2].x;
+              s2 += t[p2].y;
+            }
+          }
+          // the next tile's statistics -> L1 while this tile's epilogue runs
+          const int work_nx = work + num_clusters;
+          if (work_nx < num_tiles) {
+            const int row_nx = (tile_of(work_nx) / num_n_tiles) * kTileM + slab_row + lane;
+            if (row_nx < M && row_nx != row0 + lane) {
+#pragma unroll
+              for (int p2 = 0; p2 < 8; ++p2)
+                if (p2 < e.ln_nparts)
+                  asm volatile("prefetch.global.L1 [%0];" ::"l"(e.ln_part +
+                                                                static_cast<size_t>(p2) * M + row_nx));
+            }
           }
           const float inv_d = 1.f / static_cast<float>(e.ln_dim);
           const float mean = s1 * inv_d;
           const float var = fmaxf(fmaf(-mean, mean, s2 * inv_d), 0.f);
           ln_rstd = rsqrtf(var + e.ln_eps);
-          ln_nmu = -mean;
         }
       }
       mbar_wait(tfull_bar(acc), acc_phase);
@@ -997,8 +1021,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
             if (row0 < M && n0 < N) {
               float x0[32], x1[32];
               if (e.ln_part != nullptr) {
-                acc_ln_bias(v0, n0, N, e, ln_nmu, ln_rstd, x0);
-                acc_ln_bias(v1, n0 + 32, N, e, ln_nmu, ln_rstd, x1);
+                acc_scale_bias(v0, n0, N, e, ln_rstd, x0);
+                acc_scale_bias(v1, n0 + 32, N, e, ln_rstd, x1);
               } else {
                 acc_plus_bias<EPI>(v0, n0, N, e, x0);
                 acc_plus_bias<EPI>(v1, n0 + 32, N, e, x1);
@@ -1370,8 +1394,8 @@ int gemm_bf16_tn(const GemmProblem& p, cudaStream_t stream) {
     VITK_REQUIRE(p.epi == EPI_BF16 || p.epi == EPI_GELU_BF16 || p.epi == EPI_GELU_TANH_BF16 ||
                      p.epi == EPI_RELU_BF16,
                  "gemm: a folded LayerNorm needs a bf16-output epilogue");
-    VITK_REQUIRE(p.e.ln_colsum && p.e.bias && p.e.ln_nparts > 0 && p.e.ln_dim > 0,
-                 "gemm: folded LayerNorm needs column sums, the folded bias and the row statistics");
+    VITK_REQUIRE(p.e.bias && p.e.ln_nparts > 0 && p.e.ln_nparts <= 8 && p.e.ln_dim > 0,
+                 "gemm: folded LayerNorm needs the folded bias and the row statistics");
     VITK_REQUIRE(tma_epilogue_ok(p, false), "gemm: folded LayerNorm needs 16-byte aligned outputs");
     switch (p.epi) {
       case EPI_BF16: return dispatch_tile<EPI_BF16, true, false>(p, stream);

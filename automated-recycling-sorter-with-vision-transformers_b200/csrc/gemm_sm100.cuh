@@ -69,12 +69,12 @@ struct GemmEpilogue {
   // (sum x, sum x^2) over that group; gemm_stats_parts(N) groups per row, summed by the consumer
   // in a fixed order (deterministic, no atomics).
   float2* ln_part_out = nullptr;
-  // Consumer (EPI_BF16 / EPI_GELU_*): A holds bf16(x) (NOT normalised), B holds bf16(W * gamma);
-  // with mu / rstd of the row from ln_part[0 .. ln_nparts) (rows of `ln_rows` entries, features
-  // ln_dim), out = rstd * (acc - mu * ln_colsum[n]) + bias[n] where ln_colsum[n] = sum_k B[n,k]
-  // and bias[n] = b[n] + sum_k W[n,k] beta[k] (ln_fold, rowops.cuh) == Linear(LayerNorm(x)).
+  // Consumer (EPI_BF16 / EPI_GELU_*): A holds bf16(x) (NOT normalised), B holds the row-centred
+  // bf16(W * gamma - mean_k(W * gamma)): a zero-sum weight row makes the contraction itself drop
+  // the row mean of x, so with rstd of the row from ln_part[0 .. ln_nparts) (M entries each;
+  // ln_dim features) out = rstd * acc + bias[n], bias[n] = b[n] + sum_k W[n,k] beta[k]
+  // (ln_fold, rowops.cuh) == Linear(LayerNorm(x)).
   const float2* ln_part = nullptr;
-  const float* ln_colsum = nullptr;
   int ln_nparts = 0;
   int ln_dim = 0;
 };

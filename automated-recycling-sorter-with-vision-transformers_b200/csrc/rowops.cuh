@@ -14,7 +14,8 @@ int layernorm_fwd(const float* x, long long in_stride, const float* gamma, const
 
 // LayerNorm folded into the neighbouring GEMMs (gemm_sm100.cuh, GemmEpilogue::ln_part):
 // row_stats: y = bf16(x) and part[r] = (sum, sum of squares) of row r - the entry of the chain;
-// ln_fold: w_out = bf16(W * gamma), colsum[n] = sum_k w_out[n,k], bias_out = b + W beta.
+// ln_fold: w_out = bf16(W * gamma - row mean) (zero-sum rows), colsum[n] = what rounding leaves of
+// the row sum (optional), bias_out = b + W beta.
 int row_stats(const float* x, long long in_stride, void* y_bf16, long long out_stride, float2* part,
               int rows, int D, cudaStream_t stream);
 int ln_fold(const float* W, const float* gamma, const float* beta, const float* b, void* w_out_bf16,

@@ -90,10 +90,10 @@ class EncoderEngine:
                 # vitk_forward then runs no LayerNorm pass between the blocks
                 for name, ln, lin in (("qkv", blk.layer_norm1, blk.attention.qkv),
                                       ("fc1", blk.layer_norm2, blk.mlp.linear1)):
-                    folded = ops.fold_layernorm(lin.weight, ln.weight, ln.bias, lin.bias)
-                    keep.extend(folded)
-                    for suffix, t in zip(("_w_ln", "_colsum", "_b_ln"), folded):
-                        setattr(b, name + suffix, t.data_ptr())
+                    w_ln, b_ln, _ = ops.fold_layernorm(lin.weight, ln.weight, ln.bias, lin.bias)
+                    keep.extend((w_ln, b_ln))
+                    setattr(b, name + "_w_ln", w_ln.data_ptr())
+                    setattr(b, name + "_b_ln", b_ln.data_ptr())
         w = VitkWeights()
         w.patch_w = bf16(m.patch_embedding.projection.weight)
         w.patch_b = f32(m.patch_embedding.projection.bias)

@@ -95,19 +95,20 @@ def gemm_resid_layernorm(a: torch.Tensor, w: torch.Tensor, x: torch.Tensor, gamm
 
 def fold_layernorm(weight: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, bias=None):
     """Linear(LayerNorm(.)) in the folded form (vitk_fold_layernorm): returns
-    (w_ln bf16 [out, in] = weight * gamma, colsum f32 [out], b_ln f32 [out] = bias + weight beta)."""
+    (w_ln bf16 [out, in] = weight * gamma with zero-sum rows, b_ln f32 [out] = bias + weight beta,
+    rowsum f32 [out] = what bf16 rounding leaves of the row sums of w_ln)."""
     _need_cuda(weight, gamma, beta)
     weight = weight.detach().float().contiguous()
     N, K = weight.shape
     w_ln = torch.empty((N, K), dtype=torch.bfloat16, device=weight.device)
-    colsum = torch.empty(N, dtype=torch.float32, device=weight.device)
+    rowsum = torch.empty(N, dtype=torch.float32, device=weight.device)
     b_ln = torch.empty(N, dtype=torch.float32, device=weight.device)
     g, b = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
     bb = bias.detach().float().contiguous() if bias is not None else None
     check(lib().vitk_fold_layernorm(weight.data_ptr(), g.data_ptr(), b.data_ptr(), _ptr(bb),
-                                    w_ln.data_ptr(), colsum.data_ptr(), b_ln.data_ptr(), N, K,
+                                    w_ln.data_ptr(), b_ln.data_ptr(), rowsum.data_ptr(), N, K,
                                     _stream()))
-    return w_ln, colsum, b_ln
+    return w_ln, b_ln, rowsum
 
 
 def row_stats(x: torch.Tensor):
@@ -140,8 +141,8 @@ def gemm_resid_stats(a: torch.Tensor, w: torch.Tensor, x: torch.Tensor, *, bias=
     return xb, stats
 
 
-def gemm_layernorm_folded(xb: torch.Tensor, w_ln: torch.Tensor, colsum: torch.Tensor,
-                          b_ln: torch.Tensor, stats: torch.Tensor, *, eps: float = 1e-5,
+def gemm_layernorm_folded(xb: torch.Tensor, w_ln: torch.Tensor, b_ln: torch.Tensor,
+                          stats: torch.Tensor, *, eps: float = 1e-5,
                           epilogue: int = _lib.EPI_BF16) -> torch.Tensor:
     """epilogue(Linear(LayerNorm(x))) from bf16(x), the folded weights and the row statistics."""
     _need_cuda(xb, w_ln, stats)
@@ -152,7 +153,7 @@ def gemm_layernorm_folded(xb: torch.Tensor, w_ln: torch.Tensor, colsum: torch.Te
     assert stats.shape[1] == M and stats.shape[2] == 2
     out = torch.empty((M, N), dtype=torch.bfloat16, device=xb.device)
     check(lib().vitk_gemm_layernorm_folded(xb.data_ptr(), xb.stride(0), w_ln.data_ptr(),
-                                           w_ln.stride(0), M, N, K, epilogue, colsum.data_ptr(),
+                                           w_ln.stride(0), M, N, K, epilogue,
                                            b_ln.data_ptr(), stats.data_ptr(), stats.shape[0], eps,
                                            out.data_ptr(), out.stride(0), _stream()))
     return out

@@ -73,16 +73,14 @@ typedef struct VitkBlockWeights {
   const void* fc2_w; /* bf16 [D, M] */
   const float* fc2_b;
   /* Optional (inference, bf16 mode): layer_norm1 folded into qkv and layer_norm2 into linear1 by
-   * vitk_fold_layernorm - *_w_ln bf16 [out, D] = W * gamma, *_colsum f32 [out], *_b_ln f32 [out].
-   * When all six are set for every block, vitk_forward runs no LayerNorm pass between the
+   * vitk_fold_layernorm - *_w_ln bf16 [out, D], *_b_ln f32 [out].
+   * When all four are set for every block, vitk_forward runs no LayerNorm pass between the
    * blocks: the projection / linear2 GEMMs leave the row statistics and a bf16 copy of the
    * residual stream, the qkv / linear1 GEMMs normalise in their epilogue.  NULL: separate
    * LayerNorm launches (the training entry points never read these). */
   const void* qkv_w_ln;
-  const float* qkv_colsum;
   const float* qkv_b_ln;
   const void* fc1_w_ln;
-  const float* fc1_colsum;
   const float* fc1_b_ln;
 } VitkBlockWeights;
 
@@ -239,15 +237,17 @@ int vitk_gemm_resid_layernorm(const void* A, int lda, const void* W, int ldb, in
 /* ---- LayerNorm folded into the two GEMMs around it (train.py:584-591: x = x + f(..);
  * Linear(layer_norm(x))).  Instead of a LayerNorm pass over the fp32 residual stream between two
  * GEMMs, the residual GEMM's epilogue (thread == row) leaves per-row partial sums and a bf16 copy
- * of x, and the next GEMM contracts that copy against W * gamma and normalises in its epilogue:
- *   Linear(LN(x))[m,n] = rstd_m * (sum_k x[m,k] gamma_k W[n,k] - mu_m * sum_k gamma_k W[n,k])
- *                        + b[n] + sum_k beta_k W[n,k]. */
+ * of x, and the next GEMM contracts that copy against the ROW-CENTRED matrix
+ * V[n,k] = gamma_k W[n,k] - mean_k(gamma_k W[n,k]) and scales in its epilogue.  A zero-sum row
+ * drops the mean of x inside the contraction (sum_k mu V[n,k] = 0), so
+ *   Linear(LN(x))[m,n] = rstd_m * sum_k x[m,k] V[n,k] + b[n] + sum_k beta_k W[n,k]. */
 
 /* Weights of the folded form.  weight f32 [out, in], gamma / beta f32 [in], bias f32 [out] or NULL
- * -> w_ln bf16 [out, in] = weight * gamma, colsum f32 [out] = row sums of the ROUNDED w_ln,
- * b_ln f32 [out] = bias + weight beta. */
+ * -> w_ln bf16 [out, in] = V (above), b_ln f32 [out] = bias + weight beta; rowsum_or_null f32
+ * [out]: what bf16 rounding leaves of the row sums of w_ln (the mean of x leaks into the output
+ * as mu * rstd * rowsum[n]; ~1e-3 for ViT weights, below the bf16 output resolution). */
 int vitk_fold_layernorm(const float* weight, const float* gamma, const float* beta,
-                        const float* bias, void* w_ln_bf16, float* colsum, float* b_ln,
+                        const float* bias, void* w_ln_bf16, float* b_ln, float* rowsum_or_null,
                         int out_features, int in_features, vitk_stream_t stream);
 
 /* Partial sums per row that vitk_gemm_resid_stats writes for an N-column output. */
@@ -269,9 +269,8 @@ int vitk_gemm_resid_stats(const void* A, int lda, const void* W, int ldb, int M,
  * row statistics (n_parts partials of M pairs; K features per row).  epilogue: VITK_EPI_BF16,
  * VITK_EPI_GELU_BF16, VITK_EPI_GELU_TANH_BF16 or VITK_EPI_RELU_BF16. */
 int vitk_gemm_layernorm_folded(const void* x_bf16, int lda, const void* w_ln, int ldb, int M, int N,
-                               int K, int epilogue, const float* colsum, const float* b_ln,
-                               const float* stats, int n_parts, float eps, void* out, int ldo,
-                               vitk_stream_t stream);
+                               int K, int epilogue, const float* b_ln, const float* stats,
+                               int n_parts, float eps, void* out, int ldo, vitk_stream_t stream);
 
 /* Weight-gradient contraction C[M,N] (+)= A^T B with A stored [K, lda] (M contiguous) and B stored
  * [K, ldb] (N contiguous): dW[out,in] = sum over tokens of dY[token,out] * X[token,in] - the

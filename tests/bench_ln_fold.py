@@ -40,7 +40,7 @@ for K, N2, epi, name in ((768, 3072, EPI.EPI_GELU_TANH_BF16, "proj -> LN2 -> fc1
     W2 = torch.randn(N2, D, generator=g, device="cuda") / D ** 0.5
     b2 = torch.zeros(N2, device="cuda")
     w2 = W2.bfloat16()
-    w_ln, colsum, b_ln = vitk.ops.fold_layernorm(W2, gamma, beta, b2)
+    w_ln, b_ln, _ = vitk.ops.fold_layernorm(W2, gamma, beta, b2)
     out2 = torch.empty(M, N2, dtype=torch.bfloat16, device="cuda")
     for rnd in range(2):
         r = {}
@@ -50,7 +50,7 @@ for K, N2, epi, name in ((768, 3072, EPI.EPI_GELU_TANH_BF16, "proj -> LN2 -> fc1
         r["consumer"] = timed(lambda: vitk.ops.gemm(xn, w2, epi, bias=b2, out=out2))
         r["resid + stats"] = timed(lambda: vitk.ops.gemm_resid_stats(a, w, x, bias=bias))
         xb, st = vitk.ops.gemm_resid_stats(a, w, x, bias=bias)
-        r["consumer (folded LN)"] = timed(lambda: vitk.ops.gemm_layernorm_folded(xb, w_ln, colsum, b_ln, st, epilogue=epi))
+        r["consumer (folded LN)"] = timed(lambda: vitk.ops.gemm_layernorm_folded(xb, w_ln, b_ln, st, epilogue=epi))
         plain = r["resid (reduce-add)"][0] + r["layernorm"][0] + r["consumer"][0]
         fold = r["resid + stats"][0] + r["consumer (folded LN)"][0]
         print(f"{name} round {rnd}: " + ", ".join(f"{k} {v[0]:.1f} (best {v[1]:.1f})" for k, v in r.items()))

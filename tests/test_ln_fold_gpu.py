@@ -40,12 +40,15 @@ def test_fold_layernorm(vitk):
     gamma = torch.rand(400, generator=g, device="cuda") + 0.5
     beta = torch.randn(400, generator=g, device="cuda") * 0.1
     b = torch.randn(200, generator=g, device="cuda")
-    w_ln, colsum, b_ln = vitk.ops.fold_layernorm(W, gamma, beta, b)
-    ref_w = (W * gamma).bfloat16()
-    assert torch.equal(w_ln, ref_w)
-    torch.testing.assert_close(colsum, ref_w.float().sum(1), rtol=1e-5, atol=1e-5)
+    w_ln, b_ln, rowsum = vitk.ops.fold_layernorm(W, gamma, beta, b)
+    v = W * gamma
+    ref_w = v - v.mean(1, keepdim=True)
+    # centred rows, rounded to bf16 (a last-bit difference where fma and mul + sub round apart)
+    torch.testing.assert_close(w_ln.float(), ref_w, rtol=2 ** -7, atol=1e-6)
+    torch.testing.assert_close(rowsum, w_ln.float().sum(1), rtol=1e-4, atol=1e-5)
+    assert rowsum.abs().max().item() < 5e-3      # what rounding leaves of a zero row sum
     torch.testing.assert_close(b_ln, b + W @ beta, rtol=1e-5, atol=1e-5)
-    _, _, b0 = vitk.ops.fold_layernorm(W, gamma, beta, None)
+    _, b0, _ = vitk.ops.fold_layernorm(W, gamma, beta, None)
     torch.testing.assert_close(b0, W @ beta, rtol=1e-5, atol=1e-5)
 
 
@@ -90,9 +93,9 @@ def test_linear_of_layernorm_folded(vitk, M, N, K, epi):
     gamma = torch.rand(N, generator=g, device="cuda") + 0.5
     beta = torch.randn(N, generator=g, device="cuda") * 0.1
     xb, st = vitk.ops.gemm_resid_stats(a, w, x, bias=bias)
-    w_ln, colsum, b_ln = vitk.ops.fold_layernorm(W2, gamma, beta, b2)
+    w_ln, b_ln, _ = vitk.ops.fold_layernorm(W2, gamma, beta, b2)
     e = vitk._lib.EPI_BF16 if epi == "bf16" else vitk._lib.EPI_GELU_TANH_BF16
-    out = vitk.ops.gemm_layernorm_folded(xb, w_ln, colsum, b_ln, st, epilogue=e)
+    out = vitk.ops.gemm_layernorm_folded(xb, w_ln, b_ln, st, epilogue=e)
     ref = F.linear(F.layer_norm(x, (N,), gamma, beta, 1e-5), W2, b2)
     if epi == "gelu":
         ref = F.gelu(ref)
@@ -106,22 +109,23 @@ def test_linear_of_layernorm_folded(vitk, M, N, K, epi):
     assert err < max(3 * err_two, 3e-2), (err, err_two)
     # entry of the chain (one partial per row) gives the same answer from the same x
     xb1, st1 = vitk.ops.row_stats(x)
-    out1 = vitk.ops.gemm_layernorm_folded(xb1, w_ln, colsum, b_ln, st1, epilogue=e)
+    out1 = vitk.ops.gemm_layernorm_folded(xb1, w_ln, b_ln, st1, epilogue=e)
     torch.testing.assert_close(out1.float(), out.float(), rtol=2e-2, atol=2e-2)
 
 
 def test_rows_with_a_large_common_offset(vitk):
-    """The folded form subtracts mu * colsum after the contraction: rows whose mean is large
-    against their spread are where it loses accuracy first - it must still meet the 2e-2 bar of
-    the model at a ratio |mean| / std of 4 (encoder rows sit far below 1)."""
+    """The folded form relies on zero-sum weight rows to drop the row mean inside the contraction;
+    bf16 rounding leaves ~1e-3 of the row sum, and the bf16 copy of x is rounded relative to |x|
+    and not |x - mean|: rows whose mean is large against their spread are where it loses accuracy
+    first.  Still inside the bar at |mean| / std = 4 (encoder rows sit far below 1)."""
     M, N = 256, 768
     g = torch.Generator(device="cuda").manual_seed(7)
     x = torch.randn(M, N, generator=g, device="cuda") + 4.0
     W2 = torch.randn(N, N, generator=g, device="cuda") / N ** 0.5
     gamma, beta = torch.ones(N, device="cuda"), torch.zeros(N, device="cuda")
     xb, st = vitk.ops.row_stats(x)
-    w_ln, colsum, b_ln = vitk.ops.fold_layernorm(W2, gamma, beta, None)
-    out = vitk.ops.gemm_layernorm_folded(xb, w_ln, colsum, b_ln, st)
+    w_ln, b_ln, _ = vitk.ops.fold_layernorm(W2, gamma, beta, None)
+    out = vitk.ops.gemm_layernorm_folded(xb, w_ln, b_ln, st)
     ref = F.linear(F.layer_norm(x, (N,)), W2)
     assert (out.float() - ref).abs().max().item() < 6e-2
 
@@ -132,6 +136,8 @@ def test_model_folded_matches_unfolded(vitk):
     model = vitk.ViTClassifier(num_classes=6, dropout=0.0, image_size=224, patch_size=16,
                                embed_dim=768, num_layers=4, num_heads=12, mlp_dim=3072).cuda().eval()
     x = torch.randn(5, 3, 224, 224, device="cuda")
+    with torch.no_grad():
+        model(x)                       # packs the weights (launches of its own)
     n0 = vitk.launch_count()
     with torch.no_grad():
         a = model(x)

@@ -126,9 +126,9 @@ def test_attention_long_sequence_moving_maximum(vitk, N, gap):
 
 
 def test_attention_rejects_other_head_dims(vitk):
-    qkv = torch.zeros(10, 3 * 32, device="cuda").bfloat16()
+    qkv = torch.zeros(10, 3 * 24, device="cuda").bfloat16()
     with pytest.raises(vitk.VitkError):
-        vitk.ops.attention(qkv, 1, 10, 2)   # head_dim 16
+        vitk.ops.attention(qkv, 1, 10, 2)   # head_dim 12: not a multiple of 8
 
 
 @pytest.mark.parametrize("rows,D,n_out", [(8, 768, 6), (3, 64, 6), (128, 1024, 256)])
