@@ -36,6 +36,8 @@ def test_workspace_query_and_config_validation(vitk):
     M = 256 * 197
     expect = M * 768 * 4 + M * 768 * 2 + M * 2304 * 2 + M * 768 * 2 + M * 3072 * 2 + 256 * 196 * 768 * 2
     expect += 256 * (768 * 4 + 768 * 2 + 3072 * 2)     # CLS-only tail of vitk_forward_cls
+    expect += lib.vitk_stats_parts(768) * M * 8         # row statistics of the folded LayerNorms
+    assert lib.vitk_stats_parts(768) == 6 and lib.vitk_stats_parts(1024) == 8
     assert expect <= need.value <= expect + 16 * 1024
     cfg.image_size = 225   # not a multiple of the patch size
     rc = lib.vitk_workspace_bytes(C.byref(cfg), 256, C.byref(need))
