@@ -10,7 +10,7 @@ from .modules import (DataEfficientImageTransformer, MLPBlock,  # noqa: F401
                       MultiHeadSelfAttention, PatchEmbedding, TransformerBlock, ViTClassifier,
                       VisionTransformer)
 from .detection import (DeiTObjectDetector, ObjectDetectionHead, ViTObjectDetector,  # noqa: F401
-                        post_process_predictions)
+                        post_process_predictions, weighted_cross_entropy)
 
 from .pipeline import HostBatchRunner  # noqa: E402,F401
 from .trainer import FineTuner, TrainState  # noqa: E402,F401
@@ -19,6 +19,6 @@ __all__ = [
     "HostBatchRunner", "FineTuner", "TrainState",
     "PatchEmbedding", "MultiHeadSelfAttention", "MLPBlock", "TransformerBlock",
     "VisionTransformer", "DataEfficientImageTransformer", "ViTClassifier", "VitkError",
-    "ObjectDetectionHead", "ViTObjectDetector", "DeiTObjectDetector", "post_process_predictions",
+    "ObjectDetectionHead", "ViTObjectDetector", "DeiTObjectDetector", "post_process_predictions", "weighted_cross_entropy",
     "launch_count", "ops",
 ]

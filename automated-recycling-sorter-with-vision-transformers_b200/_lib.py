@@ -91,6 +91,28 @@ class VitkDetectionHeadWeights(C.Structure):
                 ("class_b", C.c_void_p), ("bbox_w", C.c_void_p), ("bbox_b", C.c_void_p)]
 
 
+class VitkDecoderLayerWeightsT(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("sa_in_wt", "sa_out_wt", "ca_q_wt", "ca_out_wt", "ff1_wt",
+                                          "ff2_wt")]
+
+
+class VitkDetectionHeadWeightsT(C.Structure):
+    _fields_ = [("layers", C.POINTER(VitkDecoderLayerWeightsT)), ("ca_kv_wt", C.c_void_p)]
+
+
+class VitkDecoderLayerGrads(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "sa_in_w", "sa_in_b", "sa_out_w", "sa_out_b", "ca_q_w", "ca_q_b", "ca_out_w", "ca_out_b",
+        "ff1_w", "ff1_b", "ff2_w", "ff2_b", "norm1_w", "norm1_b", "norm2_w", "norm2_b", "norm3_w",
+        "norm3_b")]
+
+
+class VitkDetectionHeadGrads(C.Structure):
+    _fields_ = [("object_queries", C.c_void_p), ("layers", C.POINTER(VitkDecoderLayerGrads)),
+                ("ca_kv_w", C.c_void_p), ("ca_kv_b", C.c_void_p), ("class_w", C.c_void_p),
+                ("class_b", C.c_void_p), ("bbox_w", C.c_void_p), ("bbox_b", C.c_void_p)]
+
+
 # name -> (restype, argtypes); must list every symbol include/vitk.h declares.
 _SIGNATURES = {
     "vitk_abi_version": (C.c_int, []),
@@ -198,6 +220,23 @@ _SIGNATURES = {
                                               C.POINTER(VitkDetectionHeadWeights), C.c_void_p,
                                               C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                               C.c_void_p, C.c_size_t, C.c_void_p]),
+    "vitk_detection_head_train_bytes": (C.c_int, [C.POINTER(VitkDetectionHeadConfig), C.c_int,
+                                                  C.c_int, C.c_int, C.POINTER(C.c_size_t),
+                                                  C.POINTER(C.c_size_t)]),
+    "vitk_detection_head_forward_train": (C.c_int, [C.POINTER(VitkDetectionHeadConfig),
+                                                    C.POINTER(VitkDetectionHeadWeights), C.c_void_p,
+                                                    C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                                    C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p,
+                                                    C.c_size_t, C.c_void_p]),
+    "vitk_detection_head_backward": (C.c_int, [C.POINTER(VitkDetectionHeadConfig),
+                                               C.POINTER(VitkDetectionHeadWeights),
+                                               C.POINTER(VitkDetectionHeadWeightsT),
+                                               C.POINTER(VitkDetectionHeadGrads), C.c_void_p,
+                                               C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vitk_weighted_cross_entropy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_float,
+                                              C.c_void_p]),
 }
 
 

@@ -512,6 +512,14 @@ int vitk_attention_bwd(const void* qkv_bf16, const void* ctx_bf16, const void* d
                        head_dim, static_cast<cudaStream_t>(stream));
 }
 
+int vitk_weighted_cross_entropy(const float* logits, const long long* targets,
+                                const float* class_weight, int rows, int n_classes, float* loss_out,
+                                float* sums_ws, float* dlogits_out, float grad_scale,
+                                vitk_stream_t stream) {
+  return weighted_cross_entropy(logits, targets, class_weight, rows, n_classes, loss_out, sums_ws,
+                                dlogits_out, grad_scale, static_cast<cudaStream_t>(stream));
+}
+
 int vitk_colsum_bf16(const void* y, long long ld, int M, int N, float* out, vitk_stream_t stream) {
   return colsum_bf16(y, ld, M, N, out, static_cast<cudaStream_t>(stream));
 }

@@ -272,6 +272,184 @@ attn_gen_bwd_kernel(const GenParams p) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Generic-source form (decoder layers of the detection head under training, train.py:691-731 /
+// 842-845 differentiated at :1455): queries, keys / values, context and every gradient have their
+// own base pointer, row pitch and per-image pitch, and there may be a different number of queries
+// and keys (100 object queries against 196 patch tokens).  Same arithmetic as the kernels above.
+// ---------------------------------------------------------------------------------------------
+struct XParams {
+  const __nv_bfloat16 *q, *k, *v, *ctx, *dctx;
+  __nv_bfloat16 *out, *dq, *dk, *dv;
+  float* lse;
+  long long q_img, kv_img, ctx_img, dq_img, dkv_img;
+  int ldq, ldkv, ldc, lddq, lddkv;
+  int Nq, Nk, H, hd, hdp;
+  float scale;
+};
+
+// forward: K, V of the head resident in shared memory; one warp per query row
+__global__ void __launch_bounds__(kGenThreads)
+attn_xgen_fwd_kernel(const XParams p) {
+  extern __shared__ __align__(16) uint8_t smem_gen[];
+  const int Nk = p.Nk, hd = p.hd, hdp = p.hdp;
+  __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(smem_gen);
+  __nv_bfloat16* sV = sK + Nk * hdp;
+  float* sw = reinterpret_cast<float*>(sV + Nk * hdp);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* sq = sw + warp * (hd + Nk);
+  float* sp = sq + hd;
+  const int bh = blockIdx.y, b = bh / p.H, h = bh - b * p.H;
+  stage_rows(sK, p.k + b * p.kv_img + h * hd, p.ldkv, Nk, hd, hdp);
+  stage_rows(sV, p.v + b * p.kv_img + h * hd, p.ldkv, Nk, hd, hdp);
+  __syncthreads();
+  const __nv_bfloat16* qb = p.q + b * p.q_img + h * hd;
+  const int i_end = min(p.Nq, (blockIdx.x + 1) * kGenRowsPerBlock);
+  for (int i = blockIdx.x * kGenRowsPerBlock + warp; i < i_end; i += kGenWarps) {
+    for (int d = lane; d < hd; d += 32) sq[d] = __bfloat162float(qb[static_cast<long long>(i) * p.ldq + d]);
+    __syncwarp();
+    float s[kGenMaxKeysPerLane];
+    float m = -INFINITY;
+#pragma unroll
+    for (int t = 0; t < kGenMaxKeysPerLane; ++t) {
+      const int j = lane + 32 * t;
+      if (j < Nk) {
+        s[t] = dot_row(sq, sK + j * hdp, hd) * p.scale;
+        m = fmaxf(m, s[t]);
+      }
+    }
+    m = warp_max(m);
+    float sum = 0.f;
+#pragma unroll
+    for (int t = 0; t < kGenMaxKeysPerLane; ++t) {
+      const int j = lane + 32 * t;
+      if (j < Nk) {
+        s[t] = __expf(s[t] - m);
+        sum += s[t];
+      }
+    }
+    sum = warp_add(sum);
+    const float inv = 1.f / sum;
+    if (lane == 0 && p.lse != nullptr) p.lse[static_cast<long long>(bh) * p.Nq + i] = m + __logf(sum);
+#pragma unroll
+    for (int t = 0; t < kGenMaxKeysPerLane; ++t) {
+      const int j = lane + 32 * t;
+      if (j < Nk) sp[j] = s[t] * inv;
+    }
+    __syncwarp();
+    float o[4];
+    weighted_sum(sp, sV, Nk, hd, hdp, lane, o);
+    __nv_bfloat16* orow = p.out + b * p.ctx_img + static_cast<long long>(i) * p.ldc + h * hd;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (lane + 32 * q < hd) orow[lane + 32 * q] = __float2bfloat16_rn(o[q]);
+    __syncwarp();
+  }
+}
+
+// backward.  blockIdx.z == 0: query rows (K, V resident) -> dQ;  == 1: key rows (Q, dO, lse and
+// dO . O resident) -> dK, dV.  Per-warp scratch: two fp32 vectors [hd] and two fp32 arrays of the
+// other side's length.
+__global__ void __launch_bounds__(kGenThreads)
+attn_xgen_bwd_kernel(const XParams p) {
+  extern __shared__ __align__(16) uint8_t smem_gen[];
+  const int Nq = p.Nq, Nk = p.Nk, hd = p.hd, hdp = p.hdp;
+  const int pass = blockIdx.z;
+  const int n_res = pass == 0 ? Nk : Nq;   // rows resident in shared memory
+  const int n_own = pass == 0 ? Nq : Nk;   // rows distributed over the warps
+  if (blockIdx.x * kGenRowsPerBlock >= n_own) return;
+  __nv_bfloat16* sA = reinterpret_cast<__nv_bfloat16*>(smem_gen);
+  __nv_bfloat16* sB = sA + n_res * hdp;
+  float* s_lse = reinterpret_cast<float*>(sB + n_res * hdp);
+  float* s_drow = s_lse + n_res;
+  float* sw = s_drow + n_res;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* v0 = sw + warp * (2 * hd + 2 * n_res);
+  float* v1 = v0 + hd;
+  float* w0 = v1 + hd;
+  float* w1 = w0 + n_res;
+  const int bh = blockIdx.y, b = bh / p.H, h = bh - b * p.H;
+  const __nv_bfloat16* q = p.q + b * p.q_img + h * hd;
+  const __nv_bfloat16* k = p.k + b * p.kv_img + h * hd;
+  const __nv_bfloat16* v = p.v + b * p.kv_img + h * hd;
+  const __nv_bfloat16* ctx = p.ctx + b * p.ctx_img + h * hd;
+  const __nv_bfloat16* dctx = p.dctx + b * p.ctx_img + h * hd;
+  const float* lse = p.lse + static_cast<long long>(bh) * Nq;
+  if (pass == 0) {
+    stage_rows(sA, k, p.ldkv, Nk, hd, hdp);
+    stage_rows(sB, v, p.ldkv, Nk, hd, hdp);
+  } else {
+    stage_rows(sA, q, p.ldq, Nq, hd, hdp);
+    stage_rows(sB, dctx, p.ldc, Nq, hd, hdp);
+    for (int i = threadIdx.x; i < Nq; i += blockDim.x) s_lse[i] = lse[i];
+  }
+  __syncthreads();
+  if (pass == 1) {
+    for (int i = warp; i < Nq; i += kGenWarps) {
+      float acc = 0.f;
+      for (int d = lane; d < hd; d += 32)
+        acc = fmaf(__bfloat162float(sB[i * hdp + d]),
+                   __bfloat162float(ctx[static_cast<long long>(i) * p.ldc + d]), acc);
+      acc = warp_add(acc);
+      if (lane == 0) s_drow[i] = acc;
+    }
+    __syncthreads();
+  }
+  const int r_end = min(n_own, (blockIdx.x + 1) * kGenRowsPerBlock);
+  for (int r = blockIdx.x * kGenRowsPerBlock + warp; r < r_end; r += kGenWarps) {
+    if (pass == 0) {
+      const int i = r;
+      float dr = 0.f;
+      for (int d = lane; d < hd; d += 32) {
+        const float go = __bfloat162float(dctx[static_cast<long long>(i) * p.ldc + d]);
+        v0[d] = __bfloat162float(q[static_cast<long long>(i) * p.ldq + d]);
+        v1[d] = go;
+        dr = fmaf(go, __bfloat162float(ctx[static_cast<long long>(i) * p.ldc + d]), dr);
+      }
+      dr = warp_add(dr);
+      const float lse_i = lse[i];
+      __syncwarp();
+      for (int j = lane; j < Nk; j += 32) {
+        const float pij = __expf(dot_row(v0, sA + j * hdp, hd) * p.scale - lse_i);
+        const float dp = dot_row(v1, sB + j * hdp, hd);
+        w0[j] = pij * (dp - dr) * p.scale;
+      }
+      __syncwarp();
+      float o[4];
+      weighted_sum(w0, sA, Nk, hd, hdp, lane, o);
+      __nv_bfloat16* out = p.dq + b * p.dq_img + static_cast<long long>(i) * p.lddq + h * hd;
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+        if (lane + 32 * t < hd) out[lane + 32 * t] = __float2bfloat16_rn(o[t]);
+    } else {
+      const int j = r;
+      for (int d = lane; d < hd; d += 32) {
+        v0[d] = __bfloat162float(k[static_cast<long long>(j) * p.ldkv + d]);
+        v1[d] = __bfloat162float(v[static_cast<long long>(j) * p.ldkv + d]);
+      }
+      __syncwarp();
+      for (int i = lane; i < Nq; i += 32) {
+        const float pij = __expf(dot_row(v0, sA + i * hdp, hd) * p.scale - s_lse[i]);
+        const float dp = dot_row(v1, sB + i * hdp, hd);
+        w0[i] = pij * (dp - s_drow[i]) * p.scale;
+        w1[i] = pij;
+      }
+      __syncwarp();
+      float dk[4], dv[4];
+      weighted_sum(w0, sA, Nq, hd, hdp, lane, dk);
+      weighted_sum(w1, sB, Nq, hd, hdp, lane, dv);
+      const long long off = b * p.dkv_img + static_cast<long long>(j) * p.lddkv + h * hd;
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+        if (lane + 32 * t < hd) {
+          p.dk[off + lane + 32 * t] = __float2bfloat16_rn(dk[t]);
+          p.dv[off + lane + 32 * t] = __float2bfloat16_rn(dv[t]);
+        }
+    }
+    __syncwarp();
+  }
+}
+
 int check_shape(int B, int N, int H, int hd, const DropParams* drop) {
   VITK_REQUIRE(B > 0 && N > 0 && H > 0, "attention (generic): bad shape B=%d N=%d H=%d", B, N, H);
   VITK_REQUIRE(hd >= 8 && hd <= 128 && hd % 8 == 0,
@@ -361,6 +539,78 @@ int attention_gen_bwd(const void* qkv, const void* ctx, const void* dctx, const 
   VITK_CHECK_LAUNCH("attn_gen_bwd_kernel");
   if (dbias != nullptr)   // bias gradient of the qkv Linear: column sums of dqkv
     return colsum_bf16(dqkv, 3ll * H * hd, B * N, 3 * H * hd, dbias, stream);
+  return VITK_OK;
+}
+
+namespace {
+int xgen_check(const AttnXSrc& s, int B, int Nq, int Nk, int H, int hd) {
+  VITK_REQUIRE(s.q && s.k && s.v, "attention (generic sources): null operand");
+  VITK_REQUIRE(B > 0 && Nq > 0 && Nk > 0 && H > 0, "attention (generic sources): bad shape");
+  VITK_REQUIRE(hd >= 8 && hd <= 128 && hd % 8 == 0,
+               "attention (generic sources): head_dim %d unsupported (8 .. 128 in steps of 8)", hd);
+  VITK_REQUIRE(Nq <= 32 * kGenMaxKeysPerLane && Nk <= 32 * kGenMaxKeysPerLane,
+               "attention (generic sources): at most %d queries / keys", 32 * kGenMaxKeysPerLane);
+  VITK_REQUIRE(s.ldq % 8 == 0 && s.ldkv % 8 == 0 && s.q_img % 8 == 0 && s.kv_img % 8 == 0,
+               "attention (generic sources): pitches must be multiples of 8 elements");
+  return VITK_OK;
+}
+}  // namespace
+
+int attention_xgen_fwd(const AttnXSrc& s, void* ctx, long long ctx_img, int ldc, float* lse, int B,
+                       int Nq, int Nk, int H, int hd, cudaStream_t stream) {
+  VITK_TRY(xgen_check(s, B, Nq, Nk, H, hd));
+  VITK_REQUIRE(ctx != nullptr, "attention (generic sources): null output");
+  XParams p{};
+  p.q = static_cast<const __nv_bfloat16*>(s.q);
+  p.k = static_cast<const __nv_bfloat16*>(s.k);
+  p.v = static_cast<const __nv_bfloat16*>(s.v);
+  p.out = static_cast<__nv_bfloat16*>(ctx);
+  p.lse = lse;
+  p.q_img = s.q_img; p.kv_img = s.kv_img; p.ctx_img = ctx_img;
+  p.ldq = s.ldq; p.ldkv = s.ldkv; p.ldc = ldc;
+  p.Nq = Nq; p.Nk = Nk; p.H = H; p.hd = hd; p.hdp = hd + 8;
+  p.scale = 1.0f / sqrtf(static_cast<float>(hd));
+  const size_t smem = 2 * static_cast<size_t>(Nk) * p.hdp * 2 + kGenWarps * (static_cast<size_t>(hd) + Nk) * 4;
+  VITK_REQUIRE(smem <= 232448, "attention (generic sources): %d keys x head_dim %d do not fit in "
+               "shared memory", Nk, hd);
+  VITK_TRY(raise_smem(attn_xgen_fwd_kernel, smem, "attn_xgen_fwd_kernel"));
+  ProfileScope prof(PROF_ATTN, 4.0 * B * H * static_cast<double>(Nq) * Nk * hd, stream);
+  const dim3 grid((Nq + kGenRowsPerBlock - 1) / kGenRowsPerBlock, B * H);
+  attn_xgen_fwd_kernel<<<grid, kGenThreads, smem, stream>>>(p);
+  VITK_CHECK_LAUNCH("attn_xgen_fwd_kernel");
+  return VITK_OK;
+}
+
+int attention_xgen_bwd(const AttnXSrc& s, const void* ctx, const void* dctx, long long ctx_img,
+                       int ldc, const float* lse, void* dq, long long dq_img, int lddq, void* dk,
+                       void* dv, long long dkv_img, int lddkv, int B, int Nq, int Nk, int H, int hd,
+                       cudaStream_t stream) {
+  VITK_TRY(xgen_check(s, B, Nq, Nk, H, hd));
+  VITK_REQUIRE(ctx && dctx && lse && dq && dk && dv, "attention_bwd (generic sources): null operand");
+  XParams p{};
+  p.q = static_cast<const __nv_bfloat16*>(s.q);
+  p.k = static_cast<const __nv_bfloat16*>(s.k);
+  p.v = static_cast<const __nv_bfloat16*>(s.v);
+  p.ctx = static_cast<const __nv_bfloat16*>(ctx);
+  p.dctx = static_cast<const __nv_bfloat16*>(dctx);
+  p.dq = static_cast<__nv_bfloat16*>(dq);
+  p.dk = static_cast<__nv_bfloat16*>(dk);
+  p.dv = static_cast<__nv_bfloat16*>(dv);
+  p.lse = const_cast<float*>(lse);
+  p.q_img = s.q_img; p.kv_img = s.kv_img; p.ctx_img = ctx_img; p.dq_img = dq_img; p.dkv_img = dkv_img;
+  p.ldq = s.ldq; p.ldkv = s.ldkv; p.ldc = ldc; p.lddq = lddq; p.lddkv = lddkv;
+  p.Nq = Nq; p.Nk = Nk; p.H = H; p.hd = hd; p.hdp = hd + 8;
+  p.scale = 1.0f / sqrtf(static_cast<float>(hd));
+  const size_t nmax = static_cast<size_t>(Nq > Nk ? Nq : Nk);
+  const size_t smem = 2 * nmax * p.hdp * 2 + 2 * nmax * 4 + kGenWarps * (2 * static_cast<size_t>(hd) + 2 * nmax) * 4;
+  VITK_REQUIRE(smem <= 232448, "attention_bwd (generic sources): %d x head_dim %d do not fit in "
+               "shared memory", static_cast<int>(nmax), hd);
+  VITK_TRY(raise_smem(attn_xgen_bwd_kernel, smem, "attn_xgen_bwd_kernel"));
+  ProfileScope prof(PROF_ATTN, 10.0 * B * H * static_cast<double>(Nq) * Nk * hd, stream);
+  const int rows = Nq > Nk ? Nq : Nk;
+  const dim3 grid((rows + kGenRowsPerBlock - 1) / kGenRowsPerBlock, B * H, 2);
+  attn_xgen_bwd_kernel<<<grid, kGenThreads, smem, stream>>>(p);
+  VITK_CHECK_LAUNCH("attn_xgen_bwd_kernel");
   return VITK_OK;
 }
 

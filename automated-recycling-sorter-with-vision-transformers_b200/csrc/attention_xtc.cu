@@ -42,6 +42,7 @@ struct XtcParams {
   int ldc;
   int B, H, Nq, Nkeys, Nk;  // Nk = keys rounded up to 16
   float scale;
+  float* lse;  // optional [B, H, Nq]: natural log of the row sums of exp(scaled scores) (training)
 };
 
 template <int HD>
@@ -262,6 +263,8 @@ attn_xtc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
         tmem_st_wait();
         inv_l = 1.f / l;
+        if (p.lse != nullptr && row < p.Nq)
+          p.lse[static_cast<long long>(item) * p.Nq + row] = fmaf(m, p.scale, __logf(l));
       }
       tc_fence_before();
       __syncwarp();
@@ -348,7 +351,7 @@ bool attention_xtc_applicable(long long q_img, long long kv_img, int B, int Nq, 
 
 int attention_xtc(const void* q, long long q_img, int ldq, const void* k, const void* v,
                   long long kv_img, int ldkv, void* ctx, long long ctx_img, int ldc, int B, int Nq,
-                  int Nk, int H, int hd, cudaStream_t stream) {
+                  int Nk, int H, int hd, cudaStream_t stream, float* lse) {
   VITK_REQUIRE(q && k && v && ctx, "attention: null operand");
   VITK_REQUIRE(attention_xtc_applicable(q_img, kv_img, B, Nq, Nk, hd),
                "attention(xtc): needs <= 128 queries, <= 256 keys, head_dim 32/64/96/128");
@@ -364,6 +367,7 @@ int attention_xtc(const void* q, long long q_img, int ldq, const void* k, const 
   prm.Nkeys = Nk;
   prm.Nk = (Nk + 15) & ~15;
   prm.scale = 1.0f / sqrtf(static_cast<float>(hd));
+  prm.lse = lse;
   // a single image has no batch stride: any positive pitch describes it
   if (B == 1) {
     if (q_img <= 0) q_img = static_cast<long long>(Nq) * ldq;

@@ -91,7 +91,22 @@ int attention_x(const void* q, long long q_img, int ldq, const void* k, const vo
 bool attention_xtc_applicable(long long q_img, long long kv_img, int B, int Nq, int Nk, int hd);
 int attention_xtc(const void* q, long long q_img, int ldq, const void* k, const void* v,
                   long long kv_img, int ldkv, void* ctx, long long ctx_img, int ldc, int B, int Nq,
-                  int Nk, int H, int hd, cudaStream_t stream);
+                  int Nk, int H, int hd, cudaStream_t stream, float* lse = nullptr);
+// Generic-source attention on CUDA cores with the log-sum-exp output, and its backward
+// (attention_gen.cu): the decoder layers of the detection head under training (any head_dim
+// 8 .. 128 in steps of 8, up to 1024 queries / keys).  Strides in elements; lse f32 [B, H, Nq].
+// Backward: dq rows at dq + b*dq_img + r*lddq + h*hd, dk / dv rows at dk|dv + b*dkv_img + r*lddkv +
+// h*hd (overwritten).
+struct AttnXSrc {
+  const void* q; long long q_img; int ldq;
+  const void* k; const void* v; long long kv_img; int ldkv;
+};
+int attention_xgen_fwd(const AttnXSrc& s, void* ctx, long long ctx_img, int ldc, float* lse, int B,
+                       int Nq, int Nk, int H, int hd, cudaStream_t stream);
+int attention_xgen_bwd(const AttnXSrc& s, const void* ctx, const void* dctx, long long ctx_img,
+                       int ldc, const float* lse, void* dq, long long dq_img, int lddq, void* dk,
+                       void* dv, long long dkv_img, int lddkv, int B, int Nq, int Nk, int H, int hd,
+                       cudaStream_t stream);
 // CUDA-core attention for the shapes the tensor-core kernels do not cover (attention_gen.cu):
 // head_dim 8 .. 128 in steps of 8, up to 1024 tokens, optional log-sum-exp output and
 // attention-probability dropout - forward and (train_ops.cuh: attention_bwd) backward.

@@ -673,6 +673,75 @@ dropout_kernel(float* __restrict__ x, __nv_bfloat16* __restrict__ out_bf16,
   }
 }
 
+// SetCriterion.loss_labels (train.py:1220-1239): F.cross_entropy(logits, targets, weight) = the
+// weighted mean  sum_i w[t_i] nll_i / sum_i w[t_i].  Pass 1: thread = row, log-sum-exp over the few
+// classes, block-reduced (sum w nll, sum w) -> two atomics per block.  Pass 2: loss and
+// dlogits[i, c] = grad_scale * w[t_i] (softmax_ic - [c == t_i]) / sum w.
+__global__ void __launch_bounds__(256)
+wce_sums_kernel(const float* __restrict__ logits, const long long* __restrict__ targets,
+                const float* __restrict__ weight, int rows, int C, float* __restrict__ sums) {
+  __shared__ float s_red[2][8];
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  float wn = 0.f, ws = 0.f;
+  if (r < rows) {
+    const float* lr = logits + static_cast<long long>(r) * C;
+    float m = -INFINITY;
+    for (int c = 0; c < C; ++c) m = fmaxf(m, lr[c]);
+    float z = 0.f;
+    for (int c = 0; c < C; ++c) z += __expf(lr[c] - m);
+    const long long t = targets[r];
+    if (t >= 0 && t < C) {   // (F.cross_entropy's ignore_index rows carry no weight)
+      const float w = weight != nullptr ? weight[t] : 1.f;
+      wn = w * (m + __logf(z) - lr[t]);
+      ws = w;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    wn += __shfl_xor_sync(0xffffffffu, wn, o);
+    ws += __shfl_xor_sync(0xffffffffu, ws, o);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+    s_red[0][warp] = wn;
+    s_red[1][warp] = ws;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, b = 0.f;
+    for (int i = 0; i < 8; ++i) {
+      a += s_red[0][i];
+      b += s_red[1][i];
+    }
+    atomicAdd(sums, a);
+    atomicAdd(sums + 1, b);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+wce_grad_kernel(const float* __restrict__ logits, const long long* __restrict__ targets,
+                const float* __restrict__ weight, int rows, int C, const float* __restrict__ sums,
+                float* __restrict__ loss_out, float* __restrict__ dlogits, float grad_scale) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  const float wsum = sums[1];
+  if (r == 0 && loss_out != nullptr) *loss_out = sums[0] / wsum;
+  if (dlogits == nullptr || r >= rows) return;
+  const float* lr = logits + static_cast<long long>(r) * C;
+  float* dr = dlogits + static_cast<long long>(r) * C;
+  const long long t = targets[r];
+  if (t < 0 || t >= C) {
+    for (int c = 0; c < C; ++c) dr[c] = 0.f;
+    return;
+  }
+  float m = -INFINITY;
+  for (int c = 0; c < C; ++c) m = fmaxf(m, lr[c]);
+  float z = 0.f;
+  for (int c = 0; c < C; ++c) z += __expf(lr[c] - m);
+  const float k = grad_scale * (weight != nullptr ? weight[t] : 1.f) / wsum;
+  const float inv_z = 1.f / z;
+  for (int c = 0; c < C; ++c) dr[c] = k * (__expf(lr[c] - m) * inv_z - (c == t ? 1.f : 0.f));
+}
+
 }  // namespace
 
 int dropout_f32_inplace(float* x, long long n, const DropParams& d, cudaStream_t stream) {
@@ -900,6 +969,23 @@ int adamw_flat(float* p, const float* g, float* m, float* v, void* shadow_bf16, 
       static_cast<float>(beta2), static_cast<float>(1.0 - beta1), static_cast<float>(1.0 - beta2),
       step_size, inv_sqrt_bc2, static_cast<float>(eps), grad_scale, guard, lr, beta1, beta2, step);
   VITK_CHECK_LAUNCH("adamw_kernel");
+  return VITK_OK;
+}
+
+int weighted_cross_entropy(const float* logits, const long long* targets, const float* weight,
+                           int rows, int C, float* loss_out, float* sums_ws, float* dlogits,
+                           float grad_scale, cudaStream_t stream) {
+  VITK_REQUIRE(logits && targets && sums_ws && (loss_out || dlogits),
+               "weighted_cross_entropy: null operand");
+  VITK_REQUIRE(rows > 0 && C > 0 && C <= 4096, "weighted_cross_entropy: bad shape %d x %d", rows, C);
+  VITK_CHECK_CUDA(cudaMemsetAsync(sums_ws, 0, 2 * sizeof(float), stream));
+  ProfileScope prof(PROF_OTHER, static_cast<double>(rows) * C * 12.0, stream);
+  const int grid = (rows + 255) / 256;
+  wce_sums_kernel<<<grid, 256, 0, stream>>>(logits, targets, weight, rows, C, sums_ws);
+  VITK_CHECK_LAUNCH("wce_sums_kernel");
+  wce_grad_kernel<<<grid, 256, 0, stream>>>(logits, targets, weight, rows, C, sums_ws, loss_out,
+                                            dlogits, grad_scale);
+  VITK_CHECK_LAUNCH("wce_grad_kernel");
   return VITK_OK;
 }
 

@@ -27,6 +27,12 @@ int cls_loss_bwd(const float* x, long long row_stride, const float* gamma, const
                  float* dlogits_ws, float* dx, void* dx_bf16, float* dgamma, float* dbeta,
                  float* dhead_w, float* dhead_b, cudaStream_t stream);
 
+// F.cross_entropy(logits, targets, weight) - the weighted mean of SetCriterion.loss_labels
+// (train.py:1220-1239) - and grad_scale * its gradient.  sums_ws: 2 floats of scratch.
+int weighted_cross_entropy(const float* logits, const long long* targets, const float* weight,
+                           int rows, int C, float* loss_out, float* sums_ws, float* dlogits,
+                           float grad_scale, cudaStream_t stream);
+
 // dpos[t,:] += sum_b dx[b,t,:]; dxp = bf16 copy of the patch rows of dx.
 int token_grads(const float* dx, int B, int Ntok, int D, int prefix, float* dpos, float* dcls,
                 float* ddist, void* dxp_bf16, cudaStream_t stream);

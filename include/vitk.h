@@ -514,6 +514,96 @@ int vitk_detection_head_forward(const VitkDetectionHeadConfig* cfg,
                                 float* bbox_out, void* workspace, size_t workspace_bytes,
                                 vitk_stream_t stream);
 
+/* ---- training through the head (train.py:842-845 under losses.backward(), train.py:1455) ----
+ * The forward below is the eval-mode arithmetic (the decoder layers' dropout is not applied:
+ * p = 0 semantics) with every activation the backward needs kept in `saved`. */
+
+/* W^T copies (bf16 [in, out]) for the input-gradient GEMMs. */
+typedef struct VitkDecoderLayerWeightsT {
+  const void* sa_in_wt;  /* [D, 3D] */
+  const void* sa_out_wt; /* [D, D]  */
+  const void* ca_q_wt;   /* [D, D]  */
+  const void* ca_out_wt; /* [D, D]  */
+  const void* ff1_wt;    /* [D, F]  */
+  const void* ff2_wt;    /* [F, D]  */
+} VitkDecoderLayerWeightsT;
+
+typedef struct VitkDetectionHeadWeightsT {
+  const VitkDecoderLayerWeightsT* layers; /* HOST array of num_layers entries */
+  const void* ca_kv_wt;                   /* [D, L*2D] */
+} VitkDetectionHeadWeightsT;
+
+/* fp32 gradient buffers with the shapes of VitkDecoderLayerWeights / VitkDetectionHeadWeights;
+ * the backward ACCUMULATES into them, the caller zeroes them once per step. */
+typedef struct VitkDecoderLayerGrads {
+  float* sa_in_w;
+  float* sa_in_b;
+  float* sa_out_w;
+  float* sa_out_b;
+  float* ca_q_w;
+  float* ca_q_b;
+  float* ca_out_w;
+  float* ca_out_b;
+  float* ff1_w;
+  float* ff1_b;
+  float* ff2_w;
+  float* ff2_b;
+  float* norm1_w;
+  float* norm1_b;
+  float* norm2_w;
+  float* norm2_b;
+  float* norm3_w;
+  float* norm3_b;
+} VitkDecoderLayerGrads;
+
+typedef struct VitkDetectionHeadGrads {
+  float* object_queries;               /* [Q, D] */
+  const VitkDecoderLayerGrads* layers; /* HOST array of num_layers entries */
+  float* ca_kv_w;                      /* [L*2D, D] */
+  float* ca_kv_b;                      /* [L*2D] */
+  float* class_w;
+  float* class_b;
+  float* bbox_w;
+  float* bbox_b;
+} VitkDetectionHeadGrads;
+
+/* Bytes of the saved-activation buffer and of the scratch shared by forward and backward. */
+int vitk_detection_head_train_bytes(const VitkDetectionHeadConfig* cfg, int batch, int n_tokens,
+                                    int skip_tokens, size_t* saved_bytes, size_t* workspace_bytes);
+
+/* vitk_detection_head_forward keeping the activations (both buffers 1024-byte aligned). */
+int vitk_detection_head_forward_train(const VitkDetectionHeadConfig* cfg,
+                                      const VitkDetectionHeadWeights* w, const float* tokens,
+                                      int batch, int n_tokens, int skip_tokens,
+                                      float* class_logits_out, float* bbox_out, void* saved,
+                                      size_t saved_bytes, void* workspace, size_t workspace_bytes,
+                                      vitk_stream_t stream);
+
+/* Backward of the above: d_class_logits f32 [batch, Q, num_outputs] and d_bbox f32 [batch, Q, 4]
+ * (gradient w.r.t. the SIGMOID output; bbox = what the forward returned) ->
+ * every parameter gradient (accumulated) and d_tokens_out f32 [batch, n_tokens, D] (overwritten;
+ * rows of the skipped prefix tokens are zero; may be NULL).  All hand-written kernels: tcgen05
+ * GEMMs for the input and weight gradients, CUDA-core attention backward with separate query and
+ * key / value sources, fused LayerNorm backward. */
+int vitk_detection_head_backward(const VitkDetectionHeadConfig* cfg,
+                                 const VitkDetectionHeadWeights* w,
+                                 const VitkDetectionHeadWeightsT* wt,
+                                 const VitkDetectionHeadGrads* grads, const float* d_class_logits,
+                                 const float* d_bbox, const float* bbox, int batch, int n_tokens,
+                                 int skip_tokens, float* d_tokens_out, void* saved, void* workspace,
+                                 vitk_stream_t stream);
+
+/* SetCriterion.loss_labels (train.py:1220-1239): F.cross_entropy(logits, targets, class_weight) -
+ * the weighted mean  sum_i w[t_i] * (-log softmax(logits_i)[t_i]) / sum_i w[t_i]  over `rows`
+ * predictions (every query of every image; background weight 0.1, train.py:1215-1217).
+ * logits f32 [rows, n_classes], targets i64 [rows], class_weight f32 [n_classes] or NULL (ones).
+ * loss_out: 1 float; sums_ws: 2 floats of scratch; dlogits_out (optional) f32 [rows, n_classes] =
+ * grad_scale * dLoss/dlogits. */
+int vitk_weighted_cross_entropy(const float* logits, const long long* targets,
+                                const float* class_weight, int rows, int n_classes, float* loss_out,
+                                float* sums_ws, float* dlogits_out, float grad_scale,
+                                vitk_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -213,9 +213,9 @@ def test_head_rejects_bad_arguments(vitk):
             head(torch.zeros(1, 4, 256))                       # CPU tensor: no fallback
         with pytest.raises(vitk.VitkError):
             head.decode(torch.zeros(1, 2, 256, device="cuda"), skip_tokens=2)   # empty memory
-    head.train()
-    with pytest.raises(vitk.VitkError):
-        head(torch.zeros(1, 4, 256, device="cuda"))            # training mode is not accelerated
+    head.train()                                               # training mode: the autograd path
+    out = head(torch.zeros(1, 4, 256, device="cuda"))
+    assert out["class_logits"].requires_grad and out["bbox_coords"].requires_grad
     bad = vitk.ObjectDetectionHead(embed_dim=64, num_classes=6, num_queries=4).eval().cuda()
     with torch.no_grad(), pytest.raises(vitk.VitkError):
         bad(torch.zeros(1, 4, 64, device="cuda"))              # head_dim 8 unsupported
