@@ -833,6 +833,27 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
       }
     };
     [[maybe_unused]] int ln_pending = -1;
+    // folded LayerNorm (consumer side): partial sums of the next tile's row, in flight
+    [[maybe_unused]] float2 ln_next[8];
+    [[maybe_unused]] float ln_rstd_next = 1.f;
+    [[maybe_unused]] bool ln_have_next = false;
+    [[maybe_unused]] auto ln_load_stats = [&](int m, float2 (&t)[8]) {
+#pragma unroll
+      for (int p2 = 0; p2 < 8; ++p2) {
+        t[p2] = make_float2(0.f, 0.f);
+        // volatile: issued HERE (before the wait for the accumulator), not sunk to the use
+        if (p2 < e.ln_nparts && m < M)
+          asm volatile("ld.global.nc.v2.f32 {%0, %1}, [%2];"
+                       : "=f"(t[p2].x), "=f"(t[p2].y)
+                       : "l"(e.ln_part + static_cast<size_t>(p2) * M + m));
+      }
+    };
+    [[maybe_unused]] auto ln_finish = [&](float s1, float s2) {
+      const float inv_d = 1.f / static_cast<float>(e.ln_dim);
+      const float mean = s1 * inv_d;
+      const float var = fmaxf(fmaf(-mean, mean, s2 * inv_d), 0.f);
+      return rsqrtf(var + e.ln_eps);
+    };
     for (int work = cluster_id; work < num_tiles; work += num_clusters) {
       const int tile = tile_of(work);
       const int m_blk = tile / num_n_tiles;
@@ -868,37 +889,26 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
       [[maybe_unused]] float ln_rstd = 1.f;
       if constexpr (TMA_EPI && (EPI == EPI_BF16 || is_gelu_epi<EPI>())) {
         if (e.ln_part != nullptr) {
-          // up to 8 independent loads in flight (a runtime-bounded loop would serialise them)
-          float s1 = 0.f, s2 = 0.f;
-          if (row0 + lane < M) {
-            float2 t[8];
-#pragma unroll
-            for (int p2 = 0; p2 < 8; ++p2)
-              t[p2] = p2 < e.ln_nparts
-                          ? __ldg(e.ln_part + static_cast<size_t>(p2) * M + (row0 + lane))
-                          : make_float2(0.f, 0.f);
+          // rstd of this thread's row of THIS tile: reduced at the end of the previous tile's
+          // epilogue from loads issued at its start (below), so the round trip to L2 is hidden;
+          // only the first tile of a CTA pays it
+          if (ln_have_next) {
+            ln_rstd = ln_rstd_next;
+          } else {
+            float s1 = 0.f, s2 = 0.f;
+            ln_load_stats(row0 + lane, ln_next);
 #pragma unroll
             for (int p2 = 0; p2 < 8; ++p2) {
-              s1 += t[p2].x;
-              s2 += t[p2].y;
+              s1 += ln_next[p2].x;
+              s2 += ln_next[p2].y;
             }
+            ln_rstd = ln_finish(s1, s2);
           }
-          // the next tile's statistics -> L1 while this tile's epilogue runs
+          // the next tile's partial sums: up to 8 independent loads in flight under this epilogue
           const int work_nx = work + num_clusters;
-          if (work_nx < num_tiles) {
-            const int row_nx = (tile_of(work_nx) / num_n_tiles) * kTileM + slab_row + lane;
-            if (row_nx < M && row_nx != row0 + lane) {
-#pragma unroll
-              for (int p2 = 0; p2 < 8; ++p2)
-                if (p2 < e.ln_nparts)
-                  asm volatile("prefetch.global.L1 [%0];" ::"l"(e.ln_part +
-                                                                static_cast<size_t>(p2) * M + row_nx));
-            }
-          }
-          const float inv_d = 1.f / static_cast<float>(e.ln_dim);
-          const float mean = s1 * inv_d;
-          const float var = fmaxf(fmaf(-mean, mean, s2 * inv_d), 0.f);
-          ln_rstd = rsqrtf(var + e.ln_eps);
+          ln_have_next = work_nx < num_tiles;
+          if (ln_have_next)
+            ln_load_stats((tile_of(work_nx) / num_n_tiles) * kTileM + slab_row + lane, ln_next);
         }
       }
       mbar_wait(tfull_bar(acc), acc_phase);
@@ -1130,6 +1140,17 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
       if (++acc == kAccStages) {
         acc = 0;
         acc_phase ^= 1u;
+      }
+      if constexpr (TMA_EPI && (EPI == EPI_BF16 || is_gelu_epi<EPI>())) {
+        if (e.ln_part != nullptr && ln_have_next) {
+          float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+          for (int p2 = 0; p2 < 8; ++p2) {
+            s1 += ln_next[p2].x;
+            s2 += ln_next[p2].y;
+          }
+          ln_rstd_next = ln_finish(s1, s2);
+        }
       }
       if constexpr (LNF) {
         // The PREVIOUS tile's reductions had this whole tile's epilogue to land: waiting for all

@@ -353,6 +353,61 @@ def measure_detector(vitk, dev, world, barrier, batch: int, steps: int = 6, warm
                    "vitk_detection_head_forward"}
 
 
+def measure_detector_train(vitk, dev, world, barrier, batch: int = 64, steps: int = 4,
+                           warmup: int = 2) -> dict:
+    """SURVEY.md 8 rows f1 / f3 under training: train.py:1441-1455 for the detector -
+    predictions = model(images) through the encoder bridge and the detection head, the device-side
+    SetCriterion.loss_labels (weighted cross-entropy, background weight 0.1) + an L1 box term on
+    synthetic targets (the Hungarian assignment is host-side control plane, out of scope), then
+    loss.backward() through head and encoder.  No optimizer step: that is the caller's torch.optim."""
+    import torch
+    import torch.distributed as dist
+    torch.manual_seed(0)
+    det = vitk.ViTObjectDetector(num_classes=N_CLASSES, num_queries=100, dropout=0.0,
+                                 **VIT_B16).to(dev).train()
+    x = torch.randn(batch, 3, VIT_B16["image_size"], VIT_B16["image_size"], device=dev)
+    tgt = torch.randint(0, N_CLASSES + 1, (batch, 100), device=dev)
+    box = torch.rand(batch, 100, 4, device=dev)
+    w = torch.ones(N_CLASSES + 1, device=dev)
+    w[-1] = 0.1
+
+    def step():
+        for p in det.parameters():
+            p.grad = None
+        out = det(x)
+        loss = vitk.weighted_cross_entropy(out["class_logits"], tgt, w) + \
+            (out["bbox_coords"] - box).abs().mean()
+        loss.backward()
+        return loss
+
+    for _ in range(warmup):
+        loss = step()
+    barrier()
+    n0 = vitk.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = vitk.launch_count() - n0
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ok = bool(torch.isfinite(loss).item()) and all(p.grad is not None for p in det.parameters())
+    del det
+    torch.cuda.empty_cache()
+    return {"metric": "vit_b16_224_detector_fwd_bwd_images_per_sec",
+            "value": world * batch * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps,
+            "batch_per_gpu": batch, "steps": steps, "warmup": warmup, "gpu_launches": int(launches),
+            "finite_loss_and_all_grads": ok,
+            "what": "ViTObjectDetector forward + weighted CE / L1 loss + backward through the "
+                    "detection head (vitk_detection_head_backward) and the encoder "
+                    "(vitk_backward_tokens); decoder dropout off (p = 0); no optimizer step"}
+
+
 def _max_over_ranks(vals, dev, world):
     import torch
     import torch.distributed as dist
@@ -708,6 +763,7 @@ def run_vitk(args) -> None:
                                                            steps=5, dropout=0.0)
 
     detector = None if args.no_train else measure_detector(vitk, dev, world, barrier, B)
+    detector_train = None if args.no_train else measure_detector_train(vitk, dev, world, barrier)
 
     # ---- the other BASELINE.json configurations, each under the same timing rules
     legs = []
@@ -794,6 +850,8 @@ def run_vitk(args) -> None:
     line["cls_only_tail"] = pruned
     if detector is not None:
         line["detector"] = detector
+    if detector_train is not None:
+        line["detector_train"] = detector_train
     if legs:
         line["configs"] = legs
     line["parity_check"] = parity
