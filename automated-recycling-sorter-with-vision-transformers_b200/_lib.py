@@ -75,7 +75,7 @@ class VitkWeights(C.Structure):
 class VitkDetectionHeadConfig(C.Structure):
     _fields_ = [("embed_dim", C.c_int), ("num_heads", C.c_int), ("ffn_dim", C.c_int),
                 ("num_layers", C.c_int), ("num_queries", C.c_int), ("num_outputs", C.c_int),
-                ("ln_eps", C.c_float)]
+                ("ln_eps", C.c_float), ("dropout_p", C.c_float), ("seed", C.c_uint64)]
 
 
 class VitkDecoderLayerWeights(C.Structure):

@@ -368,7 +368,8 @@ extern "C" {
 
 int vitk_dropout_keep_mask(float p, unsigned int seed, int site, int layer, long long n,
                            unsigned char* out, vitk_stream_t stream) {
-  VITK_REQUIRE(site >= 0 && site <= 4 && layer >= 0, "bad dropout site / layer");
+  VITK_REQUIRE(((site >= 0 && site <= 4) || (site >= 8 && site <= 13)) && layer >= 0,
+               "bad dropout site / layer (encoder sites 0..4, decoder-layer sites 8..13)");
   return dropout_keep_mask(out, n, make_drop_params(p, seed, site, layer),
                            static_cast<cudaStream_t>(stream));
 }

@@ -285,8 +285,18 @@ struct XParams {
   long long q_img, kv_img, ctx_img, dq_img, dkv_img;
   int ldq, ldkv, ldc, lddq, lddkv;
   int Nq, Nk, H, hd, hdp;
+  int Nkp;      // keys rounded up to 16: row pitch of the dropout element index
   float scale;
+  DropParams drop;
 };
+
+__device__ __forceinline__ bool keep_prob_x(const XParams& p, int bh, int i, int j) {
+  if (p.drop.thresh == 0u) return true;
+  const uint32_t idx = (static_cast<uint32_t>(bh) * static_cast<uint32_t>(p.Nq) +
+                        static_cast<uint32_t>(i)) * static_cast<uint32_t>(p.Nkp) +
+                       static_cast<uint32_t>(j);
+  return drop_keep(idx, p.drop.key, p.drop.thresh);
+}
 
 // forward: K, V of the head resident in shared memory; one warp per query row
 __global__ void __launch_bounds__(kGenThreads)
@@ -334,7 +344,7 @@ attn_xgen_fwd_kernel(const XParams p) {
 #pragma unroll
     for (int t = 0; t < kGenMaxKeysPerLane; ++t) {
       const int j = lane + 32 * t;
-      if (j < Nk) sp[j] = s[t] * inv;
+      if (j < Nk) sp[j] = keep_prob_x(p, bh, i, j) ? s[t] * inv * p.drop.scale : 0.f;
     }
     __syncwarp();
     float o[4];
@@ -411,7 +421,8 @@ attn_xgen_bwd_kernel(const XParams p) {
       __syncwarp();
       for (int j = lane; j < Nk; j += 32) {
         const float pij = __expf(dot_row(v0, sA + j * hdp, hd) * p.scale - lse_i);
-        const float dp = dot_row(v1, sB + j * hdp, hd);
+        float dp = dot_row(v1, sB + j * hdp, hd);
+        dp = keep_prob_x(p, bh, i, j) ? dp * p.drop.scale : 0.f;
         w0[j] = pij * (dp - dr) * p.scale;
       }
       __syncwarp();
@@ -430,9 +441,11 @@ attn_xgen_bwd_kernel(const XParams p) {
       __syncwarp();
       for (int i = lane; i < Nq; i += 32) {
         const float pij = __expf(dot_row(v0, sA + i * hdp, hd) * p.scale - s_lse[i]);
-        const float dp = dot_row(v1, sB + i * hdp, hd);
+        float dp = dot_row(v1, sB + i * hdp, hd);
+        const bool keep = keep_prob_x(p, bh, i, j);
+        dp = keep ? dp * p.drop.scale : 0.f;
         w0[i] = pij * (dp - s_drow[i]) * p.scale;
-        w1[i] = pij;
+        w1[i] = keep ? pij * p.drop.scale : 0.f;
       }
       __syncwarp();
       float dk[4], dv[4];
@@ -543,7 +556,10 @@ int attention_gen_bwd(const void* qkv, const void* ctx, const void* dctx, const 
 }
 
 namespace {
-int xgen_check(const AttnXSrc& s, int B, int Nq, int Nk, int H, int hd) {
+int xgen_check(const AttnXSrc& s, int B, int Nq, int Nk, int H, int hd, const DropParams* drop) {
+  VITK_REQUIRE(drop == nullptr || drop->thresh == 0u ||
+                   static_cast<long long>(B) * H * Nq * ((Nk + 15) & ~15) < (1ll << 32),
+               "attention dropout: batch * heads * queries * keys must stay below 2^32");
   VITK_REQUIRE(s.q && s.k && s.v, "attention (generic sources): null operand");
   VITK_REQUIRE(B > 0 && Nq > 0 && Nk > 0 && H > 0, "attention (generic sources): bad shape");
   VITK_REQUIRE(hd >= 8 && hd <= 128 && hd % 8 == 0,
@@ -557,8 +573,8 @@ int xgen_check(const AttnXSrc& s, int B, int Nq, int Nk, int H, int hd) {
 }  // namespace
 
 int attention_xgen_fwd(const AttnXSrc& s, void* ctx, long long ctx_img, int ldc, float* lse, int B,
-                       int Nq, int Nk, int H, int hd, cudaStream_t stream) {
-  VITK_TRY(xgen_check(s, B, Nq, Nk, H, hd));
+                       int Nq, int Nk, int H, int hd, cudaStream_t stream, const DropParams* drop) {
+  VITK_TRY(xgen_check(s, B, Nq, Nk, H, hd, drop));
   VITK_REQUIRE(ctx != nullptr, "attention (generic sources): null output");
   XParams p{};
   p.q = static_cast<const __nv_bfloat16*>(s.q);
@@ -569,7 +585,9 @@ int attention_xgen_fwd(const AttnXSrc& s, void* ctx, long long ctx_img, int ldc,
   p.q_img = s.q_img; p.kv_img = s.kv_img; p.ctx_img = ctx_img;
   p.ldq = s.ldq; p.ldkv = s.ldkv; p.ldc = ldc;
   p.Nq = Nq; p.Nk = Nk; p.H = H; p.hd = hd; p.hdp = hd + 8;
+  p.Nkp = (Nk + 15) & ~15;
   p.scale = 1.0f / sqrtf(static_cast<float>(hd));
+  if (drop != nullptr) p.drop = *drop;
   const size_t smem = 2 * static_cast<size_t>(Nk) * p.hdp * 2 + kGenWarps * (static_cast<size_t>(hd) + Nk) * 4;
   VITK_REQUIRE(smem <= 232448, "attention (generic sources): %d keys x head_dim %d do not fit in "
                "shared memory", Nk, hd);
@@ -584,8 +602,8 @@ int attention_xgen_fwd(const AttnXSrc& s, void* ctx, long long ctx_img, int ldc,
 int attention_xgen_bwd(const AttnXSrc& s, const void* ctx, const void* dctx, long long ctx_img,
                        int ldc, const float* lse, void* dq, long long dq_img, int lddq, void* dk,
                        void* dv, long long dkv_img, int lddkv, int B, int Nq, int Nk, int H, int hd,
-                       cudaStream_t stream) {
-  VITK_TRY(xgen_check(s, B, Nq, Nk, H, hd));
+                       cudaStream_t stream, const DropParams* drop) {
+  VITK_TRY(xgen_check(s, B, Nq, Nk, H, hd, drop));
   VITK_REQUIRE(ctx && dctx && lse && dq && dk && dv, "attention_bwd (generic sources): null operand");
   XParams p{};
   p.q = static_cast<const __nv_bfloat16*>(s.q);
@@ -600,7 +618,9 @@ int attention_xgen_bwd(const AttnXSrc& s, const void* ctx, const void* dctx, lon
   p.q_img = s.q_img; p.kv_img = s.kv_img; p.ctx_img = ctx_img; p.dq_img = dq_img; p.dkv_img = dkv_img;
   p.ldq = s.ldq; p.ldkv = s.ldkv; p.ldc = ldc; p.lddq = lddq; p.lddkv = lddkv;
   p.Nq = Nq; p.Nk = Nk; p.H = H; p.hd = hd; p.hdp = hd + 8;
+  p.Nkp = (Nk + 15) & ~15;
   p.scale = 1.0f / sqrtf(static_cast<float>(hd));
+  if (drop != nullptr) p.drop = *drop;
   const size_t nmax = static_cast<size_t>(Nq > Nk ? Nq : Nk);
   const size_t smem = 2 * nmax * p.hdp * 2 + 2 * nmax * 4 + kGenWarps * (2 * static_cast<size_t>(hd) + 2 * nmax) * 4;
   VITK_REQUIRE(smem <= 232448, "attention_bwd (generic sources): %d x head_dim %d do not fit in "

@@ -229,12 +229,19 @@ int check(const VitkDetectionHeadConfig* cfg, int batch, int n_tokens, int skip,
   d->M = static_cast<long long>(batch) * d->Q;
   d->Mm = static_cast<long long>(batch) * n_tokens;
   VITK_REQUIRE(d->M < (1ll << 29) && d->Mm < (1ll << 29), "detection head: batch too large");
+  VITK_REQUIRE(cfg->dropout_p >= 0.f && cfg->dropout_p < 1.f, "detection head: dropout_p %g outside "
+               "[0, 1)", static_cast<double>(cfg->dropout_p));
+  if (cfg->dropout_p > 0.f)   // element indices of the masks are 32-bit; the fused LayerNorm backward
+    VITK_REQUIRE(cfg->embed_dim <= 768 && d->M * static_cast<long long>(cfg->ffn_dim) < (1ll << 32),
+                 "detection head: dropout needs embed_dim <= 768 and batch * queries * ffn_dim < 2^32");
   return VITK_OK;
 }
 
 int linear(const void* A, int lda, const void* W, int M, int N, int K, GemmEpi epi,
-           const float* bias, float* resid_out, void* out, int ldo, cudaStream_t stream) {
+           const float* bias, float* resid_out, void* out, int ldo, cudaStream_t stream,
+           const DropParams& drop = DropParams()) {
   GemmProblem p;
+  p.e.drop = drop;
   p.A = A;
   p.lda = lda;
   p.B = W;
@@ -328,8 +335,11 @@ int head_forward(const VitkDetectionHeadConfig* cfg, const VitkDetectionHeadWeig
 
 // =============================================================================================
 // Training through the head (train.py:842-845 inside the forward of :1441-1444, differentiated by
-// losses.backward() at :1455).  Dropout of the decoder layers is NOT applied (p = 0 semantics):
-// the forward is the eval-mode arithmetic above with every activation the backward needs kept.
+// losses.backward() at :1455): the arithmetic above with every activation the backward needs
+// kept.  cfg->dropout_p > 0 applies nn.TransformerDecoderLayer's dropout at its six sites per
+// layer (dropout.cuh: DROP_DEC_*) with masks that are regenerated, never stored; layer 0 then runs
+// on all batch * Q rows (every image draws its own masks) and the attention with dropped
+// probabilities uses the CUDA-core kernel.
 // =============================================================================================
 struct SavedLayer {
   void *xb_in, *qkv, *ctx_sa;     // self-attention operands (layer 0: Q rows, else M rows)
@@ -436,10 +446,36 @@ HeadTrainWs carve_train_ws(const HeadDims& d, void* base) {
   return w;
 }
 
+struct HeadDrop {
+  float p;
+  uint32_t seed;
+  bool on() const { return p > 0.f; }
+  DropParams at(int site, int layer) const { return make_drop_params(p, seed, site, layer); }
+};
+
+// out_f32[row] = in[row % in_rows] (+ bf16 copy): object_queries.unsqueeze(0).expand(B, -1, -1)
+__global__ void __launch_bounds__(256)
+broadcast_rows_kernel(const float* __restrict__ in, int in_rows, float* __restrict__ out_f32,
+                      __nv_bfloat16* __restrict__ out_bf16, long long rows, int D) {
+  const long long i = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) * 4;
+  if (i >= rows * D) return;
+  const long long row = i / D;
+  const int col = static_cast<int>(i - row * D);
+  const float4 v = *reinterpret_cast<const float4*>(in + (row % in_rows) * D + col);
+  *reinterpret_cast<float4*>(out_f32 + i) = v;
+  uint2 pk;
+  pk.x = pack_bf16x2(v.x, v.y);
+  pk.y = pack_bf16x2(v.z, v.w);
+  *reinterpret_cast<uint2*>(out_bf16 + i) = pk;
+}
+
 // attention with the log-sum-exp output: tcgen05 when the shape fits one query tile / key block
+// (no dropout on the probabilities), else the CUDA-core kernel
 int attn_train(const HeadDims& d, int B, const AttnXSrc& s, int Nk, void* ctx, float* lse,
-               cudaStream_t stream) {
+               cudaStream_t stream, const DropParams& drop = DropParams()) {
   const long long ctx_img = static_cast<long long>(d.Q) * d.D;
+  if (drop.thresh != 0u)
+    return attention_xgen_fwd(s, ctx, ctx_img, d.D, lse, B, d.Q, Nk, d.H, d.hd, stream, &drop);
   if (attention_impl() != 1 && attention_xtc_applicable(s.q_img, s.kv_img, B, d.Q, Nk, d.hd))
     return attention_xtc(s.q, s.q_img, s.ldq, s.k, s.v, s.kv_img, s.ldkv, ctx, ctx_img, d.D, B, d.Q,
                          Nk, d.H, d.hd, stream, lse);
@@ -450,6 +486,7 @@ int head_forward_train(const VitkDetectionHeadConfig* cfg, const VitkDetectionHe
                        const float* tokens, const HeadDims& d, float* class_logits, float* bbox,
                        const SavedHead& sv, const HeadTrainWs& ws, cudaStream_t stream) {
   const int D = d.D, M = static_cast<int>(d.M), Q = d.Q;
+  const HeadDrop drop{cfg->dropout_p, static_cast<uint32_t>(cfg->seed)};
   const __nv_bfloat16* kv = static_cast<const __nv_bfloat16*>(sv.kv);
   const int ldkv = d.L * 2 * D;
   VITK_TRY(cast_f32_to_bf16(tokens, sv.mem, d.Mm * D, stream));
@@ -459,7 +496,12 @@ int head_forward_train(const VitkDetectionHeadConfig* cfg, const VitkDetectionHe
     const VitkDecoderLayerWeights& lw = w->layers[l];
     const SavedLayer sl = carve_layer(d, l, sv.layers + l * sv.layer_bytes, nullptr);
     const __nv_bfloat16* qkv = static_cast<const __nv_bfloat16*>(sl.qkv);
-    if (l == 0) {
+    if (l == 0 && drop.on()) {
+      broadcast_rows_kernel<<<static_cast<unsigned>((d.M * D / 4 + 255) / 256), 256, 0, stream>>>(
+          w->object_queries, Q, ws.x, static_cast<__nv_bfloat16*>(sl.xb_in), d.M, D);
+      VITK_CHECK_LAUNCH("broadcast_rows_kernel");
+    }
+    if (l == 0 && !drop.on()) {
       VITK_CHECK_CUDA(cudaMemcpyAsync(ws.xq, w->object_queries, static_cast<size_t>(Q) * D * 4,
                                       cudaMemcpyDeviceToDevice, stream));
       VITK_TRY(cast_f32_to_bf16(w->object_queries, sl.xb_in, static_cast<long long>(Q) * D, stream));
@@ -477,9 +519,10 @@ int head_forward_train(const VitkDetectionHeadConfig* cfg, const VitkDetectionHe
                       3 * D, stream));
       const long long img = static_cast<long long>(Q) * 3 * D;
       const AttnXSrc src{qkv, img, 3 * D, qkv + D, qkv + 2 * D, img, 3 * D};
-      VITK_TRY(attn_train(d, d.B, src, Q, sl.ctx_sa, sl.lse_sa, stream));
+      VITK_TRY(attn_train(d, d.B, src, Q, sl.ctx_sa, sl.lse_sa, stream,
+                          drop.at(DROP_DEC_SA_ATTN, l)));
       VITK_TRY(linear(sl.ctx_sa, D, lw.sa_out_w, M, D, D, EPI_RESID_F32, lw.sa_out_b, ws.x, nullptr,
-                      D, stream));
+                      D, stream, drop.at(DROP_DEC_SA_OUT, l)));
       VITK_TRY(ln_post(ws.x, M, lw.norm1_w, lw.norm1_b, ws.x, sl.xb1, M, D, cfg->ln_eps, stream,
                        sl.r1, sl.mean1, sl.rstd1));
     }
@@ -488,15 +531,17 @@ int head_forward_train(const VitkDetectionHeadConfig* cfg, const VitkDetectionHe
       const __nv_bfloat16* kl = kv + static_cast<size_t>(d.skip) * ldkv + static_cast<size_t>(l) * 2 * D;
       const AttnXSrc src{sl.qc, static_cast<long long>(Q) * D, D, kl, kl + D,
                          static_cast<long long>(d.Ntok) * ldkv, ldkv};
-      VITK_TRY(attn_train(d, d.B, src, d.P, sl.ctx_ca, sl.lse_ca, stream));
+      VITK_TRY(attn_train(d, d.B, src, d.P, sl.ctx_ca, sl.lse_ca, stream,
+                          drop.at(DROP_DEC_CA_ATTN, l)));
     }
     VITK_TRY(linear(sl.ctx_ca, D, lw.ca_out_w, M, D, D, EPI_RESID_F32, lw.ca_out_b, ws.x, nullptr, D,
-                    stream));
+                    stream, drop.at(DROP_DEC_CA_OUT, l)));
     VITK_TRY(ln_post(ws.x, M, lw.norm2_w, lw.norm2_b, ws.x, sl.xb2, M, D, cfg->ln_eps, stream, sl.r2,
                      sl.mean2, sl.rstd2));
     VITK_TRY(linear(sl.xb2, D, lw.ff1_w, M, d.F, D, EPI_RELU_BF16, lw.ff1_b, nullptr, sl.h, d.F,
-                    stream));
-    VITK_TRY(linear(sl.h, d.F, lw.ff2_w, M, D, d.F, EPI_RESID_F32, lw.ff2_b, ws.x, nullptr, D, stream));
+                    stream, drop.at(DROP_DEC_FFN, l)));
+    VITK_TRY(linear(sl.h, d.F, lw.ff2_w, M, D, d.F, EPI_RESID_F32, lw.ff2_b, ws.x, nullptr, D, stream,
+                    drop.at(DROP_DEC_FF2, l)));
     const bool last = (l == d.L - 1);
     void* xb_next = last ? sv.xb_last
                          : carve_layer(d, l + 1, sv.layers + (l + 1) * sv.layer_bytes, nullptr).xb_in;
@@ -576,9 +621,11 @@ det_heads_bwd_w_kernel(const float* __restrict__ dz, const float* __restrict__ x
   if (c == 0) atomicAdd(o < n_cls ? dcb + o : dbb + (o - n_cls), accb);
 }
 
-// dh <- dh where the forward's ReLU output h was positive, else 0 (bf16, 8 elements per thread)
+// dh <- scale * dh where the forward's (dropped) ReLU output h was positive, else 0: h > 0 means
+// pre-activation > 0 AND kept by the FFN dropout, scale = 1 / (1 - p) (bf16, 8 elements per thread)
 __global__ void __launch_bounds__(256)
-relu_bwd_kernel(__nv_bfloat16* __restrict__ dh, const __nv_bfloat16* __restrict__ h, long long n8) {
+relu_bwd_kernel(__nv_bfloat16* __restrict__ dh, const __nv_bfloat16* __restrict__ h, long long n8,
+                float scale) {
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     uint4 g = reinterpret_cast<uint4*>(dh)[i];
@@ -593,6 +640,12 @@ relu_bwd_kernel(__nv_bfloat16* __restrict__ dh, const __nv_bfloat16* __restrict_
     g.y = mask(g.y, a.y);
     g.z = mask(g.z, a.z);
     g.w = mask(g.w, a.w);
+    if (scale != 1.f) {
+      g.x = pack_bf16x2(bf16lo_to_f32(g.x) * scale, bf16hi_to_f32(g.x) * scale);
+      g.y = pack_bf16x2(bf16lo_to_f32(g.y) * scale, bf16hi_to_f32(g.y) * scale);
+      g.z = pack_bf16x2(bf16lo_to_f32(g.z) * scale, bf16hi_to_f32(g.z) * scale);
+      g.w = pack_bf16x2(bf16lo_to_f32(g.w) * scale, bf16hi_to_f32(g.w) * scale);
+    }
     reinterpret_cast<uint4*>(dh)[i] = g;
   }
 }
@@ -668,18 +721,19 @@ int wgrad(const void* dY, int out_f, const void* X, int in_f, int rows, float* d
 // norm backward in place on the fp32 gradient stream: dx <- LN'(dx), bf16 copy, dgamma / dbeta
 // accumulated, column sums of the result into `colsum` (the bias gradient of the Linear whose
 // output the normalised sum received)
+// `drop`: mask of the branch output the bf16 copy enters (dropout1 / 2 / 3 of the decoder layer)
 int norm_bwd(float* dx, void* dxb, const float* r, const float* mean, const float* rstd,
              const float* gamma, float* dgamma, float* dbeta, float* colsum, int rows, int D,
-             cudaStream_t stream) {
+             cudaStream_t stream, const DropParams& drop = DropParams()) {
   return layernorm_bwd(dx, 1, D, r, D, mean, rstd, gamma, dx, D, 0, dxb, D, dgamma, dbeta, rows, D,
-                       stream, colsum);
+                       stream, colsum, drop.thresh != 0u ? &drop : nullptr);
 }
 
 int head_backward(const VitkDetectionHeadConfig* cfg, const VitkDetectionHeadWeights* w,
                   const VitkDetectionHeadWeightsT* wt, const VitkDetectionHeadGrads* g,
                   const float* d_logits, const float* d_box, const float* box, const HeadDims& d,
                   float* d_tokens, const SavedHead& sv, const HeadTrainWs& ws, cudaStream_t stream) {
-  (void)cfg;
+  const HeadDrop drop{cfg->dropout_p, static_cast<uint32_t>(cfg->seed)};
   const int D = d.D, M = static_cast<int>(d.M), Q = d.Q, F = d.F;
   const int ldkv = d.L * 2 * D;
   const long long imgD = static_cast<long long>(Q) * D;
@@ -709,13 +763,14 @@ int head_backward(const VitkDetectionHeadConfig* cfg, const VitkDetectionHeadWei
     const SavedLayer sl = carve_layer(d, l, sv.layers + l * sv.layer_bytes, nullptr);
     // ---- x = norm3(x2 + linear2(relu(linear1(x2))))
     VITK_TRY(norm_bwd(ws.x, ws.dxb, sl.r3, sl.mean3, sl.rstd3, lw.norm3_w, lg.norm3_w, lg.norm3_b,
-                      lg.ff2_b, M, D, stream));
+                      lg.ff2_b, M, D, stream, drop.at(DROP_DEC_FF2, l)));
     VITK_TRY(dgrad(ws.dxb, D, lt.ff2_wt, M, F, ws.dh, nullptr, 0.f, stream));
     {
       const long long n8 = static_cast<long long>(M) * F / 8;
       ProfileScope prof(PROF_OTHER, static_cast<double>(M) * F * 6.0, stream);
-      relu_bwd_kernel<<<sm_count() * 8, 256, 0, stream>>>(static_cast<__nv_bfloat16*>(ws.dh),
-                                                          static_cast<const __nv_bfloat16*>(sl.h), n8);
+      relu_bwd_kernel<<<sm_count() * 8, 256, 0, stream>>>(
+          static_cast<__nv_bfloat16*>(ws.dh), static_cast<const __nv_bfloat16*>(sl.h), n8,
+          drop.at(DROP_DEC_FFN, l).scale);
       VITK_CHECK_LAUNCH("relu_bwd_kernel");
     }
     VITK_TRY(wgrad(ws.dxb, D, sl.h, F, M, lg.ff2_w, nullptr, stream));
@@ -723,32 +778,44 @@ int head_backward(const VitkDetectionHeadConfig* cfg, const VitkDetectionHeadWei
     VITK_TRY(wgrad(ws.dh, F, sl.xb2, D, M, lg.ff1_w, lg.ff1_b, stream));
     // ---- x2 = norm2(x1 + multihead_attn(x1, memory, memory))
     VITK_TRY(norm_bwd(ws.x, ws.dxb, sl.r2, sl.mean2, sl.rstd2, lw.norm2_w, lg.norm2_w, lg.norm2_b,
-                      lg.ca_out_b, M, D, stream));
+                      lg.ca_out_b, M, D, stream, drop.at(DROP_DEC_CA_OUT, l)));
     VITK_TRY(dgrad(ws.dxb, D, lt.ca_out_wt, M, D, ws.dctx, nullptr, 0.f, stream));
     VITK_TRY(wgrad(ws.dxb, D, sl.ctx_ca, D, M, lg.ca_out_w, nullptr, stream));
     {
       const size_t koff = static_cast<size_t>(d.skip) * ldkv + static_cast<size_t>(l) * 2 * D;
       const AttnXSrc src{sl.qc, imgD, D, kv + koff, kv + koff + D,
                          static_cast<long long>(d.Ntok) * ldkv, ldkv};
+      const DropParams drop_ca = drop.at(DROP_DEC_CA_ATTN, l);
       VITK_TRY(attention_xgen_bwd(src, sl.ctx_ca, ws.dctx, imgD, D, sl.lse_ca, dqkv, imgD, D,
                                   dkv + koff, dkv + koff + D, static_cast<long long>(d.Ntok) * ldkv,
-                                  ldkv, d.B, Q, d.P, d.H, d.hd, stream));
+                                  ldkv, d.B, Q, d.P, d.H, d.hd, stream, &drop_ca));
     }
     VITK_TRY(dgrad(dqkv, D, lt.ca_q_wt, M, D, nullptr, ws.x, 1.f, stream));
     VITK_TRY(wgrad(dqkv, D, sl.xb1, D, M, lg.ca_q_w, lg.ca_q_b, stream));
     // ---- x1 = norm1(x0 + self_attn(x0, x0, x0))
-    if (l > 0) {
+    if (l > 0 || drop.on()) {
       VITK_TRY(norm_bwd(ws.x, ws.dxb, sl.r1, sl.mean1, sl.rstd1, lw.norm1_w, lg.norm1_w, lg.norm1_b,
-                        lg.sa_out_b, M, D, stream));
+                        lg.sa_out_b, M, D, stream, drop.at(DROP_DEC_SA_OUT, l)));
       VITK_TRY(dgrad(ws.dxb, D, lt.sa_out_wt, M, D, ws.dctx, nullptr, 0.f, stream));
       VITK_TRY(wgrad(ws.dxb, D, sl.ctx_sa, D, M, lg.sa_out_w, nullptr, stream));
       const __nv_bfloat16* qkv = static_cast<const __nv_bfloat16*>(sl.qkv);
       const long long img = static_cast<long long>(Q) * 3 * D;
       const AttnXSrc src{qkv, img, 3 * D, qkv + D, qkv + 2 * D, img, 3 * D};
+      const DropParams drop_sa = drop.at(DROP_DEC_SA_ATTN, l);
       VITK_TRY(attention_xgen_bwd(src, sl.ctx_sa, ws.dctx, imgD, D, sl.lse_sa, dqkv, img, 3 * D,
-                                  dqkv + D, dqkv + 2 * D, img, 3 * D, d.B, Q, Q, d.H, d.hd, stream));
+                                  dqkv + D, dqkv + 2 * D, img, 3 * D, d.B, Q, Q, d.H, d.hd, stream,
+                                  &drop_sa));
       VITK_TRY(dgrad(dqkv, 3 * D, lt.sa_in_wt, M, D, nullptr, ws.x, 1.f, stream));
       VITK_TRY(wgrad(dqkv, 3 * D, sl.xb_in, D, M, lg.sa_in_w, lg.sa_in_b, stream));
+      if (l == 0) {
+        // (dropout: layer 0 ran on every image's own copy of the queries) d queries = sum over images
+        batch_sum_kernel<<<static_cast<unsigned>((imgD / 4 + 255) / 256), 256, 0, stream>>>(
+            ws.x, ws.xq, d.B, imgD);
+        VITK_CHECK_LAUNCH("batch_sum_kernel");
+        accumulate_kernel<<<static_cast<unsigned>((imgD + 255) / 256), 256, 0, stream>>>(
+            g->object_queries, ws.xq, imgD);
+        VITK_CHECK_LAUNCH("accumulate_kernel");
+      }
     } else {
       // the block ran once on the bare queries and norm1 broadcast it: LayerNorm's backward is
       // linear in the incoming gradient, so the gradients of the images are summed first

@@ -20,6 +20,15 @@ enum DropSite : int {
   DROP_PROJ = 2,   // attention output projection          train.py:553
   DROP_GELU = 3,   // MLP hidden activation                train.py:570
   DROP_FC2 = 4,    // MLP output                           train.py:572
+  // nn.TransformerDecoderLayer(dropout=0.1) of the detection head (train.py:701-707): torch applies
+  // it to the attention probabilities of both attentions, to each of the three branch outputs
+  // before the residual add (dropout1 / dropout2 / dropout3) and to the ReLU output of the FFN
+  DROP_DEC_SA_ATTN = 8,
+  DROP_DEC_SA_OUT = 9,
+  DROP_DEC_CA_ATTN = 10,
+  DROP_DEC_CA_OUT = 11,
+  DROP_DEC_FFN = 12,
+  DROP_DEC_FF2 = 13,
 };
 
 struct DropParams {

@@ -1408,7 +1408,8 @@ int gemm_bf16_tn(const GemmProblem& p, cudaStream_t stream) {
   VITK_REQUIRE(device_cc() >= 100, "gemm: requires an sm_100 device (found sm_%d)", device_cc());
   VITK_REQUIRE(p.e.drop.thresh == 0u ||
                    ((p.epi == EPI_RESID_F32 || p.epi == EPI_DGELU_BF16 || p.epi == EPI_GELU_BF16 ||
-                     p.epi == EPI_GELU_TANH_BF16) && p.e.rows_per_group == 0 && p.N % 2 == 0 &&
+                     p.epi == EPI_GELU_TANH_BF16 || p.epi == EPI_RELU_BF16) &&
+                    p.e.rows_per_group == 0 && p.N % 2 == 0 &&
                     static_cast<long long>(p.M) * p.N < (1ll << 32)),
                "gemm: dropout needs a residual / GELU / GELU' epilogue without row remap");
   if (p.e.ln_part != nullptr) {

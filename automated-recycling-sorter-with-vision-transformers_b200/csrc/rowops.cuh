@@ -102,11 +102,12 @@ struct AttnXSrc {
   const void* k; const void* v; long long kv_img; int ldkv;
 };
 int attention_xgen_fwd(const AttnXSrc& s, void* ctx, long long ctx_img, int ldc, float* lse, int B,
-                       int Nq, int Nk, int H, int hd, cudaStream_t stream);
+                       int Nq, int Nk, int H, int hd, cudaStream_t stream,
+                       const DropParams* drop = nullptr);
 int attention_xgen_bwd(const AttnXSrc& s, const void* ctx, const void* dctx, long long ctx_img,
                        int ldc, const float* lse, void* dq, long long dq_img, int lddq, void* dk,
                        void* dv, long long dkv_img, int lddkv, int B, int Nq, int Nk, int H, int hd,
-                       cudaStream_t stream);
+                       cudaStream_t stream, const DropParams* drop = nullptr);
 // CUDA-core attention for the shapes the tensor-core kernels do not cover (attention_gen.cu):
 // head_dim 8 .. 128 in steps of 8, up to 1024 tokens, optional log-sum-exp output and
 // attention-probability dropout - forward and (train_ops.cuh: attention_bwd) backward.

@@ -16,8 +16,9 @@ Under autograd (grad enabled and the features or a head parameter require grad) 
 through `vitk_detection_head_forward_train` / `vitk_detection_head_backward`: gradients reach every
 head parameter and the encoder features (and, through the encoder bridge, the backbone), so the
 reference's training loop - model(images) -> SetCriterion -> losses.backward() -> optimizer.step(),
-train.py:1441-1460 - runs on this head unchanged.  The decoder layers' dropout (0.1 in train mode
-in the reference) is not applied: p = 0 semantics, the arithmetic of eval().
+train.py:1441-1460 - runs on this head unchanged.  In train() mode the decoder layers' dropout
+(nn.TransformerDecoderLayer(dropout=0.1), train.py:701-707) is applied at its six sites per layer
+with masks regenerated from a per-call seed (never stored).
 `weighted_cross_entropy` is the device-side SetCriterion.loss_labels (train.py:1220-1239).
 """
 from __future__ import annotations
@@ -50,7 +51,16 @@ class _DetectionHeadFunction(torch.autograd.Function):
     def forward(ctx, tokens, head, skip, *params):
         tokens = tokens.detach().float().contiguous()
         B, N, _ = tokens.shape
-        cfg, (w, _, _) = head._pack()
+        cfg0, (w, _, _) = head._pack()
+        # nn.TransformerDecoderLayer's dropout is active in train() mode, as in the reference; the
+        # mask seed is drawn from torch's generator so that torch.manual_seed makes runs
+        # reproducible (the backward of this call regenerates the same masks)
+        cfg = VitkDetectionHeadConfig.from_buffer_copy(cfg0)
+        p_drop = float(head.decoder.layers[0].dropout1.p) if head.training else 0.0
+        if p_drop > 0.0:
+            cfg.dropout_p = p_drop
+            cfg.seed = head.__dict__.get("_vitk_forced_seed") or \
+                int(torch.randint(0, 2 ** 31 - 1, (1,)).item())
         saved_b, ws_b = C.c_size_t(0), C.c_size_t(0)
         check(lib().vitk_detection_head_train_bytes(C.byref(cfg), B, N, skip, C.byref(saved_b),
                                                     C.byref(ws_b)))
@@ -65,7 +75,7 @@ class _DetectionHeadFunction(torch.autograd.Function):
             C.byref(cfg), C.byref(w), tokens.data_ptr(), B, N, skip, logits.data_ptr(),
             boxes.data_ptr(), _align1k(saved_t), saved_b.value, _align1k(ws_t), ws_b.value,
             _stream()))
-        ctx.head, ctx.skip, ctx.shape = head, skip, (B, N)
+        ctx.head, ctx.skip, ctx.shape, ctx.cfg = head, skip, (B, N), cfg
         ctx.saved_t, ctx.ws_t, ctx.boxes = saved_t, ws_t, boxes
         ctx.need_tokens = ctx.needs_input_grad[0]
         return logits, boxes
@@ -76,7 +86,8 @@ class _DetectionHeadFunction(torch.autograd.Function):
         if ctx.saved_t is None:
             raise _lib.VitkError("backward through the vitk detection head a second time: the saved "
                                  "activations were released (retain_graph is not supported)")
-        cfg, (w, _, _) = head._pack()
+        _, (w, _, _) = head._pack()
+        cfg = ctx.cfg
         wt = head._pack_transposed()
         dev = ctx.boxes.device
         Q, D, L = head.num_queries, cfg.embed_dim, cfg.num_layers

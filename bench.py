@@ -365,6 +365,11 @@ def measure_detector_train(vitk, dev, world, barrier, batch: int = 64, steps: in
     torch.manual_seed(0)
     det = vitk.ViTObjectDetector(num_classes=N_CLASSES, num_queries=100, dropout=0.0,
                                  **VIT_B16).to(dev).train()
+    for m in det.modules():      # p = 0 everywhere: the configuration the parity tests pin
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+        if isinstance(m, torch.nn.MultiheadAttention):
+            m.dropout = 0.0
     x = torch.randn(batch, 3, VIT_B16["image_size"], VIT_B16["image_size"], device=dev)
     tgt = torch.randint(0, N_CLASSES + 1, (batch, 100), device=dev)
     box = torch.rand(batch, 100, 4, device=dev)

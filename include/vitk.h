@@ -364,6 +364,10 @@ int vitk_train_workspace_bytes(const VitkConfig* cfg, int batch, size_t* saved_b
  * seed; change the seed every step.  Sites: 0 tokens+position embedding (index = flat [B*N, D]),
  * 1 attention probabilities (index = ((b*H + h)*N + i)*Nk + j with Nk = N rounded up to 16),
  * 2 projection output, 3 MLP hidden activation, 4 MLP output (index = row * width + column).
+ * Detection head (VitkDetectionHeadConfig.dropout_p; layer = decoder layer): 8 self-attention
+ * probabilities, 10 cross-attention probabilities (index = ((b*8 + h)*Q + i)*Nk + j, Nk = keys
+ * rounded up to 16), 9 / 11 / 13 the self-attention / cross-attention / linear2 outputs before
+ * their residual adds, 12 the ReLU output of linear1 (index = row * width + column).
  * vitk_dropout_keep_mask writes the 0/1 keep decisions of elements [0, n) of one site (n even) -
  * what the parity tests inject into the oracle.  p is quantised to 1/65536. */
 int vitk_dropout_keep_mask(float p, unsigned int seed, int site, int layer, long long n,
@@ -464,6 +468,12 @@ typedef struct VitkDetectionHeadConfig {
   int num_queries; /* 100 */
   int num_outputs; /* num_classes + 1 (background) */
   float ln_eps;    /* 1e-5 */
+  /* nn.TransformerDecoderLayer(dropout=0.1) (train.py:701-707), applied by the *_train / backward
+   * entry points only: attention probabilities of both attentions, the three branch outputs before
+   * their residual adds, the ReLU output of the feed-forward.  Masks are a hash of (seed, site,
+   * layer, element): forward and backward must be given the same seed.  0 = off. */
+  float dropout_p;
+  uint64_t seed;
 } VitkDetectionHeadConfig;
 
 typedef struct VitkDecoderLayerWeights {
@@ -515,8 +525,9 @@ int vitk_detection_head_forward(const VitkDetectionHeadConfig* cfg,
                                 vitk_stream_t stream);
 
 /* ---- training through the head (train.py:842-845 under losses.backward(), train.py:1455) ----
- * The forward below is the eval-mode arithmetic (the decoder layers' dropout is not applied:
- * p = 0 semantics) with every activation the backward needs kept in `saved`. */
+ * The forward below keeps every activation the backward needs in `saved`; with
+ * VitkDetectionHeadConfig.dropout_p > 0 the decoder layers' dropout is applied (same seed for the
+ * forward and the backward of a step). */
 
 /* W^T copies (bf16 [in, out]) for the input-gradient GEMMs. */
 typedef struct VitkDecoderLayerWeightsT {

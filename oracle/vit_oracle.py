@@ -213,7 +213,7 @@ def train_step(sd: dict, images: torch.Tensor, labels: torch.Tensor, num_heads: 
 # Pinned by tests/golden/det_head_*.npz (the reference's own class run in the build container).
 # --------------------------------------------------------------------------------------------
 def multihead_attention(q_in: torch.Tensor, kv_in: torch.Tensor, in_w, in_b, out_w, out_b,
-                        num_heads: int) -> torch.Tensor:
+                        num_heads: int, masks=None, site: str = "", layer: int = 0) -> torch.Tensor:
     B, Nq, D = q_in.shape
     Nk = kv_in.shape[1]
     hd = D // num_heads
@@ -224,30 +224,34 @@ def multihead_attention(q_in: torch.Tensor, kv_in: torch.Tensor, in_w, in_b, out
     k = k.reshape(B, Nk, num_heads, hd).transpose(1, 2)
     v = v.reshape(B, Nk, num_heads, hd).transpose(1, 2)
     probs = torch.softmax((q @ k.transpose(-2, -1)) / math.sqrt(hd), dim=-1)
+    probs = _drop(probs, masks, site, layer)       # nn.MultiheadAttention(dropout=0.1), train mode
     ctx = (probs @ v).transpose(1, 2).reshape(B, Nq, D)
     return ctx @ out_w.t() + out_b
 
 
 def decoder_layer(x: torch.Tensor, memory: torch.Tensor, sd: dict, prefix: str,
-                  num_heads: int = 8) -> torch.Tensor:
+                  num_heads: int = 8, masks=None, layer: int = 0) -> torch.Tensor:
+    """Train mode (train.py:701-707, dropout = 0.1) when `masks` is given: explicit dropout masks
+    keyed (site, layer), sites dec_sa_attn / dec_sa_out (dropout1) / dec_ca_attn / dec_ca_out
+    (dropout2) / dec_ffn (after the ReLU) / dec_ff2 (dropout3) - see _drop."""
     g = lambda k: sd[prefix + k]
-    x = layer_norm(x + multihead_attention(x, x, g("self_attn.in_proj_weight"),
-                                           g("self_attn.in_proj_bias"),
-                                           g("self_attn.out_proj.weight"),
-                                           g("self_attn.out_proj.bias"), num_heads),
-                   g("norm1.weight"), g("norm1.bias"))
-    x = layer_norm(x + multihead_attention(x, memory, g("multihead_attn.in_proj_weight"),
-                                           g("multihead_attn.in_proj_bias"),
-                                           g("multihead_attn.out_proj.weight"),
-                                           g("multihead_attn.out_proj.bias"), num_heads),
-                   g("norm2.weight"), g("norm2.bias"))
-    h = torch.relu(x @ g("linear1.weight").t() + g("linear1.bias"))
-    return layer_norm(x + h @ g("linear2.weight").t() + g("linear2.bias"),
-                      g("norm3.weight"), g("norm3.bias"))
+    sa = multihead_attention(x, x, g("self_attn.in_proj_weight"), g("self_attn.in_proj_bias"),
+                             g("self_attn.out_proj.weight"), g("self_attn.out_proj.bias"),
+                             num_heads, masks, "dec_sa_attn", layer)
+    x = layer_norm(x + _drop(sa, masks, "dec_sa_out", layer), g("norm1.weight"), g("norm1.bias"))
+    ca = multihead_attention(x, memory, g("multihead_attn.in_proj_weight"),
+                             g("multihead_attn.in_proj_bias"), g("multihead_attn.out_proj.weight"),
+                             g("multihead_attn.out_proj.bias"), num_heads, masks, "dec_ca_attn",
+                             layer)
+    x = layer_norm(x + _drop(ca, masks, "dec_ca_out", layer), g("norm2.weight"), g("norm2.bias"))
+    h = _drop(torch.relu(x @ g("linear1.weight").t() + g("linear1.bias")), masks, "dec_ffn", layer)
+    ff = h @ g("linear2.weight").t() + g("linear2.bias")
+    return layer_norm(x + _drop(ff, masks, "dec_ff2", layer), g("norm3.weight"), g("norm3.bias"))
 
 
 def detection_head_forward(sd: dict, encoder_features: torch.Tensor, prefix: str = "",
-                           dtype: torch.dtype = torch.float32, num_heads: int = 8) -> dict:
+                           dtype: torch.dtype = torch.float32, num_heads: int = 8,
+                           masks=None) -> dict:
     """ObjectDetectionHead.forward - evaluation.py:183-200.  encoder_features [B, P, D] is the
     memory (the callers strip the CLS / DIST rows first: evaluation.py:235, train.py:829)."""
     sd = {k: v.to(dtype) for k, v in sd.items() if k.startswith(prefix)}
@@ -258,7 +262,7 @@ def detection_head_forward(sd: dict, encoder_features: torch.Tensor, prefix: str
     n_layers = 1 + max(int(k[len(prefix):].split(".")[2]) for k in sd
                        if k.startswith(prefix + "decoder.layers."))
     for i in range(n_layers):                                       # :189
-        x = decoder_layer(x, memory, sd, f"{prefix}decoder.layers.{i}.", num_heads)
+        x = decoder_layer(x, memory, sd, f"{prefix}decoder.layers.{i}.", num_heads, masks, i)
     class_logits = x @ g("class_head.weight").t() + g("class_head.bias")            # :192
     bbox = torch.sigmoid(x @ g("bbox_head.weight").t() + g("bbox_head.bias"))      # :193-194
     return {"class_logits": class_logits, "bbox_coords": bbox}

@@ -22,6 +22,14 @@ def _head(vitk, D, Q, n_classes, seed=1, layers=None):
     return head, sd
 
 
+def _no_dropout(module):
+    for m in module.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+        if isinstance(m, torch.nn.MultiheadAttention):
+            m.dropout = 0.0
+
+
 def _oracle_grads(sd, tokens, skip, r_logits, r_boxes):
     sd64 = {k: v.double().clone().requires_grad_(True) for k, v in sd.items()}
     tok = tokens.double().clone().requires_grad_(True)
@@ -46,6 +54,7 @@ def _rel(a, b):
 ])
 def test_head_backward_matches_oracle_autograd(vitk, D, Q, P, B, skip, L, impl):
     head, sd = _head(vitk, D, Q, 6, layers=L)
+    _no_dropout(head)
     head = head.cuda().train()
     g = torch.Generator().manual_seed(3)
     tokens = torch.randn(B, P + skip, D, generator=g)
@@ -84,6 +93,7 @@ def test_head_backward_matches_oracle_autograd(vitk, D, Q, P, B, skip, L, impl):
 
 def test_head_forward_train_equals_inference_forward(vitk):
     head, _ = _head(vitk, 768, 100, 6)
+    _no_dropout(head)
     head = head.cuda()
     tokens = torch.randn(2, 197, 768, generator=torch.Generator().manual_seed(5)).cuda()
     with torch.no_grad():
@@ -138,3 +148,75 @@ def test_weighted_cross_entropy_matches_torch(vitk, rows_shape, C):
     l2 = vitk.weighted_cross_entropy(logits.detach(), targets, None)
     torch.testing.assert_close(l2, F.cross_entropy(logits.detach().transpose(1, 2), targets),
                                rtol=1e-5, atol=1e-6)
+
+
+def _head_masks(vitk, p, seed, B, Q, P, D, F, H, L):
+    """The library's own keep masks (vitk_dropout_keep_mask) for the six dropout sites of every
+    decoder layer, scaled by 1 / (1 - p), in the oracle's layout."""
+    import ctypes as C
+    st = torch.cuda.current_stream().cuda_stream
+    t = int(p * 65536 + 0.5)
+    scale = 65536.0 / (65536 - t)
+
+    def keep(site, layer, n):
+        out = torch.empty(n, dtype=torch.uint8, device="cuda")
+        vitk._lib.check(vitk._lib.lib().vitk_dropout_keep_mask(
+            C.c_float(p), seed, site, layer, n, out.data_ptr(), st))
+        return out.float() * scale
+
+    pad = lambda n: (n + 15) // 16 * 16
+    masks = {}
+    for l in range(L):
+        masks[("dec_sa_attn", l)] = keep(8, l, B * H * Q * pad(Q)).view(B, H, Q, pad(Q))[..., :Q].cpu()
+        masks[("dec_sa_out", l)] = keep(9, l, B * Q * D).view(B, Q, D).cpu()
+        masks[("dec_ca_attn", l)] = keep(10, l, B * H * Q * pad(P)).view(B, H, Q, pad(P))[..., :P].cpu()
+        masks[("dec_ca_out", l)] = keep(11, l, B * Q * D).view(B, Q, D).cpu()
+        masks[("dec_ffn", l)] = keep(12, l, B * Q * F).view(B, Q, F).cpu()
+        masks[("dec_ff2", l)] = keep(13, l, B * Q * D).view(B, Q, D).cpu()
+    return masks
+
+
+@pytest.mark.parametrize("p,D,Q,P,B,skip,L", [(0.1, 256, 20, 30, 3, 1, 2), (0.25, 768, 100, 196, 2, 1, 2)])
+def test_head_with_dropout_matches_oracle_given_the_same_masks(vitk, p, D, Q, P, B, skip, L):
+    """nn.TransformerDecoderLayer's dropout at all six sites per layer (train.py:701-707): the
+    kernels regenerate their masks from (seed, site, layer, index); the same masks injected into
+    the oracle must reproduce the outputs, every parameter gradient and d features."""
+    head, sd = _head(vitk, D, Q, 6, layers=L)
+    for ly in head.decoder.layers:
+        for m in (ly.dropout, ly.dropout1, ly.dropout2, ly.dropout3):
+            m.p = p
+        ly.self_attn.dropout = ly.multihead_attn.dropout = p
+    head = head.cuda().train()
+    seed = 4242
+    head.__dict__["_vitk_forced_seed"] = seed
+    F_ = head.decoder.layers[0].linear1.out_features
+    masks = _head_masks(vitk, p, seed, B, Q, P, D, F_, 8, L)
+    g = torch.Generator().manual_seed(3)
+    tokens = torch.randn(B, P + skip, D, generator=g)
+    r_logits = torch.randn(B, Q, 7, generator=g)
+    r_boxes = torch.randn(B, Q, 4, generator=g)
+
+    sd64 = {k: v.double().clone().requires_grad_(True) for k, v in sd.items()}
+    tok64 = tokens.double().clone().requires_grad_(True)
+    ref = O.detection_head_forward(sd64, tok64[:, skip:, :], dtype=torch.float64, masks=masks)
+    ((ref["class_logits"] * r_logits.double()).sum() + (ref["bbox_coords"] * r_boxes.double()).sum()).backward()
+
+    tok = tokens.cuda().requires_grad_(True)
+    out = head.decode(tok, skip_tokens=skip)
+    ((out["class_logits"] * r_logits.cuda()).sum() + (out["bbox_coords"] * r_boxes.cuda()).sum()).backward()
+    torch.cuda.synchronize()
+    # bf16 ReLU outputs within rounding of zero flip their mask; everything else follows the oracle
+    assert (out["class_logits"].detach().cpu().double() - ref["class_logits"]).abs().max() < 3e-2
+    assert (out["bbox_coords"].detach().cpu().double() - ref["bbox_coords"]).abs().max() < 1e-2
+    worst = (0.0, "")
+    for name, prm in head.named_parameters():
+        rel, cos = _rel(prm.grad.cpu(), sd64[name].grad)
+        worst = max(worst, (rel, name))
+        assert cos > 0.995 and rel < 9e-2, (name, rel, cos)
+    rel, cos = _rel(tok.grad.cpu(), tok64.grad)
+    print("dropout", p, "worst parameter gradient error", worst, "d tokens", rel, cos)
+    assert cos > 0.995 and rel < 9e-2
+    # and the masks really were applied: the eval-mode output differs
+    with torch.no_grad():
+        ev = head.eval().decode(tokens.cuda(), skip_tokens=skip)
+    assert (ev["class_logits"] - out["class_logits"].detach()).abs().max() > 1e-2

@@ -59,6 +59,7 @@ def test_reference_train_one_epoch_runs_on_the_vitk_detector(vitk, monkeypatch):
     sd["detection_head.bbox_head.bias"] = torch.tensor([-1.0, -1.0, 1.0, 1.0])
     theirs.load_state_dict(sd)
     mine = vitk.DeiTObjectDetector(**KW)
+    _no_dropout(mine)               # (the mirror applies the decoder layers' dropout in train())
     mine.load_state_dict(sd)
 
     def epoch(model):
