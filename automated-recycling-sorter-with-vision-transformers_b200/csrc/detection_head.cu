@@ -474,12 +474,14 @@ broadcast_rows_kernel(const float* __restrict__ in, int in_rows, float* __restri
 int attn_train(const HeadDims& d, int B, const AttnXSrc& s, int Nk, void* ctx, float* lse,
                cudaStream_t stream, const DropParams& drop = DropParams()) {
   const long long ctx_img = static_cast<long long>(d.Q) * d.D;
-  if (drop.thresh != 0u)
-    return attention_xgen_fwd(s, ctx, ctx_img, d.D, lse, B, d.Q, Nk, d.H, d.hd, stream, &drop);
-  if (attention_impl() != 1 && attention_xtc_applicable(s.q_img, s.kv_img, B, d.Q, Nk, d.hd))
-    return attention_xtc(s.q, s.q_img, s.ldq, s.k, s.v, s.kv_img, s.ldkv, ctx, ctx_img, d.D, B, d.Q,
-                         Nk, d.H, d.hd, stream, lse);
-  return attention_xgen_fwd(s, ctx, ctx_img, d.D, lse, B, d.Q, Nk, d.H, d.hd, stream);
+  if (attention_impl() != 1) {
+    if (drop.thresh == 0u && attention_xtc_applicable(s.q_img, s.kv_img, B, d.Q, Nk, d.hd))
+      return attention_xtc(s.q, s.q_img, s.ldq, s.k, s.v, s.kv_img, s.ldkv, ctx, ctx_img, d.D, B,
+                           d.Q, Nk, d.H, d.hd, stream, lse);
+    if (attention_xmma_bwd_applicable(d.Q, Nk, d.hd))   // dropout, or beyond one tcgen05 tile
+      return attention_xmma_fwd(s, ctx, ctx_img, d.D, lse, B, d.Q, Nk, d.H, d.hd, stream, &drop);
+  }
+  return attention_xgen_fwd(s, ctx, ctx_img, d.D, lse, B, d.Q, Nk, d.H, d.hd, stream, &drop);
 }
 
 int head_forward_train(const VitkDetectionHeadConfig* cfg, const VitkDetectionHeadWeights* w,
@@ -672,6 +674,19 @@ accumulate_kernel(float* __restrict__ dst, const float* __restrict__ src, long l
   if (i < n) dst[i] += src[i];
 }
 
+// attention backward with separate sources: tensor cores (mma.sync) for head_dim 32 / 64 / 96,
+// the CUDA-core kernel otherwise (attention impl 1 forces the latter: tests, A/B)
+int attn_bwd_x(const AttnXSrc& s, const void* ctx, const void* dctx, long long ctx_img, int ldc,
+               const float* lse, void* dq, long long dq_img, int lddq, void* dk, void* dv,
+               long long dkv_img, int lddkv, int B, int Nq, int Nk, int H, int hd,
+               cudaStream_t stream, const DropParams* drop) {
+  if (attention_impl() != 1 && attention_xmma_bwd_applicable(Nq, Nk, hd))
+    return attention_xmma_bwd(s, ctx, dctx, ctx_img, ldc, lse, dq, dq_img, lddq, dk, dv, dkv_img,
+                              lddkv, B, Nq, Nk, H, hd, stream, drop);
+  return attention_xgen_bwd(s, ctx, dctx, ctx_img, ldc, lse, dq, dq_img, lddq, dk, dv, dkv_img,
+                            lddkv, B, Nq, Nk, H, hd, stream, drop);
+}
+
 // dX[M, in] = dY[M, out] W[out, in] with W^T [in, out] as the K-major B operand; bf16 out, or
 // accumulated into an fp32 stream (TMA reduce-add) / written as fp32
 int dgrad(const void* dY, int out_f, const void* Wt, int M, int in_f, void* dX_bf16, float* dX_f32,
@@ -786,7 +801,7 @@ int head_backward(const VitkDetectionHeadConfig* cfg, const VitkDetectionHeadWei
       const AttnXSrc src{sl.qc, imgD, D, kv + koff, kv + koff + D,
                          static_cast<long long>(d.Ntok) * ldkv, ldkv};
       const DropParams drop_ca = drop.at(DROP_DEC_CA_ATTN, l);
-      VITK_TRY(attention_xgen_bwd(src, sl.ctx_ca, ws.dctx, imgD, D, sl.lse_ca, dqkv, imgD, D,
+      VITK_TRY(attn_bwd_x(src, sl.ctx_ca, ws.dctx, imgD, D, sl.lse_ca, dqkv, imgD, D,
                                   dkv + koff, dkv + koff + D, static_cast<long long>(d.Ntok) * ldkv,
                                   ldkv, d.B, Q, d.P, d.H, d.hd, stream, &drop_ca));
     }
@@ -802,7 +817,7 @@ int head_backward(const VitkDetectionHeadConfig* cfg, const VitkDetectionHeadWei
       const long long img = static_cast<long long>(Q) * 3 * D;
       const AttnXSrc src{qkv, img, 3 * D, qkv + D, qkv + 2 * D, img, 3 * D};
       const DropParams drop_sa = drop.at(DROP_DEC_SA_ATTN, l);
-      VITK_TRY(attention_xgen_bwd(src, sl.ctx_sa, ws.dctx, imgD, D, sl.lse_sa, dqkv, img, 3 * D,
+      VITK_TRY(attn_bwd_x(src, sl.ctx_sa, ws.dctx, imgD, D, sl.lse_sa, dqkv, img, 3 * D,
                                   dqkv + D, dqkv + 2 * D, img, 3 * D, d.B, Q, Q, d.H, d.hd, stream,
                                   &drop_sa));
       VITK_TRY(dgrad(dqkv, 3 * D, lt.sa_in_wt, M, D, nullptr, ws.x, 1.f, stream));
@@ -831,8 +846,8 @@ int head_backward(const VitkDetectionHeadConfig* cfg, const VitkDetectionHeadWei
       VITK_TRY(wgrad(ws.dsumb, D, sl.ctx_sa, D, Q, lg.sa_out_w, nullptr, stream));
       const __nv_bfloat16* qkv = static_cast<const __nv_bfloat16*>(sl.qkv);
       const AttnXSrc src{qkv, 0, 3 * D, qkv + D, qkv + 2 * D, 0, 3 * D};
-      VITK_TRY(attention_xgen_bwd(src, sl.ctx_sa, ws.dctx, 0, D, sl.lse_sa, dqkv, 0, 3 * D, dqkv + D,
-                                  dqkv + 2 * D, 0, 3 * D, 1, Q, Q, d.H, d.hd, stream));
+      VITK_TRY(attn_bwd_x(src, sl.ctx_sa, ws.dctx, 0, D, sl.lse_sa, dqkv, 0, 3 * D, dqkv + D,
+                          dqkv + 2 * D, 0, 3 * D, 1, Q, Q, d.H, d.hd, stream, nullptr));
       VITK_TRY(dgrad(dqkv, 3 * D, lt.sa_in_wt, Q, D, nullptr, ws.xq, 1.f, stream));
       VITK_TRY(wgrad(dqkv, 3 * D, sl.xb_in, D, Q, lg.sa_in_w, lg.sa_in_b, stream));
       accumulate_kernel<<<static_cast<unsigned>((imgD + 255) / 256), 256, 0, stream>>>(

@@ -104,6 +104,16 @@ struct AttnXSrc {
 int attention_xgen_fwd(const AttnXSrc& s, void* ctx, long long ctx_img, int ldc, float* lse, int B,
                        int Nq, int Nk, int H, int hd, cudaStream_t stream,
                        const DropParams* drop = nullptr);
+// Tensor-core (mma.sync) form of attention_xgen_bwd for head_dim 32 / 64 / 96 (attention_xmma.cu):
+// what the detection head's backward uses; same contract.
+bool attention_xmma_bwd_applicable(int Nq, int Nk, int hd);
+int attention_xmma_fwd(const AttnXSrc& s, void* ctx, long long ctx_img, int ldc, float* lse, int B,
+                       int Nq, int Nk, int H, int hd, cudaStream_t stream,
+                       const DropParams* drop = nullptr);
+int attention_xmma_bwd(const AttnXSrc& s, const void* ctx, const void* dctx, long long ctx_img,
+                       int ldc, const float* lse, void* dq, long long dq_img, int lddq, void* dk,
+                       void* dv, long long dkv_img, int lddkv, int B, int Nq, int Nk, int H, int hd,
+                       cudaStream_t stream, const DropParams* drop = nullptr);
 int attention_xgen_bwd(const AttnXSrc& s, const void* ctx, const void* dctx, long long ctx_img,
                        int ldc, const float* lse, void* dq, long long dq_img, int lddq, void* dk,
                        void* dv, long long dkv_img, int lddkv, int B, int Nq, int Nk, int H, int hd,
