@@ -261,11 +261,18 @@ int attention_fwd(const void* qkv, void* ctx, float* lse, int B, int N, int H, i
     // training (log-sum-exp / dropout) and head sizes the mma.sync kernel has no form for (e.g.
     // the 16 of train.py's Config): the CUDA-core kernel; inference at 32 / 96 / 128: the
     // generic-source mma.sync kernel on the packed activation
-    if (lse != nullptr || dropping || !(hd == 32 || hd == 96 || hd == 128))
-      return attention_gen_fwd(qkv, ctx, lse, B, N, H, hd, stream, drop);
     const __nv_bfloat16* p = static_cast<const __nv_bfloat16*>(qkv);
     const int D = H * hd;
     const long long img = static_cast<long long>(N) * 3 * D;
+    if (lse != nullptr || dropping || !(hd == 32 || hd == 96 || hd == 128)) {
+      // tensor cores (mma.sync, whole head in shared memory) when the shape allows, else CUDA cores
+      if (g_attn_impl != 1 && attention_xmma_bwd_applicable(N, N, hd)) {
+        const AttnXSrc src{p, img, 3 * D, p + D, p + 2 * D, img, 3 * D};
+        return attention_xmma_fwd(src, ctx, static_cast<long long>(N) * D, D, lse, B, N, N, H, hd,
+                                  stream, drop);
+      }
+      return attention_gen_fwd(qkv, ctx, lse, B, N, H, hd, stream, drop);
+    }
     return attention_x(p, img, 3 * D, p + D, p + 2 * D, img, 3 * D, ctx,
                        static_cast<long long>(N) * D, D, B, N, N, H, hd, stream);
   }

@@ -271,8 +271,21 @@ int attention_bwd(const void* qkv, const void* ctx, const void* dctx, const floa
   if ((attention_impl() != 1 || dropping) && hd == 64 && N <= 256 && device_cc() >= 100)
     return attention_bwd_tc(qkv, ctx, dctx, lse, dqkv, B, N, H, hd, stream, drop, dbias);
   // other head sizes, longer sequences, dropout without the tcgen05 kernel: CUDA-core kernel
-  if (hd != 64 || N > 256 || dropping)
+  if (hd != 64 || N > 256 || dropping) {
+    if (attention_impl() != 1 && attention_xmma_bwd_applicable(N, N, hd)) {
+      // tensor cores (mma.sync) on the packed activation: q, k, v are column blocks of qkv
+      const __nv_bfloat16* p = static_cast<const __nv_bfloat16*>(qkv);
+      __nv_bfloat16* dp = static_cast<__nv_bfloat16*>(dqkv);
+      const int D = H * hd;
+      const long long img = static_cast<long long>(N) * 3 * D, cimg = static_cast<long long>(N) * D;
+      const AttnXSrc src{p, img, 3 * D, p + D, p + 2 * D, img, 3 * D};
+      VITK_TRY(attention_xmma_bwd(src, ctx, dctx, cimg, D, lse, dp, img, 3 * D, dp + D, dp + 2 * D, img,
+                                  3 * D, B, N, N, H, hd, stream, drop));
+      if (dbias != nullptr) return colsum_bf16(dqkv, 3ll * D, B * N, 3 * D, dbias, stream);
+      return VITK_OK;
+    }
     return attention_gen_bwd(qkv, ctx, dctx, lse, dqkv, B, N, H, hd, stream, drop, dbias);
+  }
   VITK_REQUIRE(B > 0 && H > 0 && N > 0, "attention_bwd: bad shape");
   const int Nkv = (N + 15) & ~15;
   const size_t smem = 4 * static_cast<size_t>(Nkv) * 128 + 2 * 256 * sizeof(float);

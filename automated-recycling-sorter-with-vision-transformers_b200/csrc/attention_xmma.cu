@@ -3,7 +3,9 @@
 // layers of the detection head under training (nn.MultiheadAttention inside
 // nn.TransformerDecoderLayer, train.py:701-707, differentiated at train.py:1455): 100 object
 // queries against 100 (self-attention) or 196 (cross-attention onto the patch tokens) keys, 8 heads
-// of dimension 96.  head_dim 32 / 64 / 96; any number of queries and keys that fits shared memory.
+// of dimension 96 - and the encoder's own attention under training when head_dim != 64 (the
+// reference's shipped Config: 25 heads of 16, train.py:1345-1356).  head_dim 16 .. 128 in steps of
+// 16; any number of queries and keys that fits shared memory.
 //
 //   P  = exp(q k^T * scale - lse)           dP = d_ctx v^T           Drow = rowsum(d_ctx * ctx)
 //   dS = P * (dropmask(dP) - Drow) * scale  dq = dS k     dk = dS^T q     dv = dropmask(P)^T d_ctx
@@ -59,6 +61,11 @@ __device__ __forceinline__ void ldsm4(uint32_t addr, uint32_t& r0, uint32_t& r1,
                : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
                : "r"(addr));
 }
+__device__ __forceinline__ void ldsm2(uint32_t addr, uint32_t& r0, uint32_t& r1) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];"
+               : "=r"(r0), "=r"(r1)
+               : "r"(addr));
+}
 __device__ __forceinline__ void ldsm4t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2,
                                        uint32_t& r3) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
@@ -110,6 +117,11 @@ struct Tile {
           ldsm4(at(sB, row, (lane >> 3) + 4 * q4), b0, b1, b2, b3);
           mma16816(acc[j], a[2 * q4], b0, b1);
           mma16816(acc[j], a[2 * q4 + 1], b2, b3);
+        }
+        if constexpr (HD % 32 != 0) {   // odd number of k-steps: the last one alone
+          uint32_t b0, b1;
+          ldsm2(at(sB, row, ((lane >> 3) & 1) + 4 * (HD / 32)), b0, b1);
+          mma16816(acc[j], a[kKS - 1], b0, b1);
         }
       }
     }
@@ -458,7 +470,7 @@ int launch_xmma(const XmParams& p, int B, cudaStream_t stream) {
 }  // namespace
 
 bool attention_xmma_bwd_applicable(int Nq, int Nk, int hd) {
-  if (!(hd == 32 || hd == 64 || hd == 96)) return false;
+  if (hd < 16 || hd > 128 || hd % 16 != 0) return false;
   if (Nq <= 0 || Nk <= 0) return false;
   const int Nq16 = (Nq + 15) & ~15, Nk16 = (Nk + 15) & ~15;
   const size_t smem = static_cast<size_t>(2 * Nq16 + 2 * Nk16) * (hd * 2 + 16) +
@@ -473,7 +485,7 @@ int attention_xmma_bwd(const AttnXSrc& s, const void* ctx, const void* dctx, lon
   VITK_REQUIRE(s.q && s.k && s.v && ctx && dctx && lse && dq && dk && dv,
                "attention_bwd (tensor-core, generic sources): null operand");
   VITK_REQUIRE(B > 0 && H > 0 && attention_xmma_bwd_applicable(Nq, Nk, hd),
-               "attention_bwd (tensor-core, generic sources): head_dim 32 / 64 / 96 and queries + "
+               "attention_bwd (tensor-core, generic sources): head_dim a multiple of 16 up to 128 and queries + "
                "keys within shared memory (got %d x %d, head_dim %d)", Nq, Nk, hd);
   // 16-byte cp.async / uint4 reads and 4-byte paired stores
   VITK_REQUIRE(s.ldq % 8 == 0 && s.ldkv % 8 == 0 && ldc % 8 == 0 && lddq % 2 == 0 && lddkv % 2 == 0 &&
@@ -501,9 +513,14 @@ int attention_xmma_bwd(const AttnXSrc& s, const void* ctx, const void* dctx, lon
   if (drop != nullptr) p.drop = *drop;
   ProfileScope prof(PROF_ATTN, 10.0 * B * H * static_cast<double>(Nq) * Nk * hd, stream);
   switch (hd) {
+    case 16: return launch_xmma<16>(p, B, stream);
     case 32: return launch_xmma<32>(p, B, stream);
+    case 48: return launch_xmma<48>(p, B, stream);
     case 64: return launch_xmma<64>(p, B, stream);
-    default: return launch_xmma<96>(p, B, stream);
+    case 80: return launch_xmma<80>(p, B, stream);
+    case 96: return launch_xmma<96>(p, B, stream);
+    case 112: return launch_xmma<112>(p, B, stream);
+    default: return launch_xmma<128>(p, B, stream);
   }
 }
 
@@ -511,7 +528,7 @@ int attention_xmma_fwd(const AttnXSrc& s, void* ctx, long long ctx_img, int ldc,
                        int Nq, int Nk, int H, int hd, cudaStream_t stream, const DropParams* drop) {
   VITK_REQUIRE(s.q && s.k && s.v && ctx, "attention (tensor-core, generic sources): null operand");
   VITK_REQUIRE(B > 0 && H > 0 && attention_xmma_bwd_applicable(Nq, Nk, hd),
-               "attention (tensor-core, generic sources): head_dim 32 / 64 / 96 and queries + keys "
+               "attention (tensor-core, generic sources): head_dim a multiple of 16 up to 128 and queries + keys "
                "within shared memory (got %d x %d, head_dim %d)", Nq, Nk, hd);
   VITK_REQUIRE(s.ldq % 8 == 0 && s.ldkv % 8 == 0 && ldc % 2 == 0 && s.q_img % 8 == 0 &&
                    s.kv_img % 8 == 0 && ctx_img % 2 == 0,
@@ -531,9 +548,14 @@ int attention_xmma_fwd(const AttnXSrc& s, void* ctx, long long ctx_img, int ldc,
   if (drop != nullptr) p.drop = *drop;
   ProfileScope prof(PROF_ATTN, 4.0 * B * H * static_cast<double>(Nq) * Nk * hd, stream);
   switch (hd) {
+    case 16: return launch_xmma_fwd<16>(p, B, ctx, lse, stream);
     case 32: return launch_xmma_fwd<32>(p, B, ctx, lse, stream);
+    case 48: return launch_xmma_fwd<48>(p, B, ctx, lse, stream);
     case 64: return launch_xmma_fwd<64>(p, B, ctx, lse, stream);
-    default: return launch_xmma_fwd<96>(p, B, ctx, lse, stream);
+    case 80: return launch_xmma_fwd<80>(p, B, ctx, lse, stream);
+    case 96: return launch_xmma_fwd<96>(p, B, ctx, lse, stream);
+    case 112: return launch_xmma_fwd<112>(p, B, ctx, lse, stream);
+    default: return launch_xmma_fwd<128>(p, B, ctx, lse, stream);
   }
 }
 

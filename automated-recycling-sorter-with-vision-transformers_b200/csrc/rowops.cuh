@@ -104,8 +104,9 @@ struct AttnXSrc {
 int attention_xgen_fwd(const AttnXSrc& s, void* ctx, long long ctx_img, int ldc, float* lse, int B,
                        int Nq, int Nk, int H, int hd, cudaStream_t stream,
                        const DropParams* drop = nullptr);
-// Tensor-core (mma.sync) form of attention_xgen_bwd for head_dim 32 / 64 / 96 (attention_xmma.cu):
-// what the detection head's backward uses; same contract.
+// Tensor-core (mma.sync) forms of attention_xgen_fwd / _bwd for head_dim 16 .. 128 in steps of 16
+// (attention_xmma.cu): the detection head under training, and the encoder's own attention under
+// training when head_dim != 64; same contracts.
 bool attention_xmma_bwd_applicable(int Nq, int Nk, int hd);
 int attention_xmma_fwd(const AttnXSrc& s, void* ctx, long long ctx_img, int ldc, float* lse, int B,
                        int Nq, int Nk, int H, int hd, cudaStream_t stream,

@@ -90,16 +90,24 @@ def test_adamw_matches_torch(vitk, n):
                                        (2, 197, 3, 96),
                                        (1, 197, 2, 128),
                                        (2, 577, 2, 64),     # 384 px: beyond the tcgen05 backward
-                                       (1, 257, 1, 8)])
-def test_generic_attention_forward_and_backward(vitk, B, N, H, hd):
-    """attention_gen.cu (CUDA-core kernels): context, log-sum-exp and d_qkv against autograd of the
-    reference's formulation (train.py:536-549) for the shapes the tensor-core kernels leave out."""
+                                       (1, 257, 1, 8),
+                                       (2, 130, 3, 48), (2, 77, 2, 80), (1, 197, 2, 112)])
+@pytest.mark.parametrize("impl", [0, 1], ids=["mma.sync-where-it-fits", "cuda-cores"])
+def test_generic_attention_forward_and_backward(vitk, B, N, H, hd, impl):
+    """The attention kernels behind every shape the tcgen05 kernels leave out - attention_xmma.cu
+    (mma.sync; head_dim a multiple of 16, the head's rows in shared memory) and attention_gen.cu
+    (CUDA cores; anything else, and everything under impl 1): context, log-sum-exp and d_qkv
+    against autograd of the reference's formulation (train.py:536-549)."""
     g = torch.Generator(device="cuda").manual_seed(N + hd)
     D = H * hd
     qkv = torch.randn(B * N, 3 * D, generator=g, device="cuda").bfloat16()
     dctx = torch.randn(B * N, D, generator=g, device="cuda").bfloat16()
-    ctx, lse = vitk.ops.attention(qkv, B, N, H, return_lse=True)
-    dqkv = vitk.ops.attention_bwd(qkv, ctx, dctx, lse, B, N, H)
+    vitk._lib.set_attention_impl(impl)
+    try:
+        ctx, lse = vitk.ops.attention(qkv, B, N, H, return_lse=True)
+        dqkv = vitk.ops.attention_bwd(qkv, ctx, dctx, lse, B, N, H)
+    finally:
+        vitk._lib.set_attention_impl(0)
     ref_in = qkv.float().requires_grad_(True)
     q, k, v = ref_in.reshape(B, N, 3, H, hd).permute(2, 0, 3, 1, 4)
     s = (q @ k.transpose(-2, -1)) / hd ** 0.5
