@@ -365,7 +365,11 @@ __device__ __forceinline__ void acc_plus_bias(const uint32_t (&v)[32], int n0, i
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float4 b = __ldg(b4 + j);
+#ifdef VITK_SCALAR_BIAS   // A/B build: the scalar form for every epilogue
+        if constexpr (true) {
+#else
         if constexpr (EPI == EPI_F32) {
+#endif
           x[4 * j + 0] = fmaf(acc_scale, __uint_as_float(v[4 * j + 0]), b.x);
           x[4 * j + 1] = fmaf(acc_scale, __uint_as_float(v[4 * j + 1]), b.y);
           x[4 * j + 2] = fmaf(acc_scale, __uint_as_float(v[4 * j + 2]), b.z);
