@@ -121,6 +121,7 @@ _SIGNATURES = {
     "vitk_gemm_set_cta_group": (C.c_int, [C.c_int]),
     "vitk_gemm_set_direct_epilogue": (C.c_int, [C.c_int]),
     "vitk_gemm_set_fused_layernorm": (C.c_int, [C.c_int]),
+    "vitk_debug_gemm_trace": (C.c_int, [C.c_void_p, C.c_int]),
     "vitk_set_layernorm_folding": (C.c_int, [C.c_int]),
     "vitk_fold_layernorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),

@@ -474,6 +474,7 @@ int vitk_gemm_set_direct_epilogue(int on) {
   gemm_force_direct_epilogue(on != 0);
   return VITK_OK;
 }
+int vitk_debug_gemm_trace(long long* out_host, int n) { return gemm_debug_trace(out_host, n); }
 int vitk_gemm_set_fused_layernorm(int on) {
   gemm_set_fused_layernorm(on != 0);
   return VITK_OK;

@@ -25,6 +25,18 @@
 namespace vitk {
 using namespace ptx;
 
+// Debug aid (build with VITK_NVCC_EXTRA=-DVITK_GEMM_TRACE): the MMA-issuing warp of every pair
+// leader accumulates the SM clocks it spends waiting for operands (full barriers), for a free
+// accumulator stage (the epilogue), and its total run time; tests/trace_gemm.py reads them back.
+#ifdef VITK_GEMM_TRACE
+__device__ long long g_gemm_trace[160][4];
+#define GT_BEGIN(v) const long long v = clock64()
+#define GT_ADD(acc, v) acc += clock64() - v
+#else
+#define GT_BEGIN(v) do { } while (0)
+#define GT_ADD(acc, v) do { } while (0)
+#endif
+
 namespace {
 
 constexpr int kBlockM = 128;
@@ -803,13 +815,19 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      [[maybe_unused]] long long gt_full = 0, gt_empty = 0;
+      GT_BEGIN(gt_start);
       for (int work = cluster_id; work < num_tiles; work += num_clusters) {
+        GT_BEGIN(gt_e);
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        GT_ADD(gt_empty, gt_e);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
         const int kb0 = kb_begin(work);
         for (int kb = kb0; kb < kb_end(work); ++kb) {
+          GT_BEGIN(gt_f);
           mbar_wait(full_bar(stage), phase);
+          GT_ADD(gt_full, gt_f);
           tc_fence_after();
           const uint32_t sa = base + stage * C::kStageBytes;
           const uint32_t sb = sa + C::kABytes;
@@ -849,6 +867,14 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
           acc_phase ^= 1u;
         }
       }
+#ifdef VITK_GEMM_TRACE
+      if (lane == 0 && cluster_id < 160) {
+        g_gemm_trace[cluster_id][0] = clock64() - gt_start;
+        g_gemm_trace[cluster_id][1] = gt_full;
+        g_gemm_trace[cluster_id][2] = gt_empty;
+        g_gemm_trace[cluster_id][3] = (num_tiles - cluster_id + num_clusters - 1) / num_clusters;
+      }
+#endif
     }
   }
   } else if (warp < kFirstEpiWarp + kNumEpiWarps) {
@@ -1442,6 +1468,17 @@ int dispatch(const GemmProblem& p, cudaStream_t stream) {
 
 }  // namespace
 
+int gemm_debug_trace(long long* out, int n) {
+#ifdef VITK_GEMM_TRACE
+  if (n > 160 * 4) n = 160 * 4;
+  return cudaMemcpyFromSymbol(out, g_gemm_trace, static_cast<size_t>(n) * sizeof(long long)) ==
+                 cudaSuccess ? n : -1;
+#else
+  (void)out;
+  (void)n;
+  return 0;   // not a trace build
+#endif
+}
 void gemm_force_cta_group(int ctas) { g_force_ctas = ctas; }
 void gemm_force_direct_epilogue(int on) { g_force_direct_epi = on; }
 void gemm_set_fused_layernorm(int on) { g_fused_ln = on; }

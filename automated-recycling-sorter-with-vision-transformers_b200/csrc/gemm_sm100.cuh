@@ -99,6 +99,10 @@ int gemm_bf16_tn(const GemmProblem& p, cudaStream_t stream);
 void gemm_force_cta_group(int ctas);
 // 1 = always use the register->global epilogue instead of the smem-staged TMA store/reduce.
 void gemm_force_direct_epilogue(int on);
+// Trace builds (-DVITK_GEMM_TRACE): copies [pair][{total, wait operands, wait accumulator stage,
+// tiles}] SM-clock counts of the last GEMM launch into out (n entries); returns the entries
+// written, 0 when the library is not a trace build.
+int gemm_debug_trace(long long* out, int n);
 // Column groups per row of EPI_RESID_STATS_F32's partial sums for an N-column output.
 int gemm_stats_parts(int N);
 // GemmEpilogue::ln_out: 0 (default) = residual GEMM, then a separate layernorm_fwd launch;

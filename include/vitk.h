@@ -116,6 +116,11 @@ int vitk_gemm_set_cta_group(int ctas);
 /* 1 = write GEMM outputs with per-thread global stores instead of the smem-staged TMA
  * store / reduce-add epilogue (tests, A/B timing). */
 int vitk_gemm_set_direct_epilogue(int on);
+/* Debug aid: in a library built with -DVITK_GEMM_TRACE the MMA-issuing warp of every CTA pair counts
+ * the SM clocks it waits for operands / for a free accumulator stage; copies
+ * [pair][{total, wait operands, wait accumulator, tiles}] of the last GEMM launch to HOST memory
+ * (n entries).  Returns the entries written; 0 in a normal build. */
+int vitk_debug_gemm_trace(long long* out_host, int n);
 /* LayerNorm after a residual GEMM (vitk_gemm_resid_layernorm and the encoder's projection /
  * linear2 launches): 0 (default) = a separate LayerNorm launch, 1 = LayerNorm warps inside the
  * GEMM kernel (one launch; measured slower on B200, kept for A/B - DESIGN.md section 6).  Same
