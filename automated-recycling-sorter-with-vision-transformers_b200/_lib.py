@@ -113,6 +113,16 @@ class VitkDetectionHeadGrads(C.Structure):
                 ("class_b", C.c_void_p), ("bbox_w", C.c_void_p), ("bbox_b", C.c_void_p)]
 
 
+MAX_PEERS = 16
+
+
+class VitkPeerBuffers(C.Structure):
+    _fields_ = [("world", C.c_int), ("rank", C.c_int),
+                ("grad", C.c_void_p * MAX_PEERS), ("param", C.c_void_p * MAX_PEERS),
+                ("shadow", C.c_void_p * MAX_PEERS), ("guard", C.c_void_p * MAX_PEERS),
+                ("grad_mc", C.c_void_p), ("param_mc", C.c_void_p), ("shadow_mc", C.c_void_p)]
+
+
 # name -> (restype, argtypes); must list every symbol include/vitk.h declares.
 _SIGNATURES = {
     "vitk_abi_version": (C.c_int, []),
@@ -235,6 +245,12 @@ _SIGNATURES = {
                                                C.POINTER(VitkDetectionHeadGrads), C.c_void_p,
                                                C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vitk_peer_reduce_scan": (C.c_int, [C.POINTER(VitkPeerBuffers), C.c_longlong, C.c_longlong,
+                                        C.c_void_p]),
+    "vitk_peer_adamw_broadcast": (C.c_int, [C.POINTER(VitkPeerBuffers), C.c_void_p, C.c_void_p,
+                                            C.c_longlong, C.c_longlong, C.c_double, C.c_double,
+                                            C.c_double, C.c_double, C.c_double, C.c_int, C.c_float,
+                                            C.c_void_p]),
     "vitk_weighted_cross_entropy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_float,
                                               C.c_void_p]),

@@ -21,7 +21,7 @@ import torch.distributed as dist
 
 from . import _lib
 from ._lib import (VitkBlockGrads, VitkBlockWeights, VitkBlockWeightsT, VitkConfig, VitkGrads,
-                   VitkWeights, VitkWeightsT, check, lib)
+                   VitkPeerBuffers, VitkWeights, VitkWeightsT, check, lib)
 
 _ALIGN = 64  # elements: keeps every parameter 256-byte (fp32) / 128-byte (bf16) aligned
 
@@ -30,9 +30,52 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+class PeerArenas:
+    """The flat parameter / gradient / bf16-shadow arenas (and the optimizer's guard flag) in
+    symmetric memory: the same allocation on every GPU of the group, mapped into every process
+    (torch.distributed._symmetric_memory; with NVSwitch also behind one multicast address).  What
+    `vitk_peer_reduce_scan` / `vitk_peer_adamw_broadcast` (csrc/peer_optim.cu) read and write."""
+
+    def __init__(self, numel: int, device, group):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        name = self.group.group_name
+        self.flat = symm_mem.empty(numel, dtype=torch.float32, device=device)
+        self.grad = symm_mem.empty(numel, dtype=torch.float32, device=device)
+        self.shadow = symm_mem.empty(numel, dtype=torch.bfloat16, device=device)
+        self.guard = symm_mem.empty(4, dtype=torch.int32, device=device)
+        for t in (self.flat, self.grad, self.shadow, self.guard):
+            t.zero_()
+        self.handles = [symm_mem.rendezvous(t, name) for t in
+                        (self.flat, self.grad, self.shadow, self.guard)]
+        h = self.handles[0]
+        self.world, self.rank = h.world_size, h.rank
+        if self.world > _lib.MAX_PEERS:
+            raise _lib.VitkError(f"peer optimizer: at most {_lib.MAX_PEERS} ranks")
+        # contiguous shards with 64-element aligned boundaries (16-byte accesses in every arena)
+        per = (numel // self.world + _ALIGN - 1) // _ALIGN * _ALIGN
+        self.bounds = [min(r * per, numel) for r in range(self.world)] + [numel]
+
+    def buffers(self, with_guard: bool, multicast: bool = True) -> VitkPeerBuffers:
+        pb = VitkPeerBuffers()
+        pb.world, pb.rank = self.world, self.rank
+        hf, hg, hs, hq = self.handles
+        for r in range(self.world):
+            pb.param[r], pb.grad[r], pb.shadow[r] = hf.buffer_ptrs[r], hg.buffer_ptrs[r], hs.buffer_ptrs[r]
+            pb.guard[r] = hq.buffer_ptrs[r] if with_guard else None
+        self.multicast = bool(multicast) and all(int(h.multicast_ptr or 0) != 0 for h in (hf, hg, hs))
+        if self.multicast:
+            pb.param_mc, pb.grad_mc, pb.shadow_mc = hf.multicast_ptr, hg.multicast_ptr, hs.multicast_ptr
+        return pb
+
+    def barrier(self, channel: int = 0) -> None:
+        """Cross-rank barrier enqueued on the current stream (signal pads of the parameter arena)."""
+        self.handles[0].barrier(channel=channel)
+
+
 class TrainState:
     def __init__(self, backbone: torch.nn.Module, head: torch.nn.Linear | None, n_prefix: int,
-                 bind_grads: bool = True):
+                 bind_grads: bool = True, peer_group=None, use_peer_memory: bool = False):
         self.backbone, self.head, self.n_prefix = backbone, head, n_prefix
         named = [("backbone." + n, p) for n, p in backbone.named_parameters()]
         if head is not None:
@@ -49,12 +92,16 @@ class TrainState:
             off += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
         self.numel = off
         z = lambda dt: torch.zeros(self.numel, dtype=dt, device=dev)
-        self.flat, self.grad = z(torch.float32), z(torch.float32)
+        self.peer = PeerArenas(self.numel, dev, peer_group) if use_peer_memory else None
+        if self.peer is not None:
+            self.flat, self.grad = self.peer.flat, self.peer.grad
+        else:
+            self.flat, self.grad = z(torch.float32), z(torch.float32)
         # Adam moments only where the fused optimizer runs (FineTuner); the autograd bridge hands
         # gradients to whatever torch.optim optimizer the caller uses
         self.exp_avg, self.exp_avg_sq = (z(torch.float32), z(torch.float32)) if bind_grads \
             else (None, None)
-        self.shadow = z(torch.bfloat16)
+        self.shadow = self.peer.shadow if self.peer is not None else z(torch.bfloat16)
         for n, p in named:                      # re-home parameters into the arena
             o = self.offsets[n]
             view = self.flat[o:o + p.numel()].view(p.shape)
@@ -219,21 +266,43 @@ class FineTuner:
 
     def __init__(self, model, lr=1e-4, weight_decay=1e-4, betas=(0.9, 0.999), eps=1e-8,
                  process_group=None, overlap_allreduce: bool = True, reserve_sms: int = 0,
-                 seed: int = 0, data_parallel: bool = True, skip_nonfinite: bool = True):
+                 seed: int = 0, data_parallel: bool = True, skip_nonfinite: bool = True,
+                 grad_sync: str = "auto"):
         """overlap_allreduce: start each gradient bucket's all-reduce on a side stream as soon as
         the backward has produced it (events recorded by vitk_classifier_loss_backward_ev), instead
         of reducing everything after the backward.  reserve_sms: SMs kept out of the persistent
         kernels' grids during the backward so that the NCCL kernels do not have to displace them
         (pair with a communicator limited to as many CTAs: ProcessGroupNCCL.Options.config.max_ctas)."""
+        """grad_sync (data parallel only): "nccl" = all-reduce of the flat gradient slices, then
+        the same AdamW on every rank; "peer" = sharded reduce + AdamW + broadcast through symmetric
+        memory (csrc/peer_optim.cu: multimem.ld_reduce / multimem.st over NVSwitch when the fabric
+        has multicast, peer loads / stores otherwise; Adam moments sharded over the ranks); "auto"
+        (default; VITK_GRAD_SYNC overrides) = "peer" when every rank can set it up, else "nccl"."""
+        import os
         self.model = model
         self.lr, self.wd, self.betas, self.eps = lr, weight_decay, betas, eps
-        self.state = TrainState(model.backbone, model.head, model.backbone._n_prefix)
         self.pg = process_group
         # data_parallel=False: a single-process step even inside an initialised process group
         # (bench.py's dp_check compares it with the data-parallel step on the same weights)
         ddp = data_parallel and dist.is_available() and dist.is_initialized()
         self.world = dist.get_world_size(process_group) if ddp else 1
         rank = dist.get_rank(process_group) if ddp else 0
+        grad_sync = os.environ.get("VITK_GRAD_SYNC", grad_sync)
+        if grad_sync not in ("auto", "nccl", "peer"):
+            raise _lib.VitkError(f"grad_sync must be 'auto', 'nccl' or 'peer' (got {grad_sync!r})")
+        self.state, self.peer, self.grad_sync = None, None, "none" if self.world == 1 else "nccl"
+        if self.world > 1 and grad_sync in ("auto", "peer"):
+            self.state, why = self._try_peer_state(model, process_group, rank)
+            if self.state is not None:
+                self.peer, self.grad_sync = self.state.peer, "peer"
+            elif grad_sync == "peer":
+                raise _lib.VitkError(f"grad_sync='peer' is not available here: {why}")
+            elif rank == 0:
+                import sys
+                print(f"vitk: gradient exchange over NCCL (peer-memory path unavailable: {why})",
+                      file=sys.stderr)
+        if self.state is None:
+            self.state = TrainState(model.backbone, model.head, model.backbone._n_prefix)
         # dropout mask stream: step k uses seed + k; every data-parallel rank draws its own masks
         # (the same masks on every shard would correlate the ranks' gradients)
         self.seed = (int(seed) + 0x9E3779B1 * rank) & 0x7FFFFFFF
@@ -242,12 +311,17 @@ class FineTuner:
         # when a gradient is inf / nan; device int[2] {flag, steps skipped}, never read by the
         # host inside step().  Off: every gradient slice is updated as soon as its own all-reduce
         # has finished (the optimizer then runs under the reductions still in flight).
-        self._guard = torch.zeros(2, dtype=torch.int32, device=self.state.device) \
-            if skip_nonfinite else None
+        if not skip_nonfinite:
+            self._guard = None
+        elif self.peer is not None:
+            self._guard = self.peer.guard[:2]       # symmetric: a rank raises the flag on all ranks
+        else:
+            self._guard = torch.zeros(2, dtype=torch.int32, device=self.state.device)
+        self._peer_buffers = self.peer.buffers(skip_nonfinite) if self.peer is not None else None
         self._comm_stream = (torch.cuda.Stream(device=self.state.device, priority=-1)
                              if self.world > 1 else None)
         self._loss = torch.zeros(1, dtype=torch.float32, device=self.state.device)
-        self.overlap = bool(overlap_allreduce) and self.world > 1
+        self.overlap = bool(overlap_allreduce) and self.world > 1 and self.peer is None
         self.reserve_sms = int(reserve_sms) if self.overlap else 0
         self._slices = self.state.bucket_slices()
         self._events, self._event_arr = None, None
@@ -279,6 +353,8 @@ class FineTuner:
         logits = torch.empty((B, cfg.n_classes), dtype=torch.float32, device=st.device)
         st.grad.zero_()
         self._loss.zero_()
+        if self.peer is not None and self._guard is not None:
+            self._guard[0:1].zero_()   # local flag; peers may raise it again after the barrier below
         s = _stream()
         check(lib().vitk_forward_train(C.byref(cfg), C.byref(st.W), images.data_ptr(), B, None,
                                        saved, saved_bytes, ws, ws_bytes, s))
@@ -322,7 +398,9 @@ class FineTuner:
                                                  1 if first[0] else 0, s))
                 first[0] = False
 
-        if guard is None:
+        if self.peer is not None:
+            self._peer_step(ranges, s)
+        elif guard is None:
             if self.world > 1:
                 self._allreduce_grads(on_slice_done=lambda k, a, b: adamw(a, b))
             else:
@@ -345,6 +423,49 @@ class FineTuner:
         torch._C._increment_version(st.params)
         st._versions = [p._version for p in st.params]
         return self._loss, logits
+
+    # ------------------------------------------------------------------ peer-memory optimizer step
+    def _try_peer_state(self, model, group, rank):
+        """TrainState with its arenas in symmetric memory, or (None, reason).  Collective: every
+        rank calls it, and all ranks agree on the outcome."""
+        state, why = None, ""
+        try:
+            state = TrainState(model.backbone, model.head, model.backbone._n_prefix,
+                               peer_group=group, use_peer_memory=True)
+        except Exception as e:   # no symmetric-memory support in this build / on this fabric
+            why = f"{type(e).__name__}: {e}"
+        ok = torch.tensor([1 if state is not None else 0], device=model.head.weight.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) == 0:
+            if state is not None:
+                # parameters were re-homed into the symmetric arena: the NCCL state re-homes them again
+                why = "another rank could not set it up"
+            return None, why or "another rank could not set it up"
+        return state, ""
+
+    def reduced_grad_range(self) -> tuple[int, int]:
+        """[lo, hi) of the flat gradient arena that holds the cross-rank SUM after step(): everything
+        with NCCL, this rank's shard with the peer-memory optimizer."""
+        if self.peer is None:
+            return 0, self.state.numel
+        return self.peer.bounds[self.peer.rank], self.peer.bounds[self.peer.rank + 1]
+
+    def _peer_step(self, ranges, s):
+        st, pr = self.state, self.peer
+        lo, hi = pr.bounds[pr.rank], pr.bounds[pr.rank + 1]
+        pb = C.byref(self._peer_buffers)
+        pr.barrier(0)                      # every rank's backward has finished: gradients final
+        own = [(max(a, lo), min(b, hi)) for a, b in ranges if min(b, hi) > max(a, lo)]
+        for a, b in own:
+            check(lib().vitk_peer_reduce_scan(pb, a, b, s))
+        pr.barrier(1)                      # the skip flag is final on every rank
+        for a, b in own:
+            check(lib().vitk_peer_adamw_broadcast(
+                pb, st.exp_avg.data_ptr(), st.exp_avg_sq.data_ptr(), a, b, self.lr, self.betas[0],
+                self.betas[1], self.eps, self.wd, st.step_count, 1.0, s))
+        if self._guard is not None:
+            check(lib().vitk_grad_guard_finish(self._guard.data_ptr(), s))
+        pr.barrier(2)                      # every rank's parameters and shadows are in place
 
     @property
     def skipped_steps(self) -> int:
@@ -376,7 +497,17 @@ class FineTuner:
     # model.parameters() order), so a checkpoint written by either implementation resumes in the
     # other.
     def optimizer_state_dict(self) -> dict:
+        """torch.optim.AdamW's state layout.  With the peer-memory optimizer the Adam moments are
+        sharded over the ranks: this call is then COLLECTIVE (every rank must make it) - each shard
+        is broadcast from its owner first."""
         st = self.state
+        if self.peer is not None:
+            for r in range(self.peer.world):
+                a, b = self.peer.bounds[r], self.peer.bounds[r + 1]
+                if b > a:
+                    src = dist.get_global_rank(self.peer.group, r)
+                    dist.broadcast(st.exp_avg[a:b], src=src, group=self.peer.group)
+                    dist.broadcast(st.exp_avg_sq[a:b], src=src, group=self.peer.group)
         state = {}
         for i, (name, p) in enumerate(zip(st.names, st.params)):
             o = st.offsets[name]

@@ -267,7 +267,8 @@ def measure_train_step(vitk, O, dev, world, rank, barrier, steps: int = 8, warmu
     ips = world * B * steps / (ms * 1e-3)
     flops = 3.0 * fwd_flops_per_image()
     peaks, _ = measured_peaks()
-    tuner_overlap = tuner.overlap
+    tuner_overlap, tuner_sync = tuner.overlap, tuner.grad_sync
+    tuner_mc = bool(tuner.peer is not None and tuner.peer.multicast)
     del tuner, model
     torch.cuda.empty_cache()
     return {"metric": "vit_b16_224_finetune_images_per_sec", "value": ips, "unit": UNIT,
@@ -280,9 +281,13 @@ def measure_train_step(vitk, O, dev, world, rank, barrier, steps: int = 8, warmu
             "optimizer": "fused AdamW lr 1e-4 wd 1e-4 (train.py:1598-1602)",
             "dropout": dropout,
             "grad_allreduce": ("none (1 GPU)" if world == 1 else
-                               ("NCCL sum over 14 flat fp32 slices, each started when the backward "
-                                "has produced it (overlapped)" if tuner_overlap else
-                                "NCCL sum over 14 flat fp32 slices after the backward"))}
+                               (("sharded reduce + AdamW + broadcast over symmetric memory "
+                                 "(csrc/peer_optim.cu; " + ("multimem.ld_reduce / multimem.st through "
+                                 "the NVSwitch" if tuner_mc else "peer loads / stores over NVLink") +
+                                 "), Adam moments sharded over the ranks") if tuner_sync == "peer" else
+                                ("NCCL sum over 14 flat fp32 slices, each started when the backward "
+                                 "has produced it (overlapped)" if tuner_overlap else
+                                 "NCCL sum over 14 flat fp32 slices after the backward")))}
 
 
 def measure_detector(vitk, dev, world, barrier, batch: int, steps: int = 6, warmup: int = 3) -> dict:
@@ -587,7 +592,10 @@ def dp_check(vitk, O, dev, world, rank, steps: int = 3, batch: int = 8) -> dict:
     x = O.synthetic_images(batch, DP_CHECK_KW["image_size"], seed=777 + rank).to(dev)
     y = O.synthetic_labels(batch, N_CLASSES, seed=55 + rank).to(dev)
     loss, _ = tuner.step(x, y)
-    g_dp = tuner.state.grad.clone()            # summed over ranks, already scaled by 1/(B*world)
+    # summed over ranks, already scaled by 1/(B*world); with the peer-memory optimizer every rank
+    # holds the sum of its own shard only
+    lo_g, hi_g = tuner.reduced_grad_range()
+    g_dp = tuner.state.grad[lo_g:hi_g].clone()
     lt = loss.clone()
     dist.all_reduce(lt)
     # the single-GPU step on the concatenated batch, from the same initial weights
@@ -600,18 +608,34 @@ def dp_check(vitk, O, dev, world, rank, steps: int = 3, batch: int = 8) -> dict:
     solo.load_state_dict(sd0)
     solo_tuner = vitk.FineTuner(solo, lr=1e-4, weight_decay=1e-4, data_parallel=False)
     loss1, _ = solo_tuner.step(torch.cat(xs), torch.cat(ys))
-    g1 = solo_tuner.state.grad
-    rel = float((g_dp - g1).norm() / (g1.norm() + 1e-30))
+    g1 = solo_tuner.state.grad[lo_g:hi_g]
+    sq = torch.stack([(g_dp - g1).double().pow(2).sum(), g1.double().pow(2).sum()])
+    dist.all_reduce(sq)
+    rel = float((sq[0] / (sq[1] + 1e-60)).sqrt())
     loss_diff = abs(float(lt.item()) - float(loss1.item()))
     for _ in range(steps - 1):
         tuner.step(x, y)
+    # the same steps with the gradient exchange over NCCL (all-reduce + replicated AdamW): the two
+    # transports must agree up to the order of the cross-rank sum
+    sync = tuner.grad_sync
+    vs_nccl = None
+    if sync == "peer":
+        torch.manual_seed(0)
+        other = vitk.ViTClassifier(num_classes=N_CLASSES, dropout=0.0, **DP_CHECK_KW).to(dev).train()
+        other.load_state_dict(sd0)
+        other_tuner = vitk.FineTuner(other, lr=1e-4, weight_decay=1e-4, grad_sync="nccl")
+        for _ in range(steps):
+            other_tuner.step(x, y)
+        vs_nccl = float((other_tuner.state.flat - tuner.state.flat).abs().max().item())
+        del other_tuner, other
     flat = tuner.state.flat
     lo, hi = flat.clone(), flat.clone()
     dist.all_reduce(lo, op=dist.ReduceOp.MIN)
     dist.all_reduce(hi, op=dist.ReduceOp.MAX)
     identical = bool(torch.equal(lo, hi))
-    ok = identical and rel < 2e-2 and loss_diff < 1e-3
-    out = {"ok": ok, "params_bitwise_identical_across_ranks": identical, "steps": steps,
+    ok = identical and rel < 2e-2 and loss_diff < 1e-3 and (vs_nccl is None or vs_nccl < 1e-5)
+    out = {"ok": ok, "grad_sync": sync, "params_bitwise_identical_across_ranks": identical,
+           "peer_vs_nccl_param_max_abs_diff": vs_nccl, "steps": steps,
            "grad_rel_l2_vs_single_gpu_concatenated_batch": rel, "grad_tolerance": 2e-2,
            "loss_abs_diff_vs_single_gpu": loss_diff,
            "config": f"ViT-B/16 width, 2 blocks, {batch} images per rank x {world} ranks, dropout 0"}

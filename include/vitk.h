@@ -609,6 +609,41 @@ int vitk_detection_head_backward(const VitkDetectionHeadConfig* cfg,
                                  int skip_tokens, float* d_tokens_out, void* saved, void* workspace,
                                  vitk_stream_t stream);
 
+/* ---- data-parallel optimizer step over peer memory (NVLink / NVSwitch) ----
+ * Replaces "all-reduce the gradients, then every rank runs the same AdamW" (the data-parallel
+ * form of train.py:1455-1460) by a sharded reduce + update + broadcast through symmetric memory:
+ * rank r owns the elements [lo_r, hi_r) of the flat arenas.  The caller provides every rank's
+ * arenas as peer-mapped device pointers (e.g. torch.distributed._symmetric_memory) and, when the
+ * fabric supports it, their multicast addresses; it also enqueues a cross-rank barrier before
+ * vitk_peer_reduce_scan, between the two calls and after vitk_peer_adamw_broadcast. */
+#define VITK_MAX_PEERS 16
+typedef struct VitkPeerBuffers {
+  int world;
+  int rank;
+  const float* grad[VITK_MAX_PEERS]; /* fp32 gradient arena of every rank ([rank] = local) */
+  float* param[VITK_MAX_PEERS];      /* fp32 parameter arena of every rank */
+  void* shadow[VITK_MAX_PEERS];      /* bf16 shadow arena of every rank */
+  int* guard[VITK_MAX_PEERS];        /* int[2] {non-finite flag, steps skipped} of every rank, or all NULL */
+  const float* grad_mc;              /* multicast address of the gradient arenas, or NULL */
+  float* param_mc;                   /* multicast addresses of the parameter / shadow arenas, or NULL */
+  void* shadow_mc;
+} VitkPeerBuffers;
+
+/* grad[rank][lo, hi) = sum over ranks of grad[r][lo, hi) (multimem.ld_reduce through the switch
+ * when grad_mc is given, else peer loads in rank order); with guard buffers, a non-finite sum sets
+ * the flag of EVERY rank.  lo, hi: element offsets, multiples of 4. */
+int vitk_peer_reduce_scan(const VitkPeerBuffers* pb, long long lo, long long hi,
+                          vitk_stream_t stream);
+
+/* AdamW (the arithmetic of vitk_adamw_step_guarded) on the elements [lo, hi) of the LOCAL arenas
+ * with the local exp_avg / exp_avg_sq (full-size arrays indexed by the same offsets: only the owned
+ * shard is ever touched), the updated fp32 parameters and bf16 shadows stored to every rank
+ * (multimem.st when param_mc / shadow_mc are given).  Skipped when guard[rank][0] != 0. */
+int vitk_peer_adamw_broadcast(const VitkPeerBuffers* pb, float* exp_avg, float* exp_avg_sq,
+                              long long lo, long long hi, double lr, double beta1, double beta2,
+                              double eps, double weight_decay, int step, float grad_scale,
+                              vitk_stream_t stream);
+
 /* SetCriterion.loss_labels (train.py:1220-1239): F.cross_entropy(logits, targets, class_weight) -
  * the weighted mean  sum_i w[t_i] * (-log softmax(logits_i)[t_i]) / sum_i w[t_i]  over `rows`
  * predictions (every query of every image; background weight 0.1, train.py:1215-1217).
