@@ -28,6 +28,23 @@ def shard_range(n_items: int, rank: int, world: int) -> tuple[int, int]:
     return start, start + base + (1 if rank < extra else 0)
 
 
+def owned_pieces(slices: Sequence[tuple[int, int]], world: int, align: int = 64) -> list[list[tuple[int, int]]]:
+    """Ownership map of the peer-memory optimizer (csrc/peer_optim.cu): every slice [a, b) of the
+    flat arena is cut into `world` consecutive pieces whose inner boundaries are multiples of `align`
+    elements past a; owned[r][k] = rank r's piece of slice k (possibly empty).  The pieces of a slice
+    are disjoint and cover it exactly."""
+    if world <= 0:
+        raise ValueError(f"bad world size {world}")
+    owned: list[list[tuple[int, int]]] = [[] for _ in range(world)]
+    for a, b in slices:
+        per = ((b - a) // world + align - 1) // align * align
+        for r in range(world):
+            lo = min(a + r * per, b)
+            hi = b if r == world - 1 else min(a + (r + 1) * per, b)
+            owned[r].append((lo, hi))
+    return owned
+
+
 def allreduce_slices(flat: torch.Tensor, slices: Sequence[tuple[int, int]], group=None,
                      comm_stream=None, ready_events=None, on_slice_done=None) -> None:
     """In-place sum all-reduce of flat[a:b] for every slice, in the given order.  On CUDA the

@@ -60,14 +60,9 @@ class PeerArenas:
         completes at one point) is cut into `world` pieces with 64-element aligned boundaries, rank
         r owning piece r - so that the reduction of a bucket, started as soon as the backward has
         produced it, is spread over all ranks and links.  owned[r][k] = (lo, hi) of bucket k."""
+        from .dist import owned_pieces
         self.buckets = list(slices)
-        self.owned = [[] for _ in range(self.world)]
-        for a, b in self.buckets:
-            per = ((b - a) // self.world + _ALIGN - 1) // _ALIGN * _ALIGN
-            for r in range(self.world):
-                lo = min(a + r * per, b)
-                hi = b if r == self.world - 1 else min(a + (r + 1) * per, b)
-                self.owned[r].append((lo, hi))
+        self.owned = owned_pieces(self.buckets, self.world, _ALIGN)
 
     def buffers(self, with_guard: bool, multicast: bool = True) -> VitkPeerBuffers:
         pb = VitkPeerBuffers()
