@@ -120,3 +120,25 @@ def test_generic_attention_forward_and_backward(vitk, B, N, H, hd, impl):
     assert err < 3e-2 * max(1.0, scale), (err, scale)
     cos = torch.nn.functional.cosine_similarity(dqkv.float().flatten(), ref_in.grad.flatten(), dim=0)
     assert cos > 0.999
+
+
+def test_batched_transpose(vitk):
+    """vitk_transpose_bf16_batched (W^T copies for the input-gradient GEMMs): full 64 x 64 tiles take
+    the 16-byte path, ragged / unaligned matrices the element-wise one; several jobs per launch."""
+    import ctypes as C
+    g = torch.Generator(device="cuda").manual_seed(0)
+    shapes = [(768, 2304), (3072, 768), (100, 70), (64, 64), (130, 200), (8, 8)]
+    srcs = [torch.randn(r, c, generator=g, device="cuda").bfloat16() for r, c in shapes]
+    # an unaligned source: same data, shifted by one element
+    buf = torch.zeros(128 * 128 + 1, device="cuda").bfloat16()
+    buf[1:] = srcs[3].new_tensor(torch.randn(128 * 128, generator=torch.Generator().manual_seed(1)).tolist()).bfloat16()
+    srcs.append(buf[1:].view(128, 128))
+    shapes.append((128, 128))
+    dsts = [torch.empty(c, r, dtype=torch.bfloat16, device="cuda") for r, c in shapes]
+    n = len(shapes)
+    vitk._lib.check(vitk._lib.lib().vitk_transpose_bf16_batched(
+        n, (C.c_void_p * n)(*[t.data_ptr() for t in srcs]), (C.c_void_p * n)(*[t.data_ptr() for t in dsts]),
+        (C.c_int * n)(*[r for r, _ in shapes]), (C.c_int * n)(*[c for _, c in shapes]),
+        torch.cuda.current_stream().cuda_stream))
+    for s_, d_ in zip(srcs, dsts):
+        assert torch.equal(d_, s_.t().contiguous())
