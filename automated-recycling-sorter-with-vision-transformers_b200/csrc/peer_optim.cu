@@ -60,23 +60,38 @@ __global__ void __launch_bounds__(512)
 peer_reduce_scan_kernel(const PeerPtrs a, const float* __restrict__ grad_mc,
                         float* __restrict__ grad_local, long long lo4, long long hi4, int scan) {
   bool bad = false;
-  for (long long i = lo4 + blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < hi4;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    float4 s;
-    if (grad_mc != nullptr) {
-      s = multimem_ld_reduce_add(grad_mc + 4 * i);
-    } else {
-      s = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int r = 0; r < a.world; ++r) {   // fixed order
-        const float4 v = __ldcg(reinterpret_cast<const float4*>(a.grad[r]) + i);
-        s.x += v.x;
-        s.y += v.y;
-        s.z += v.z;
-        s.w += v.w;
+  // four independent 16-byte reductions in flight per thread: a round trip through the switch is
+  // several microseconds, and the links only fill with enough requests outstanding
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i0 = lo4 + blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i0 < hi4;
+       i0 += 4 * stride) {
+    float4 s[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long i = i0 + u * stride;
+      s[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < hi4) {
+        if (grad_mc != nullptr) {
+          s[u] = multimem_ld_reduce_add(grad_mc + 4 * i);
+        } else {
+          for (int r = 0; r < a.world; ++r) {   // fixed order
+            const float4 v = __ldcg(reinterpret_cast<const float4*>(a.grad[r]) + i);
+            s[u].x += v.x;
+            s[u].y += v.y;
+            s[u].z += v.z;
+            s[u].w += v.w;
+          }
+        }
       }
     }
-    reinterpret_cast<float4*>(grad_local)[i] = s;
-    bad = bad || !(isfinite(s.x) && isfinite(s.y) && isfinite(s.z) && isfinite(s.w));
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < hi4) {
+        reinterpret_cast<float4*>(grad_local)[i] = s[u];
+        bad = bad || !(isfinite(s[u].x) && isfinite(s[u].y) && isfinite(s[u].z) && isfinite(s[u].w));
+      }
+    }
   }
   if (scan && __syncthreads_or(bad ? 1 : 0)) {
     if (threadIdx.x == 0)
