@@ -83,6 +83,10 @@ assert worst < 1e-4
 del a, b, c, p0, n0
 torch.cuda.empty_cache()
 
+if os.environ.get("VITK_PEER_CHECK_QUICK") == "1":   # the pytest wrapper: correctness only
+    dist.destroy_process_group()
+    sys.exit(0)
+
 # ---- timing at the benchmark's geometry
 VITB = dict(image_size=224, patch_size=16, embed_dim=768, num_layers=12, num_heads=12, mlp_dim=3072)
 for sync in ("nccl", "peer", "nccl", "peer"):
