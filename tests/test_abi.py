@@ -95,3 +95,40 @@ def test_product_never_imports_the_oracle():
         assert not re.search(r"^\s*(from|import)\s+\S*oracle", src, flags=re.M), \
             f"{f} imports the oracle"
         assert "#include \"../oracle" not in src and "oracle/" not in src, f"{f} uses the oracle"
+
+
+def test_ctypes_structs_match_the_header(vitk, tmp_path):
+    """Every struct of include/vitk.h, compiled by gcc, has the size and the field offsets of its
+    ctypes mirror in _lib.py (a drifted mirror would hand the library shifted pointers)."""
+    import shutil
+    import subprocess
+    L = vitk._lib
+    mirrors = {name: getattr(L, name) for name in (
+        "VitkConfig", "VitkBlockWeights", "VitkWeights", "VitkBlockWeightsT", "VitkWeightsT",
+        "VitkBlockGrads", "VitkGrads", "VitkDetectionHeadConfig", "VitkDecoderLayerWeights",
+        "VitkDetectionHeadWeights", "VitkDecoderLayerWeightsT", "VitkDetectionHeadWeightsT",
+        "VitkDecoderLayerGrads", "VitkDetectionHeadGrads", "VitkPeerBuffers")}
+    header = (ROOT / "include" / "vitk.h").read_text()
+    for name in mirrors:
+        assert re.search(r"typedef struct %s\b" % name, header), f"{name} is not in include/vitk.h"
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no C compiler")
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "vitk.h"', "int main(void) {"]
+    for name, cls in mirrors.items():
+        lines.append(f'  printf("{name} size %zu\\n", sizeof({name}));')
+        for field, _ in cls._fields_:
+            lines.append(f'  printf("{name} {field} %zu\\n", offsetof({name}, {field}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run([gcc, "-I", str(ROOT / "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    for line in out.splitlines():
+        name, field, value = line.split()
+        cls = mirrors[name]
+        if field == "size":
+            assert C.sizeof(cls) == int(value), (name, C.sizeof(cls), value)
+        else:
+            assert getattr(cls, field).offset == int(value), (name, field)
