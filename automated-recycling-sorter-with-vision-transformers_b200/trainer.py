@@ -78,7 +78,9 @@ class PeerArenas:
 
     def barrier(self, channel: int = 0) -> None:
         """Cross-rank barrier enqueued on the current stream (signal pads of the parameter arena)."""
-        self.handles[0].barrier(channel=channel)
+        # (the timeout turns a rank that never arrives into a device-side trap - an error on the
+        # host - instead of a hang)
+        self.handles[0].barrier(channel=channel, timeout_ms=120000)
 
 
 class TrainState:
