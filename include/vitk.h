@@ -313,7 +313,8 @@ int vitk_split3(const float* in, long long ld_in, void* out_bf16, long long rows
  *     outputs = model(images) ; losses.backward() ; optimizer.step()
  * The loss of north_star's fine-tune is the mean cross-entropy of the 6-class CLS head; the
  * generic vitk_backward_tokens serves any loss computed by the caller on backbone(images).
- * Dropout: only p = 0 semantics are implemented (config.dropout_p must be 0). */
+ * Dropout: config.dropout_p > 0 applies nn.Dropout at the reference's five sites (see
+ * vitk_dropout_keep_mask below); forward and backward of a step must be given the same seed. */
 
 /* W^T copies ([in, out], bf16) of the four nn.Linear weights of a block: the input-gradient GEMMs
  * read the weight with its two dimensions swapped. Kept current by the caller after every
