@@ -29,7 +29,7 @@ using namespace ptx;
 // leader accumulates the SM clocks it spends waiting for operands (full barriers), for a free
 // accumulator stage (the epilogue), and its total run time; tests/trace_gemm.py reads them back.
 #ifdef VITK_GEMM_TRACE
-__device__ long long g_gemm_trace[160][4];
+__device__ long long g_gemm_trace[160][8];
 #define GT_BEGIN(v) const long long v = clock64()
 #define GT_ADD(acc, v) acc += clock64() - v
 #else
@@ -915,6 +915,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
       }
     };
     [[maybe_unused]] int ln_pending = -1;
+    [[maybe_unused]] long long gt_epi_wait = 0, gt_epi_ld = 0, gt_epi_math = 0, gt_epi_store = 0;
     // folded LayerNorm (consumer side): partial sums of the next tile's row, in flight
     [[maybe_unused]] float2 ln_next[8];
     [[maybe_unused]] float ln_rstd_next = 1.f;
@@ -993,12 +994,27 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
             ln_load_stats((tile_of(work_nx) / num_n_tiles) * kTileM + slab_row + lane, ln_next);
         }
       }
+      GT_BEGIN(gt_w);
       mbar_wait(tfull_bar(acc), acc_phase);
+      GT_ADD(gt_epi_wait, gt_w);
       tc_fence_after();
       [[maybe_unused]] int ln_commits = 0;  // bulk groups this warp commits for this tile
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                              static_cast<uint32_t>(acc * BLOCK_N + half * kColsPerWarp);
       const int n_base = n_blk * BLOCK_N + half * kColsPerWarp;
+      // The accumulator stage goes back to the MMA warp as soon as this warp's last TMEM read has
+      // landed in registers - the arithmetic and the stores of the last chunk then run under the
+      // next-but-one tile's MMAs instead of in front of them.
+      auto release_acc = [&]() {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (CTAS == 2 && !is_leader)
+            mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));
+          else
+            mbar_arrive(tempty_bar(acc));
+        }
+      };
       if constexpr (kStats) {
         // x (fp32, in place) += acc + bias; bf16 copy; partial row sums.  Thread == row.
         float sum1 = 0.f, sum2 = 0.f;
@@ -1008,6 +1024,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
         for (int c = 0; c < kColsPerWarp / 32; ++c) {
           tmem_ld_wait();
           if (c + 1 < kColsPerWarp / 32) tmem_ld_32x32b_x32(t_row + (c + 1) * 32, v[(c + 1) & 1]);
+          else release_acc();
           const int n0 = n_base + c * 32;
           if (row0 < M && n0 < N) {
             float x[32];
@@ -1086,6 +1103,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
           for (int c = 0; c < kColsPerWarp / 32; ++c) {
             tmem_ld_wait();
             if (c + 1 < kColsPerWarp / 32) tmem_ld_32x32b_x32(t_row + (c + 1) * 32, v[(c + 1) & 1]);
+            else release_acc();
             const int n0 = n_base + c * 32;
             if (row0 < M && n0 < N) {
               float x[32];
@@ -1106,9 +1124,13 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
 #pragma unroll 1
           for (int g = 0; g < kColsPerWarp / 64; ++g) {
             uint32_t v0[32], v1[32];
+            GT_BEGIN(gt_l);
             tmem_ld_32x32b_x32(t_row + g * 64, v0);
             tmem_ld_32x32b_x32(t_row + g * 64 + 32, v1);
             tmem_ld_wait();
+            if (g + 1 == kColsPerWarp / 64) release_acc();
+            GT_ADD(gt_epi_ld, gt_l);
+            GT_BEGIN(gt_m);
             const int n0 = n_base + g * 64;
             if (row0 < M && n0 < N) {
               float x0[32], x1[32];
@@ -1194,7 +1216,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 pk[j] = pack_bf16x2(x0[2 * j], x0[2 * j + 1]);
                 pk[16 + j] = pack_bf16x2(x1[2 * j], x1[2 * j + 1]);
               }
+              GT_ADD(gt_epi_math, gt_m);
+              GT_BEGIN(gt_s);
               stage_and_store(pk, stg, buf, lane, &tmap_c, n0, row0, false);
+              GT_ADD(gt_epi_store, gt_s);
             }
           }
         }
@@ -1207,6 +1232,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
         for (int c = 0; c < kColsPerWarp / 32; ++c) {
           tmem_ld_wait();
           if (c + 1 < kColsPerWarp / 32) tmem_ld_32x32b_x32(t_row + (c + 1) * 32, v[(c + 1) & 1]);
+          else release_acc();
           const int n0 = n_base + c * 32;
           if constexpr (EPI == EPI_RESID_F32) {
             if (row0 < M && n0 < N) resid_chunk_staged(v[c & 1], row0, n0, M, N, e, stg, lane);
@@ -1214,14 +1240,6 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
             if (m < M && n0 < N) epilogue_chunk<EPI>(v[c & 1], m, n0, N, e);
           }
         }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (CTAS == 2 && !is_leader)
-          mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));
-        else
-          mbar_arrive(tempty_bar(acc));
       }
       if (++acc == kAccStages) {
         acc = 0;
@@ -1250,6 +1268,14 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
         ln_pending = m_blk * CTAS + static_cast<int>(cta_rank);
       }
     }
+#ifdef VITK_GEMM_TRACE
+    if (lane == 0 && warp == kFirstEpiWarp && is_leader && cluster_id < 160) {
+      g_gemm_trace[cluster_id][4] = gt_epi_wait;
+      g_gemm_trace[cluster_id][5] = gt_epi_ld;
+      g_gemm_trace[cluster_id][6] = gt_epi_math;
+      g_gemm_trace[cluster_id][7] = gt_epi_store;
+    }
+#endif
     if constexpr (TMA_EPI) {
       if (lane == 0) tma_store_wait<0>();  // all bulk stores of this warp have completed
     }
@@ -1470,7 +1496,7 @@ int dispatch(const GemmProblem& p, cudaStream_t stream) {
 
 int gemm_debug_trace(long long* out, int n) {
 #ifdef VITK_GEMM_TRACE
-  if (n > 160 * 4) n = 160 * 4;
+  if (n > 160 * 8) n = 160 * 8;
   return cudaMemcpyFromSymbol(out, g_gemm_trace, static_cast<size_t>(n) * sizeof(long long)) ==
                  cudaSuccess ? n : -1;
 #else

@@ -22,19 +22,23 @@ def trace(name, fn):
         flush.zero_()
         fn()
     torch.cuda.synchronize()
-    buf = (C.c_longlong * 640)()
-    n = E.lib().vitk_debug_gemm_trace(buf, 640)
+    buf = (C.c_longlong * 1280)()
+    n = E.lib().vitk_debug_gemm_trace(buf, 1280)
     if n <= 0:
         print("not a trace build")
         sys.exit(0)
     npairs = (148 - (int(sys.argv[1]) if len(sys.argv) > 1 else 0)) // 2
-    rows = [buf[4 * i:4 * i + 4] for i in range(npairs)]
+    rows = [buf[8 * i:8 * i + 8] for i in range(npairs)]
     tot = sum(r[0] for r in rows) / npairs
     full = sum(r[1] for r in rows) / npairs
     empty = sum(r[2] for r in rows) / npairs
     tiles = sum(r[3] for r in rows) / npairs
     print(f"{name:28s} issuing warp: {tot:9.0f} clk total ({tot / tiles:6.0f} per tile), waits for "
           f"operands {100 * full / tot:5.1f} %, for an accumulator stage {100 * empty / tot:5.1f} %")
+    ep = [sum(r[k] for r in rows) / npairs / tiles for k in (4, 5, 6, 7)]
+    if any(ep):
+        print(f"{'':28s} epilogue warp 0, clk per tile: waits for the accumulator {ep[0]:6.0f}, TMEM "
+              f"loads {ep[1]:6.0f}, bias / activation / pack {ep[2]:6.0f}, staging + TMA store {ep[3]:6.0f}")
 
 
 x = torch.randn(M, D, generator=g, device="cuda")
