@@ -64,7 +64,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv,   // box {64, Nk,
   const uint32_t sdS = sdO + tile_bytes;        // 2 chunks x [128 keys x 128 B]
   const uint32_t sStage = sdS + 32768u;         // 8 warps x 4 KB
   const uint32_t vec_off = 4u * tile_bytes + 32768u + 32768u;
-  // two item parities x { lse_q * log2(e) [256], D_q = rowsum(d_ctx * ctx) [256] }
+  // two item parities x { lse_q * log2(e) [256], -scale * D_q [256] with D_q = rowsum(d_ctx * ctx) }
   float* sVec = reinterpret_cast<float*>(smem + vec_off);
   const uint32_t bar_base = base + vec_off + 4096u;
   auto bar = [&](int i) { return bar_base + 8u * i; };
@@ -236,7 +236,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv,   // box {64, Nk,
           l2 = p.lse[(static_cast<long long>(b) * p.H + h) * N + r] * kLog2e;
         }
         vLse[r] = l2;
-        vD[r] = dsum;
+        vD[r] = -dsum * p.scale;
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(9 + (it & 1)));
@@ -336,34 +336,39 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv,   // box {64, Nk,
             }
             uint32_t pp[16], ds[16];
             const int q0 = qt * 128 + ch * 32;
+            // branch-free over the key mask (sixteen predicated regions would serialise the
+            // lse load -> exp2 -> product chains of the pairs); rows of missing keys are zeroed after
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              float p0 = 0.f, p1 = 0.f, d0 = 0.f, d1 = 0.f;
-              if (key_ok) {
-                p0 = ex2_approx(fmaf(__uint_as_float(s[2 * j]), c, -sLse[q0 + 2 * j]));
-                p1 = ex2_approx(fmaf(__uint_as_float(s[2 * j + 1]), c, -sLse[q0 + 2 * j + 1]));
-                float g0 = __uint_as_float(dp[2 * j]), g1 = __uint_as_float(dp[2 * j + 1]);
-                float pd0 = p0, pd1 = p1;
-                if constexpr (DROP) {
-                  // one hash per element here: the pairs run along the keys, the thread owns one key
-                  const uint32_t half_nk = static_cast<uint32_t>(Nk >> 1);
-                  const uint32_t kp = static_cast<uint32_t>(key >> 1);
-                  const uint32_t b0 = drop_bits((drop_item_rows + q0 + 2 * j) * half_nk + kp, p.drop.key);
-                  const uint32_t b1 = drop_bits((drop_item_rows + q0 + 2 * j + 1) * half_nk + kp, p.drop.key);
-                  const bool k0 = (key & 1) ? drop_keep_hi(b0, p.drop.thresh) : drop_keep_lo(b0, p.drop.thresh);
-                  const bool k1 = (key & 1) ? drop_keep_hi(b1, p.drop.thresh) : drop_keep_lo(b1, p.drop.thresh);
-                  pd0 = k0 ? p0 * p.drop.scale : 0.f;
-                  pd1 = k1 ? p1 * p.drop.scale : 0.f;
-                  g0 = k0 ? g0 * p.drop.scale : 0.f;
-                  g1 = k1 ? g1 * p.drop.scale : 0.f;
-                }
-                d0 = p0 * (g0 - sD[q0 + 2 * j]) * p.scale;
-                d1 = p1 * (g1 - sD[q0 + 2 * j + 1]) * p.scale;
-                p0 = pd0;   // the dV product uses the dropped probabilities
-                p1 = pd1;
+              const float2 l2 = *reinterpret_cast<const float2*>(sLse + q0 + 2 * j);
+              const float2 dn = *reinterpret_cast<const float2*>(sD + q0 + 2 * j);  // -D_q * scale
+              float p0 = ex2_approx(fmaf(__uint_as_float(s[2 * j]), c, -l2.x));
+              float p1 = ex2_approx(fmaf(__uint_as_float(s[2 * j + 1]), c, -l2.y));
+              float g0 = __uint_as_float(dp[2 * j]), g1 = __uint_as_float(dp[2 * j + 1]);
+              float pd0 = p0, pd1 = p1;
+              if constexpr (DROP) {
+                // one hash per element here: the pairs run along the keys, the thread owns one key
+                const uint32_t half_nk = static_cast<uint32_t>(Nk >> 1);
+                const uint32_t kp = static_cast<uint32_t>(key >> 1);
+                const uint32_t b0 = drop_bits((drop_item_rows + q0 + 2 * j) * half_nk + kp, p.drop.key);
+                const uint32_t b1 = drop_bits((drop_item_rows + q0 + 2 * j + 1) * half_nk + kp, p.drop.key);
+                const bool k0 = (key & 1) ? drop_keep_hi(b0, p.drop.thresh) : drop_keep_lo(b0, p.drop.thresh);
+                const bool k1 = (key & 1) ? drop_keep_hi(b1, p.drop.thresh) : drop_keep_lo(b1, p.drop.thresh);
+                pd0 = k0 ? p0 * p.drop.scale : 0.f;
+                pd1 = k1 ? p1 * p.drop.scale : 0.f;
+                g0 = k0 ? g0 * p.drop.scale : 0.f;
+                g1 = k1 ? g1 * p.drop.scale : 0.f;
               }
-              pp[j] = pack_bf16x2(p0, p1);
-              ds[j] = pack_bf16x2(d0, d1);
+              // dS = P (dP - D) scale; the dV product uses the dropped probabilities
+              pp[j] = pack_bf16x2(pd0, pd1);
+              ds[j] = pack_bf16x2(p0 * fmaf(g0, p.scale, dn.x), p1 * fmaf(g1, p.scale, dn.y));
+            }
+            if (!key_ok) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                pp[j] = 0u;
+                ds[j] = 0u;
+              }
             }
             if (half_chunk) {
               uint32_t a8[8], b8[8];

@@ -75,5 +75,11 @@ int attention_bwd(const void* qkv, const void* ctx, const void* dctx, const floa
 int attention_bwd_tc(const void* qkv, const void* ctx, const void* dctx, const float* lse,
                      void* dqkv, int B, int N, int H, int hd, cudaStream_t stream,
                      const DropParams* drop = nullptr, float* dbias = nullptr);
+// Software-pipelined form of the same kernel (attention_bwd_tc2.cu: 64-query sub-blocks, score
+// tiles double-buffered in TMEM); preferred whenever its larger shared-memory footprint fits.
+bool attention_bwd_tc2_fits(int N, int H, bool with_dbias);
+int attention_bwd_tc2(const void* qkv, const void* ctx, const void* dctx, const float* lse,
+                      void* dqkv, int B, int N, int H, int hd, cudaStream_t stream,
+                      const DropParams* drop = nullptr, float* dbias = nullptr);
 
 }  // namespace vitk

@@ -29,7 +29,9 @@ def test_layernorm_backward(vitk, rows, D, dy_dtype):
 
 
 @pytest.mark.parametrize("B,N,H", [(2, 197, 12), (1, 5, 1), (3, 17, 2), (2, 64, 3), (1, 198, 4),
-                                   (1, 129, 2), (1, 256, 1), (1, 128, 2), (30, 197, 12)])
+                                   (1, 129, 2), (1, 256, 1), (1, 128, 2), (30, 197, 12),
+                                   # ragged 64-query sub-tiles of the pipelined tcgen05 kernel
+                                   (1, 224, 2), (2, 160, 2), (1, 176, 1), (2, 65, 2), (1, 240, 1)])
 @pytest.mark.parametrize("impl", [1, 2], ids=["mma_sync", "tcgen05"])
 def test_attention_backward(vitk, impl, B, N, H):
     vitk._lib.set_attention_impl(impl)
