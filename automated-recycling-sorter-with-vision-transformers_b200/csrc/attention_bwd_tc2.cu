@@ -558,11 +558,16 @@ attn_bwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_qkv,   // box {64, mi
               float g0 = __uint_as_float(dp[2 * j]), g1 = __uint_as_float(dp[2 * j + 1]);
               float pd0 = p0, pd1 = p1;
               if constexpr (DROP) {
-                // one hash per element here: the pairs run along the keys, the thread owns one key
+                // The mask's pairs run along the keys and the thread owns one key, so a hash serves
+                // the two lanes of a key pair: the even lane hashes query 2j, the odd lane query
+                // 2j + 1, and they swap (one hash + one shuffle per two elements instead of two).
                 const uint32_t half_nk = static_cast<uint32_t>(Nk >> 1);
                 const uint32_t kp = static_cast<uint32_t>(key >> 1);
-                const uint32_t b0 = drop_bits((drop_item_rows + q0 + 2 * j) * half_nk + kp, p.drop.key);
-                const uint32_t b1 = drop_bits((drop_item_rows + q0 + 2 * j + 1) * half_nk + kp, p.drop.key);
+                const uint32_t hm = drop_bits(
+                    (drop_item_rows + q0 + 2 * j + (lane & 1)) * half_nk + kp, p.drop.key);
+                const uint32_t ho = __shfl_xor_sync(0xffffffffu, hm, 1);
+                const uint32_t b0 = (lane & 1) ? ho : hm;
+                const uint32_t b1 = (lane & 1) ? hm : ho;
                 const bool k0 = (key & 1) ? drop_keep_hi(b0, p.drop.thresh) : drop_keep_lo(b0, p.drop.thresh);
                 const bool k1 = (key & 1) ? drop_keep_hi(b1, p.drop.thresh) : drop_keep_lo(b1, p.drop.thresh);
                 pd0 = k0 ? p0 * p.drop.scale : 0.f;
