@@ -107,18 +107,20 @@ def _library_masks(vitk, p, seed, B, N, D, H, Mlp, L):
     return masks
 
 
-@pytest.mark.parametrize("p,deit", [(0.1, False), (0.25, True)])
-def test_train_step_with_dropout_matches_oracle_given_the_same_masks(vitk, p, deit):
+@pytest.mark.parametrize("p,deit,size", [(0.1, False, 96), (0.25, True, 96),
+                                         # 170 tokens: two key tiles, three 64-query sub-tiles
+                                         (0.1, False, 208)])
+def test_train_step_with_dropout_matches_oracle_given_the_same_masks(vitk, p, deit, size):
     """nn.Dropout at all five sites of train.py (embedding, attention probabilities, projection,
     GELU, linear2): the kernels regenerate their masks from (seed, site, layer, index); injecting
     the same masks into the oracle must reproduce loss, every gradient and the AdamW update."""
-    kw = dict(image_size=96, patch_size=16, embed_dim=128, num_layers=2, num_heads=2, mlp_dim=256,
+    kw = dict(image_size=size, patch_size=16, embed_dim=128, num_layers=2, num_heads=2, mlp_dim=256,
               dropout=p)
     torch.manual_seed(33)
     model = vitk.ViTClassifier(num_classes=6, deit=deit, **kw)
     sd = {k: v.clone() for k, v in model.state_dict().items()}
-    B, N = 5, 36 + (2 if deit else 1)
-    x, y = O.synthetic_images(B, 96, seed=17), O.synthetic_labels(B, 6, seed=4)
+    B, N = 5, (size // 16) ** 2 + (2 if deit else 1)
+    x, y = O.synthetic_images(B, size, seed=17), O.synthetic_labels(B, 6, seed=4)
     masks = _library_masks(vitk, p, 77, B, N, 128, 2, 256, 2)
     keep_rate = masks[("gelu", 0)].ne(0).float().mean().item()
     assert abs(keep_rate - (1 - p)) < 0.02, keep_rate
