@@ -555,8 +555,8 @@ attn_bwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_qkv,   // box {64, mi
               const float2 dn = *reinterpret_cast<const float2*>(sD + q0 + 2 * j);  // -D_q * scale
               float p0 = ex2_approx(fmaf(__uint_as_float(s[2 * j]), c, -l2.x));
               float p1 = ex2_approx(fmaf(__uint_as_float(s[2 * j + 1]), c, -l2.y));
-              float g0 = __uint_as_float(dp[2 * j]), g1 = __uint_as_float(dp[2 * j + 1]);
-              float pd0 = p0, pd1 = p1;
+              const float g0 = __uint_as_float(dp[2 * j]), g1 = __uint_as_float(dp[2 * j + 1]);
+              float pd0 = p0, pd1 = p1, gs0 = p.scale, gs1 = p.scale;
               if constexpr (DROP) {
                 // The mask's pairs run along the keys and the thread owns one key, so a hash serves
                 // the two lanes of a key pair: the even lane hashes query 2j, the odd lane query
@@ -568,16 +568,18 @@ attn_bwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_qkv,   // box {64, mi
                 const uint32_t ho = __shfl_xor_sync(0xffffffffu, hm, 1);
                 const uint32_t b0 = (lane & 1) ? ho : hm;
                 const uint32_t b1 = (lane & 1) ? hm : ho;
-                const bool k0 = (key & 1) ? drop_keep_hi(b0, p.drop.thresh) : drop_keep_lo(b0, p.drop.thresh);
-                const bool k1 = (key & 1) ? drop_keep_hi(b1, p.drop.thresh) : drop_keep_lo(b1, p.drop.thresh);
-                pd0 = k0 ? p0 * p.drop.scale : 0.f;
-                pd1 = k1 ? p1 * p.drop.scale : 0.f;
-                g0 = k0 ? g0 * p.drop.scale : 0.f;
-                g1 = k1 ? g1 * p.drop.scale : 0.f;
+                // this key's 16 bits moved to the top: keep iff (bits << sh) >= thresh << 16
+                const uint32_t sh = (key & 1) ? 0u : 16u;
+                const uint32_t t16 = p.drop.thresh << 16;
+                const bool k0 = (b0 << sh) >= t16, k1 = (b1 << sh) >= t16;
+                pd0 = p0 * (k0 ? p.drop.scale : 0.f);
+                pd1 = p1 * (k1 ? p.drop.scale : 0.f);
+                gs0 = k0 ? p.drop.scale * p.scale : 0.f;   // dropout mask and scale of dP in one factor
+                gs1 = k1 ? p.drop.scale * p.scale : 0.f;
               }
               // dS = P (dP - D) scale; the dV product uses the dropped probabilities
               pp[j] = pack_bf16x2(pd0, pd1);
-              ds[j] = pack_bf16x2(p0 * fmaf(g0, p.scale, dn.x), p1 * fmaf(g1, p.scale, dn.y));
+              ds[j] = pack_bf16x2(p0 * fmaf(g0, gs0, dn.x), p1 * fmaf(g1, gs1, dn.y));
             }
             if (!key_ok) {
 #pragma unroll
