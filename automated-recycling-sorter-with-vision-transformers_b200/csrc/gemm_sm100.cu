@@ -1017,6 +1017,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
       };
       if constexpr (kStats) {
         // x (fp32, in place) += acc + bias; bf16 copy; partial row sums.  Thread == row.
+        const bool o2_wide =
+            ((reinterpret_cast<uintptr_t>(e.out2) | static_cast<uintptr_t>(e.ldo * 2)) & 31u) == 0;
         float sum1 = 0.f, sum2 = 0.f;
         uint32_t v[2][32];
         tmem_ld_32x32b_x32(t_row, v[0]);
@@ -1066,7 +1068,20 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
             if (row0 + lane < M) {
               __nv_bfloat16* o2 = reinterpret_cast<__nv_bfloat16*>(e.out2) +
                                   static_cast<size_t>(row0 + lane) * e.ldo + n0;
-              if (n0 + 32 <= N) {
+              if (n0 + 32 <= N && o2_wide) {
+                // two 32-byte stores: whole sectors (four 16-byte stores per row reach the L2 as
+                // half-sector writes and count twice against its slice throughput)
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+                  st_global_v8(o2 + 16 * j, pack_bf16x2(x[16 * j + 0], x[16 * j + 1]),
+                               pack_bf16x2(x[16 * j + 2], x[16 * j + 3]),
+                               pack_bf16x2(x[16 * j + 4], x[16 * j + 5]),
+                               pack_bf16x2(x[16 * j + 6], x[16 * j + 7]),
+                               pack_bf16x2(x[16 * j + 8], x[16 * j + 9]),
+                               pack_bf16x2(x[16 * j + 10], x[16 * j + 11]),
+                               pack_bf16x2(x[16 * j + 12], x[16 * j + 13]),
+                               pack_bf16x2(x[16 * j + 14], x[16 * j + 15]));
+              } else if (n0 + 32 <= N) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                   uint4 pk;
